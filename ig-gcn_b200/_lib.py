@@ -1,0 +1,67 @@
+"""ctypes binding of the C ABI declared in include/igcn_b200.h.
+
+There is deliberately no fallback: if the CUDA library is missing or a call fails, a RuntimeError is
+raised (north star: "no CPU fallback").  Tensors cross the boundary as raw device pointers + sizes; the
+current torch stream is passed as the cudaStream_t.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libigcn_b200.so")
+_lib = None
+
+_P, _I = ctypes.c_void_p, ctypes.c_int64
+
+# name -> (restype, argtypes)
+SIGNATURES = {
+    "igcn_last_error": (ctypes.c_char_p, []),
+    "igcn_version": (ctypes.c_int, []),
+    "igcn_sm_count": (ctypes.c_int, []),
+    "igcn_collate_csr": (ctypes.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "igcn_csr_from_edge_index": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "igcn_sgcn_param_count": (_I, [_I, _I, _I, _I]),
+    "igcn_sgcn_bwd_ctas": (_I, [_I, _I, _I, _I, _I, _I]),
+    "igcn_sgcn_encoder_fwd": (ctypes.c_int, [_P] * 7 + [_I] * 6 + [_P, _P, _P]),
+    "igcn_sgcn_encoder_bwd": (ctypes.c_int, [_P] * 12 + [_I] * 6 + [_P, _P, _I, _P, _P]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "igcn_b200: CUDA library %s is missing -- run `python -m igcn_b200.build` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL). Tensors must be contiguous."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "igcn_b200: non-contiguous tensor at the C boundary"
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, lib().igcn_last_error().decode()))
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("igcn_b200 operators run on CUDA tensors only (no CPU fallback); got a %s tensor" % t.device)

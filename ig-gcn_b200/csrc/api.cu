@@ -1,0 +1,32 @@
+// Error channel + small queries of the C ABI (include/igcn_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace igcn {
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+}  // namespace igcn
+
+extern "C" const char* igcn_last_error(void) { return igcn::g_err; }
+extern "C" int igcn_version(void) { return 100; }
+extern "C" int igcn_sm_count(void) { return igcn::sm_count(); }

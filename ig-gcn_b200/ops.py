@@ -1,0 +1,83 @@
+"""autograd wrappers around the C-ABI kernels (include/igcn_b200.h).  CUDA tensors only."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .data import GraphCSR
+
+
+def pack_layer_params(weights, biases):
+    """[W_1 (H,F0) | b_1 | W_2 (H,H) | b_2 | ...] -- the `wb` layout of igcn_sgcn_encoder_*."""
+    parts = []
+    for w, b in zip(weights, biases):
+        parts.append(w.reshape(-1))
+        parts.append(b.reshape(-1))
+    return torch.cat(parts) if parts else None
+
+
+class _SGCNEncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, prob, prob_bias, wb, csr: GraphCSR, L: int, H: int, want_pe: bool):
+        _lib.require_cuda(x, prob, prob_bias, wb)
+        lib = _lib.lib()
+        x = x.contiguous().float()
+        B, R, F0 = csr.B, csr.R, x.shape[1]
+        if x.shape[0] != B * R:
+            raise RuntimeError("sgcn_encoder: x has %d rows, batch structure has %d" % (x.shape[0], B * R))
+        explain = prob is not None
+        probc = prob.contiguous().float() if explain else None
+        pbc = prob_bias.contiguous().float().view(-1) if explain else None
+        wbc = wb.contiguous().float() if wb is not None else None
+        out = torch.empty((B, R, L * H), dtype=torch.float32, device=x.device)
+        p_e = torch.empty(csr.E, dtype=torch.float32, device=x.device) if (explain and want_pe) else None
+        with torch.cuda.device(x.device):
+            rc = lib.igcn_sgcn_encoder_fwd(_lib.ptr(x), _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(csr.csr_w),
+                                           _lib.ptr(probc), _lib.ptr(pbc), _lib.ptr(wbc), B, R, F0, H, L, csr.max_eg,
+                                           _lib.ptr(out), _lib.ptr(p_e), _lib.stream())
+        _lib.check(rc, "igcn_sgcn_encoder_fwd")
+        ctx.csr, ctx.L, ctx.H, ctx.explain = csr, L, H, explain
+        ctx.save_for_backward(x, probc, pbc, wbc, out)
+        if p_e is None:
+            p_e = x.new_empty(0)
+            ctx.mark_non_differentiable(p_e)
+        return out, p_e
+
+    @staticmethod
+    def backward(ctx, g_out, g_pe):
+        x, prob, pb, wb, out = ctx.saved_tensors
+        csr, L, H = ctx.csr, ctx.L, ctx.H
+        lib = _lib.lib()
+        B, R, F0 = csr.B, csr.R, x.shape[1]
+        P = lib.igcn_sgcn_param_count(R, F0, H, L)
+        n_cta = lib.igcn_sgcn_bwd_ctas(B, R, F0, H, L, csr.max_eg)
+        dx = torch.empty_like(x)
+        partials = torch.empty((max(n_cta, 1), P), dtype=torch.float32, device=x.device)
+        grads = torch.empty(P, dtype=torch.float32, device=x.device)
+        g_out = g_out.contiguous() if L > 0 else None
+        gpe = g_pe.contiguous() if (ctx.explain and g_pe is not None and g_pe.numel() == csr.E and csr.E > 0) else None
+        with torch.cuda.device(x.device):
+            rc = lib.igcn_sgcn_encoder_bwd(_lib.ptr(x), _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(csr.csr_w),
+                                           _lib.ptr(csr.rowptr_s), _lib.ptr(csr.csc_pos), _lib.ptr(prob), _lib.ptr(pb),
+                                           _lib.ptr(wb), _lib.ptr(out), _lib.ptr(g_out), _lib.ptr(gpe), B, R, F0, H, L,
+                                           csr.max_eg, _lib.ptr(dx), _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream())
+        _lib.check(rc, "igcn_sgcn_encoder_bwd")
+        nwb = P - R * F0 - 2 * F0
+        d_wb = grads[:nwb] if wb is not None else None
+        d_prob = grads[nwb:nwb + R * F0].view(R, F0) if ctx.explain else None
+        d_pb = grads[nwb + R * F0:].view(2 * F0, 1) if ctx.explain else None
+        return dx, d_prob, d_pb, d_wb, None, None, None, None
+
+
+def sgcn_encoder(x, csr: GraphCSR, weights, biases, prob=None, prob_bias=None, want_pe=False):
+    """Fused SGCN encoder. Returns (out (B,R,L*H), p_e (E,) in CSR-slot order or empty)."""
+    L = len(weights)
+    H = weights[0].shape[0] if L else 0
+    wb = pack_layer_params(weights, biases)
+    return _SGCNEncoderFn.apply(x, prob, prob_bias, wb, csr, L, H, want_pe)
+
+
+def edge_mask(x, csr: GraphCSR, prob, prob_bias):
+    """p_e of cal_probability (kernel/sgcn_img_snp.py:141-142) in CSR-slot order (masks only, L=0)."""
+    _, p_e = _SGCNEncoderFn.apply(x, prob, prob_bias, None, csr, 0, 0, True)
+    return p_e

@@ -1,0 +1,100 @@
+/*
+ * igcn_b200 -- C ABI of the B200-native IG-GCN graph-convolution hot path.
+ *
+ * Boundary contract:
+ *   - every pointer is a DEVICE pointer unless the parameter is named host_*;
+ *   - the caller (PyTorch) owns every buffer: inputs, outputs and workspaces.  The library never
+ *     allocates, frees or retains device memory;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*); no internal
+ *     synchronisation, no host read-back;
+ *   - return value 0 = success, otherwise one of IGCN_ERR_*; igcn_last_error() gives the text.
+ *     Nothing throws, nothing calls exit().  There is no CPU fallback: an unsupported shape is an error;
+ *   - outputs are fully overwritten unless the parameter comment says "accumulates".
+ *
+ * Each entry point names the reference interface it replaces (file:line in Houliang-Zhou/IG-GCN).
+ */
+#ifndef IGCN_B200_H_
+#define IGCN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IGCN_OK 0
+#define IGCN_ERR_BAD_ARG 1     /* null pointer, negative size, misaligned buffer             */
+#define IGCN_ERR_UNSUPPORTED 2 /* shape outside what the sm_100a kernels are built for        */
+#define IGCN_ERR_LAUNCH 3      /* cudaGetLastError() != cudaSuccess after the launch          */
+
+const char* igcn_last_error(void);
+int igcn_version(void);
+/* number of SMs of the current device (used by the host side to size partial-sum workspaces) */
+int igcn_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Collation: replaces Batch.from_data_list (batch.py:24-123) as driven by DataLoader.collate
+ * (dataloader.py:26-29), plus the per-call index juggling inside PyG's gcn_norm / propagate.
+ *
+ * in : graph_ptr (B+1) i64  prefix sums of edges per graph of this batch
+ *      loc_src/loc_dst (E) i32  LOCAL node ids (0..R-1) of every edge, graph after graph, in the
+ *                               reference's order (row-major COO, util_gdc.py:84-86)
+ *      w (E) f32  edge_attr in the same order
+ * out: edge_index (2,E) i64  global ids = local + g*R            -- bit exact with batch.py:54-55
+ *      batch (B*R) i64       graph id per node                   -- bit exact with batch.py:96-99
+ *      rowptr_t (B*R+1) i32, csr_src (E) i32 (global ids), csr_perm (E) i32 (original edge id of
+ *        every CSR slot), csr_w (E) f32: in-edges grouped by TARGET, stable in original edge order
+ *      rowptr_s (B*R+1) i32, csc_pos (E) i32: out-edges grouped by SOURCE (stable); csc_pos is the
+ *        CSR slot of that edge (the transposed operator of the backward pass)
+ * One CTA per graph, counting sort in shared memory, no global atomics.  max_eg = max edges of
+ * any graph in the batch (host knows graph_ptr).
+ */
+int igcn_collate_csr(const int64_t* graph_ptr, const int32_t* loc_src, const int32_t* loc_dst, const float* w,
+                     int64_t B, int64_t R, int64_t E, int64_t max_eg,
+                     int64_t* edge_index, int64_t* batch,
+                     int32_t* rowptr_t, int32_t* csr_src, int32_t* csr_perm, float* csr_w,
+                     int32_t* rowptr_s, int32_t* csc_pos, void* stream);
+
+/* Same CSR products from an already-collated global edge_index (2,E) i64 whose graphs each own R
+ * consecutive node ids (what a reference Batch moved to the device looks like). */
+int igcn_csr_from_edge_index(const int64_t* edge_index, const float* w, int64_t B, int64_t R, int64_t E,
+                             int64_t max_eg, int32_t* graph_eptr /* (B+1) i32 out */,
+                             int32_t* rowptr_t, int32_t* csr_src, int32_t* csr_perm, float* csr_w,
+                             int32_t* rowptr_s, int32_t* csc_pos, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused SGCN encoder: replaces cal_probability (kernel/sgcn_img_snp.py:133-151), L x PyG GCNConv
+ * (gcn_norm + Linear + propagate + bias; call sites kernel/sgcn_img_snp.py:218-221, kernel/sgcn.py:363-366),
+ * relu, torch.cat and to_dense_batch (kernel/sgcn_img_snp.py:223-228) in ONE kernel.
+ *
+ *   x (B*R,F0) f32; CSR by target from igcn_collate_csr; prob (R,F0) / prob_bias (2*F0) f32 or NULL
+ *   for the plain (isExplain=False) pass; wb = packed layer parameters
+ *   [W_1 (H,F0) | b_1 (H) | W_2 (H,H) | b_2 (H) | ...] f32.
+ *   out (B,R,L*H) f32: relu(conv_l) in concat layout;  p_e (E) f32 in CSR-slot order or NULL.
+ * L == 0 computes the masks only (p_e), which is what loss_probability needs.
+ */
+int igcn_sgcn_encoder_fwd(const float* x, const int32_t* rowptr_t, const int32_t* csr_src, const float* csr_w,
+                          const float* prob, const float* prob_bias, const float* wb,
+                          int64_t B, int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg,
+                          float* out, float* p_e, void* stream);
+
+/* Backward of the above (the autograd graph of cal_probability + gcn_norm + GCNConv x L + relu + cat).
+ *   g_out (B,R,L*H) f32 = dLoss/d out;  g_pe (E) f32 = extra dLoss/d p_e in CSR-slot order or NULL.
+ *   dx (B*R,F0) f32 out.
+ *   partials (n_cta, P) f32 workspace, P = igcn_sgcn_param_count(...): per-CTA partial parameter
+ *   gradients in the order [wb layout | dprob (R*F0) | dprob_bias (2*F0)]; reduced in a fixed order
+ *   into grads (P) f32 by the same call (deterministic, no float atomics).
+ */
+int64_t igcn_sgcn_param_count(int64_t R, int64_t F0, int64_t H, int64_t L);
+int64_t igcn_sgcn_bwd_ctas(int64_t B, int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg);
+int igcn_sgcn_encoder_bwd(const float* x, const int32_t* rowptr_t, const int32_t* csr_src, const float* csr_w,
+                          const int32_t* rowptr_s, const int32_t* csc_pos,
+                          const float* prob, const float* prob_bias, const float* wb,
+                          const float* out, const float* g_out, const float* g_pe,
+                          int64_t B, int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg,
+                          float* dx, float* partials, int64_t n_cta, float* grads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IGCN_B200_H_ */
