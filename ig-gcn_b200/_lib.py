@@ -24,8 +24,14 @@ SIGNATURES = {
     "igcn_csr_from_edge_index": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "igcn_sgcn_param_count": (_I, [_I, _I, _I, _I]),
     "igcn_sgcn_bwd_ctas": (_I, [_I, _I, _I, _I, _I, _I]),
-    "igcn_sgcn_encoder_fwd": (ctypes.c_int, [_P] * 7 + [_I] * 6 + [_P, _P, _P]),
-    "igcn_sgcn_encoder_bwd": (ctypes.c_int, [_P] * 12 + [_I] * 6 + [_P, _P, _I, _P, _P]),
+    "igcn_sgcn_encoder_fwd": (ctypes.c_int, [_P] * 7 + [_I] * 7 + [_P, _P, _P]),
+    "igcn_sgcn_encoder_bwd": (ctypes.c_int, [_P] * 12 + [_I] * 7 + [_P, _P, _I, _P, _P]),
+    "igcn_go_spmm_fwd": (ctypes.c_int, [_P] * 4 + [_I] * 5 + [_P, _P]),
+    "igcn_go_spmm_bwd": (ctypes.c_int, [_P] * 8 + [_I] * 5 + [_P, _P, _P]),
+    "igcn_go_layer_param_count": (_I, [_I, _I, _I]),
+    "igcn_go_layer_bwd_ctas": (_I, [_I] * 7),
+    "igcn_go_layer_fwd": (ctypes.c_int, [_P] * 13 + [_I] * 9 + [_P, _P, _P]),
+    "igcn_go_layer_bwd": (ctypes.c_int, [_P] * 13 + [_I] * 9 + [_P, _P, _P, _P, _I, _P, _P]),
 }
 
 

@@ -34,7 +34,8 @@ struct EncArgs {
     float* dx;
     float* partials;
     int B, R, F0, H, L, maxEg;
-    int P;  // param count (bwd)
+    int P;     // param count (bwd)
+    int relu;  // 1: relu after every layer (SGCN encoder); 0: plain GCNConv output (single-layer operator)
 };
 
 __host__ __device__ inline int layer_fin(int l, int F0, int H) { return l == 0 ? F0 : H; }
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(256) sgcn_encoder_fwd_kernel(EncArgs a) {
                 for (int k = rp[i]; k < rp[i + 1]; ++k) acc = fmaf(enorm[k], U[esrc[k] * H + f], acc);
                 acc = fmaf(nii[i], U[idx], acc);  // self loop last, as scatter_add sees it
                 acc += bias[f];
-                Hbuf[i * LH + l * H + f] = fmaxf(acc, 0.f);
+                Hbuf[i * LH + l * H + f] = a.relu ? fmaxf(acc, 0.f) : acc;
             }
             __syncthreads();
         }
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(256) sgcn_encoder_bwd_kernel(EncArgs a) {
                 const int i = idx / H, f = idx - i * H;
                 float gsum = go[i * LH + l * H + f];
                 if (l < L - 1) gsum += Gl[idx];  // dH^{l} left here (layout [i*H+f]) by the previous iteration
-                Gl[idx] = (fo[i * LH + l * H + f] > 0.f) ? gsum : 0.f;
+                Gl[idx] = (!a.relu || fo[i * LH + l * H + f] > 0.f) ? gsum : 0.f;
             }
             // H^{l-1}
             if (l == 0) {
@@ -475,7 +476,7 @@ extern "C" int64_t igcn_sgcn_bwd_ctas(int64_t B, int64_t R, int64_t F0, int64_t 
 
 extern "C" int igcn_sgcn_encoder_fwd(const float* x, const int32_t* rowptr_t, const int32_t* csr_src, const float* csr_w,
                                      const float* prob, const float* prob_bias, const float* wb, int64_t B, int64_t R,
-                                     int64_t F0, int64_t H, int64_t L, int64_t max_eg, float* out, float* p_e, void* stream) {
+                                     int64_t F0, int64_t H, int64_t L, int64_t max_eg, int64_t relu, float* out, float* p_e, void* stream) {
     int rc = check_shapes("sgcn_encoder_fwd", B, R, F0, H, L, max_eg);
     if (rc) return rc;
     IGCN_REQUIRE(x && rowptr_t, IGCN_ERR_BAD_ARG, "sgcn_encoder_fwd: null x/rowptr");
@@ -485,7 +486,7 @@ extern "C" int igcn_sgcn_encoder_fwd(const float* x, const int32_t* rowptr_t, co
     if (B == 0) return IGCN_OK;
     EncArgs a{};
     a.x = x; a.rowptr_t = rowptr_t; a.csr_src = csr_src; a.csr_w = csr_w; a.prob = prob; a.prob_bias = prob_bias; a.wb = wb;
-    a.out_w = out; a.pe_w = p_e; a.B = (int)B; a.R = (int)R; a.F0 = (int)F0; a.H = (int)H; a.L = (int)L; a.maxEg = (int)max_eg;
+    a.out_w = out; a.pe_w = p_e; a.relu = relu ? 1 : 0; a.B = (int)B; a.R = (int)R; a.F0 = (int)F0; a.H = (int)H; a.L = (int)L; a.maxEg = (int)max_eg;
     size_t smem = fwd_smem(a.R, a.F0, a.H, a.L, a.maxEg);
     rc = allow_smem(sgcn_encoder_fwd_kernel, smem, "sgcn_encoder_fwd");
     if (rc) return rc;
@@ -497,7 +498,7 @@ extern "C" int igcn_sgcn_encoder_fwd(const float* x, const int32_t* rowptr_t, co
 extern "C" int igcn_sgcn_encoder_bwd(const float* x, const int32_t* rowptr_t, const int32_t* csr_src, const float* csr_w,
                                      const int32_t* rowptr_s, const int32_t* csc_pos, const float* prob, const float* prob_bias,
                                      const float* wb, const float* out, const float* g_out, const float* g_pe, int64_t B,
-                                     int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg, float* dx, float* partials,
+                                     int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg, int64_t relu, float* dx, float* partials,
                                      int64_t n_cta, float* grads, void* stream) {
     int rc = check_shapes("sgcn_encoder_bwd", B, R, F0, H, L, max_eg);
     if (rc) return rc;
@@ -511,6 +512,7 @@ extern "C" int igcn_sgcn_encoder_bwd(const float* x, const int32_t* rowptr_t, co
     a.prob = prob; a.prob_bias = prob_bias; a.wb = wb; a.out = out; a.g_out = g_out; a.g_pe = g_pe; a.dx = dx; a.partials = partials;
     a.B = (int)B; a.R = (int)R; a.F0 = (int)F0; a.H = (int)H; a.L = (int)L; a.maxEg = (int)max_eg;
     a.P = (int)igcn_sgcn_param_count(R, F0, H, L);
+    a.relu = relu ? 1 : 0;
     const int want = (int)igcn_sgcn_bwd_ctas(B, R, F0, H, L, max_eg);
     IGCN_REQUIRE(B == 0 || n_cta == want, IGCN_ERR_BAD_ARG, "sgcn_encoder_bwd: n_cta=%lld, expected igcn_sgcn_bwd_ctas()=%d",
                  (long long)n_cta, want);

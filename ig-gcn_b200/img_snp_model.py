@@ -1,0 +1,310 @@
+"""`SGCN_GCN_IMGSNP` on the fused kernels (reference: kernel/sgcn_img_snp.py).
+
+Constructor arguments, forward signature `model(data, temperature, device, isExplain=False)`, the 6-tuple it
+returns, the helper methods the training loop calls (`loss_probability`, `consist_loss`,
+`OrthogonalConstraint`, `cal_probability`) and every parameter name/shape follow the reference, so
+kernel/train_eval_sgcn_img_snps.py::train() runs against it unchanged and checkpoints interchange.
+
+What changed inside:
+  * mask -> norm -> L x GCNConv -> relu -> cat -> to_dense_batch is ONE kernel (ops.sgcn_encoder); the two
+    `x.min().item()` host syncs (sgcn_img_snp.py:225,293) disappear because every graph has `rois` nodes,
+    so to_dense_batch is a view;
+  * loss_probability reuses the p_e computed by the explain pass instead of a third cal_probability;
+  * consist_loss / OrthogonalConstraint use the B x B Gram form (no D x D intermediates);
+  * `n_snps` comes from A_g (the reference hard-codes 54, sgcn_img_snp.py:96).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn import init
+from torch.nn.parameter import Parameter
+
+from . import ops
+from .data import Batch
+from .go_net import Gene_ontology_network
+
+
+class _Lin(nn.Module):
+    """Holds `weight` so the GCN weight sits at `<conv>.lin.weight` as in PyG 2.0.2."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.weight = Parameter(torch.empty(cout, cin))
+
+    def reset_parameters(self):
+        a = math.sqrt(6.0 / (self.weight.size(0) + self.weight.size(1)))     # PyG glorot
+        with torch.no_grad():
+            self.weight.uniform_(-a, a)
+
+
+class GCNConv(nn.Module):
+    """Parameter container with PyG's GCNConv names (`lin.weight` (out,in), `bias` (out,)).  The SGCN models
+    run all their GCNConv layers through one fused kernel; see ops.sgcn_encoder."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin = _Lin(in_channels, out_channels)
+        self.bias = Parameter(torch.zeros(out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.lin.reset_parameters()
+        init.zeros_(self.bias)
+
+    def forward(self, x, edge_index, edge_weight=None, csr=None):
+        if edge_weight is not None and edge_weight.requires_grad:
+            raise RuntimeError("igcn_b200.GCNConv: gradients w.r.t. edge_weight are produced by the fused encoder "
+                               "(ops.sgcn_encoder with prob/prob_bias), not by the single-layer operator")
+        if csr is None:
+            w = edge_weight if edge_weight is not None else torch.ones(edge_index.shape[1], device=x.device)
+            csr = Batch.from_device_tensors(x.detach(), edge_index, w, x.shape[0]).csr      # one graph of N nodes
+        out, _ = ops.sgcn_encoder(x, csr, [self.lin.weight], [self.bias], relu=False)
+        return out.view(x.shape[0], self.out_channels)
+
+
+def get_csr(data):
+    csr = getattr(data, "csr", None) if isinstance(data, Batch) else getattr(data, "_igcn_csr", None)
+    return csr
+
+
+class MaskedEncoderMixin:
+    """cal_probability / loss bookkeeping shared by the SGCN model family."""
+
+    def _csr_for(self, data, rois):
+        csr = get_csr(data)
+        if csr is None:
+            b = Batch.from_device_tensors(data.x.detach(), data.edge_index, data.edge_attr, rois)
+            csr = b.csr
+            try:
+                data._igcn_csr = csr
+            except Exception:
+                pass
+        self._last_csr = (data.edge_index.data_ptr(), data.edge_index.shape[1], csr)
+        return csr
+
+    def _csr_lookup(self, x, edge_index, edge_weight):
+        last = getattr(self, "_last_csr", None)
+        if last is not None and last[0] == edge_index.data_ptr() and last[1] == edge_index.shape[1]:
+            return last[2]
+        return Batch.from_device_tensors(x.detach(), edge_index, edge_weight, self.rois).csr
+
+    def _conv_params(self):
+        convs = [self.conv1] + list(self.convs)
+        return [c.lin.weight for c in convs], [c.bias for c in convs]
+
+    def _edge_prob(self, x, edge_index, edge_weight):
+        """p_e in CSR-slot order; reuses the explain pass's value when it was computed on the same inputs."""
+        c = getattr(self, "_pe_cache", None)
+        key = (x.data_ptr(), edge_index.data_ptr(), self.prob._version, self.prob_bias._version)
+        if c is not None and c[0] == key and torch.is_grad_enabled() == c[2]:
+            return c[1]
+        csr = self._csr_lookup(x, edge_index, edge_weight)
+        return ops.edge_mask(x, csr, self.prob, self.prob_bias)
+
+    def cal_probability(self, x, edge_index, edge_weight, snps_feat=None):
+        """Reference surface (sgcn_img_snp.py:133-151).  edge outputs are returned in ORIGINAL edge order."""
+        csr = self._csr_lookup(x, edge_index, edge_weight)
+        N, D = x.shape
+        x_feat_prob = (x.view(N // self.rois, self.rois, D) * self.prob).reshape(N, D)
+        pe_csr = ops.edge_mask(x, csr, self.prob, self.prob_bias)
+        edge_prob = torch.empty_like(pe_csr).index_copy(0, csr.csr_perm.long(), pe_csr)
+        edge_weight_prob = edge_weight * edge_prob
+        if snps_feat is not None:
+            sp = torch.sigmoid(self.snps_prob)
+            return x_feat_prob, edge_weight_prob, self.prob, edge_prob, snps_feat * sp, sp
+        return x_feat_prob, edge_weight_prob, self.prob, edge_prob
+
+
+def _l1_entropy(p, eps=1e-6):
+    n = p.numel()
+    return p.abs().sum() / n, -(p * torch.log(p + eps) + (1 - p) * torch.log(1 - p + eps)).sum() / n
+
+
+class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
+
+    def __init__(self, num_layers, hidden, A_g, A, pool_dim, l_dim, device, *args, hidden_linear=64, rois=90, H_0=3,
+                 num_classes=2, isCrossAtten=False, isSoftSimilarity=False, rbf_gamma=0.005, graph_pool=False,
+                 isuseProb4Regr=False, num_regr=4, model4eachregr=False, isImageOnly=True, isSNPsOnly=False,
+                 isMultiFusion=False, **kwargs):
+        super().__init__()
+        self.device = device
+        self.isCrossAtten, self.isSoftSimilarity, self.rbf_gamma = isCrossAtten, isSoftSimilarity, rbf_gamma
+        self.model4eachregr, self.isuseProb4Regr = model4eachregr, isuseProb4Regr
+        self.isImageOnly, self.isSNPsOnly, self.num_regr = isImageOnly, isSNPsOnly, num_regr
+        self.input = None
+        self.final_conv_acts = None
+        self.final_conv_grads = None
+        self.rois, self.prob_dim, self.isMultiFusion = rois, H_0, isMultiFusion
+        self.num_layers, self.hidden = num_layers, hidden
+        n_snps = int(A_g.shape[1])
+        self.n_snps = n_snps
+        self.conv1 = GCNConv(H_0, hidden)
+        self.convs = nn.ModuleList()
+        n_l = 2
+        dim_snps_atten = hidden
+        if isCrossAtten:
+            for _ in range(num_layers - 2):
+                self.convs.append(GCNConv(hidden, hidden))
+                dim_snps_atten += hidden
+            self.convs.append(GCNConv(hidden, hidden))
+            dim_snps_atten += hidden
+            self.pool = pool_dim[0]
+            self.multihead_attn = nn.MultiheadAttention(dim_snps_atten, 2, batch_first=True)
+        else:
+            for _ in range(num_layers - 1):
+                self.convs.append(GCNConv(hidden, hidden))
+        self.graph_pool = graph_pool
+        enc_dim = rois * (1 + len(self.convs)) * hidden
+        if graph_pool:
+            self.lin1 = nn.Linear(3 * num_layers * hidden + l_dim, hidden_linear)
+            self.lin1_regr = nn.Linear(3 * num_layers * hidden + l_dim, hidden_linear)
+        else:
+            if isImageOnly:
+                self.lin1 = nn.Linear(rois * num_layers * hidden, hidden_linear)
+            elif isSNPsOnly:
+                self.lin1 = nn.Linear(l_dim + n_snps, hidden_linear)
+            else:
+                self.lin1 = nn.Linear(rois * num_layers * hidden + l_dim, hidden_linear)
+            extra = rois * H_0 if isuseProb4Regr else 0
+            if isImageOnly:
+                self.lin1_regr = nn.Linear(rois * num_layers * hidden + extra, hidden_linear)
+            elif isSNPsOnly:
+                self.lin1_regr = nn.Linear(l_dim + n_snps, hidden_linear)
+            else:
+                self.lin1_regr = nn.Linear(rois * num_layers * hidden + l_dim + extra, hidden_linear)
+        self.lin2 = nn.Linear(hidden_linear, num_classes)
+        self.lin2_regr = nn.Linear(hidden_linear, num_regr)
+        self.batch_norm_1d = nn.BatchNorm1d(num_features=rois * num_layers * hidden + l_dim)     # unused, kept for state_dict parity
+        self.prob = Parameter(torch.empty((rois, H_0)))
+        self.prob_bias = Parameter(torch.empty((H_0 * 2, 1)))
+        init.kaiming_uniform_(self.prob_bias, a=math.sqrt(5))
+        self.edge_prob = Parameter(torch.empty((rois, rois)))                                      # unused by the reference too
+        init.kaiming_uniform_(self.prob, a=math.sqrt(5))
+        init.kaiming_uniform_(self.edge_prob, a=math.sqrt(5))
+        self.snps_prob = Parameter(torch.empty((1, n_snps)))
+        init.kaiming_uniform_(self.snps_prob, a=math.sqrt(5))
+        self.go_network = Gene_ontology_network(A_g, A, 2, n_l, [5, 5], pool_dim, l_dim, device, dim_snps_atten=dim_snps_atten)
+        self.batch_norm = nn.BatchNorm1d(num_layers * hidden)                                      # unused, state_dict parity
+        self.dropout_masks = None     # test hook: dict name -> scale tensor (oracle.MODEL_MASK_NAMES)
+        self._enc_dim = enc_dim
+
+    def reset_parameters(self):
+        self.conv1.reset_parameters()
+        for conv in self.convs:
+            conv.reset_parameters()
+        for m in (self.lin1, self.lin2, self.lin1_regr, self.lin2_regr):
+            m.reset_parameters()
+        with torch.no_grad():
+            init.kaiming_uniform_(self.prob_bias, a=math.sqrt(5))
+            init.kaiming_uniform_(self.prob, a=math.sqrt(5))
+            init.kaiming_uniform_(self.edge_prob, a=math.sqrt(5))
+            init.kaiming_uniform_(self.snps_prob, a=math.sqrt(5))
+
+    def activations_hook(self, grad):
+        self.final_conv_grads = grad
+
+    # --------------------------------------------------------------------------------------------------
+    def loss_probability(self, x, edge_index, edge_weight, hp, eps=1e-6):
+        """sgcn_img_snp.py:153-181 (sums over edges are order independent, so CSR-slot order is used as is)."""
+        edge_prob = self._edge_prob(x, edge_index, edge_weight)
+        f_l1, f_en = _l1_entropy(torch.sigmoid(self.prob), eps)
+        e_l1, e_en = _l1_entropy(edge_prob, eps)
+        s_l1, s_en = _l1_entropy(torch.sigmoid(self.snps_prob), eps)
+        loss_l1 = hp.lamda_x_l1 * f_l1 + hp.lamda_e_l1 * e_l1 + hp.lamda_x_l1 * s_l1
+        loss_entropy = hp.lamda_x_ent * f_en + hp.lamda_e_ent * e_en + hp.lamda_x_ent * s_en
+        return loss_l1 + loss_entropy
+
+    def consist_loss(self, s, tsne_result=None):
+        """tr(s^T (D-W) s)/B^2 (sgcn_img_snp.py:183-196) in Gram form: sum_i d_i |s_i|^2 - sum_ij W_ij <s_i,s_j>."""
+        n = s.shape[0]
+        if n == 0:
+            return 0
+        gram = s @ s.t()
+        if self.isSoftSimilarity and tsne_result is not None:
+            W = torch.exp(-self.rbf_gamma * torch.cdist(tsne_result, tsne_result, p=2) ** 2)
+        else:
+            W = torch.ones(n, n, device=s.device, dtype=s.dtype)
+        return ((W.sum(1) * gram.diagonal()).sum() - (W * gram).sum()) / (n * n)
+
+    def OrthogonalConstraint(self, w):
+        """||w^T w - I_D||_F^2 / B^2 with row-normalised w (sgcn_img_snp.py:198-205) = (||w w^T||_F^2 - 2B + D)/B^2."""
+        wn = w / w.norm(dim=1)[:, None]
+        gram = wn @ wn.t()
+        n, d = wn.shape
+        return ((gram * gram).sum() - 2.0 * gram.diagonal().sum() + d) / (n * n)
+
+    # --------------------------------------------------------------------------------------------------
+    def _mask(self, name, t, p):
+        if not self.training:
+            return t
+        if self.dropout_masks is not None:
+            return t * self.dropout_masks[name].to(t.device).float()
+        return F.dropout(t, p=p, training=True)
+
+    def forward(self, data, temperature=None, device=None, isExplain=False):
+        x, edge_index, edge_weight = data.x, data.edge_index, data.edge_attr
+        snps_feat = data.snps_feat
+        if not x.requires_grad and x.is_leaf:
+            x.requires_grad = True                     # the reference wants dLoss/dx (sgcn_img_snp.py:210)
+        self.input = x
+        csr = self._csr_for(data, self.rois)
+        Ws, bs = self._conv_params()
+        if isExplain:
+            batch_x, p_e = ops.sgcn_encoder(x, csr, Ws, bs, self.prob, self.prob_bias, want_pe=True)
+            self._pe_cache = ((x.data_ptr(), edge_index.data_ptr(), self.prob._version, self.prob_bias._version), p_e,
+                              torch.is_grad_enabled())
+            snps_feat_prob = snps_feat * torch.sigmoid(self.snps_prob)
+        else:
+            batch_x, _ = ops.sgcn_encoder(x, csr, Ws, bs)
+            snps_feat_prob = snps_feat
+        B = batch_x.shape[0]
+        img_out = batch_x.view(B, -1)
+        if self.graph_pool:
+            img_out = torch.cat([batch_x.mean(1), batch_x.max(1)[0], batch_x.sum(1)], 1)
+        go = self.go_network
+        go.dropout_masks = self.dropout_masks
+        latent, x_hat, _, atten_out = go(snps_feat_prob, temperature, device)
+        if self.isCrossAtten:
+            attn_output, _ = self.multihead_attn(batch_x, atten_out, atten_out, need_weights=False)
+            out_cross = F.relu(attn_output)
+        else:
+            out_cross = torch.cat((img_out, latent), -1)
+        if self.graph_pool:
+            out_cross = torch.cat([out_cross.mean(1), out_cross.max(1)[0], out_cross.sum(1)], 1)
+        else:
+            out_cross = out_cross.reshape(B, -1)
+
+        def regr_head(out_lin):
+            if self.isuseProb4Regr:
+                img_feat = (x.view(B, self.rois, -1) * self.prob).reshape(B, -1)       # data.x (unmasked) * prob (:293-297)
+                feat = torch.cat((out_lin, img_feat), -1)
+            else:
+                feat = out_lin
+            r = self._mask("lin1_regr", F.relu(self.lin1_regr(feat)), 0.3)
+            return self.lin2_regr(r)
+
+        if self.isImageOnly:
+            out_z = img_out
+            out_lin = out_z
+        elif self.isSNPsOnly:
+            out_z = latent
+            out_lin = torch.cat((snps_feat_prob, latent), -1)
+        else:
+            out_z = (img_out + out_cross) / 2
+            out_lin = torch.cat((out_z, latent), -1)
+        linear_outf = F.relu(self.lin1(out_lin))
+        logits = self.lin2(self._mask("lin1", linear_outf, 0.5))
+        if self.isSNPsOnly:
+            r = self._mask("lin1_regr", F.relu(self.lin1_regr(out_lin)), 0.3)
+            our_reg = self.lin2_regr(r)
+        else:
+            our_reg = regr_head(out_lin)
+        return F.log_softmax(logits, dim=-1), x_hat, out_z, out_lin, linear_outf, our_reg
+
+    def __repr__(self):
+        return self.__class__.__name__

@@ -18,7 +18,7 @@ def pack_layer_params(weights, biases):
 
 class _SGCNEncoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, prob, prob_bias, wb, csr: GraphCSR, L: int, H: int, want_pe: bool):
+    def forward(ctx, x, prob, prob_bias, wb, csr: GraphCSR, L: int, H: int, want_pe: bool, relu: bool = True):
         _lib.require_cuda(x, prob, prob_bias, wb)
         lib = _lib.lib()
         x = x.contiguous().float()
@@ -33,10 +33,10 @@ class _SGCNEncoderFn(torch.autograd.Function):
         p_e = torch.empty(csr.E, dtype=torch.float32, device=x.device) if (explain and want_pe) else None
         with torch.cuda.device(x.device):
             rc = lib.igcn_sgcn_encoder_fwd(_lib.ptr(x), _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(csr.csr_w),
-                                           _lib.ptr(probc), _lib.ptr(pbc), _lib.ptr(wbc), B, R, F0, H, L, csr.max_eg,
+                                           _lib.ptr(probc), _lib.ptr(pbc), _lib.ptr(wbc), B, R, F0, H, L, csr.max_eg, int(relu),
                                            _lib.ptr(out), _lib.ptr(p_e), _lib.stream())
         _lib.check(rc, "igcn_sgcn_encoder_fwd")
-        ctx.csr, ctx.L, ctx.H, ctx.explain = csr, L, H, explain
+        ctx.csr, ctx.L, ctx.H, ctx.explain, ctx.relu = csr, L, H, explain, bool(relu)
         ctx.save_for_backward(x, probc, pbc, wbc, out)
         if p_e is None:
             p_e = x.new_empty(0)
@@ -60,24 +60,24 @@ class _SGCNEncoderFn(torch.autograd.Function):
             rc = lib.igcn_sgcn_encoder_bwd(_lib.ptr(x), _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(csr.csr_w),
                                            _lib.ptr(csr.rowptr_s), _lib.ptr(csr.csc_pos), _lib.ptr(prob), _lib.ptr(pb),
                                            _lib.ptr(wb), _lib.ptr(out), _lib.ptr(g_out), _lib.ptr(gpe), B, R, F0, H, L,
-                                           csr.max_eg, _lib.ptr(dx), _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream())
+                                           csr.max_eg, int(ctx.relu), _lib.ptr(dx), _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream())
         _lib.check(rc, "igcn_sgcn_encoder_bwd")
         nwb = P - R * F0 - 2 * F0
         d_wb = grads[:nwb] if wb is not None else None
         d_prob = grads[nwb:nwb + R * F0].view(R, F0) if ctx.explain else None
         d_pb = grads[nwb + R * F0:].view(2 * F0, 1) if ctx.explain else None
-        return dx, d_prob, d_pb, d_wb, None, None, None, None
+        return dx, d_prob, d_pb, d_wb, None, None, None, None, None
 
 
-def sgcn_encoder(x, csr: GraphCSR, weights, biases, prob=None, prob_bias=None, want_pe=False):
+def sgcn_encoder(x, csr: GraphCSR, weights, biases, prob=None, prob_bias=None, want_pe=False, relu=True):
     """Fused SGCN encoder. Returns (out (B,R,L*H), p_e (E,) in CSR-slot order or empty)."""
     L = len(weights)
     H = weights[0].shape[0] if L else 0
     wb = pack_layer_params(weights, biases)
-    return _SGCNEncoderFn.apply(x, prob, prob_bias, wb, csr, L, H, want_pe)
+    return _SGCNEncoderFn.apply(x, prob, prob_bias, wb, csr, L, H, want_pe, relu)
 
 
 def edge_mask(x, csr: GraphCSR, prob, prob_bias):
     """p_e of cal_probability (kernel/sgcn_img_snp.py:141-142) in CSR-slot order (masks only, L=0)."""
-    _, p_e = _SGCNEncoderFn.apply(x, prob, prob_bias, None, csr, 0, 0, True)
+    _, p_e = _SGCNEncoderFn.apply(x, prob, prob_bias, None, csr, 0, 0, True, True)
     return p_e

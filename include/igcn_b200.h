@@ -72,10 +72,11 @@ int igcn_csr_from_edge_index(const int64_t* edge_index, const float* w, int64_t 
  *   [W_1 (H,F0) | b_1 (H) | W_2 (H,H) | b_2 (H) | ...] f32.
  *   out (B,R,L*H) f32: relu(conv_l) in concat layout;  p_e (E) f32 in CSR-slot order or NULL.
  * L == 0 computes the masks only (p_e), which is what loss_probability needs.
+ * relu = 1: ReLU after every layer (the SGCN encoder); relu = 0: raw GCNConv output (single-layer operator).
  */
 int igcn_sgcn_encoder_fwd(const float* x, const int32_t* rowptr_t, const int32_t* csr_src, const float* csr_w,
                           const float* prob, const float* prob_bias, const float* wb,
-                          int64_t B, int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg,
+                          int64_t B, int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg, int64_t relu,
                           float* out, float* p_e, void* stream);
 
 /* Backward of the above (the autograd graph of cal_probability + gcn_norm + GCNConv x L + relu + cat).
@@ -91,8 +92,51 @@ int igcn_sgcn_encoder_bwd(const float* x, const int32_t* rowptr_t, const int32_t
                           const int32_t* rowptr_s, const int32_t* csc_pos,
                           const float* prob, const float* prob_bias, const float* wb,
                           const float* out, const float* g_out, const float* g_pe,
-                          int64_t B, int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg,
+                          int64_t B, int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg, int64_t relu,
                           float* dx, float* partials, int64_t n_cta, float* grads, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GO-hierarchy encoder (reference: kernel/go_model.py).  The DAG is static: the host builds, once per
+ * model (replacing go_model.py:42-74,161-168), a CSR by row (rowptr,col,row_of) and a CSC by column
+ * (colptr,crow,cpos: row and CSR slot of every column entry) for each layer's sub-adjacency.
+ *
+ * igcn_go_spmm_*: SNP->GO encode (go_model.py:208-215; channels=2, values t[0],t[1]) and GO->SNP decode
+ * (go_model.py:281-282; channels=1, values t_D[0]) with learnable per-nnz values:
+ *     out[b,r,c] = sum_{k in row r} vals[c*nnz+k] * in[b, col[k]]
+ *   in (B,n_in) f32, vals (channels,nnz) f32, out (B,n_row,channels) f32.
+ *   bwd: d_in (B,n_in) or NULL, d_vals (channels,nnz) (summed over the batch in subject order).
+ */
+int igcn_go_spmm_fwd(const float* in, const int32_t* rowptr, const int32_t* col, const float* vals,
+                     int64_t B, int64_t n_in, int64_t n_row, int64_t nnz, int64_t channels, float* out, void* stream);
+int igcn_go_spmm_bwd(const float* g_out, const float* in, const int32_t* row_of, const int32_t* col,
+                     const int32_t* colptr, const int32_t* crow, const int32_t* cpos, const float* vals,
+                     int64_t B, int64_t n_in, int64_t n_row, int64_t nnz, int64_t channels,
+                     float* d_in, float* d_vals, void* stream);
+
+/* igcn_go_layer_*: one hierarchy layer, fused per subject.
+ *   attn=1 (encoder, go_model.py:219-251): x_in = X Wa^T, x_s = X Ws^T, a_e = exp(tanh(u.[x_in_row|x_in_col])),
+ *          row-normalise, aggregate, + x_s*sigmoid(v.x_s); square (m_in == m_row), self_off = 0.
+ *   attn=0 (decoder, go_model.py:258-275): uniform 1/|row| weights, self term x_s[i-self_off] on rows >= self_off.
+ *   then LayerNorm over the node axis per (subject, channel) with gamma/beta (m_row), ReLU, optional dropout
+ *   scale mask (B,m_row) (Dropout2d drops whole nodes per subject), output rows [keep_from, m_row).
+ *   x (B,m_in,din), Wa/Ws (dout,din), u (2*dout), v (dout), y (B,m_row-keep_from,dout), stats (B,2*dout) = mean|rstd.
+ *   bwd: dx (B,m_in,din); grads (P) = [dWa | dWs | du | dv | dgamma | dbeta], P = igcn_go_layer_param_count;
+ *   partials (n_cta,P) workspace, n_cta = igcn_go_layer_bwd_ctas(...).  Deterministic (no float atomics).
+ *   Instantiated (din,dout,attn): (2,5,1) (5,5,1) (5,5,0) (5,2,0) -- the reference's f_dim=[5,5], in_f_dim=2.
+ */
+int64_t igcn_go_layer_param_count(int64_t din, int64_t dout, int64_t m_row);
+int64_t igcn_go_layer_bwd_ctas(int64_t B, int64_t din, int64_t dout, int64_t m_in, int64_t m_row, int64_t nnz, int64_t attn);
+int igcn_go_layer_fwd(const float* x, const float* Wa, const float* Ws, const float* u, const float* v,
+                      const float* gamma, const float* beta, const float* mask,
+                      const int32_t* rowptr, const int32_t* col, const int32_t* colptr, const int32_t* crow, const int32_t* cpos,
+                      int64_t B, int64_t m_in, int64_t m_row, int64_t nnz, int64_t din, int64_t dout, int64_t attn,
+                      int64_t self_off, int64_t keep_from, float* y, float* stats, void* stream);
+int igcn_go_layer_bwd(const float* x, const float* Wa, const float* Ws, const float* u, const float* v,
+                      const float* gamma, const float* beta, const float* mask,
+                      const int32_t* rowptr, const int32_t* col, const int32_t* colptr, const int32_t* crow, const int32_t* cpos,
+                      int64_t B, int64_t m_in, int64_t m_row, int64_t nnz, int64_t din, int64_t dout, int64_t attn,
+                      int64_t self_off, int64_t keep_from, const float* stats, const float* g_y,
+                      float* dx, float* partials, int64_t n_cta, float* grads, void* stream);
 
 #ifdef __cplusplus
 }

@@ -159,7 +159,10 @@ def case_model(name, L, H, R, B, pool, S, seed, skip_big_grads=False, steps=0):
     out.update({"sub/" + k: np.asarray(v) for k, v in sub.items()})
     out.update(adj=adj, go_snps=go_snps, pool=np.asarray(pool_dim[0]),
                cfg=np.asarray([L, H, R, B, S]))
-    lam = [0.7, 1.0, 0.5, 1.5e-6, 0.1, 0.05]       # all six terms active (main.py:73-78 defaults have [0]=[5]=0)
+    # classification terms switched on (default main.py:73 has [0]=0); orthogonality weight at its default 0
+    # (main.py:78): the reference evaluates that term as an fp32 D x D product that is ~2e-3 off its own fp64
+    # value, so it is pinned separately (see "orthogonal") instead of contaminating the step loss
+    lam = [0.7, 1.0, 0.5, 1.5e-6, 0.1, 0.0]
     out["lambda_loss"] = np.asarray(lam)
     names = ["logp", "x_hat", "out_z", "out_lin", "linear_outf", "our_reg"]
 
@@ -196,7 +199,7 @@ def case_model(name, L, H, R, B, pool, S, seed, skip_big_grads=False, steps=0):
     out["orthogonal"] = m.OrthogonalConstraint(o[2]).detach().numpy()
     cp = m.cal_probability(b.x, b.edge_index, b.edge_attr, b.snps_feat)
     for n, t in zip(["x_feat_prob", "edge_weight_prob", "x_prob", "edge_prob", "snps_feat_prob", "snps_prob"], cp):
-        out["calprob/" + n] = t.detach().numpy()
+        out["calprob/" + n] = t.detach().numpy().copy()      # x_prob IS the parameter: copy before Adam touches it
     # restore BN running stats so the step below starts from the stored state_dict
     m.load_state_dict({**m.state_dict(), **bn_before})
 
