@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the IG-GCN hot path: fwd+bwd graphs/s of the SGCN img+SNP training step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2|config4] [--impl igcn|reference]
+
+One JSON line on stdout (rank 0).  A step = the body of the reference's train()
+(kernel/train_eval_sgcn_img_snps.py:516-547): zero_grad, plain forward, explain forward, mask / regression /
+reconstruction / consistency losses, backward, gradient all-reduce (N>1), Adam step -- on one batch of synthetic
+ADNI-shaped subjects.  Nothing is skipped inside the timed region.
+
+  value : graphs/s with the collated batch already resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e   : graphs/s through the public API: pinned host arrays -> DataLoader-style collation (H2D + collate
+          kernel) -> train step -> loss read back to the host, every step
+  roofline     : the dominant igcn kernel, algorithmic bytes / CUDA-event duration measured inside the timed steps
+  cpu_baseline : the oracle port of the reference's CPU path (with its per-subject GO loop) on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: SGCN img+SNP, 90 ROIs, batch 256, learned node/edge masks
+    "config2": dict(B=256, R=90, S=54, L=2, H=16, pool=[20, 15, 10, 8, 1], num_classes=3, num_regr=3,
+                    desc="SGCN_GCN_IMGSNP img+SNP, 90-ROI brain graphs (top-k=3 GDC), S=54 SNPs, GO 54 terms, batch 256/GPU"),
+    # BASELINE.json configs[3]: 264 ROIs, batch 4096
+    "config4": dict(B=4096, R=264, S=54, L=2, H=16, pool=[20, 15, 10, 8, 1], num_classes=3, num_regr=3,
+                    desc="SGCN_GCN_IMGSNP img+SNP+GO, 264-ROI brain graphs, batch 4096/GPU"),
+}
+LAMBDA = [0.0, 1.0, 0.5, 0.0000015, 0.1, 0.0]      # main.py:73-78 defaults
+METRIC, UNIT = "fwd+bwd graphs/s, SGCN img+SNP", "graphs/s"
+CPU_SAMPLE_B = 32                                  # the reference's own default batch size (main.py:94)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.rows, self.proc, self.index = [], None, index
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def build_problem(w, rank, dev):
+    from igcn_b200 import synthetic as syn
+    from igcn_b200.data import SubjectSet
+    from igcn_b200.img_snp_model import SGCN_GCN_IMGSNP
+    adj, go_snps, pool_dim = syn.make_go_hierarchy(w["pool"], w["S"], seed=0)
+    A = torch.tensor(adj).float().t().to_sparse().coalesce()
+    A_g = torch.tensor(go_snps).float().to_sparse().coalesce()
+    torch.manual_seed(0)                                   # identical replicas on every rank
+    model = SGCN_GCN_IMGSNP(w["L"], w["H"], A_g, A, pool_dim, 32, dev, rois=w["R"], H_0=3, num_classes=w["num_classes"],
+                            isCrossAtten=True, isSoftSimilarity=True, rbf_gamma=0.01, isuseProb4Regr=True,
+                            num_regr=w["num_regr"], isImageOnly=False, isSNPsOnly=False)
+    sub = syn.make_subjects(w["B"], rois=w["R"], n_snps=w["S"], seed=1234, first_id=rank * w["B"],
+                            num_classes=w["num_classes"], num_regr=w["num_regr"])
+    return model, sub, (adj, go_snps, pool_dim)
+
+
+def algorithmic_bytes(tag, w, E):
+    """SURVEY.md 8(d) per-unit figures x units per launch (pre-built i32 CSR; each compulsory tensor once)."""
+    B, R, LH, F0 = w["B"], w["R"], w["L"] * w["H"], 3
+    N = B * R
+    if tag.startswith("sgcn_encoder_fwd"):
+        L = int(tag.split("L=")[1].rstrip("]"))
+        b = N * F0 * 4 + E * 8 + (N + 1) * 4 + N * L * w["H"] * 4
+        if "explain" in tag:
+            b += E * 4 + R * F0 * 4
+        return b
+    if tag.startswith("sgcn_encoder_bwd"):
+        L = int(tag.split("L=")[1].rstrip("]"))
+        b = 2 * N * L * w["H"] * 4 + N * F0 * 4 + E * 8 + (N + 1) * 4 + E * 4 + (N + 1) * 4 + N * F0 * 4
+        if "explain" in tag:
+            b += E * 4
+        return b
+    return None
+
+
+def run_igcn(args, w):
+    import torch.distributed as dist
+    from igcn_b200 import _lib, train as T
+    from igcn_b200.data import Batch, SubjectSet
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model, sub, _ = build_problem(w, rank, dev)
+    model = model.to(dev).train()
+    ss = SubjectSet(sub)
+    B = w["B"]
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0, capturable=not args.eager)
+    flat = T.FlatGradAllReduce(model)
+    batch = Batch.collate(ss, np.arange(B), dev)
+    E = batch.csr.E
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # 256 MB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def eager_step(data):
+        return T.train_step(model, data, opt, LAMBDA, flat, True)
+
+    launches_per_step0 = _lib.launch_count
+    eager_step(batch)
+    launches_per_step = _lib.launch_count - launches_per_step0
+    if args.eager:
+        step = eager_step
+        collate_into = None
+    else:
+        graphed = T.GraphedTrainStep(model, opt, batch, LAMBDA, flat, True)      # the step, captured once
+
+        def step(data):
+            assert data is batch
+            return graphed()
+        collate_into = batch
+    for _ in range(max(args.warmup, 3)):
+        step(batch)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    # ---- timed region: K steps, device-timed, L2 flushed between steps ---------------------------------------
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = step(batch)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = launches_per_step * args.steps
+    ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    # ---- e2e: host arrays -> collate -> step -> loss on the host, every step ----------------------------------
+    staging = {}
+    rng = np.random.default_rng(rank)
+    for _ in range(3):
+        step(Batch.collate(ss, rng.permutation(B), dev, staging, out=collate_into)).item()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        idx = rng.permutation(B)
+        loss = step(Batch.collate(ss, idx, dev, staging, out=collate_into))
+        loss_host = loss.item()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop() if sampler else None
+    # ---- per-kernel CUDA-event timing of the igcn kernels: the same step run eagerly (events cannot be read back
+    #      from inside a graph replay), L2 flushed before every step, on the launching stream -------------------
+    n_prof = min(args.steps, 5)
+    _lib.profile_begin()
+    for _ in range(n_prof):
+        flush.zero_()
+        eager_step(batch)
+    prof = _lib.profile_end()
+    h2d = sum(getattr(ss, k)[:1].element_size() * int(np.prod(getattr(ss, k).shape[1:])) * B for k in ss.FIELDS) + \
+        E * (4 + 4 + 4) + (B + 1) * 8
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    # dominant igcn kernel by total device time inside the timed steps
+    kern = {k: dict(calls=c, ms_per_call=tot / max(c, 1), share_of_step=tot / n_prof / ms) for k, (c, tot) in prof.items()}
+    cand = [(v["calls"] * v["ms_per_call"], k) for k, v in kern.items() if algorithmic_bytes(k, w, E) is not None]
+    top = max(cand)[1]
+    ab = algorithmic_bytes(top, w, E)
+    ach = ab / (kern[top]["ms_per_call"] * 1e-3) / 1e9
+    out = dict(metric=METRIC, value=B * world / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+               ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+               config=dict(workload=args.workload, description=w["desc"], graphs_per_gpu=B, rois=w["R"], layers=w["L"], hidden=w["H"],
+                           edges_per_batch=E, step="zero_grad + plain fwd + explain fwd + losses + bwd + grad all-reduce + Adam",
+                           lambda_loss=LAMBDA, l2="flushed between timed steps (256 MB write)", parallelism="dp%d" % world,
+                           launch="eager" if args.eager else "whole step captured in one CUDA graph",
+                           batchnorm="per-rank batch statistics", loss_last=float(loss_host)),
+               e2e=dict(value=B * world / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
+                        ms_per_step=e2e_ms),
+               gpu_launches=int(launches),
+               roofline=dict(bound="hbm", kernel=top, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
+                             peak_source=peak_src, algorithmic_bytes_per_launch=int(ab), us_per_launch=kern[top]["ms_per_call"] * 1e3),
+               kernels=kern, clocks=clocks, wall_s_timed_region=t_wall)
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(w, steps=3, warmup=1)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(w, steps, warmup, threads=None):
+    """Oracle port of the reference's CPU path (per-subject GO loop as in go_model.py:236-244) on a bounded sample."""
+    from igcn_b200 import synthetic as syn
+    from oracle import igcn_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    Bc = min(CPU_SAMPLE_B, w["B"])
+    model, _, (adj, go_snps, pool_dim) = build_problem(dict(w, B=Bc), 0, "cpu")
+    P = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in model.state_dict().items()}
+    sub = syn.make_subjects(Bc, rois=w["R"], n_snps=w["S"], seed=1234, num_classes=w["num_classes"], num_regr=w["num_regr"])
+    c = O.collate(sub, np.arange(Bc))
+    b = {k: torch.from_numpy(v) for k, v in c.items()}
+    prep = O.go_index_prep(adj.T, go_snps, w["pool"])
+    leaves = [v for v in P.values() if v.requires_grad]
+    opt = torch.optim.Adam(leaves, lr=1e-3)
+    gen = torch.Generator().manual_seed(0)
+    shapes = dict(go_enc0=(Bc, sum(w["pool"]), 1), go_enc1=(Bc, sum(w["pool"][1:]), 1), go_B=(Bc, sum(w["pool"][2:])),
+                  go_dec0=(Bc, sum(w["pool"][1:]), 1), go_dec1=(Bc, sum(w["pool"]), 1), go_BD=(Bc, sum(w["pool"])),
+                  go_latent=(Bc, 32), lin1=(Bc, 64), lin1_regr=(Bc, 64))
+    ps = dict(go_enc0=0.4, go_enc1=0.4, go_B=0.5, go_dec0=0.4, go_dec1=0.4, go_BD=0.5, go_latent=0.5, lin1=0.5, lin1_regr=0.3)
+
+    def masks():
+        return {k: (torch.rand(s, generator=gen) >= ps[k]).float() / (1 - ps[k]) for k, s in shapes.items()}
+
+    def one():
+        opt.zero_grad()
+        b["x"].grad = None
+        b["x"].requires_grad_(True)
+        loss, _, _ = O.train_step_loss(P, prep, b, w["L"], w["R"], LAMBDA, 0.01, True, masks(), masks(), per_subject_loop=True,
+                                       with_orth=True)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        one()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one()
+        ts.append(time.perf_counter() - t0)
+    s = float(np.median(ts))
+    return dict(value=Bc / s, unit=UNIT, cores=threads, kind="port", s_per_step=s,
+                sample="%d-graph batch (reference default batch size) of the same workload, %d timed steps, torch CPU fp32, "
+                       "oracle/igcn_oracle.py with the reference's per-subject GO loop" % (Bc, steps))
+
+
+def run_reference(args, w):
+    """The reference arm: the reference's CPU implementation of the path (oracle port; the Python reference itself cannot
+    travel to the GPU box) with all host threads, on bounded samples of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cb = cpu_baseline(w, steps=max(args.steps, 1), warmup=max(args.warmup, 1))
+    out = dict(impl="reference", metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+               ms_per_step=cb["s_per_step"] * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+               config=dict(workload=args.workload, description=w["desc"], graphs_per_step=min(CPU_SAMPLE_B, w["B"]), rois=w["R"],
+                           layers=w["L"], hidden=w["H"], step="zero_grad + plain fwd + explain fwd + losses + bwd + Adam (CPU)",
+                           lambda_loss=LAMBDA),
+               cpu_baseline=cb,
+               e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="igcn", choices=["igcn", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying the CUDA graph")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        import __graft_entry__ as ge
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            ge.build()
+        run_igcn(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,45 @@ def lib():
     return _lib
 
 
+# ---- launch accounting (bench.py: gpu_launches, per-kernel CUDA-event timing) -------------------------------
+KERNELS_PER_CALL = {
+    "igcn_collate_csr": 1, "igcn_csr_from_edge_index": 2, "igcn_sgcn_encoder_fwd": 1, "igcn_sgcn_encoder_bwd": 2,
+    "igcn_go_spmm_fwd": 1, "igcn_go_spmm_bwd": 2, "igcn_go_layer_fwd": 1, "igcn_go_layer_bwd": 2,
+}
+launch_count = 0          # number of igcn kernels launched by this process
+_profile = None           # None, or dict name -> list[(start_event, end_event)]
+
+
+def profile_begin():
+    global _profile
+    _profile = {}
+
+
+def profile_end():
+    """Returns {name: (calls, total_ms)}; synchronises."""
+    global _profile
+    prof, _profile = _profile, None
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (prof or {}).items()}
+
+
+def call(name, *args, tag=None):
+    """Invoke one C-ABI entry point on the current stream; raises on a non-zero status."""
+    global launch_count
+    fn = getattr(lib(), name)
+    if _profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _profile.setdefault(tag or name, []).append((e0, e1))
+    else:
+        rc = fn(*args)
+    launch_count += KERNELS_PER_CALL.get(name, 1)
+    if rc != 0:
+        raise RuntimeError("%s failed (code %d): %s" % (name, rc, lib().igcn_last_error().decode()))
+
+
 def ptr(t):
     """Device pointer of a tensor (None -> NULL). Tensors must be contiguous."""
     if t is None:

@@ -84,24 +84,29 @@ __global__ void __launch_bounds__(256) go_spmm_bwd_in_kernel(const float* __rest
     }
 }
 
-// d_vals[c][k] = sum_b g[b,row(k),c] * in[b,col[k]]  -- one thread per nnz, batch walked in order (deterministic)
+// d_vals[c][k] = sum_b g[b,row(k),c] * in[b,col[k]]  -- one WARP per nnz: lanes stride over the batch, fixed-order
+// shuffle reduction (deterministic).  g and in are small (B x n_row x C, B x n_in) and stay L2 resident.
 template <int C>
 __global__ void __launch_bounds__(256) go_spmm_bwd_vals_kernel(const float* __restrict__ g, const float* __restrict__ in,
                                                                const int32_t* __restrict__ row_of, const int32_t* __restrict__ col,
                                                                int B, int Nin, int Nrow, int nnz, float* __restrict__ d_vals) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (k >= nnz) return;
     const int r = row_of[k], s = col[k];
     float acc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.f;
-    for (int b = 0; b < B; ++b) {
+    for (int b = lane; b < B; b += 32) {
         const float xv = in[(int64_t)b * Nin + s];
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[c] = fmaf(g[((int64_t)b * Nrow + r) * C + c], xv, acc[c]);
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) d_vals[(int64_t)c * nnz + k] = acc[c];
+    for (int c = 0; c < C; ++c) {
+        const float t = warp_sum(acc[c]);
+        if (lane == 0) d_vals[(int64_t)c * nnz + k] = t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -506,14 +511,6 @@ __global__ void __launch_bounds__(256) go_layer_bwd_kernel(GoLayerArgs a) {
     }
 }
 
-__global__ void go_reduce_partials_kernel(const float* __restrict__ partials, int n_rows, int P, float* __restrict__ grads) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P) return;
-    float s = 0.f;
-    for (int c = 0; c < n_rows; ++c) s += partials[(int64_t)c * P + j];
-    grads[j] = s;
-}
-
 static size_t go_fwd_smem(int din, int dout, int Min, int Mrow) {
     return 4 * ((size_t)2 * dout * din + 3 * dout + 8 * dout + 2 * (size_t)Min * dout + (size_t)Mrow * dout);
 }
@@ -552,7 +549,7 @@ static int launch_go_bwd(const GoLayerArgs& a, int n_cta, float* grads, cudaStre
     if (rc) return rc;
     k<<<n_cta, 256, smem, st>>>(a);
     IGCN_CHECK_LAUNCH("go_layer_bwd");
-    go_reduce_partials_kernel<<<(a.P + 127) / 128, 128, 0, st>>>(a.partials, n_cta, a.P, grads);
+    reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(a.partials, n_cta, a.P, grads);
     IGCN_CHECK_LAUNCH("go_reduce_partials");
     return IGCN_OK;
 }
@@ -602,13 +599,13 @@ extern "C" int igcn_go_spmm_bwd(const float* g_out, const float* in, const int32
             if ((rc = allow_smem(go_spmm_bwd_in_kernel<1>, smem, "go_spmm_bwd"))) return rc;
             go_spmm_bwd_in_kernel<1><<<grid, 256, smem, st>>>(g_out, colptr, crow, cpos, vals, (int)B, (int)n_in, (int)n_row, (int)nnz, d_in);
         }
-        if (nnz) go_spmm_bwd_vals_kernel<1><<<(int)((nnz + 255) / 256), 256, 0, st>>>(g_out, in, row_of, col, (int)B, (int)n_in, (int)n_row, (int)nnz, d_vals);
+        if (nnz) go_spmm_bwd_vals_kernel<1><<<(int)((nnz + 7) / 8), 256, 0, st>>>(g_out, in, row_of, col, (int)B, (int)n_in, (int)n_row, (int)nnz, d_vals);
     } else {
         if (d_in) {
             if ((rc = allow_smem(go_spmm_bwd_in_kernel<2>, smem, "go_spmm_bwd"))) return rc;
             go_spmm_bwd_in_kernel<2><<<grid, 256, smem, st>>>(g_out, colptr, crow, cpos, vals, (int)B, (int)n_in, (int)n_row, (int)nnz, d_in);
         }
-        if (nnz) go_spmm_bwd_vals_kernel<2><<<(int)((nnz + 255) / 256), 256, 0, st>>>(g_out, in, row_of, col, (int)B, (int)n_in, (int)n_row, (int)nnz, d_vals);
+        if (nnz) go_spmm_bwd_vals_kernel<2><<<(int)((nnz + 7) / 8), 256, 0, st>>>(g_out, in, row_of, col, (int)B, (int)n_in, (int)n_row, (int)nnz, d_vals);
     }
     IGCN_CHECK_LAUNCH("go_spmm_bwd");
     return IGCN_OK;

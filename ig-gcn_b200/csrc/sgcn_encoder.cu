@@ -12,6 +12,8 @@
 // sees each compulsory byte once: x, CSR (src,w), and the (B,R,L*H) output.  Parameter gradients are
 // accumulated per CTA in shared memory across the graphs it owns, written as one partial row per CTA and
 // reduced in a fixed order by a second tiny kernel (deterministic; no float atomics anywhere).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace igcn {
@@ -421,13 +423,14 @@ __global__ void __launch_bounds__(256) sgcn_encoder_bwd_kernel(EncArgs a) {
     for (int i = tid; i < a.P; i += nt) prow[i] = acc[i];
 }
 
-// grads[j] = sum_c partials[c][j] in CTA order (deterministic)
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_rows, int P, float* __restrict__ grads) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P) return;
-    float s = 0.f;
-    for (int c = 0; c < n_rows; ++c) s += partials[(int64_t)c * P + j];
-    grads[j] = s;
+}  // namespace igcn
+#include "sgcn_fast.cuh"
+namespace igcn {
+
+static bool use_fast(int64_t F0, int64_t H, int64_t L) {
+    const char* e = getenv("IGCN_FORCE_GENERIC");   // test hook: exercise the shape-generic kernels
+    if (e && e[0] == '1') return false;
+    return F0 == kF0 && H == kH && L >= 1;
 }
 
 static size_t fwd_smem(int R, int F0, int H, int L, int maxEg) {
@@ -487,6 +490,20 @@ extern "C" int igcn_sgcn_encoder_fwd(const float* x, const int32_t* rowptr_t, co
     EncArgs a{};
     a.x = x; a.rowptr_t = rowptr_t; a.csr_src = csr_src; a.csr_w = csr_w; a.prob = prob; a.prob_bias = prob_bias; a.wb = wb;
     a.out_w = out; a.pe_w = p_e; a.relu = relu ? 1 : 0; a.B = (int)B; a.R = (int)R; a.F0 = (int)F0; a.H = (int)H; a.L = (int)L; a.maxEg = (int)max_eg;
+    if (use_fast(F0, H, L)) {
+        size_t smem = fwd_fast_smem(a.R, a.L, a.maxEg);
+        if (smem <= 227 * 1024) {
+            rc = allow_smem(sgcn_fwd_h16_kernel, smem, "sgcn_fwd_h16");
+            if (rc) return rc;
+            int per_sm = (int)((227 * 1024) / (smem + 1024));
+            if (per_sm > 2) per_sm = 2;
+            int64_t grid = (int64_t)sm_count() * per_sm;
+            if (grid > B) grid = B;
+            sgcn_fwd_h16_kernel<<<(int)grid, 256, smem, (cudaStream_t)stream>>>(a);
+            IGCN_CHECK_LAUNCH("sgcn_fwd_h16");
+            return IGCN_OK;
+        }
+    }
     size_t smem = fwd_smem(a.R, a.F0, a.H, a.L, a.maxEg);
     rc = allow_smem(sgcn_encoder_fwd_kernel, smem, "sgcn_encoder_fwd");
     if (rc) return rc;
@@ -526,7 +543,7 @@ extern "C" int igcn_sgcn_encoder_bwd(const float* x, const int32_t* rowptr_t, co
     if (rc) return rc;
     sgcn_encoder_bwd_kernel<<<want, 256, smem, st>>>(a);
     IGCN_CHECK_LAUNCH("sgcn_encoder_bwd");
-    reduce_partials_kernel<<<(a.P + 127) / 128, 128, 0, st>>>(partials, want, a.P, grads);
+    reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(partials, want, a.P, grads);
     IGCN_CHECK_LAUNCH("sgcn_reduce_partials");
     return IGCN_OK;
 }

@@ -146,8 +146,10 @@ class Batch(Data):
 
     # ------------------------------------------------------------------------------------------
     @staticmethod
-    def collate(ss: SubjectSet, idx, device, staging: Optional[dict] = None) -> "Batch":
-        """Gather subjects `idx` (host, pinned), copy to `device`, collate + build CSR with one kernel."""
+    def collate(ss: SubjectSet, idx, device, staging: Optional[dict] = None, out: Optional["Batch"] = None) -> "Batch":
+        """Gather subjects `idx` (host, pinned), copy to `device`, collate + build CSR with one kernel.
+        `out`: a Batch of the same (B, E) whose device buffers are overwritten in place (static buffers of a
+        captured CUDA graph)."""
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("igcn_b200.Batch.collate needs a CUDA device (no CPU fallback)")
@@ -186,38 +188,53 @@ class Batch(Data):
             sel = torch.cat([torch.arange(int(ep[g]), int(ep[g + 1])) for g in idx_t.tolist()]) if B else torch.zeros(0, dtype=torch.int64)
             for name in ("edge_src", "edge_dst", "edge_attr"):
                 src = getattr(ss, name)
-                out = torch.empty(E, dtype=src.dtype, pin_memory=pin)
-                torch.index_select(src, 0, sel, out=out)
-                h[name] = out
+                buf = torch.empty(E, dtype=src.dtype, pin_memory=pin)
+                torch.index_select(src, 0, sel, out=buf)
+                h[name] = buf
         max_eg = int(counts.max()) if B else 0
-        d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
-        d_gptr = gptr.to(dev, non_blocking=True)
+        if out is not None:
+            if out._num_graphs != B or out._csr.E != E or out._csr.max_eg < max_eg:
+                raise RuntimeError("Batch.collate(out=...): static batch has B=%d,E=%d, new batch B=%d,E=%d"
+                                   % (out._num_graphs, out._csr.E, B, E))
+            d = out._raw
+            for k, v in h.items():
+                d[k].copy_(v, non_blocking=True)
+            out._gptr.copy_(gptr, non_blocking=True)
+            d_gptr = out._gptr
+        else:
+            d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+            d_gptr = gptr.to(dev, non_blocking=True)
         if staging is not None:
             ev = staging.get("_event") or torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
             staging["_event"] = ev
-        return Batch._finish(d, d_gptr, B, R, E, max_eg, dev)
+        return Batch._finish(d, d_gptr, B, R, E, max_eg, dev, out)
 
     @staticmethod
-    def _finish(d, d_gptr, B, R, E, max_eg, dev) -> "Batch":
+    def _finish(d, d_gptr, B, R, E, max_eg, dev, out=None) -> "Batch":
         N = B * R
         i32 = dict(dtype=torch.int32, device=dev)
-        b = Batch()
-        b.edge_index = torch.empty((2, E), dtype=torch.int64, device=dev)
-        b.batch = torch.empty(N, dtype=torch.int64, device=dev)
-        csr = GraphCSR(rowptr_t=torch.empty(N + 1, **i32), csr_src=torch.empty(E, **i32), csr_perm=torch.empty(E, **i32),
-                       csr_w=torch.empty(E, dtype=torch.float32, device=dev), rowptr_s=torch.empty(N + 1, **i32),
-                       csc_pos=torch.empty(E, **i32), max_eg=max_eg, B=B, R=R, E=E)
-        if B == 0:
-            csr.rowptr_t.zero_()
-            csr.rowptr_s.zero_()
+        if out is not None:
+            b, csr = out, out._csr
+        else:
+            b = Batch()
+            b.edge_index = torch.empty((2, E), dtype=torch.int64, device=dev)
+            b.batch = torch.empty(N, dtype=torch.int64, device=dev)
+            csr = GraphCSR(rowptr_t=torch.empty(N + 1, **i32), csr_src=torch.empty(E, **i32), csr_perm=torch.empty(E, **i32),
+                           csr_w=torch.empty(E, dtype=torch.float32, device=dev), rowptr_s=torch.empty(N + 1, **i32),
+                           csc_pos=torch.empty(E, **i32), max_eg=max_eg, B=B, R=R, E=E)
+            if B == 0:
+                csr.rowptr_t.zero_()
+                csr.rowptr_s.zero_()
         L = _lib.lib()
         with torch.cuda.device(dev):
-            rc = L.igcn_collate_csr(_lib.ptr(d_gptr), _lib.ptr(d["edge_src"]), _lib.ptr(d["edge_dst"]), _lib.ptr(d["edge_attr"]),
+            _lib.call("igcn_collate_csr", _lib.ptr(d_gptr), _lib.ptr(d["edge_src"]), _lib.ptr(d["edge_dst"]), _lib.ptr(d["edge_attr"]),
                                     B, R, E, max_eg, _lib.ptr(b.edge_index), _lib.ptr(b.batch), _lib.ptr(csr.rowptr_t),
                                     _lib.ptr(csr.csr_src), _lib.ptr(csr.csr_perm), _lib.ptr(csr.csr_w), _lib.ptr(csr.rowptr_s),
                                     _lib.ptr(csr.csc_pos), _lib.stream())
-        _lib.check(rc, "igcn_collate_csr")
+        if out is not None:
+            return b                      # every attribute already aliases the static buffers
+        b._raw, b._gptr = d, d_gptr
         b.x = d["x"].view(N, d["x"].shape[-1])
         b.edge_attr = d["edge_attr"]
         b.snps_feat = d["snps_feat"]
@@ -254,10 +271,9 @@ class Batch(Data):
                        csc_pos=torch.empty(E, **i32), max_eg=max_eg, B=B, R=rois, E=E)
         L = _lib.lib()
         with torch.cuda.device(dev):
-            rc = L.igcn_csr_from_edge_index(_lib.ptr(ei), _lib.ptr(edge_attr.contiguous()), B, rois, E, max_eg, _lib.ptr(eptr),
+            _lib.call("igcn_csr_from_edge_index", _lib.ptr(ei), _lib.ptr(edge_attr.contiguous()), B, rois, E, max_eg, _lib.ptr(eptr),
                                             _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(csr.csr_perm),
                                             _lib.ptr(csr.csr_w), _lib.ptr(csr.rowptr_s), _lib.ptr(csr.csc_pos), _lib.stream())
-        _lib.check(rc, "igcn_csr_from_edge_index")
         b = Batch()
         b.x, b.edge_index, b.edge_attr = x, ei, edge_attr
         b.batch = torch.arange(B, device=dev).repeat_interleave(rois)

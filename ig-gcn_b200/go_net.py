@@ -47,9 +47,8 @@ class _GoSpmmFn(torch.autograd.Function):
         B, C = data.shape[0], vals.shape[0]
         out = torch.empty((B, g["n_rows"], C), dtype=torch.float32, device=data.device)
         with torch.cuda.device(data.device):
-            rc = lib.igcn_go_spmm_fwd(_lib.ptr(data), _lib.ptr(g["rowptr"]), _lib.ptr(g["col"]), _lib.ptr(vals), B, g["n_cols"],
+            _lib.call("igcn_go_spmm_fwd", _lib.ptr(data), _lib.ptr(g["rowptr"]), _lib.ptr(g["col"]), _lib.ptr(vals), B, g["n_cols"],
                                       g["n_rows"], g["nnz"], C, _lib.ptr(out), _lib.stream())
-        _lib.check(rc, "igcn_go_spmm_fwd")
         ctx.g = g
         ctx.need_in = data.requires_grad
         ctx.save_for_backward(data, vals)
@@ -64,10 +63,9 @@ class _GoSpmmFn(torch.autograd.Function):
         d_in = torch.empty_like(data) if ctx.need_in else None
         d_vals = torch.empty_like(vals)
         with torch.cuda.device(data.device):
-            rc = lib.igcn_go_spmm_bwd(_lib.ptr(g_out), _lib.ptr(data), _lib.ptr(g["row_of"]), _lib.ptr(g["col"]), _lib.ptr(g["colptr"]),
+            _lib.call("igcn_go_spmm_bwd", _lib.ptr(g_out), _lib.ptr(data), _lib.ptr(g["row_of"]), _lib.ptr(g["col"]), _lib.ptr(g["colptr"]),
                                       _lib.ptr(g["crow"]), _lib.ptr(g["cpos"]), _lib.ptr(vals), B, g["n_cols"], g["n_rows"], g["nnz"],
                                       C, _lib.ptr(d_in), _lib.ptr(d_vals), _lib.stream())
-        _lib.check(rc, "igcn_go_spmm_bwd")
         return d_in, d_vals, None
 
 
@@ -88,11 +86,10 @@ class _GoLayerFn(torch.autograd.Function):
         y = torch.empty((B, m_row - keep_from, dout), dtype=torch.float32, device=x.device)
         stats = torch.empty((B, 2 * dout), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            rc = lib.igcn_go_layer_fwd(_lib.ptr(x), _lib.ptr(Wa), _lib.ptr(Ws), _lib.ptr(u), _lib.ptr(v), _lib.ptr(gamma), _lib.ptr(beta),
+            _lib.call("igcn_go_layer_fwd", _lib.ptr(x), _lib.ptr(Wa), _lib.ptr(Ws), _lib.ptr(u), _lib.ptr(v), _lib.ptr(gamma), _lib.ptr(beta),
                                        _lib.ptr(mask), _lib.ptr(g["rowptr"]), _lib.ptr(g["col"]), _lib.ptr(g["colptr"]), _lib.ptr(g["crow"]),
                                        _lib.ptr(g["cpos"]), B, m_in, m_row, g["nnz"], din, dout, int(attn), self_off, keep_from,
-                                       _lib.ptr(y), _lib.ptr(stats), _lib.stream())
-        _lib.check(rc, "igcn_go_layer_fwd")
+                                       _lib.ptr(y), _lib.ptr(stats), _lib.stream(), tag="go_layer_fwd[%s,M=%d]" % ("attn" if attn else "dec", m_row))
         ctx.g, ctx.attn, ctx.self_off, ctx.keep_from = g, attn, self_off, keep_from
         ctx.save_for_backward(x, Wa, Ws, u, v, gamma, beta, mask, stats)
         return y
@@ -110,11 +107,11 @@ class _GoLayerFn(torch.autograd.Function):
         grads = torch.empty(P, dtype=torch.float32, device=x.device)
         gy = gy.contiguous()
         with torch.cuda.device(x.device):
-            rc = lib.igcn_go_layer_bwd(_lib.ptr(x), _lib.ptr(Wa), _lib.ptr(Ws), _lib.ptr(u), _lib.ptr(v), _lib.ptr(gamma), _lib.ptr(beta),
+            _lib.call("igcn_go_layer_bwd", _lib.ptr(x), _lib.ptr(Wa), _lib.ptr(Ws), _lib.ptr(u), _lib.ptr(v), _lib.ptr(gamma), _lib.ptr(beta),
                                        _lib.ptr(mask), _lib.ptr(g["rowptr"]), _lib.ptr(g["col"]), _lib.ptr(g["colptr"]), _lib.ptr(g["crow"]),
                                        _lib.ptr(g["cpos"]), B, m_in, m_row, g["nnz"], din, dout, int(attn), ctx.self_off, ctx.keep_from,
-                                       _lib.ptr(stats), _lib.ptr(gy), _lib.ptr(dx), _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream())
-        _lib.check(rc, "igcn_go_layer_bwd")
+                                       _lib.ptr(stats), _lib.ptr(gy), _lib.ptr(dx), _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream(),
+                      tag="go_layer_bwd[%s,M=%d]" % ("attn" if attn else "dec", m_row))
         n = dout * din
         dWa, dWs = grads[:n].view(dout, din), grads[n:2 * n].view(dout, din)
         du = grads[2 * n:2 * n + 2 * dout].view(1, 2 * dout) if attn else None

@@ -32,10 +32,10 @@ class _SGCNEncoderFn(torch.autograd.Function):
         out = torch.empty((B, R, L * H), dtype=torch.float32, device=x.device)
         p_e = torch.empty(csr.E, dtype=torch.float32, device=x.device) if (explain and want_pe) else None
         with torch.cuda.device(x.device):
-            rc = lib.igcn_sgcn_encoder_fwd(_lib.ptr(x), _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(csr.csr_w),
+            _lib.call("igcn_sgcn_encoder_fwd", _lib.ptr(x), _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(csr.csr_w),
                                            _lib.ptr(probc), _lib.ptr(pbc), _lib.ptr(wbc), B, R, F0, H, L, csr.max_eg, int(relu),
-                                           _lib.ptr(out), _lib.ptr(p_e), _lib.stream())
-        _lib.check(rc, "igcn_sgcn_encoder_fwd")
+                                           _lib.ptr(out), _lib.ptr(p_e), _lib.stream(),
+                      tag="sgcn_encoder_fwd[%s,L=%d]" % ("explain" if explain else "plain", L))
         ctx.csr, ctx.L, ctx.H, ctx.explain, ctx.relu = csr, L, H, explain, bool(relu)
         ctx.save_for_backward(x, probc, pbc, wbc, out)
         if p_e is None:
@@ -57,11 +57,11 @@ class _SGCNEncoderFn(torch.autograd.Function):
         g_out = g_out.contiguous() if L > 0 else None
         gpe = g_pe.contiguous() if (ctx.explain and g_pe is not None and g_pe.numel() == csr.E and csr.E > 0) else None
         with torch.cuda.device(x.device):
-            rc = lib.igcn_sgcn_encoder_bwd(_lib.ptr(x), _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(csr.csr_w),
+            _lib.call("igcn_sgcn_encoder_bwd", _lib.ptr(x), _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(csr.csr_w),
                                            _lib.ptr(csr.rowptr_s), _lib.ptr(csr.csc_pos), _lib.ptr(prob), _lib.ptr(pb),
                                            _lib.ptr(wb), _lib.ptr(out), _lib.ptr(g_out), _lib.ptr(gpe), B, R, F0, H, L,
-                                           csr.max_eg, int(ctx.relu), _lib.ptr(dx), _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream())
-        _lib.check(rc, "igcn_sgcn_encoder_bwd")
+                                           csr.max_eg, int(ctx.relu), _lib.ptr(dx), _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream(),
+                      tag="sgcn_encoder_bwd[%s,L=%d]" % ("explain" if ctx.explain else "plain", L))
         nwb = P - R * F0 - 2 * F0
         d_wb = grads[:nwb] if wb is not None else None
         d_prob = grads[nwb:nwb + R * F0].view(R, F0) if ctx.explain else None

@@ -81,8 +81,43 @@ def train_step(model, data, optimizer=None, lambda_loss=None, flat: FlatGradAllR
         optimizer.zero_grad()
     loss = step_loss(model, data, lambda_loss, isSoftSimilarity)
     loss.backward()
+    if getattr(model, "_pe_cache", None) is not None:
+        model._pe_cache = None            # drop the last reference to this step's autograd graph
     if flat is not None:
         flat.reduce()
     if optimizer is not None:
         optimizer.step()
     return loss.detach()
+
+
+class GraphedTrainStep(object):
+    """The whole training step captured ONCE in a CUDA graph and replayed per batch.
+
+    Every launch of the step (the igcn kernels through the C ABI, torch's small ops, the NCCL all-reduce and the
+    capturable Adam update) is static for a fixed (B, E): after removing the reference's host syncs
+    (`x.min().item()`, boolean-mask indexing in gcn_norm, `num_graphs`) nothing in the step depends on device data,
+    so one graph launch replaces several hundred kernel launches.  New batches are collated straight into the
+    graph's static input buffers (Batch.collate(out=...)).
+    """
+
+    def __init__(self, model, optimizer, static_batch, lambda_loss=None, flat: FlatGradAllReduce = None,
+                 isSoftSimilarity=True, warmup=3):
+        self.model, self.opt, self.batch, self.flat = model, optimizer, static_batch, flat
+        self.lambda_loss, self.soft = lambda_loss, isSoftSimilarity
+        dev = static_batch.x.device
+        model._pe_cache = None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                train_step(model, static_batch, optimizer, lambda_loss, flat, isSoftSimilarity)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        static_batch.x.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = train_step(model, static_batch, optimizer, lambda_loss, flat, isSoftSimilarity)
+
+    def __call__(self):
+        self.graph.replay()
+        return self.loss

@@ -146,6 +146,14 @@ def test_sgcn_encoder_fwd_bwd(n, R, L, Hd, ragged, explain):
         assert Pc["prob"].grad is None
 
 
+def test_generic_kernels_on_default_shape(monkeypatch):
+    """F0=3/H=16 normally takes the register-tiled kernels; IGCN_FORCE_GENERIC=1 sends the same shape through the
+    shape-generic kernels so both stay covered."""
+    monkeypatch.setenv("IGCN_FORCE_GENERIC", "1")
+    test_sgcn_encoder_fwd_bwd(6, 90, 2, 16, True, True)
+    test_sgcn_encoder_fwd_bwd(6, 90, 2, 16, False, False)
+
+
 def test_sgcn_encoder_deterministic_and_full_size_properties():
     """BASELINE config-4 shape (R=264, B=4096 scaled to what generates in seconds: B=512): run-to-run bit
     identical (no float atomics), and the plain pass is linear in x before the first ReLU => homogeneity
