@@ -493,13 +493,15 @@ extern "C" int igcn_sgcn_encoder_fwd(const float* x, const int32_t* rowptr_t, co
     if (use_fast(F0, H, L)) {
         size_t smem = fwd_fast_smem(a.R, a.L, a.maxEg);
         if (smem <= 227 * 1024) {
-            rc = allow_smem(sgcn_fwd_h16_kernel, smem, "sgcn_fwd_h16");
+            auto kern = (L == 2) ? sgcn_fwd_h16_kernel<true> : sgcn_fwd_h16_kernel<false>;
+            rc = allow_smem(kern, smem, "sgcn_fwd_h16");
             if (rc) return rc;
+            const int nthr = fast_threads(a.R);
             int per_sm = (int)((227 * 1024) / (smem + 1024));
             if (per_sm > 2) per_sm = 2;
             int64_t grid = (int64_t)sm_count() * per_sm;
             if (grid > B) grid = B;
-            sgcn_fwd_h16_kernel<<<(int)grid, 256, smem, (cudaStream_t)stream>>>(a);
+            kern<<<(int)grid, nthr, smem, (cudaStream_t)stream>>>(a);
             IGCN_CHECK_LAUNCH("sgcn_fwd_h16");
             return IGCN_OK;
         }

@@ -40,31 +40,53 @@ __device__ __forceinline__ void axpy4(float s, float4 v, float4& acc) {
     acc.w = fmaf(s, v.w, acc.w);
 }
 
-// Per-graph prologue for the fast kernels (F0 = 3): masks, self-loop merge, degrees, normalised weights.
-//   edges[k] = (local src, bits of norm_e)   [norm 0 on self-loop slots]
+// ---- cp.async (LDGSTS) staging of one graph's inputs: x slab, rowptr slice, CSR (src, w) slices -----------------
+__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct Stage {
+    float* x;    // R*3 raw features
+    int* rp;     // R+1 global CSR offsets
+    int* src;    // maxEg global source ids
+    float* w;    // maxEg raw edge weights
+};
+
+__device__ __forceinline__ void stage_issue(const EncArgs& a, int g, int e0, int Eg, const Stage& st) {
+    const int tid = threadIdx.x, nt = blockDim.x, R = a.R;
+    const int64_t node0 = (int64_t)g * R;
+    const float* xg = a.x + node0 * kF0;
+    for (int i = tid; i < R * kF0; i += nt) cp_async4(st.x + i, xg + i);
+    for (int i = tid; i <= R; i += nt) cp_async4(st.rp + i, a.rowptr_t + node0 + i);
+    for (int k = tid; k < Eg; k += nt) {
+        cp_async4(st.src + k, a.csr_src + e0 + k);
+        cp_async4(st.w + k, a.csr_w + e0 + k);
+    }
+    cp_async_commit();
+}
+
+// Per-graph prologue for the fast kernels (F0 = 3), reading the staged inputs: masks, self-loop merge, degrees,
+// normalised weights.   edges[k] = (local src, bits of norm_e)   [norm 0 on self-loop slots]
 template <bool kKeep>
-__device__ __forceinline__ void fast_prologue(const EncArgs& a, int g, int e0, int Eg, float* xs, float* xraw, int* rp, int2* edges,
-                                              float* dinv, float* nii, float* ew, float* epe, float* ell, const float* pb) {
+__device__ __forceinline__ void fast_prologue(const EncArgs& a, int g, int e0, int Eg, const Stage& st, float* xs, int* rp,
+                                              int2* edges, float* dinv, float* nii, float* ew, float* epe, float* ell,
+                                              const float* pb) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int R = a.R;
     const bool explain = a.prob != nullptr;
-    const int64_t node0 = (int64_t)g * R;
-    const float* xg = a.x + node0 * kF0;
-    for (int i = tid; i < R * kF0; i += nt) {
-        const float v = xg[i];
-        if (kKeep) xraw[i] = v;
-        xs[i] = explain ? v * a.prob[i] : v;
-    }
-    for (int i = tid; i <= R; i += nt) rp[i] = a.rowptr_t[node0 + i] - e0;
-    for (int k = tid; k < Eg; k += nt) edges[k] = make_int2(a.csr_src[e0 + k] - (int)node0, __float_as_int(a.csr_w[e0 + k]));
+    const int node0 = g * R;
+    for (int i = tid; i < R * kF0; i += nt) xs[i] = explain ? st.x[i] * a.prob[i] : st.x[i];
+    for (int i = tid; i <= R; i += nt) rp[i] = st.rp[i] - e0;
     __syncthreads();
     for (int i = tid; i < R; i += nt) {
         float deg = 0.f, loopw = 1.f;
         const float xi0 = xs[i * 3], xi1 = xs[i * 3 + 1], xi2 = xs[i * 3 + 2];
-        for (int k = rp[i]; k < rp[i + 1]; ++k) {
-            const int2 e = edges[k];
-            const int s = e.x;
-            float wt = __int_as_float(e.y);
+        const int k1 = rp[i + 1];
+        for (int k = rp[i]; k < k1; ++k) {
+            const int s = st.src[k] - node0;
+            float wt = st.w[k];
             if (explain) {
                 // same association as the reference's [x_src | x_dst] . prob_bias : pairs (src_c, dst_c) summed in order
                 float z = pb[0] * xs[s * 3] + pb[3] * xi0;
@@ -76,7 +98,7 @@ __device__ __forceinline__ void fast_prologue(const EncArgs& a, int g, int e0, i
                 if (kKeep) epe[k] = p;
             }
             if (kKeep) ew[k] = wt;
-            edges[k].y = __float_as_int(wt);
+            edges[k] = make_int2(s, __float_as_int(wt));
             if (s == i)
                 loopw = wt;  // last self loop wins
             else
@@ -91,7 +113,8 @@ __device__ __forceinline__ void fast_prologue(const EncArgs& a, int g, int e0, i
     __syncthreads();
     for (int i = tid; i < R; i += nt) {
         const float di = dinv[i];
-        for (int k = rp[i]; k < rp[i + 1]; ++k) {
+        const int k1 = rp[i + 1];
+        for (int k = rp[i]; k < k1; ++k) {
             const int2 e = edges[k];
             const float n = (e.x == i) ? 0.f : dinv[e.x] * __int_as_float(e.y) * di;
             edges[k].y = __float_as_int(n);
@@ -101,8 +124,7 @@ __device__ __forceinline__ void fast_prologue(const EncArgs& a, int g, int e0, i
 }
 
 // U[i][4fg..4fg+3] = H_prev[i][0..15] . W[4fg+a][0..15]     (layer >= 2)
-__device__ __forceinline__ float4 xw16(const float* hrow, const float4 (&w)[4][4]) {
-    const float4 h0 = ld4(hrow), h1 = ld4(hrow + 4), h2 = ld4(hrow + 8), h3 = ld4(hrow + 12);
+__device__ __forceinline__ float4 xw16(const float4 h0, const float4 h1, const float4 h2, const float4 h3, const float4 (&w)[4][4]) {
     float4 r;
     r.x = dot4(h3, w[0][3], dot4(h2, w[0][2], dot4(h1, w[0][1], dot4(h0, w[0][0], 0.f))));
     r.y = dot4(h3, w[1][3], dot4(h2, w[1][2], dot4(h1, w[1][1], dot4(h0, w[1][0], 0.f))));
@@ -111,6 +133,31 @@ __device__ __forceinline__ float4 xw16(const float* hrow, const float4 (&w)[4][4
     return r;
 }
 
+// Y[i][4fg..] = sum_{k in row i} norm_k U[src_k][4fg..] + n_ii U[i][4fg..]   (edge order, self loop last)
+__device__ __forceinline__ float4 spmm_row(const float* U, const int2* edges, const int* rp, const float* nii, int i, int fg) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int k = rp[i];
+    const int k1 = rp[i + 1];
+    // rows of GDC top-k graphs have 3 in-edges: fetch up to 4 (src,norm) pairs and their feature quads before the FMAs
+    for (; k < k1; k += 4) {
+        const int n = k1 - k;
+        const int2 e0 = edges[k];
+        const int2 e1 = (n > 1) ? edges[k + 1] : make_int2(i, 0);
+        const int2 e2 = (n > 2) ? edges[k + 2] : make_int2(i, 0);
+        const int2 e3 = (n > 3) ? edges[k + 3] : make_int2(i, 0);
+        const float4 u0 = ld4(U + e0.x * kH + 4 * fg), u1 = ld4(U + e1.x * kH + 4 * fg);
+        const float4 u2 = ld4(U + e2.x * kH + 4 * fg), u3 = ld4(U + e3.x * kH + 4 * fg);
+        axpy4(__int_as_float(e0.y), u0, acc);
+        if (n > 1) axpy4(__int_as_float(e1.y), u1, acc);
+        if (n > 2) axpy4(__int_as_float(e2.y), u2, acc);
+        if (n > 3) axpy4(__int_as_float(e3.y), u3, acc);
+    }
+    axpy4(nii[i], ld4(U + i * kH + 4 * fg), acc);
+    return acc;
+}
+
+// kHoist: L == 2, both layers' weights stay in registers across all graphs of the CTA.
+template <bool kHoist>
 __global__ void __launch_bounds__(256, 2) sgcn_fwd_h16_kernel(EncArgs a) {
     extern __shared__ __align__(16) float smf[];
     const int R = a.R, L = a.L, LH = L * kH, maxEg = a.maxEg;
@@ -127,27 +174,71 @@ __global__ void __launch_bounds__(256, 2) sgcn_fwd_h16_kernel(EncArgs a) {
     float* nii = dinv + R;                              // R
     float* pb = nii + R;                                // 8
     int* rp = reinterpret_cast<int*>(pb + 8);           // R+1
-
+    float* stage_base = reinterpret_cast<float*>(rp + R + 1);
+    const int stage_len = R * kF0 + R + 1 + 2 * maxEg;
+    auto stage_of = [&](int s) {
+        Stage q;
+        float* p = stage_base + s * stage_len;
+        q.x = p;
+        q.rp = reinterpret_cast<int*>(p + R * kF0);
+        q.src = q.rp + R + 1;
+        q.w = reinterpret_cast<float*>(q.src + maxEg);
+        return q;
+    };
     for (int i = tid; i < WB; i += nt) Wsm[i] = a.wb[i];
     if (a.prob_bias && tid < 6) pb[tid] = a.prob_bias[tid];
     __syncthreads();
     const int ntask = R * 4;
     bool store_pending = false;
 
-    for (int g = blockIdx.x; g < a.B; g += gridDim.x) {
-        const int e0 = a.rowptr_t[(int64_t)g * R];
-        const int Eg = a.rowptr_t[(int64_t)(g + 1) * R] - e0;
+    float w0[4][3];
+    float4 w1[4][4];
+    float4 bias0, bias1;
+    if (kHoist) {
+        const int off1 = layer_off(1, kF0, kH);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) w0[q][k] = Wsm[(4 * fg + q) * 3 + k];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) w1[q][c] = ld4(Wsm + off1 + (4 * fg + q) * kH + 4 * c);
+        }
+        bias0 = ld4(Wsm + kH * kF0 + 4 * fg);
+        bias1 = ld4(Wsm + off1 + kH * kH + 4 * fg);
+    }
+
+    int g = blockIdx.x;
+    int e0 = 0, Eg = 0, e0n = 0, Egn = 0;
+    if (g < a.B) {
+        e0 = a.rowptr_t[(int64_t)g * R];
+        Eg = a.rowptr_t[(int64_t)(g + 1) * R] - e0;
         if (Eg > maxEg) __trap();
-        fast_prologue<false>(a, g, e0, Eg, xs, nullptr, rp, edges, dinv, nii, nullptr, nullptr, nullptr, pb);
+        stage_issue(a, g, e0, Eg, stage_of(0));
+    }
+    int cur = 0;
+    for (; g < a.B; g += gridDim.x, cur ^= 1) {
+        const int gn = g + gridDim.x;
+        if (gn < a.B) {   // offsets of the NEXT graph: issued now, consumed after the prologue
+            e0n = a.rowptr_t[(int64_t)gn * R];
+            Egn = a.rowptr_t[(int64_t)(gn + 1) * R] - e0n;
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        fast_prologue<false>(a, g, e0, Eg, stage_of(cur), xs, rp, edges, dinv, nii, nullptr, nullptr, nullptr, pb);
+        if (gn < a.B) {
+            if (Egn > maxEg) __trap();
+            stage_issue(a, gn, e0n, Egn, stage_of(cur ^ 1));   // lands while this graph's layers run
+        }
         for (int l = 0; l < L; ++l) {
             const int off = layer_off(l, kF0, kH);
             // ---- U = H_prev . W^T --------------------------------------------------------------------------
             if (l == 0) {
-                float w0[4][3];
+                if (!kHoist) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                    for (int q = 0; q < 4; ++q)
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) w0[q][k] = Wsm[off + (4 * fg + q) * 3 + k];
+                        for (int k = 0; k < 3; ++k) w0[q][k] = Wsm[off + (4 * fg + q) * 3 + k];
+                }
                 for (int t = tid; t < ntask; t += nt) {
                     const int i = t >> 2;
                     const float x0 = xs[i * 3], x1 = xs[i * 3 + 1], x2 = xs[i * 3 + 2];
@@ -159,29 +250,36 @@ __global__ void __launch_bounds__(256, 2) sgcn_fwd_h16_kernel(EncArgs a) {
                     st4(U + i * kH + 4 * fg, r);
                 }
             } else {
-                float4 w[4][4];
+                if (!kHoist) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                    for (int q = 0; q < 4; ++q)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) w[q][c] = ld4(Wsm + off + (4 * fg + q) * kH + 4 * c);
-                for (int t = tid; t < ntask; t += nt) {
+                        for (int c = 0; c < 4; ++c) w1[q][c] = ld4(Wsm + off + (4 * fg + q) * kH + 4 * c);
+                }
+                // two tasks per iteration: the second task's row loads are in flight during the first task's FMAs
+                for (int t = tid; t < ntask; t += 2 * nt) {
                     const int i = t >> 2;
-                    st4(U + i * kH + 4 * fg, xw16(Hbuf + i * LH + (l - 1) * kH, w));
+                    const bool two = (t + nt) < ntask;
+                    const int j = two ? ((t + nt) >> 2) : i;
+                    const float* hi = Hbuf + i * LH + (l - 1) * kH;
+                    const float* hj = Hbuf + j * LH + (l - 1) * kH;
+                    const float4 a0 = ld4(hi), a1 = ld4(hi + 4), a2 = ld4(hi + 8), a3 = ld4(hi + 12);
+                    const float4 b0 = ld4(hj), b1 = ld4(hj + 4), b2 = ld4(hj + 8), b3 = ld4(hj + 12);
+                    st4(U + i * kH + 4 * fg, xw16(a0, a1, a2, a3, w1));
+                    if (two) st4(U + j * kH + 4 * fg, xw16(b0, b1, b2, b3, w1));
                 }
             }
             if (l == 0 && store_pending && tid == 0) bulk_store_wait_read();   // previous graph's slab has left Hbuf
             __syncthreads();
             // ---- Y = A_norm U + bias ; relu -> concat slot l ---------------------------------------------------
-            const float4 bias = ld4(Wsm + off + kH * layer_fin(l, kF0, kH) + 4 * fg);
+            float4 bias;
+            if (kHoist)
+                bias = (l == 0) ? bias0 : bias1;
+            else
+                bias = ld4(Wsm + off + kH * layer_fin(l, kF0, kH) + 4 * fg);
             for (int t = tid; t < ntask; t += nt) {
                 const int i = t >> 2;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int k1 = rp[i + 1];
-                for (int k = rp[i]; k < k1; ++k) {
-                    const int2 e = edges[k];
-                    axpy4(__int_as_float(e.y), ld4(U + e.x * kH + 4 * fg), acc);
-                }
-                axpy4(nii[i], ld4(U + i * kH + 4 * fg), acc);   // self loop last, as scatter_add sees it
+                float4 acc = spmm_row(U, edges, rp, nii, i, fg);
                 acc.x += bias.x; acc.y += bias.y; acc.z += bias.z; acc.w += bias.w;
                 if (a.relu) {
                     acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
@@ -193,13 +291,33 @@ __global__ void __launch_bounds__(256, 2) sgcn_fwd_h16_kernel(EncArgs a) {
         // ---- one TMA bulk store of the (R, L*16) slab ---------------------------------------------------------
         if (tid == 0) bulk_store_slab(a.out_w + (int64_t)g * R * LH, Hbuf, (uint32_t)(R * LH * sizeof(float)));
         store_pending = true;
+        e0 = e0n;
+        Eg = Egn;
     }
     if (store_pending && tid == 0) bulk_store_wait_all();
 }
 
 static size_t fwd_fast_smem(int R, int L, int maxEg) {
     const int WB = wb_size(kF0, kH, L);
-    return 4 * ((size_t)R * L * kH + (size_t)R * kH + ((WB + 3) & ~3) + 2 * (size_t)maxEg + (size_t)R * kF0 + 2 * (size_t)R + 8 + R + 1) + 16;
+    const size_t stage = (size_t)R * kF0 + R + 1 + 2 * (size_t)maxEg;
+    return 4 * ((size_t)R * L * kH + (size_t)R * kH + ((WB + 3) & ~3) + 2 * (size_t)maxEg + (size_t)R * kF0 + 2 * (size_t)R + 8 + R + 1 +
+                2 * stage) + 16;
+}
+
+// threads per CTA: a multiple of 32 from {128..256} that wastes the fewest (node, feature-group) task slots
+static int fast_threads(int R) {
+    const int ntask = 4 * R;
+    int best = 256;
+    double best_u = 0.0;
+    for (int nt = 128; nt <= 256; nt += 32) {
+        const int iters = (ntask + nt - 1) / nt;
+        const double u = (double)ntask / ((double)iters * nt);
+        if (u >= best_u - 1e-9) {
+            best_u = u > best_u ? u : best_u;
+            best = nt;
+        }
+    }
+    return best;
 }
 
 }  // namespace igcn
