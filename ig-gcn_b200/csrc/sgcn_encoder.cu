@@ -472,7 +472,16 @@ static int ctas_for(size_t smem, int64_t B) {
     return (int)n;
 }
 
+static bool use_fast_bwd(int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg) {
+    return use_fast(F0, H, L) && L == 2 && bwd_fast_smem((int)R, (int)max_eg) <= 227 * 1024;
+}
+
 extern "C" int64_t igcn_sgcn_bwd_ctas(int64_t B, int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg) {
+    if (use_fast_bwd(R, F0, H, L, max_eg)) {
+        int64_t n = sm_count();
+        if (n > B) n = B;
+        return n < 1 ? 1 : n;
+    }
     int P = (int)igcn_sgcn_param_count(R, F0, H, L);
     return ctas_for(bwd_smem((int)R, (int)F0, (int)H, (int)L, (int)max_eg, P), B);
 }
@@ -498,7 +507,9 @@ extern "C" int igcn_sgcn_encoder_fwd(const float* x, const int32_t* rowptr_t, co
             if (rc) return rc;
             const int nthr = fast_threads(a.R);
             int per_sm = (int)((227 * 1024) / (smem + 1024));
-            if (per_sm > 2) per_sm = 2;
+            const int by_regs = 65536 / (128 * nthr);
+            if (per_sm > by_regs) per_sm = by_regs;
+            if (per_sm < 1) per_sm = 1;
             int64_t grid = (int64_t)sm_count() * per_sm;
             if (grid > B) grid = B;
             kern<<<(int)grid, nthr, smem, (cudaStream_t)stream>>>(a);
@@ -540,11 +551,20 @@ extern "C" int igcn_sgcn_encoder_bwd(const float* x, const int32_t* rowptr_t, co
         cudaMemsetAsync(grads, 0, sizeof(float) * a.P, st);
         return IGCN_OK;
     }
-    size_t smem = bwd_smem(a.R, a.F0, a.H, a.L, a.maxEg, a.P);
-    rc = allow_smem(sgcn_encoder_bwd_kernel, smem, "sgcn_encoder_bwd");
-    if (rc) return rc;
-    sgcn_encoder_bwd_kernel<<<want, 256, smem, st>>>(a);
-    IGCN_CHECK_LAUNCH("sgcn_encoder_bwd");
+    if (use_fast_bwd(R, F0, H, L, max_eg)) {
+        size_t smem = bwd_fast_smem(a.R, a.maxEg);
+        auto kern = prob ? sgcn_bwd_h16_kernel<true> : sgcn_bwd_h16_kernel<false>;
+        rc = allow_smem(kern, smem, "sgcn_bwd_h16");
+        if (rc) return rc;
+        kern<<<want, fast_threads_bwd(a.R), smem, st>>>(a);
+        IGCN_CHECK_LAUNCH("sgcn_bwd_h16");
+    } else {
+        size_t smem = bwd_smem(a.R, a.F0, a.H, a.L, a.maxEg, a.P);
+        rc = allow_smem(sgcn_encoder_bwd_kernel, smem, "sgcn_encoder_bwd");
+        if (rc) return rc;
+        sgcn_encoder_bwd_kernel<<<want, 256, smem, st>>>(a);
+        IGCN_CHECK_LAUNCH("sgcn_encoder_bwd");
+    }
     reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(partials, want, a.P, grads);
     IGCN_CHECK_LAUNCH("sgcn_reduce_partials");
     return IGCN_OK;
