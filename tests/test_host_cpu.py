@@ -1,0 +1,158 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, host-side logic (packing, GO index
+preparation, synthetic generator), and the data-parallel gradient plumbing on a 2-process gloo group."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from igcn_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "igcn_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(igcn_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), "symbol %s declared in include/igcn_b200.h is not exported" % name
+    # every bound signature refers to a declared symbol
+    for name in _lib.SIGNATURES:
+        assert name in declared, name
+    l = _lib.lib()
+    assert l.igcn_version() >= 100
+    assert l.igcn_sgcn_param_count(90, 3, 16, 2) == 16 * 3 + 16 + 16 * 16 + 16 + 90 * 3 + 6
+    assert l.igcn_go_layer_param_count(2, 5, 54) == 2 * 10 + 15 + 108
+
+
+def test_no_cpu_fallback():
+    from igcn_b200 import ops
+    from igcn_b200.data import Batch, SubjectSet
+    from igcn_b200 import synthetic as syn
+    sub = syn.make_subjects(2, rois=10, n_snps=4, seed=0)
+    with pytest.raises(RuntimeError):
+        Batch.collate(SubjectSet(sub, pin=False), np.arange(2), "cpu")
+    with pytest.raises(RuntimeError):
+        ops.sgcn_encoder(torch.zeros(20, 3), None, [torch.zeros(4, 3)], [torch.zeros(4)])
+
+
+def test_subjectset_packing_roundtrip():
+    from igcn_b200.data import Data, SubjectSet
+    from igcn_b200 import synthetic as syn
+    sub = syn.make_subjects(5, rois=12, n_snps=6, seed=3)
+    ep = sub["edge_ptr"]
+    dl = []
+    for i in range(5):
+        e0, e1 = ep[i], ep[i + 1]
+        dl.append(Data(x=torch.from_numpy(sub["x"][i]), edge_index=torch.from_numpy(np.vstack([sub["edge_src"][e0:e1], sub["edge_dst"][e0:e1]])),
+                       edge_attr=torch.from_numpy(sub["edge_attr"][e0:e1]), y=torch.tensor([sub["y"][i]]),
+                       clust_y=torch.tensor([sub["clust_y"][i]]), snps_feat=torch.from_numpy(sub["snps_feat"][i:i + 1]),
+                       sbjID=torch.tensor([sub["sbjID"][i]]), tsne_fdim=torch.from_numpy(sub["tsne_fdim"][i:i + 1]),
+                       clini_score=torch.from_numpy(sub["clini_score"][i])))
+    ss = SubjectSet.from_data_list(dl, pin=False)
+    assert len(ss) == 5 and ss.rois == 12
+    assert np.array_equal(ss.edge_ptr.numpy(), ep)
+    assert np.array_equal(ss.edge_src.numpy(), sub["edge_src"]) and np.array_equal(ss.edge_dst.numpy(), sub["edge_dst"])
+    assert np.array_equal(ss.x.numpy(), sub["x"]) and np.array_equal(ss.clini_score.numpy(), sub["clini_score"])
+
+
+def test_go_index_prep_bit_exact_on_host():
+    from igcn_b200.go_net import Gene_ontology_network
+    g = H.load("go_mid")
+    A = torch.tensor(g["adj"]).float().t().to_sparse().coalesce()
+    A_g = torch.tensor(g["go_snps"]).float().to_sparse().coalesce()
+    net = Gene_ontology_network(A_g, A, 2, 2, [5, 5], [list(g["pool"])], 32, "cpu", dim_snps_atten=7)
+    for j in range(2):
+        assert np.array_equal(net.n_loc_in[j].numpy(), g["prep/enc%d/index" % j])
+        assert np.array_equal(net.store_in[j].numpy(), g["prep/enc%d/store" % j])
+        assert np.array_equal(net.n_loc_out[j].numpy(), g["prep/dec%d/index" % j])
+        assert np.array_equal(net.store_out[j].numpy(), g["prep/dec%d/store" % j])
+    assert np.array_equal(net.i.numpy(), g["prep/ag"]) and np.array_equal(net.i_D.numpy(), g["prep/ag_t"])
+    # the state_dict of the reference loads (names and shapes match), apart from the 54-SNP `classification` head
+    sd = {k: torch.from_numpy(v) for k, v in H.sub_dict(g, "P/").items() if not k.startswith("classification")}
+    res = net.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all(k.startswith("classification") for k in res.missing_keys)
+
+
+def test_model_state_dict_matches_reference_names():
+    from igcn_b200.img_snp_model import SGCN_GCN_IMGSNP
+    g = H.load("imgsnp_adni")
+    L, Hd, R, B, S = [int(v) for v in g["cfg"]]
+    A = torch.tensor(g["adj"]).float().t().to_sparse().coalesce()
+    A_g = torch.tensor(g["go_snps"]).float().to_sparse().coalesce()
+    m = SGCN_GCN_IMGSNP(L, Hd, A_g, A, [list(g["pool"])], 32, "cpu", rois=R, H_0=3, num_classes=3, isCrossAtten=True,
+                        isSoftSimilarity=True, isuseProb4Regr=True, num_regr=3, isImageOnly=False, isSNPsOnly=False)
+    ref = {k: v.shape for k, v in H.sub_dict(g, "P/").items()}
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert set(ref) == set(mine)
+    for k in ref:
+        assert tuple(ref[k]) == mine[k], k
+
+
+def test_synthetic_generator_pattern():
+    from igcn_b200 import synthetic as syn
+    sub = syn.make_subjects(4, rois=40, n_snps=9, seed=5)
+    ep = sub["edge_ptr"]
+    for i in range(4):
+        s, d, w = (sub[k][ep[i]:ep[i + 1]] for k in ("edge_src", "edge_dst", "edge_attr"))
+        assert np.all(np.bincount(d, minlength=40) == 3)                 # top-k=3 in-edges per node (util_gdc.py:25-31)
+        assert np.all(np.diff(s * 40 + d) > 0)                           # row-major COO order (util_gdc.py:84-86)
+        colsum = np.zeros(40)
+        np.add.at(colsum, d, w)
+        assert np.allclose(colsum, 1.0, atol=1e-5)                       # column normalised
+    again = syn.make_subjects(4, rois=40, n_snps=9, seed=5)
+    assert all(np.array_equal(sub[k], again[k]) for k in ("x", "edge_src", "edge_attr", "snps_feat"))
+    adj, go_snps, pool = syn.make_go_hierarchy([6, 4, 3, 2, 1], 9, seed=1)
+    assert adj.shape == (16, 16) and go_snps[-1].all() and pool == [[6, 4, 3, 2, 1]]
+    assert np.all(np.triu(adj, 1) == adj)                                # children precede parents (deepest level first)
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from igcn_b200 import train as T
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+    unused = torch.nn.Parameter(torch.ones(3))            # a parameter that never receives a gradient
+    model.register_parameter("unused", unused)
+    flat = T.FlatGradAllReduce(model)
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn(8, 6, generator=g), torch.randn(8, 2, generator=g)
+    lo, hi = rank * 4, rank * 4 + 4                          # contiguous shard of the global batch
+    flat.zero()
+    ((model(X[lo:hi]) - Y[lo:hi]) ** 2).mean().backward()
+    flat.reduce()
+    q.put((rank, flat.flat.clone().numpy()))
+    dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_world2_gloo():
+    """W-rank gradients (contiguous shards, one flat all-reduce, mean) == single-process gradients of the global batch."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn(8, 6, generator=g), torch.randn(8, 2, generator=g)
+    ((model(X) - Y) ** 2).mean().backward()
+    ref = torch.cat([torch.zeros(3)] + [p.grad.reshape(-1) for p in model.parameters()]).numpy()   # `unused` is listed first
+    assert np.allclose(res[0], res[1])
+    assert np.allclose(res[0], ref, atol=1e-6)
