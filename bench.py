@@ -130,8 +130,8 @@ def run_igcn(args, w):
     model = model.to(dev).train()
     ss = SubjectSet(sub)
     B = w["B"]
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0, capturable=not args.eager)
-    flat = T.FlatGradAllReduce(model)
+    opt = T.FlatAdam(model.parameters(), lr=1e-3)        # one fused kernel; its flat gradient buffer is what NCCL all-reduces
+    flat = None
     batch = Batch.collate(ss, np.arange(B), dev)
     E = batch.csr.E
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # 256 MB > 126 MB L2

@@ -215,7 +215,8 @@ class Gene_ontology_network(nn.Module):
         if not self.training:
             return None
         if self.dropout_masks is not None:
-            return self.dropout_masks[name].to(dev).float().reshape(shape)
+            m = self.dropout_masks[name].to(dev).float()
+            return m.expand(shape) if m.numel() == 1 else m.reshape(shape)
         return torch.bernoulli(torch.full(shape, 1.0 - p, device=dev)) / (1.0 - p)
 
     def _drop(self, name, t, p):

@@ -73,12 +73,81 @@ class FlatGradAllReduce(object):
             self.flat.mul_(1.0 / dist.get_world_size(self.group))
 
 
+class FlatAdam(object):
+    """Adam over ONE flat fp32 parameter buffer, one fused kernel per step (igcn_adam_step).
+
+    Every parameter is re-pointed to a view of `flat_param` (names, shapes and state_dict are unchanged); gradients are
+    gathered into `flat_grad` -- the buffer the data-parallel all-reduce runs on -- by one multi-tensor copy after
+    backward, so autograd never pays a per-parameter `grad += g` kernel for the first use of a parameter.
+    Semantics = torch.optim.Adam(lr, betas=(0.9,0.999), eps=1e-8, weight_decay=0) as the reference uses it
+    (kernel/train_eval_sgcn_img_snps.py:108); parameters that receive no gradient keep zero moments and do not move.
+    `param_groups[0]['lr']` is honoured (the reference decays it in place, :169-171)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None):
+        self.params = [p for p in params]
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatAdam runs on CUDA parameters only (no CPU fallback)")
+        sizes = [p.numel() for p in self.params]
+        self.offsets, off = [], 0
+        for n in sizes:
+            self.offsets.append(off)
+            off += (n + 3) // 4 * 4                    # keep every parameter 16-byte aligned inside the flat buffers
+        self.n = off
+        f = lambda: torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq = f(), f(), f(), f()
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                v = self.flat_param[o:o + p.numel()].view_as(p)
+                v.copy_(p.data)
+                p.data = v
+        self.grad_views = [self.flat_grad[o:o + p.numel()].view_as(p) for p, o in zip(self.params, self.offsets)]
+        self.step_t = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.lr_t = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self.param_groups = [dict(params=self.params, lr=float(lr), betas=betas, eps=eps)]
+        self._lr_seen = float(lr)
+        self.group = process_group
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            p.grad = None
+
+    def sync_lr(self):
+        """Call outside a captured graph after changing param_groups[0]['lr']."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_seen:
+            self.lr_t.fill_(lr)
+            self._lr_seen = lr
+
+    def gather_grads(self):
+        have = [(v, p.grad) for v, p in zip(self.grad_views, self.params) if p.grad is not None]
+        self.flat_grad.zero_()
+        if have:
+            torch._foreach_copy_([a for a, _ in have], [b for _, b in have])
+
+    def step(self):
+        from . import _lib
+        self.gather_grads()
+        scale = 1.0
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            scale = 1.0 / dist.get_world_size(self.group)
+        self.step_t += 1.0
+        g = self.param_groups[0]
+        with torch.cuda.device(self.flat_param.device):
+            _lib.call("igcn_adam_step", _lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
+                      _lib.ptr(self.exp_avg_sq), _lib.ptr(self.step_t), _lib.ptr(self.lr_t), float(g["betas"][0]),
+                      float(g["betas"][1]), float(g["eps"]), scale, self.n, _lib.stream())
+
+
 def train_step(model, data, optimizer=None, lambda_loss=None, flat: FlatGradAllReduce = None, isSoftSimilarity=True):
     """zero_grad -> 2 forwards + losses -> backward -> (all-reduce) -> optimizer.step. Returns the detached loss."""
     if flat is not None:
         flat.zero()
     elif optimizer is not None:
         optimizer.zero_grad()
+    if data.x.grad is not None:
+        data.x.grad = None
     loss = step_loss(model, data, lambda_loss, isSoftSimilarity)
     loss.backward()
     if getattr(model, "_pe_cache", None) is not None:
@@ -102,6 +171,8 @@ class GraphedTrainStep(object):
 
     def __init__(self, model, optimizer, static_batch, lambda_loss=None, flat: FlatGradAllReduce = None,
                  isSoftSimilarity=True, warmup=3):
+        if isinstance(optimizer, FlatAdam):
+            optimizer.sync_lr()
         self.model, self.opt, self.batch, self.flat = model, optimizer, static_batch, flat
         self.lambda_loss, self.soft = lambda_loss, isSoftSimilarity
         dev = static_batch.x.device

@@ -138,6 +138,16 @@ int igcn_go_layer_bwd(const float* x, const float* Wa, const float* Ws, const fl
                       int64_t self_off, int64_t keep_from, const float* stats, const float* g_y,
                       float* dx, float* partials, int64_t n_cta, float* grads, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused flat-buffer Adam (replaces torch.optim.Adam.step as called at kernel/train_eval_sgcn_img_snps.py:547;
+ * lr 1e-3, betas (0.9,0.999), eps 1e-8, weight_decay 0 -- :108).  One launch for the whole model.
+ *   params / grads / exp_avg / exp_avg_sq: (n) f32, 16-byte aligned; updates params and both moments in place.
+ *   step (1) f32 device scalar = the 1-based update count (the caller increments it before the call);
+ *   lr (1) f32 device scalar.  grad_scale multiplies the gradient on the fly (1/world after a SUM all-reduce).
+ */
+int igcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* step, const float* lr,
+                   double beta1, double beta2, double eps, double grad_scale, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -175,3 +175,57 @@ def test_full_model_golden(case):
             continue
         H.assert_close(m.state_dict()[k], v, rtol=2e-4, what="bn " + k)
 
+
+
+def test_adam_trajectory_golden_flat_adam_and_graph():
+    """Loop-level parity: 3 reference train() epochs with Adam (golden) vs FlatAdam (one fused kernel), eager;
+    learned masks prob / prob_bias / snps_prob and the per-step losses within 1e-4."""
+    from igcn_b200.data import Batch, SubjectSet
+    from igcn_b200 import train as T
+    g = H.load("imgsnp_small")
+    m, (L, Hd, R, B, S) = _build(g)
+    b = Batch.collate(SubjectSet(H.subjects(g)), np.arange(B), torch.device(DEV))
+    m.train()
+    opt = T.FlatAdam(m.parameters(), lr=1e-3)
+    lam = list(g["lambda_loss"])
+    orig_forward = m.forward
+    state = {"s": 0}
+
+    def fwd(data, temperature=None, device=None, isExplain=False):
+        tag = "explain" if isExplain else "plain"
+        m.dropout_masks = {k: torch.from_numpy(v) for k, v in H.sub_dict(g, "adam/mask/%d/%s/" % (state["s"], tag)).items()}
+        return orig_forward(data, temperature, device, isExplain)
+    m.forward = fwd
+    losses = []
+    for s in range(len(g["adam/losses"])):
+        state["s"] = s
+        losses.append(float(T.train_step(m, b, opt, lam)))
+    H.assert_close(np.asarray(losses), g["adam/losses"], what="loss trajectory")
+    P = dict(m.named_parameters())
+    for k, v in H.sub_dict(g, "adam/final/").items():
+        H.assert_close(P[k], v, rtol=2e-4, what="after 3 Adam steps: " + k)
+
+
+def test_graphed_step_matches_eager():
+    """The CUDA-graph replay of the whole step (eval-mode dropout off, so it is deterministic) == the eager step."""
+    import copy
+    from igcn_b200.data import Batch, SubjectSet
+    from igcn_b200 import train as T
+    g = H.load("imgsnp_small")
+    m1, (L, Hd, R, B, S) = _build(g)
+    m2 = copy.deepcopy(m1)
+    b = Batch.collate(SubjectSet(H.subjects(g)), np.arange(B), torch.device(DEV))
+    lam = list(g["lambda_loss"])
+    for m in (m1, m2):
+        m.train()
+        for mod in m.modules():                      # no dropout: both executions must see identical arithmetic
+            if isinstance(mod, (torch.nn.Dropout, torch.nn.Dropout2d)):
+                mod.p = 0.0
+        m.dropout_masks = {k: torch.ones(1, device=DEV) for k in O.MODEL_MASK_NAMES}
+    o1, o2 = T.FlatAdam(m1.parameters(), lr=1e-3), T.FlatAdam(m2.parameters(), lr=1e-3)
+    eager = [float(T.train_step(m1, b, o1, lam)) for _ in range(6)]       # other side: 3 warm-up steps + 3 replays (capture runs nothing)
+    gs = T.GraphedTrainStep(m2, o2, b, lam, warmup=3)
+    graphed = [float(gs()) for _ in range(3)]
+    H.assert_close(np.asarray(graphed), np.asarray(eager[3:6]), rtol=1e-5, what="graphed vs eager losses")
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        H.assert_close(p2, p1, rtol=1e-5, what="param " + k)
