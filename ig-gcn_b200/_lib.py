@@ -26,6 +26,10 @@ SIGNATURES = {
     "igcn_sgcn_bwd_ctas": (_I, [_I, _I, _I, _I, _I, _I]),
     "igcn_sgcn_encoder_fwd": (ctypes.c_int, [_P] * 7 + [_I] * 7 + [_P, _P, _P]),
     "igcn_sgcn_encoder_bwd": (ctypes.c_int, [_P] * 12 + [_I] * 7 + [_P, _P, _I, _P, _P]),
+    "igcn_gat_param_count": (_I, [_I, _I]),
+    "igcn_gat_bwd_ctas": (_I, [_I] * 5),
+    "igcn_gat_layer_fwd": (ctypes.c_int, [_P] * 10 + [_I] * 5 + [ctypes.c_double, _P, _P]),
+    "igcn_gat_layer_bwd": (ctypes.c_int, [_P] * 13 + [_I] * 5 + [ctypes.c_double, _P, _P, _P, _I, _P, _P]),
     "igcn_adam_step": (ctypes.c_int, [_P] * 6 + [ctypes.c_double] * 4 + [_I, _P]),
     "igcn_go_spmm_fwd": (ctypes.c_int, [_P] * 4 + [_I] * 5 + [_P, _P]),
     "igcn_go_spmm_bwd": (ctypes.c_int, [_P] * 8 + [_I] * 5 + [_P, _P, _P]),
@@ -54,8 +58,12 @@ def lib():
 # ---- launch accounting (bench.py: gpu_launches, per-kernel CUDA-event timing) -------------------------------
 KERNELS_PER_CALL = {
     "igcn_collate_csr": 1, "igcn_csr_from_edge_index": 2, "igcn_sgcn_encoder_fwd": 1, "igcn_sgcn_encoder_bwd": 2,
+    "igcn_gat_param_count": (_I, [_I, _I]),
+    "igcn_gat_bwd_ctas": (_I, [_I] * 5),
+    "igcn_gat_layer_fwd": (ctypes.c_int, [_P] * 10 + [_I] * 5 + [ctypes.c_double, _P, _P]),
+    "igcn_gat_layer_bwd": (ctypes.c_int, [_P] * 13 + [_I] * 5 + [ctypes.c_double, _P, _P, _P, _I, _P, _P]),
     "igcn_adam_step": (ctypes.c_int, [_P] * 6 + [ctypes.c_double] * 4 + [_I, _P]),
-    "igcn_go_spmm_fwd": 1, "igcn_go_spmm_bwd": 2, "igcn_go_layer_fwd": 1, "igcn_go_layer_bwd": 2, "igcn_adam_step": 1,
+    "igcn_go_spmm_fwd": 1, "igcn_go_spmm_bwd": 2, "igcn_go_layer_fwd": 1, "igcn_go_layer_bwd": 2, "igcn_adam_step": 1, "igcn_gat_layer_fwd": 1, "igcn_gat_layer_bwd": 2,
 }
 launch_count = 0          # number of igcn kernels launched by this process
 _profile = None           # None, or dict name -> list[(start_event, end_event)]

@@ -81,3 +81,49 @@ def edge_mask(x, csr: GraphCSR, prob, prob_bias):
     """p_e of cal_probability (kernel/sgcn_img_snp.py:141-142) in CSR-slot order (masks only, L=0)."""
     _, p_e = _SGCNEncoderFn.apply(x, prob, prob_bias, None, csr, 0, 0, True, True)
     return p_e
+
+
+class _GATConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ea_csr, W, att_src, att_dst, lin_edge, att_edge, bias, csr: GraphCSR, slope: float):
+        _lib.require_cuda(x, ea_csr, W)
+        c = lambda t: t.contiguous().float().view(-1)
+        x = x.contiguous().float()
+        B, R, Fin, H = csr.B, csr.R, x.shape[1], W.shape[0]
+        Wc, a_s, a_d, le, ae, b = W.contiguous().float(), c(att_src), c(att_dst), c(lin_edge), c(att_edge), c(bias)
+        ea = c(ea_csr)
+        out = torch.empty((B * R, H), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.call("igcn_gat_layer_fwd", _lib.ptr(x), _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(ea), _lib.ptr(Wc),
+                      _lib.ptr(a_s), _lib.ptr(a_d), _lib.ptr(le), _lib.ptr(ae), _lib.ptr(b), B, R, Fin, H, csr.max_eg, float(slope),
+                      _lib.ptr(out), _lib.stream())
+        ctx.csr, ctx.slope = csr, float(slope)
+        ctx.shapes = (att_src.shape, att_dst.shape, lin_edge.shape, att_edge.shape, bias.shape)
+        ctx.save_for_backward(x, ea, Wc, a_s, a_d, le, ae, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, ea, W, a_s, a_d, le, ae, b = ctx.saved_tensors
+        csr, lib = ctx.csr, _lib.lib()
+        B, R, Fin, H = csr.B, csr.R, x.shape[1], W.shape[0]
+        P = lib.igcn_gat_param_count(Fin, H)
+        n_cta = lib.igcn_gat_bwd_ctas(B, R, Fin, H, csr.max_eg)
+        dx, d_ea = torch.empty_like(x), torch.empty_like(ea)
+        partials = torch.empty((max(n_cta, 1), P), dtype=torch.float32, device=x.device)
+        grads = torch.empty(P, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.call("igcn_gat_layer_bwd", _lib.ptr(x), _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(ea),
+                      _lib.ptr(csr.rowptr_s), _lib.ptr(csr.csc_pos), _lib.ptr(W), _lib.ptr(a_s), _lib.ptr(a_d), _lib.ptr(le), _lib.ptr(ae),
+                      _lib.ptr(b), _lib.ptr(g_out.contiguous()), B, R, Fin, H, csr.max_eg, ctx.slope, _lib.ptr(dx), _lib.ptr(d_ea),
+                      _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream())
+        o = H * Fin
+        sh = ctx.shapes
+        return (dx, d_ea, grads[:o].view(H, Fin), grads[o:o + H].view(sh[0]), grads[o + H:o + 2 * H].view(sh[1]),
+                grads[o + 2 * H:o + 3 * H].view(sh[2]), grads[o + 3 * H:o + 4 * H].view(sh[3]), grads[o + 4 * H:o + 5 * H].view(sh[4]),
+                None, None)
+
+
+def gat_conv(x, csr: GraphCSR, edge_attr_csr, W, att_src, att_dst, lin_edge, att_edge, bias, negative_slope=0.2):
+    """Fused GATConv(heads=1, edge_dim=1). edge_attr_csr is per CSR slot (edge_attr[csr.csr_perm])."""
+    return _GATConvFn.apply(x, edge_attr_csr, W, att_src, att_dst, lin_edge, att_edge, bias, csr, negative_slope)

@@ -139,6 +139,28 @@ int igcn_go_layer_bwd(const float* x, const float* Wa, const float* Ws, const fl
                       float* dx, float* partials, int64_t n_cta, float* grads, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused GATConv(in, out, heads=1, edge_dim=1) layer (PyG 2.0.2 semantics; reference call sites kernel/sgcn.py:163-166):
+ * h = x W^T; self loops removed and re-added with the MEAN incoming edge attribute; LeakyReLU(negative_slope) edge
+ * scores a_src.h_s + a_dst.h_t + ea*<lin_edge, att_edge>; per-target softmax; aggregate; + bias.  Graphs own R
+ * consecutive nodes (CSR from igcn_collate_csr); edge_attr (E) is given per CSR slot.
+ *   x (B*R,Fin), W (H,Fin), att_src/att_dst/lin_edge/att_edge/bias (H), out (B*R,H).
+ *   bwd: dx (B*R,Fin), d_edge_attr (E) per CSR slot, grads (P) = [dW | datt_src | datt_dst | dlin_edge | datt_edge | dbias],
+ *   P = igcn_gat_param_count; partials (n_cta,P) workspace, n_cta = igcn_gat_bwd_ctas(...).  Deterministic.
+ */
+int64_t igcn_gat_param_count(int64_t Fin, int64_t H);
+int64_t igcn_gat_bwd_ctas(int64_t B, int64_t R, int64_t Fin, int64_t H, int64_t max_eg);
+int igcn_gat_layer_fwd(const float* x, const int32_t* rowptr_t, const int32_t* csr_src, const float* edge_attr,
+                       const float* W, const float* att_src, const float* att_dst, const float* lin_edge, const float* att_edge,
+                       const float* bias, int64_t B, int64_t R, int64_t Fin, int64_t H, int64_t max_eg, double negative_slope,
+                       float* out, void* stream);
+int igcn_gat_layer_bwd(const float* x, const int32_t* rowptr_t, const int32_t* csr_src, const float* edge_attr,
+                       const int32_t* rowptr_s, const int32_t* csc_pos,
+                       const float* W, const float* att_src, const float* att_dst, const float* lin_edge, const float* att_edge,
+                       const float* bias, const float* g_out, int64_t B, int64_t R, int64_t Fin, int64_t H, int64_t max_eg,
+                       double negative_slope, float* dx, float* d_edge_attr, float* partials, int64_t n_cta, float* grads,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused flat-buffer Adam (replaces torch.optim.Adam.step as called at kernel/train_eval_sgcn_img_snps.py:547;
  * lr 1e-3, betas (0.9,0.999), eps 1e-8, weight_decay 0 -- :108).  One launch for the whole model.
  *   params / grads / exp_avg / exp_avg_sq: (n) f32, 16-byte aligned; updates params and both moments in place.

@@ -229,3 +229,38 @@ def test_graphed_step_matches_eager():
     H.assert_close(np.asarray(graphed), np.asarray(eager[3:6]), rtol=1e-5, what="graphed vs eager losses")
     for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         H.assert_close(p2, p1, rtol=1e-5, what="param " + k)
+
+
+class _DS:
+    num_features, num_classes = 3, 2
+
+
+@pytest.mark.parametrize("kind", ["gcn", "gat"])
+def test_config1_sgcn_models_golden(kind):
+    """BASELINE config 1 (kernel/sgcn.py SGCN_GCN / SGCN_GAT, 3-term step of train_eval_sgcn.py:296-313) vs the golden
+    vectors of the reference's own classes: logits of both passes, mask loss, total loss, every gradient incl. dL/dx."""
+    from igcn_b200.data import Batch, SubjectSet
+    from igcn_b200 import train as T
+    from igcn_b200.sgcn_models import SGCN_GAT, SGCN_GCN
+    g = H.load("sgcn_cfg1")
+    L, Hd, R, B = [int(v) for v in g["cfg"]]
+    m = (SGCN_GCN(None, L, Hd, rois=R) if kind == "gcn" else SGCN_GAT(_DS, L, Hd, rois=R)).to(DEV)
+    sd = {k: torch.from_numpy(v) for k, v in H.sub_dict(g, "P_%s/" % kind).items()}
+    res = m.load_state_dict(sd, strict=True)
+    m.eval()
+    b = Batch.collate(SubjectSet(H.subjects(g)), np.arange(B), torch.device(DEV))
+    o = m(b)
+    q = m(b, True)
+    lp = m.loss_probability(b.x, b.edge_index, b.edge_attr, T.hp)
+    y = b.y.view(-1)
+    loss = torch.nn.functional.nll_loss(o, y) + lp + torch.nn.functional.nll_loss(q, y)
+    loss.backward()
+    H.assert_close(o, g["%s/logp" % kind], what="logp")
+    H.assert_close(q, g["%s/logp_explain" % kind], what="logp explain")
+    H.assert_close(lp, g["%s/loss_prob" % kind], what="loss_prob")
+    H.assert_close(loss, g["%s/loss" % kind], what="loss")
+    H.assert_close(b.x.grad, g["%s/grad/x" % kind], rtol=2e-4, what="dL/dx")
+    P = dict(m.named_parameters())
+    for k, v in H.sub_dict(g, "%s/grad/" % kind).items():
+        if k != "x":
+            H.assert_close(P[k].grad, v, rtol=2e-4, what="grad " + k)
