@@ -124,6 +124,10 @@ def run_igcn(args, w):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line: anything libraries print (NCCL's version banner goes to fd 1) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     model, sub, _ = build_problem(w, rank, dev)
@@ -208,8 +212,7 @@ def run_igcn(args, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
     peak, peak_src = peaks()
     # dominant igcn kernel by total device time inside the timed steps
@@ -233,9 +236,23 @@ def run_igcn(args, w):
                kernels=kern, clocks=clocks, wall_s_timed_region=t_wall)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(w, steps=3, warmup=1)
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(out), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """Leave without tearing NCCL down: destroy_process_group() after a captured graph that contains the all-reduce was
+    observed to hang at exit on this stack; the timed work is complete and synchronised at this point."""
+    import torch.distributed as dist
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def cpu_baseline(w, steps, warmup, threads=None):
@@ -304,6 +321,9 @@ def run_reference(args, w):
 
 
 def main():
+    import signal
+    signal.signal(signal.SIGALRM, lambda *a: (sys.stderr.write("bench.py: watchdog timeout\n"), os._exit(3)))
+    signal.alarm(1500)                       # never hang the driver
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
