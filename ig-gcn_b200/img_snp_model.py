@@ -219,17 +219,32 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         loss_entropy = hp.lamda_x_ent * f_en + hp.lamda_e_ent * e_en + hp.lamda_x_ent * s_en
         return loss_l1 + loss_entropy
 
+    def _similarity(self, n, tsne_result, like):
+        """W (n,n) and its row sums; depends on the data only, so the two passes of a step share it."""
+        if self.isSoftSimilarity and tsne_result is not None:
+            key = (tsne_result.data_ptr(), tsne_result._version, n)
+            c = getattr(self, "_w_cache", None)
+            if c is not None and c[0] == key:
+                return c[1], c[2]
+            W = torch.exp(-self.rbf_gamma * torch.cdist(tsne_result, tsne_result, p=2) ** 2)
+            d = W.sum(1)
+            self._w_cache = (key, W, d)
+            return W, d
+        W = torch.ones(n, n, device=like.device, dtype=like.dtype)
+        return W, W.sum(1)
+
     def consist_loss(self, s, tsne_result=None):
-        """tr(s^T (D-W) s)/B^2 (sgcn_img_snp.py:183-196) in Gram form: sum_i d_i |s_i|^2 - sum_ij W_ij <s_i,s_j>."""
+        """tr(s^T (D-W) s)/B^2 (sgcn_img_snp.py:183-196) in Gram form: sum_i d_i |s_i|^2 - sum_ij W_ij <s_i,s_j>.
+        The B x B x D Gram product runs on the split-K tile kernels (cuBLAS picks a 16-CTA shape for it: 50 us at B=256)."""
         n = s.shape[0]
         if n == 0:
             return 0
-        gram = s @ s.t()
-        if self.isSoftSimilarity and tsne_result is not None:
-            W = torch.exp(-self.rbf_gamma * torch.cdist(tsne_result, tsne_result, p=2) ** 2)
+        if s.is_cuda:
+            gram = ops.cat_linear([s], s, s.new_zeros(n), relu=False)
         else:
-            W = torch.ones(n, n, device=s.device, dtype=s.dtype)
-        return ((W.sum(1) * gram.diagonal()).sum() - (W * gram).sum()) / (n * n)
+            gram = s @ s.t()
+        W, d = self._similarity(n, tsne_result, s)
+        return ((d * gram.diagonal()).sum() - (W * gram).sum()) / (n * n)
 
     def OrthogonalConstraint(self, w):
         """||w^T w - I_D||_F^2 / B^2 with row-normalised w (sgcn_img_snp.py:198-205) = (||w w^T||_F^2 - 2B + D)/B^2."""
@@ -270,8 +285,8 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         go.dropout_masks = self.dropout_masks
         latent, x_hat, _, atten_out = go(snps_feat_prob, temperature, device)
         if self.isCrossAtten:
-            attn_output, _ = self.multihead_attn(batch_x, atten_out, atten_out, need_weights=False)
-            out_cross = F.relu(attn_output)
+            # relu(MHA(q = ROI tokens, k = v = GO tokens)) as one kernel (cross_attn.cu)
+            out_cross = ops.cross_attention(batch_x, atten_out, self.multihead_attn, relu=True)
         else:
             out_cross = torch.cat((img_out, latent), -1)
         if self.graph_pool:
@@ -279,31 +294,32 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         else:
             out_cross = out_cross.reshape(B, -1)
 
-        def regr_head(out_lin):
+        def regr_head(parts):
             if self.isuseProb4Regr:
                 img_feat = (x.view(B, self.rois, -1) * self.prob).reshape(B, -1)       # data.x (unmasked) * prob (:293-297)
-                feat = torch.cat((out_lin, img_feat), -1)
-            else:
-                feat = out_lin
-            r = self._mask("lin1_regr", F.relu(self.lin1_regr(feat)), 0.3)
+                parts = parts + [img_feat]
+            # relu(lin1_regr(cat(parts))) without building the concatenation (fusion_gemm.cu)
+            r = self._mask("lin1_regr", ops.cat_linear(parts, self.lin1_regr.weight, self.lin1_regr.bias, relu=True), 0.3)
             return self.lin2_regr(r)
 
         if self.isImageOnly:
             out_z = img_out
-            out_lin = out_z
+            parts = [out_z]
         elif self.isSNPsOnly:
             out_z = latent
-            out_lin = torch.cat((snps_feat_prob, latent), -1)
+            parts = [snps_feat_prob, latent]
         else:
             out_z = (img_out + out_cross) / 2
-            out_lin = torch.cat((out_z, latent), -1)
-        linear_outf = F.relu(self.lin1(out_lin))
+            parts = [out_z, latent]
+        # out_lin is part of the returned tuple (eval_scores collects it, train_eval...:626); the heads read its parts in place
+        out_lin = parts[0] if len(parts) == 1 else torch.cat(parts, -1).detach()
+        linear_outf = ops.cat_linear(parts, self.lin1.weight, self.lin1.bias, relu=True)
         logits = self.lin2(self._mask("lin1", linear_outf, 0.5))
         if self.isSNPsOnly:
-            r = self._mask("lin1_regr", F.relu(self.lin1_regr(out_lin)), 0.3)
+            r = self._mask("lin1_regr", ops.cat_linear(parts, self.lin1_regr.weight, self.lin1_regr.bias, relu=True), 0.3)
             our_reg = self.lin2_regr(r)
         else:
-            our_reg = regr_head(out_lin)
+            our_reg = regr_head(parts)
         return F.log_softmax(logits, dim=-1), x_hat, out_z, out_lin, linear_outf, our_reg
 
     def __repr__(self):

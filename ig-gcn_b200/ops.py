@@ -127,3 +127,110 @@ class _GATConvFn(torch.autograd.Function):
 def gat_conv(x, csr: GraphCSR, edge_attr_csr, W, att_src, att_dst, lin_edge, att_edge, bias, negative_slope=0.2):
     """Fused GATConv(heads=1, edge_dim=1). edge_attr_csr is per CSR slot (edge_attr[csr.csr_perm])."""
     return _GATConvFn.apply(x, edge_attr_csr, W, att_src, att_dst, lin_edge, att_edge, bias, csr, negative_slope)
+
+
+class _CatLinearFn(torch.autograd.Function):
+    """act([x0 | x1 | x2] W^T + b) via igcn_cat_linear_* (sources may be None)."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, x2, W, bias, relu: bool):
+        import ctypes
+        srcs = [x0, x1, x2]
+        _lib.require_cuda(W, bias, *[t for t in srcs if t is not None])
+        lib = _lib.lib()
+        M = next(t.shape[0] for t in srcs if t is not None)
+        cs = [None if t is None else (t.float() if t.stride(-1) == 1 else t.contiguous().float()) for t in srcs]
+        widths = [0 if t is None else t.shape[1] for t in cs]
+        strides = [0 if t is None else t.stride(0) for t in cs]
+        N, K = W.shape
+        if sum(widths) != K:
+            raise RuntimeError("cat_linear: source widths %s do not add up to in_features=%d" % (widths, K))
+        Wc, bc = W.contiguous().float(), bias.contiguous().float()
+        S = lib.igcn_cat_linear_splits(M, N, K)
+        part = torch.empty((S, M, N), dtype=torch.float32, device=W.device)
+        out = torch.empty((M, N), dtype=torch.float32, device=W.device)
+        hw, hs = (ctypes.c_int64 * 3)(*widths), (ctypes.c_int64 * 3)(*strides)
+        with torch.cuda.device(W.device):
+            _lib.call("igcn_cat_linear_fwd", _lib_ptr_strided(cs[0]), _lib_ptr_strided(cs[1]), _lib_ptr_strided(cs[2]),
+                      ctypes.addressof(hw), ctypes.addressof(hs), _lib.ptr(Wc), _lib.ptr(bc), M, N, K, int(relu), _lib.ptr(part), S,
+                      _lib.ptr(out), _lib.stream())
+        ctx.relu, ctx.widths, ctx.strides = bool(relu), widths, strides
+        ctx.need = [t is not None and t.requires_grad for t in srcs]
+        ctx.save_for_backward(Wc, out, *[t for t in cs if t is not None])
+        ctx.present = [t is not None for t in cs]
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        import ctypes
+        saved = ctx.saved_tensors
+        W, out = saved[0], saved[1]
+        it = iter(saved[2:])
+        cs = [next(it) if p else None for p in ctx.present]
+        M, (N, K) = out.shape[0], W.shape
+        dxs = [torch.empty((M, w), dtype=torch.float32, device=W.device) if (need and w) else None
+               for need, w in zip(ctx.need, ctx.widths)]
+        dW = torch.empty_like(W)
+        db = torch.empty(N, dtype=torch.float32, device=W.device)
+        hw, hs = (ctypes.c_int64 * 3)(*ctx.widths), (ctypes.c_int64 * 3)(*ctx.strides)
+        hd = (ctypes.c_int64 * 3)(*[0 if t is None else t.stride(0) for t in dxs])
+        with torch.cuda.device(W.device):
+            _lib.call("igcn_cat_linear_bwd", _lib_ptr_strided(cs[0]), _lib_ptr_strided(cs[1]), _lib_ptr_strided(cs[2]),
+                      ctypes.addressof(hw), ctypes.addressof(hs), _lib.ptr(W), _lib.ptr(out), _lib.ptr(g_out.contiguous()), M, N, K,
+                      int(ctx.relu), _lib.ptr(dxs[0]), _lib.ptr(dxs[1]), _lib.ptr(dxs[2]), ctypes.addressof(hd), _lib.ptr(dW), _lib.ptr(db),
+                      _lib.stream())
+        return dxs[0], dxs[1], dxs[2], dW, db, None
+
+
+def _lib_ptr_strided(t):
+    """device pointer of a 2-D tensor whose rows may be strided (last dim contiguous)."""
+    return None if t is None else t.data_ptr()
+
+
+def cat_linear(xs, weight, bias, relu=True):
+    """relu(cat(xs, -1) @ weight.T + bias) without building the concatenation; xs: up to three (M, w_i) tensors."""
+    xs = list(xs) + [None] * (3 - len(xs))
+    return _CatLinearFn.apply(xs[0], xs[1], xs[2], weight, bias, relu)
+
+
+class _CrossAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, kv, in_w, in_b, out_w, out_b, heads: int, relu: bool):
+        _lib.require_cuda(q, kv, in_w, in_b, out_w, out_b)
+        c = lambda t: t.contiguous().float()
+        q, kv, in_w, in_b, out_w, out_b = c(q), c(kv), c(in_w), c(in_b), c(out_w), c(out_b)
+        B, R, E = q.shape
+        M = kv.shape[1]
+        out = torch.empty_like(q)
+        with torch.cuda.device(q.device):
+            _lib.call("igcn_cross_attn_fwd", _lib.ptr(q), _lib.ptr(kv), _lib.ptr(in_w), _lib.ptr(in_b), _lib.ptr(out_w), _lib.ptr(out_b),
+                      B, R, M, E, heads, int(relu), _lib.ptr(out), _lib.stream())
+        ctx.heads, ctx.relu = heads, bool(relu)
+        ctx.save_for_backward(q, kv, in_w, in_b, out_w, out_b, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, kv, in_w, in_b, out_w, out_b, out = ctx.saved_tensors
+        lib = _lib.lib()
+        B, R, E = q.shape
+        M = kv.shape[1]
+        P = lib.igcn_cross_attn_param_count(E)
+        n_cta = lib.igcn_cross_attn_bwd_ctas(B, R, M, E, ctx.heads)
+        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+        partials = torch.empty((max(n_cta, 1), P), dtype=torch.float32, device=q.device)
+        grads = torch.empty(P, dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            _lib.call("igcn_cross_attn_bwd", _lib.ptr(q), _lib.ptr(kv), _lib.ptr(in_w), _lib.ptr(in_b), _lib.ptr(out_w), _lib.ptr(out_b),
+                      _lib.ptr(out), _lib.ptr(g.contiguous()), B, R, M, E, ctx.heads, int(ctx.relu), _lib.ptr(dq), _lib.ptr(dkv),
+                      _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream())
+        o1, o2, o3 = 3 * E * E, 3 * E * E + 3 * E, 4 * E * E + 3 * E
+        return dq, dkv, grads[:o1].view(3 * E, E), grads[o1:o2], grads[o2:o3].view(E, E), grads[o3:], None, None
+
+
+def cross_attention(q, kv, mha: torch.nn.MultiheadAttention, relu=True):
+    """relu(mha(q, kv, kv)[0]) for a batch_first nn.MultiheadAttention with packed in_proj (the reference's use)."""
+    if mha.in_proj_weight is None or mha.in_proj_bias is None or mha.bias_k is not None or mha.dropout != 0.0 or not mha.batch_first:
+        raise RuntimeError("igcn_b200.cross_attention supports the reference configuration only "
+                           "(packed in_proj with bias, no bias_kv, dropout 0, batch_first)")
+    return _CrossAttnFn.apply(q, kv, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, mha.num_heads, relu)

@@ -152,6 +152,8 @@ def train_step(model, data, optimizer=None, lambda_loss=None, flat: FlatGradAllR
     loss.backward()
     if getattr(model, "_pe_cache", None) is not None:
         model._pe_cache = None            # drop the last reference to this step's autograd graph
+    if getattr(model, "_w_cache", None) is not None:
+        model._w_cache = None             # the similarity matrix belongs to this batch only
     if flat is not None:
         flat.reduce()
     if optimizer is not None:

@@ -161,6 +161,42 @@ int igcn_gat_layer_bwd(const float* x, const int32_t* rowptr_t, const int32_t* c
                        void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused cross attention (replaces nn.MultiheadAttention(E, heads, batch_first=True)(q, kv, kv)[0] + relu at
+ * kernel/sgcn_img_snp.py:46,239-241): in-projections, per-head scaled scores, row softmax, P.V, out-projection, ReLU.
+ *   q_in (B,R,E), kv_in (B,M,E), in_proj_weight (3E,E) = [Wq;Wk;Wv], in_proj_bias (3E), out_proj_weight (E,E),
+ *   out_proj_bias (E); out (B,R,E).  relu=1 fuses the ReLU that follows the attention in the reference.
+ *   bwd: `out` = forward output (ReLU mask); d_q_in (B,R,E), d_kv_in (B,M,E); grads (P) =
+ *   [d in_proj_weight | d in_proj_bias | d out_proj_weight | d out_proj_bias], P = igcn_cross_attn_param_count(E);
+ *   partials (n_cta,P) workspace, n_cta = igcn_cross_attn_bwd_ctas(...).  Deterministic.
+ */
+int64_t igcn_cross_attn_param_count(int64_t E);
+int64_t igcn_cross_attn_bwd_ctas(int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads);
+int igcn_cross_attn_fwd(const float* q_in, const float* kv_in, const float* in_proj_weight, const float* in_proj_bias,
+                        const float* out_proj_weight, const float* out_proj_bias,
+                        int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads, int64_t relu, float* out, void* stream);
+int igcn_cross_attn_bwd(const float* q_in, const float* kv_in, const float* in_proj_weight, const float* in_proj_bias,
+                        const float* out_proj_weight, const float* out_proj_bias, const float* out, const float* g_out,
+                        int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads, int64_t relu,
+                        float* d_q_in, float* d_kv_in, float* partials, int64_t n_cta, float* grads, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fusion heads: out = act([X0 | X1 | X2] W^T + b) without materialising the concatenation (reference:
+ * kernel/sgcn_img_snp.py:287-301 -- cat(out_z, latent) -> lin1 -> relu ; cat(out_lin, img_feat) -> lin1_regr -> relu).
+ *   X_i (M, host_widths[i]) f32 with row stride host_strides[i] (width 0 = absent); W (N,K) row-major, K = sum of widths;
+ *   bias (N); relu = 1 applies ReLU.  Split-K over S = igcn_cat_linear_splits(M,N,K) chunks: partials (S,M,N) workspace,
+ *   reduced in a fixed order (deterministic).  host_* arrays are 3-element HOST arrays.
+ *   bwd: g_out = dLoss/d out, `out` = the forward output (ReLU mask); dW (N,K), db (N), dx_i (M, width_i) with row
+ *   stride host_dstrides[i] (NULL = not needed); all fully overwritten.
+ */
+int64_t igcn_cat_linear_splits(int64_t M, int64_t N, int64_t K);
+int igcn_cat_linear_fwd(const float* x0, const float* x1, const float* x2, const int64_t* host_widths, const int64_t* host_strides,
+                        const float* W, const float* bias, int64_t M, int64_t N, int64_t K, int64_t relu,
+                        float* partials, int64_t S, float* out, void* stream);
+int igcn_cat_linear_bwd(const float* x0, const float* x1, const float* x2, const int64_t* host_widths, const int64_t* host_strides,
+                        const float* W, const float* out, const float* g_out, int64_t M, int64_t N, int64_t K, int64_t relu,
+                        float* dx0, float* dx1, float* dx2, const int64_t* host_dstrides, float* dW, float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused flat-buffer Adam (replaces torch.optim.Adam.step as called at kernel/train_eval_sgcn_img_snps.py:547;
  * lr 1e-3, betas (0.9,0.999), eps 1e-8, weight_decay 0 -- :108).  One launch for the whole model.
  *   params / grads / exp_avg / exp_avg_sq: (n) f32, 16-byte aligned; updates params and both moments in place.
