@@ -29,8 +29,7 @@ struct AttnArgs {
 
 struct AttnSmem {
     float *WinT, *WoT, *bin, *bo;   // WinT[k][3E] (k-major), WoT[k][E]
-    const float *X, *A;             // this graph's inputs, read through L1 (__ldg): not staged, to fit 2 CTAs per SM
-    float *Q, *K, *V, *Pm, *O;
+    float *X, *A, *Q, *K, *V, *Pm, *O;
     float* tail;
 };
 __device__ __forceinline__ AttnSmem attn_carve(float* p, int R, int M, int E, int heads) {
@@ -39,8 +38,8 @@ __device__ __forceinline__ AttnSmem attn_carve(float* p, int R, int M, int E, in
     s.WoT = p;   p += E * E;
     s.bin = p;   p += 3 * E;
     s.bo = p;    p += E;
-    s.X = nullptr;
-    s.A = nullptr;
+    s.X = p;     p += R * E;
+    s.A = p;     p += M * E;
     s.Q = p;     p += R * (E + 1);   // row stride E+1: rows are walked by different threads at the same column
     s.K = p;     p += M * E;
     s.V = p;     p += M * E;
@@ -50,7 +49,7 @@ __device__ __forceinline__ AttnSmem attn_carve(float* p, int R, int M, int E, in
     return s;
 }
 static size_t attn_common_floats(int R, int M, int E, int heads) {
-    return (size_t)4 * E * E + 4 * E + 2 * (size_t)R * E + R + 2 * (size_t)M * E + (size_t)heads * R * M;
+    return (size_t)4 * E * E + 4 * E + 3 * (size_t)R * E + R + 3 * (size_t)M * E + (size_t)heads * R * M;
 }
 
 __device__ __forceinline__ void attn_load_params(const AttnArgs& a, const AttnSmem& s) {
@@ -72,20 +71,23 @@ __device__ __forceinline__ void attn_load_params(const AttnArgs& a, const AttnSm
 __device__ __forceinline__ void attn_forward_graph(const AttnArgs& a, AttnSmem& s, int b) {
     const int tid = threadIdx.x, nt = blockDim.x, R = a.R, M = a.M, E = a.E, H = a.heads, hd = E / H;
     const float scale = rsqrtf((float)hd);
-    s.X = a.x + (int64_t)b * R * E;
-    s.A = a.a + (int64_t)b * M * E;
+    const float* xb = a.x + (int64_t)b * R * E;
+    const float* ab = a.a + (int64_t)b * M * E;
+    for (int i = tid; i < R * E; i += nt) s.X[i] = xb[i];
+    for (int i = tid; i < M * E; i += nt) s.A[i] = ab[i];
+    __syncthreads();
     for (int idx = tid; idx < R * E; idx += nt) {
         const int i = idx / E, f = idx - i * E;
         float acc = s.bin[f];
 #pragma unroll 8
-        for (int k = 0; k < E; ++k) acc = fmaf(__ldg(s.X + i * E + k), s.WinT[k * 3 * E + f], acc);
+        for (int k = 0; k < E; ++k) acc = fmaf(s.X[i * E + k], s.WinT[k * 3 * E + f], acc);
         s.Q[i * (E + 1) + f] = acc;
     }
     for (int idx = tid; idx < M * E; idx += nt) {
         const int j = idx / E, f = idx - j * E;
         float ak = s.bin[E + f], av = s.bin[2 * E + f];
         for (int k = 0; k < E; ++k) {
-            const float v = __ldg(s.A + j * E + k);
+            const float v = s.A[j * E + k];
             ak = fmaf(v, s.WinT[k * 3 * E + E + f], ak);
             av = fmaf(v, s.WinT[k * 3 * E + 2 * E + f], av);
         }
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(256) cross_attn_fwd_kernel(AttnArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(256) cross_attn_bwd_kernel(AttnArgs a) {
+__global__ void __launch_bounds__(512) cross_attn_bwd_kernel(AttnArgs a) {
     extern __shared__ float smf[];
     const int tid = threadIdx.x, nt = blockDim.x, R = a.R, M = a.M, E = a.E, H = a.heads, hd = E / H;
     const float scale = rsqrtf((float)hd);
@@ -156,7 +158,11 @@ __global__ void __launch_bounds__(256) cross_attn_bwd_kernel(AttnArgs a) {
     float* dK = p;   p += M * E;
     float* dV = p;   p += M * E;
     float* acc = p;  p += a.P;        // [dWin (3E,E) | dbin (3E) | dWo (E,E) | dbo (E)]
+    float* WinO = p; p += 3 * E * E;  // row-major copies [f][k] for the transposed products of the backward
+    float* WoO = p;  p += E * E;
     attn_load_params(a, s);
+    for (int i = tid; i < 3 * E * E; i += nt) WinO[i] = a.Win[i];
+    for (int i = tid; i < E * E; i += nt) WoO[i] = a.Wo[i];
     for (int i = tid; i < a.P; i += nt) acc[i] = 0.f;
     const int oBin = 3 * E * E, oWo = oBin + 3 * E, oBo = oWo + E * E;
     __syncthreads();
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(256) cross_attn_bwd_kernel(AttnArgs a) {
             const int i = idx / E, k = idx - i * E;
             float v = 0.f;
 #pragma unroll 8
-            for (int f = 0; f < E; ++f) v = fmaf(dY[i * E + f], __ldg(a.Wo + f * E + k), v);   // row-major W: k is the fast index
+            for (int f = 0; f < E; ++f) v = fmaf(dY[i * E + f], WoO[f * E + k], v);   // row-major W: k is the fast index
             dO[i * (E + 1) + k] = v;
         }
         for (int idx = tid; idx < E * E; idx += nt) {
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(256) cross_attn_bwd_kernel(AttnArgs a) {
             const int i = idx / E, k = idx - i * E;
             float v = 0.f;
 #pragma unroll 8
-            for (int f = 0; f < E; ++f) v = fmaf(dQ[i * E + f], __ldg(a.Win + f * E + k), v);
+            for (int f = 0; f < E; ++f) v = fmaf(dQ[i * E + f], WinO[f * E + k], v);
             dxb[idx] = v;
         }
         float* dab = a.da + (int64_t)b * M * E;
@@ -246,8 +252,8 @@ __global__ void __launch_bounds__(256) cross_attn_bwd_kernel(AttnArgs a) {
             const int j = idx / E, k = idx - j * E;
             float v = 0.f;
             for (int f = 0; f < E; ++f) {
-                v = fmaf(dK[j * E + f], __ldg(a.Win + (E + f) * E + k), v);
-                v = fmaf(dV[j * E + f], __ldg(a.Win + (2 * E + f) * E + k), v);
+                v = fmaf(dK[j * E + f], WinO[(E + f) * E + k], v);
+                v = fmaf(dV[j * E + f], WinO[(2 * E + f) * E + k], v);
             }
             dab[idx] = v;
         }
@@ -257,13 +263,13 @@ __global__ void __launch_bounds__(256) cross_attn_bwd_kernel(AttnArgs a) {
             float v = 0.f;
             if (f3 < E) {
 #pragma unroll 4
-                for (int i = 0; i < R; ++i) v = fmaf(dQ[i * E + f3], __ldg(s.X + i * E + k), v);
+                for (int i = 0; i < R; ++i) v = fmaf(dQ[i * E + f3], s.X[i * E + k], v);
             } else if (f3 < 2 * E) {
 #pragma unroll 4
-                for (int j = 0; j < M; ++j) v = fmaf(dK[j * E + f3 - E], __ldg(s.A + j * E + k), v);
+                for (int j = 0; j < M; ++j) v = fmaf(dK[j * E + f3 - E], s.A[j * E + k], v);
             } else {
 #pragma unroll 4
-                for (int j = 0; j < M; ++j) v = fmaf(dV[j * E + f3 - 2 * E], __ldg(s.A + j * E + k), v);
+                for (int j = 0; j < M; ++j) v = fmaf(dV[j * E + f3 - 2 * E], s.A[j * E + k], v);
             }
             acc[idx] += v;
         }
@@ -286,12 +292,12 @@ __global__ void __launch_bounds__(256) cross_attn_bwd_kernel(AttnArgs a) {
 
 static size_t attn_fwd_smem(int R, int M, int E, int H) { return 4 * attn_common_floats(R, M, E, H); }
 static size_t attn_bwd_smem(int R, int M, int E, int H, int P) {
-    return 4 * (attn_common_floats(R, M, E, H) + 2 * (size_t)R * E + R + 2 * (size_t)M * E + P);
+    return 4 * (attn_common_floats(R, M, E, H) + 2 * (size_t)R * E + R + 2 * (size_t)M * E + P + 4 * (size_t)E * E);
 }
-static int attn_ctas(size_t smem, int64_t B) {
+static int attn_ctas(size_t smem, int64_t B, int nthreads = 256) {
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > 2048 / nthreads) per_sm = 2048 / nthreads;
     int64_t n = (int64_t)sm_count() * per_sm;
     if (n > B) n = B;
     return (int)(n < 1 ? 1 : n);
@@ -313,7 +319,7 @@ using namespace igcn;
 
 extern "C" int64_t igcn_cross_attn_param_count(int64_t E) { return 4 * E * E + 4 * E; }
 extern "C" int64_t igcn_cross_attn_bwd_ctas(int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads) {
-    return attn_ctas(attn_bwd_smem((int)R, (int)M, (int)E, (int)heads, (int)(4 * E * E + 4 * E)), B);
+    return attn_ctas(attn_bwd_smem((int)R, (int)M, (int)E, (int)heads, (int)(4 * E * E + 4 * E)), B, 512);
 }
 
 extern "C" int igcn_cross_attn_fwd(const float* q_in, const float* kv_in, const float* in_proj_weight, const float* in_proj_bias,
@@ -350,7 +356,7 @@ extern "C" int igcn_cross_attn_bwd(const float* q_in, const float* kv_in, const 
     a.yout = out; a.gy = g_out; a.dx = d_q_in; a.da = d_kv_in; a.partials = partials;
     size_t smem = attn_bwd_smem(a.R, a.M, a.E, a.heads, a.P);
     if ((rc = allow_smem(cross_attn_bwd_kernel, smem, "cross_attn_bwd"))) return rc;
-    cross_attn_bwd_kernel<<<want, 256, smem, st>>>(a);
+    cross_attn_bwd_kernel<<<want, 512, smem, st>>>(a);   // one graph per CTA, 16 warps: the per-graph chain is latency bound
     IGCN_CHECK_LAUNCH("cross_attn_bwd");
     reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(partials, want, a.P, grads);
     IGCN_CHECK_LAUNCH("cross_attn_reduce_partials");

@@ -520,10 +520,21 @@ static size_t go_bwd_smem(int din, int dout, int Min, int Mrow, int nnz, bool at
                 (attn ? 2 * (size_t)nnz : 0) + (size_t)Min);
 }
 
-static int go_ctas(size_t smem, int64_t B) {
+// threads per CTA: the row / column phases give one node to a thread, so a CTA wider than the node count only idles
+static int go_threads(int m_in, int m_row) {
+    const int m = m_in > m_row ? m_in : m_row;
+    int nt = (m + 31) / 32 * 32;
+    if (nt < 64) nt = 64;
+    if (nt > 256) nt = 256;
+    return nt;
+}
+
+static int go_ctas(size_t smem, int64_t B, int nthreads = 256) {
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
+    const int by_threads = 2048 / nthreads;
+    if (per_sm > by_threads) per_sm = by_threads;
+    if (per_sm > 16) per_sm = 16;
     int64_t n = (int64_t)sm_count() * per_sm;
     if (n > B) n = B;
     if (n < 1) n = 1;
@@ -536,7 +547,8 @@ static int launch_go_fwd(const GoLayerArgs& a, cudaStream_t st) {
     auto k = go_layer_fwd_kernel<DIN, DOUT, ATTN>;
     int rc = allow_smem(k, smem, "go_layer_fwd");
     if (rc) return rc;
-    k<<<go_ctas(smem, a.B), 256, smem, st>>>(a);
+    const int nthr = go_threads(a.gr.Min, a.gr.Mrow);
+    k<<<go_ctas(smem, a.B, nthr), nthr, smem, st>>>(a);
     IGCN_CHECK_LAUNCH("go_layer_fwd");
     return IGCN_OK;
 }
@@ -547,7 +559,7 @@ static int launch_go_bwd(const GoLayerArgs& a, int n_cta, float* grads, cudaStre
     auto k = go_layer_bwd_kernel<DIN, DOUT, ATTN>;
     int rc = allow_smem(k, smem, "go_layer_bwd");
     if (rc) return rc;
-    k<<<n_cta, 256, smem, st>>>(a);
+    k<<<n_cta, go_threads(a.gr.Min, a.gr.Mrow), smem, st>>>(a);
     IGCN_CHECK_LAUNCH("go_layer_bwd");
     reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(a.partials, n_cta, a.P, grads);
     IGCN_CHECK_LAUNCH("go_reduce_partials");
@@ -636,7 +648,7 @@ extern "C" int64_t igcn_go_layer_param_count(int64_t din, int64_t dout, int64_t 
 }
 
 extern "C" int64_t igcn_go_layer_bwd_ctas(int64_t B, int64_t din, int64_t dout, int64_t m_in, int64_t m_row, int64_t nnz, int64_t attn) {
-    return go_ctas(go_bwd_smem((int)din, (int)dout, (int)m_in, (int)m_row, (int)nnz, attn != 0), B);
+    return go_ctas(go_bwd_smem((int)din, (int)dout, (int)m_in, (int)m_row, (int)nnz, attn != 0), B, go_threads((int)m_in, (int)m_row));
 }
 
 extern "C" int igcn_go_layer_fwd(const float* x, const float* Wa, const float* Ws, const float* u, const float* v,
