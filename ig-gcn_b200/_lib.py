@@ -37,6 +37,7 @@ SIGNATURES = {
     "igcn_cat_linear_splits": (_I, [_I, _I, _I]),
     "igcn_cat_linear_fwd": (ctypes.c_int, [_P] * 7 + [_I] * 4 + [_P, _I, _P, _P]),
     "igcn_cat_linear_bwd": (ctypes.c_int, [_P] * 8 + [_I] * 4 + [_P] * 7),
+    "igcn_dropout_masks": (ctypes.c_int, [_P, _P, _P, _I, ctypes.c_uint64, _P, _P]),
     "igcn_adam_step": (ctypes.c_int, [_P] * 6 + [ctypes.c_double] * 4 + [_I, _P]),
     "igcn_go_spmm_fwd": (ctypes.c_int, [_P] * 4 + [_I] * 5 + [_P, _P]),
     "igcn_go_spmm_bwd": (ctypes.c_int, [_P] * 8 + [_I] * 5 + [_P, _P, _P]),
@@ -70,7 +71,7 @@ KERNELS_PER_CALL = {
     "igcn_gat_layer_fwd": (ctypes.c_int, [_P] * 10 + [_I] * 5 + [ctypes.c_double, _P, _P]),
     "igcn_gat_layer_bwd": (ctypes.c_int, [_P] * 13 + [_I] * 5 + [ctypes.c_double, _P, _P, _P, _I, _P, _P]),
     "igcn_adam_step": (ctypes.c_int, [_P] * 6 + [ctypes.c_double] * 4 + [_I, _P]),
-    "igcn_go_spmm_fwd": 1, "igcn_go_spmm_bwd": 2, "igcn_go_layer_fwd": 1, "igcn_go_layer_bwd": 2, "igcn_adam_step": 1, "igcn_cross_attn_fwd": 1, "igcn_cross_attn_bwd": 2, "igcn_cat_linear_fwd": 2, "igcn_cat_linear_bwd": 2, "igcn_gat_layer_fwd": 1, "igcn_gat_layer_bwd": 2,
+    "igcn_go_spmm_fwd": 1, "igcn_go_spmm_bwd": 2, "igcn_go_layer_fwd": 1, "igcn_go_layer_bwd": 2, "igcn_adam_step": 1, "igcn_dropout_masks": 2, "igcn_cross_attn_fwd": 1, "igcn_cross_attn_bwd": 2, "igcn_cat_linear_fwd": 2, "igcn_cat_linear_bwd": 2, "igcn_gat_layer_fwd": 1, "igcn_gat_layer_bwd": 2,
 }
 launch_count = 0          # number of igcn kernels launched by this process
 _profile = None           # None, or dict name -> list[(start_event, end_event)]

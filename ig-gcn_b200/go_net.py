@@ -17,6 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
+from .ops import MaskBank
 
 
 def _csr_csc(rows: np.ndarray, cols: np.ndarray, n_rows: int, n_cols: int):
@@ -200,6 +201,7 @@ class Gene_ontology_network(nn.Module):
                                             nn.ReLU(), nn.Dropout(0.3), nn.Linear(16, 1, bias=True), nn.Sigmoid())
         self._dev_graphs = {}
         self.dropout_masks = None     # test hook: dict name -> multiplicative scale tensor (oracle.GO_MASK_NAMES)
+        self.mask_bank = MaskBank()   # all masks of a pass from one kernel launch (shared with the enclosing model)
 
     # graph index tensors follow the module's device lazily (they are not parameters / state_dict entries)
     def _g(self, name, dev):
@@ -217,7 +219,7 @@ class Gene_ontology_network(nn.Module):
         if self.dropout_masks is not None:
             m = self.dropout_masks[name].to(dev).float()
             return m.expand(shape) if m.numel() == 1 else m.reshape(shape)
-        return torch.bernoulli(torch.full(shape, 1.0 - p, device=dev)) / (1.0 - p)
+        return self.mask_bank.get(name, shape, p)
 
     def _drop(self, name, t, p):
         m = self._mask(name, t.shape, p, t.device)
@@ -226,6 +228,9 @@ class Gene_ontology_network(nn.Module):
     def forward(self, data, T=None, device=None):
         dev = data.device
         n_l, pool = self.n_l, self.pool
+        own_pass = self.training and self.dropout_masks is None and not self.mask_bank.active
+        if own_pass:
+            self.mask_bank.begin_pass(data.shape[0], dev)
         # SNP -> GO encode: (B,S) -> (B,G,in_f_dim)
         x = _GoSpmmFn.apply(data, torch.stack(list(self.t)), self._g("ag", dev))
         for j in range(n_l):
@@ -245,4 +250,6 @@ class Gene_ontology_network(nn.Module):
         x_D = _GoSpmmFn.apply(out_D, self.t_D[0].unsqueeze(0), self._g("ag_t", dev)).squeeze(-1)
         h = self._drop("go_latent", F.relu(self.latent[1](self.latent[0](inp_out))), 0.5)
         latent = F.relu(self.latent[5](self.latent[4](h)))
+        if own_pass:
+            self.mask_bank.end_pass()
         return latent, x_D, [torch.zeros(3, device=dev)], atten_out

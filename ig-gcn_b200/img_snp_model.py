@@ -259,7 +259,7 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             return t
         if self.dropout_masks is not None:
             return t * self.dropout_masks[name].to(t.device).float()
-        return F.dropout(t, p=p, training=True)
+        return t * self.go_network.mask_bank.get(name, t.shape, p)
 
     def forward(self, data, temperature=None, device=None, isExplain=False):
         x, edge_index, edge_weight = data.x, data.edge_index, data.edge_attr
@@ -269,6 +269,10 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         self.input = x
         csr = self._csr_for(data, self.rois)
         Ws, bs = self._conv_params()
+        bank = self.go_network.mask_bank
+        use_bank = self.training and self.dropout_masks is None
+        if use_bank:
+            bank.begin_pass(csr.B, x.device)           # all nine dropout masks of this pass: one launch
         if isExplain:
             batch_x, p_e = ops.sgcn_encoder(x, csr, Ws, bs, self.prob, self.prob_bias, want_pe=True)
             self._pe_cache = ((x.data_ptr(), edge_index.data_ptr(), self.prob._version, self.prob_bias._version), p_e,
@@ -320,6 +324,8 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             our_reg = self.lin2_regr(r)
         else:
             our_reg = regr_head(parts)
+        if use_bank:
+            bank.end_pass()
         return F.log_softmax(logits, dim=-1), x_hat, out_z, out_lin, linear_outf, our_reg
 
     def __repr__(self):

@@ -234,3 +234,61 @@ def cross_attention(q, kv, mha: torch.nn.MultiheadAttention, relu=True):
         raise RuntimeError("igcn_b200.cross_attention supports the reference configuration only "
                            "(packed in_proj with bias, no bias_kv, dropout 0, batch_first)")
     return _CrossAttnFn.apply(q, kv, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, mha.num_heads, relu)
+
+
+class MaskBank(object):
+    """All dropout masks of one forward pass from ONE kernel launch (igcn_dropout_masks).
+
+    The first pass at a given batch size draws its masks with torch and records (name, shape, keep); every later pass
+    fills one flat buffer with a single Philox launch and hands out views.  Masks are multiplicative scales (0 or 1/keep)."""
+
+    def __init__(self, seed=None):
+        self.plans = {}
+        self.active = False
+        self.seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
+        self.counter = None
+
+    def begin_pass(self, key, device):
+        import ctypes
+        self.active, self.key, self.device = True, (key, str(device)), device
+        self.recording, self.views = [], None
+        plan = self.plans.get(self.key)
+        if plan is None:
+            return
+        if self.counter is None or self.counter.device != device:
+            self.counter = torch.zeros(1, dtype=torch.int64, device=device)
+        names, shapes, ends, keeps = plan
+        out = torch.empty(ends[-1], dtype=torch.float32, device=device)
+        he, hk = (ctypes.c_int64 * len(ends))(*ends), (ctypes.c_float * len(keeps))(*keeps)
+        with torch.cuda.device(device):
+            _lib.call("igcn_dropout_masks", _lib.ptr(out), ctypes.addressof(he), ctypes.addressof(hk), len(ends), self.seed,
+                      _lib.ptr(self.counter), _lib.stream())
+        self.views, start = {}, 0
+        for n, sh, e in zip(names, shapes, ends):
+            self.views[n] = out[start:e].view(sh)
+            start = e
+
+    def get(self, name, shape, p):
+        shape, keep = tuple(shape), 1.0 - p
+        if self.views is not None:
+            v = self.views.get(name)
+            if v is not None and tuple(v.shape) == shape:
+                return v
+            self.plans.pop(self.key, None)           # shapes changed: re-record next pass
+        m = torch.bernoulli(torch.full(shape, keep, device=self.device)) / keep
+        self.recording.append((name, shape, keep))
+        return m
+
+    def end_pass(self):
+        if self.active and self.views is None and self.recording and self.key not in self.plans:
+            names = [r[0] for r in self.recording]
+            if len(set(names)) == len(names) and len(names) <= 32:
+                ends, tot = [], 0
+                for _, sh, _ in self.recording:
+                    n = 1
+                    for d in sh:
+                        n *= d
+                    tot += n
+                    ends.append(tot)
+                self.plans[self.key] = (names, [r[1] for r in self.recording], ends, [r[2] for r in self.recording])
+        self.active = False

@@ -197,6 +197,16 @@ int igcn_cat_linear_bwd(const float* x0, const float* x1, const float* x2, const
                         float* dx0, float* dx1, float* dx2, const int64_t* host_dstrides, float* dW, float* db, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * All dropout masks of one forward pass in one launch (the reference draws nine per pass: Dropout2d(0.4) x4 and
+ * Dropout(0.5) x3 in kernel/go_model.py:104,113,127,135,142; F.dropout 0.5 / 0.3 at kernel/sgcn_img_snp.py:290,300).
+ *   out: flat f32 buffer; segment i covers [host_seg_end[i-1], host_seg_end[i]) and is filled with 0 or 1/keep_i,
+ *   keep_i = host_seg_keep[i].  Philox4x32-10, seed + a DEVICE call counter (u64, incremented by the call), so a
+ *   captured CUDA graph draws fresh masks on every replay.  host_* are host arrays of nseg (<= 32) entries.
+ */
+int igcn_dropout_masks(float* out, const int64_t* host_seg_end, const float* host_seg_keep, int64_t nseg, uint64_t seed,
+                       unsigned long long* counter, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused flat-buffer Adam (replaces torch.optim.Adam.step as called at kernel/train_eval_sgcn_img_snps.py:547;
  * lr 1e-3, betas (0.9,0.999), eps 1e-8, weight_decay 0 -- :108).  One launch for the whole model.
  *   params / grads / exp_avg / exp_avg_sq: (n) f32, 16-byte aligned; updates params and both moments in place.

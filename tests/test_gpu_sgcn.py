@@ -185,3 +185,28 @@ def test_sgcn_encoder_deterministic_and_full_size_properties():
     o2, _ = ops.sgcn_encoder(b.x * 3.0, b.csr, Ws, bs)
     H.assert_close(o2, o1 * 3.0, what="homogeneity")
     assert o1.shape == (n, R, L * Hd)
+
+
+def test_dropout_mask_bank_statistics_and_replay():
+    """One-launch Philox masks: values are 0 or 1/keep, keep rates match, consecutive passes differ, same seed replays."""
+    from igcn_b200.ops import MaskBank
+    dev = _dev()
+
+    def run(bank, n_pass):
+        outs = []
+        for _ in range(n_pass):
+            bank.begin_pass(64, dev)
+            a = bank.get("a", (64, 54, 1), 0.4).clone()
+            b = bank.get("b", (64, 301), 0.5).clone()
+            bank.end_pass()
+            outs.append((a, b))
+        return outs
+    o = run(MaskBank(seed=123), 4)            # pass 0 records with torch, passes 1..3 come from the kernel
+    for a, b in o[1:]:
+        assert bool(((a == 0) | ((a - 1 / 0.6).abs() < 1e-6)).all())
+        assert bool(((b == 0) | (b == 2.0)).all())
+        assert abs((a > 0).float().mean().item() - 0.6) < 0.03
+        assert abs((b > 0).float().mean().item() - 0.5) < 0.02
+    assert not torch.equal(o[1][0], o[2][0]) and not torch.equal(o[2][1], o[3][1])
+    o2 = run(MaskBank(seed=123), 4)
+    assert torch.equal(o[2][0], o2[2][0]) and torch.equal(o[3][1], o2[3][1])
