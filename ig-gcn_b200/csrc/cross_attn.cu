@@ -25,31 +25,32 @@ struct AttnArgs {
     float* da;          // (B, M, E)
     float* partials;    // (n_cta, P)  P = 3E*E + 3E + E*E + E : [dWin | dbin | dWo | dbo]
     int B, R, M, E, heads, relu, P;
+    int Rc;             // query rows staged per chunk
 };
 
 struct AttnSmem {
     float *WinT, *WoT, *bin, *bo;   // WinT[k][3E] (k-major), WoT[k][E]
-    float *X, *A, *Q, *K, *V, *Pm, *O;
+    float *X, *A, *Q, *K, *V, *Pm, *O;   // X, Q, Pm, O hold ONE CHUNK of Rc query rows
     float* tail;
 };
-__device__ __forceinline__ AttnSmem attn_carve(float* p, int R, int M, int E, int heads) {
+__device__ __forceinline__ AttnSmem attn_carve(float* p, int Rc, int M, int E, int heads) {
     AttnSmem s;
     s.WinT = p;  p += 3 * E * E;
     s.WoT = p;   p += E * E;
     s.bin = p;   p += 3 * E;
     s.bo = p;    p += E;
-    s.X = p;     p += R * E;
+    s.X = p;     p += Rc * E;
     s.A = p;     p += M * E;
-    s.Q = p;     p += R * (E + 1);   // row stride E+1: rows are walked by different threads at the same column
+    s.Q = p;     p += Rc * (E + 1);   // row stride E+1: rows are walked by different threads at the same column
     s.K = p;     p += M * E;
     s.V = p;     p += M * E;
-    s.Pm = p;    p += heads * R * M;
-    s.O = p;     p += R * E;
+    s.Pm = p;    p += heads * Rc * M;
+    s.O = p;     p += Rc * E;
     s.tail = p;
     return s;
 }
-static size_t attn_common_floats(int R, int M, int E, int heads) {
-    return (size_t)4 * E * E + 4 * E + 3 * (size_t)R * E + R + 3 * (size_t)M * E + (size_t)heads * R * M;
+static size_t attn_common_floats(int Rc, int M, int E, int heads) {
+    return (size_t)4 * E * E + 4 * E + 3 * (size_t)Rc * E + Rc + 3 * (size_t)M * E + (size_t)heads * Rc * M;
 }
 
 __device__ __forceinline__ void attn_load_params(const AttnArgs& a, const AttnSmem& s) {
@@ -67,25 +68,16 @@ __device__ __forceinline__ void attn_load_params(const AttnArgs& a, const AttnSm
     __syncthreads();
 }
 
-// Q, K, V, P, O of one graph (shared by fwd and bwd)
-__device__ __forceinline__ void attn_forward_graph(const AttnArgs& a, AttnSmem& s, int b) {
-    const int tid = threadIdx.x, nt = blockDim.x, R = a.R, M = a.M, E = a.E, H = a.heads, hd = E / H;
-    const float scale = rsqrtf((float)hd);
-    const float* xb = a.x + (int64_t)b * R * E;
+// K, V of one graph (all M key/value tokens)
+__device__ __forceinline__ void attn_keys_values(const AttnArgs& a, const AttnSmem& s, int b) {
+    const int tid = threadIdx.x, nt = blockDim.x, M = a.M, E = a.E;
     const float* ab = a.a + (int64_t)b * M * E;
-    for (int i = tid; i < R * E; i += nt) s.X[i] = xb[i];
     for (int i = tid; i < M * E; i += nt) s.A[i] = ab[i];
     __syncthreads();
-    for (int idx = tid; idx < R * E; idx += nt) {
-        const int i = idx / E, f = idx - i * E;
-        float acc = s.bin[f];
-#pragma unroll 8
-        for (int k = 0; k < E; ++k) acc = fmaf(s.X[i * E + k], s.WinT[k * 3 * E + f], acc);
-        s.Q[i * (E + 1) + f] = acc;
-    }
     for (int idx = tid; idx < M * E; idx += nt) {
         const int j = idx / E, f = idx - j * E;
         float ak = s.bin[E + f], av = s.bin[2 * E + f];
+#pragma unroll 8
         for (int k = 0; k < E; ++k) {
             const float v = s.A[j * E + k];
             ak = fmaf(v, s.WinT[k * 3 * E + E + f], ak);
@@ -95,9 +87,26 @@ __device__ __forceinline__ void attn_forward_graph(const AttnArgs& a, AttnSmem& 
         s.V[idx] = av;
     }
     __syncthreads();
-    for (int idx = tid; idx < H * R; idx += nt) {           // one (head, query) row per thread: scores, softmax
-        const int h = idx / R, i = idx - h * R;
-        float* prow = s.Pm + (h * R + i) * M;
+}
+
+// Q, P, O for the query rows [r0, r0+rc) of one graph
+__device__ __forceinline__ void attn_forward_chunk(const AttnArgs& a, const AttnSmem& s, int b, int r0, int rc) {
+    const int tid = threadIdx.x, nt = blockDim.x, R = a.R, M = a.M, E = a.E, H = a.heads, hd = E / H;
+    const float scale = rsqrtf((float)hd);
+    const float* xb = a.x + ((int64_t)b * R + r0) * E;
+    for (int i = tid; i < rc * E; i += nt) s.X[i] = xb[i];
+    __syncthreads();
+    for (int idx = tid; idx < rc * E; idx += nt) {
+        const int i = idx / E, f = idx - i * E;
+        float acc = s.bin[f];
+#pragma unroll 8
+        for (int k = 0; k < E; ++k) acc = fmaf(s.X[i * E + k], s.WinT[k * 3 * E + f], acc);
+        s.Q[i * (E + 1) + f] = acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < H * rc; idx += nt) {          // one (head, query) row per thread: scores, softmax
+        const int h = idx / rc, i = idx - h * rc;
+        float* prow = s.Pm + (h * rc + i) * M;
         const float* q = s.Q + i * (E + 1) + h * hd;
         float mx = -INFINITY;
         for (int j = 0; j < M; ++j) {
@@ -118,10 +127,11 @@ __device__ __forceinline__ void attn_forward_graph(const AttnArgs& a, AttnSmem& 
         for (int j = 0; j < M; ++j) prow[j] *= inv;
     }
     __syncthreads();
-    for (int idx = tid; idx < R * E; idx += nt) {
+    for (int idx = tid; idx < rc * E; idx += nt) {
         const int i = idx / E, f = idx - i * E, h = f / hd;
-        const float* prow = s.Pm + (h * R + i) * M;
+        const float* prow = s.Pm + (h * rc + i) * M;
         float acc = 0.f;
+#pragma unroll 4
         for (int j = 0; j < M; ++j) acc = fmaf(prow[j], s.V[j * E + f], acc);
         s.O[idx] = acc;
     }
@@ -130,35 +140,39 @@ __device__ __forceinline__ void attn_forward_graph(const AttnArgs& a, AttnSmem& 
 
 __global__ void __launch_bounds__(256) cross_attn_fwd_kernel(AttnArgs a) {
     extern __shared__ float smf[];
-    const int tid = threadIdx.x, nt = blockDim.x, R = a.R, E = a.E;
-    AttnSmem s = attn_carve(smf, R, a.M, E, a.heads);
+    const int tid = threadIdx.x, nt = blockDim.x, R = a.R, E = a.E, Rc = a.Rc;
+    AttnSmem s = attn_carve(smf, Rc, a.M, E, a.heads);
     attn_load_params(a, s);
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-        attn_forward_graph(a, s, b);
-        float* yb = a.y + (int64_t)b * R * E;
-        for (int idx = tid; idx < R * E; idx += nt) {
-            const int i = idx / E, f = idx - i * E;
-            float acc = s.bo[f];
+        attn_keys_values(a, s, b);
+        for (int r0 = 0; r0 < R; r0 += Rc) {
+            const int rc = min(Rc, R - r0);
+            attn_forward_chunk(a, s, b, r0, rc);
+            float* yb = a.y + ((int64_t)b * R + r0) * E;
+            for (int idx = tid; idx < rc * E; idx += nt) {
+                const int i = idx / E, f = idx - i * E;
+                float acc = s.bo[f];
 #pragma unroll 8
-            for (int k = 0; k < E; ++k) acc = fmaf(s.O[i * E + k], s.WoT[k * E + f], acc);
-            yb[idx] = a.relu ? fmaxf(acc, 0.f) : acc;
+                for (int k = 0; k < E; ++k) acc = fmaf(s.O[i * E + k], s.WoT[k * E + f], acc);
+                yb[idx] = a.relu ? fmaxf(acc, 0.f) : acc;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
 __global__ void __launch_bounds__(512) cross_attn_bwd_kernel(AttnArgs a) {
     extern __shared__ float smf[];
-    const int tid = threadIdx.x, nt = blockDim.x, R = a.R, M = a.M, E = a.E, H = a.heads, hd = E / H;
+    const int tid = threadIdx.x, nt = blockDim.x, R = a.R, M = a.M, E = a.E, H = a.heads, hd = E / H, Rc = a.Rc;
     const float scale = rsqrtf((float)hd);
-    AttnSmem s = attn_carve(smf, R, M, E, H);
+    AttnSmem s = attn_carve(smf, Rc, M, E, H);
     float* p = s.tail;
-    float* dY = p;   p += R * E;      // dY, later dQ
-    float* dO = p;   p += R * (E + 1);   // padded like Q
-    float* dK = p;   p += M * E;
+    float* dY = p;   p += Rc * E;        // dY, later dQ
+    float* dO = p;   p += Rc * (E + 1);  // padded like Q
+    float* dK = p;   p += M * E;         // accumulated over the row chunks of a graph
     float* dV = p;   p += M * E;
-    float* acc = p;  p += a.P;        // [dWin (3E,E) | dbin (3E) | dWo (E,E) | dbo (E)]
-    float* WinO = p; p += 3 * E * E;  // row-major copies [f][k] for the transposed products of the backward
+    float* acc = p;  p += a.P;           // [dWin (3E,E) | dbin (3E) | dWo (E,E) | dbo (E)]
+    float* WinO = p; p += 3 * E * E;     // row-major copies [f][k] for the transposed products of the backward
     float* WoO = p;  p += E * E;
     attn_load_params(a, s);
     for (int i = tid; i < 3 * E * E; i += nt) WinO[i] = a.Win[i];
@@ -167,122 +181,133 @@ __global__ void __launch_bounds__(512) cross_attn_bwd_kernel(AttnArgs a) {
     const int oBin = 3 * E * E, oWo = oBin + 3 * E, oBo = oWo + E * E;
     __syncthreads();
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-        attn_forward_graph(a, s, b);
-        const float* gb = a.gy + (int64_t)b * R * E;
-        const float* yb = a.yout + (int64_t)b * R * E;
-        for (int i = tid; i < R * E; i += nt) dY[i] = (!a.relu || yb[i] > 0.f) ? gb[i] : 0.f;
-        __syncthreads();
-        // out_proj: dO = dY Wo ; dWo += dY^T O ; dbo += colsum(dY)
-        for (int idx = tid; idx < R * E; idx += nt) {
-            const int i = idx / E, k = idx - i * E;
-            float v = 0.f;
+        attn_keys_values(a, s, b);
+        for (int i = tid; i < M * E; i += nt) {
+            dK[i] = 0.f;
+            dV[i] = 0.f;
+        }
+        for (int r0 = 0; r0 < R; r0 += Rc) {
+            const int rc = min(Rc, R - r0);
+            attn_forward_chunk(a, s, b, r0, rc);
+            const float* gb = a.gy + ((int64_t)b * R + r0) * E;
+            const float* yb = a.yout + ((int64_t)b * R + r0) * E;
+            for (int i = tid; i < rc * E; i += nt) dY[i] = (!a.relu || yb[i] > 0.f) ? gb[i] : 0.f;
+            __syncthreads();
+            // out_proj: dO = dY Wo ; dWo += dY^T O ; dbo += colsum(dY)
+            for (int idx = tid; idx < rc * E; idx += nt) {
+                const int i = idx / E, k = idx - i * E;
+                float v = 0.f;
 #pragma unroll 8
-            for (int f = 0; f < E; ++f) v = fmaf(dY[i * E + f], WoO[f * E + k], v);   // row-major W: k is the fast index
-            dO[i * (E + 1) + k] = v;
-        }
-        for (int idx = tid; idx < E * E; idx += nt) {
-            const int f = idx / E, k = idx - f * E;
-            float v = 0.f;
-#pragma unroll 4
-            for (int i = 0; i < R; ++i) v = fmaf(dY[i * E + f], s.O[i * E + k], v);
-            acc[oWo + idx] += v;
-        }
-        for (int f = tid; f < E; f += nt) {
-            float v = 0.f;
-            for (int i = 0; i < R; ++i) v += dY[i * E + f];
-            acc[oBo + f] += v;
-        }
-        __syncthreads();
-        // dV = P^T dO (per head) ; dS = P * (dP - rowsum(P*dP)), dP = dO V^T   (dS overwrites P)
-        for (int idx = tid; idx < M * E; idx += nt) {
-            const int j = idx / E, f = idx - j * E, h = f / hd;
-            float v = 0.f;
-#pragma unroll 4
-            for (int i = 0; i < R; ++i) v = fmaf(s.Pm[(h * R + i) * M + j], dO[i * (E + 1) + f], v);
-            dV[idx] = v;
-        }
-        __syncthreads();
-        for (int idx = tid; idx < H * R; idx += nt) {
-            const int h = idx / R, i = idx - h * R;
-            float* prow = s.Pm + (h * R + i) * M;
-            const float* go = dO + i * (E + 1) + h * hd;
-            float rowdot = 0.f;
-            for (int j = 0; j < M; ++j) {
-                const float* vv = s.V + j * E + h * hd;
-                float d = 0.f;
-                for (int c = 0; c < hd; ++c) d = fmaf(go[c], vv[c], d);
-                rowdot = fmaf(prow[j], d, rowdot);
+                for (int f = 0; f < E; ++f) v = fmaf(dY[i * E + f], WoO[f * E + k], v);
+                dO[i * (E + 1) + k] = v;
             }
-            for (int j = 0; j < M; ++j) {
-                const float* vv = s.V + j * E + h * hd;
-                float d = 0.f;
-                for (int c = 0; c < hd; ++c) d = fmaf(go[c], vv[c], d);
-                prow[j] = prow[j] * (d - rowdot) * scale;       // d loss / d (q.k), scale folded in
-            }
-        }
-        __syncthreads();
-        // dQ = dS K ; dK = dS^T Q
-        float* dQ = dY;
-        for (int idx = tid; idx < R * E; idx += nt) {
-            const int i = idx / E, f = idx - i * E, h = f / hd;
-            const float* srow = s.Pm + (h * R + i) * M;
-            float v = 0.f;
-            for (int j = 0; j < M; ++j) v = fmaf(srow[j], s.K[j * E + f], v);
-            dQ[idx] = v;
-        }
-        for (int idx = tid; idx < M * E; idx += nt) {
-            const int j = idx / E, f = idx - j * E, h = f / hd;
-            float v = 0.f;
+            for (int idx = tid; idx < E * E; idx += nt) {
+                const int f = idx / E, k = idx - f * E;
+                float v = 0.f;
 #pragma unroll 4
-            for (int i = 0; i < R; ++i) v = fmaf(s.Pm[(h * R + i) * M + j], s.Q[i * (E + 1) + f], v);
-            dK[idx] = v;
-        }
-        __syncthreads();
-        // input gradients
-        float* dxb = a.dx + (int64_t)b * R * E;
-        for (int idx = tid; idx < R * E; idx += nt) {
-            const int i = idx / E, k = idx - i * E;
-            float v = 0.f;
+                for (int i = 0; i < rc; ++i) v = fmaf(dY[i * E + f], s.O[i * E + k], v);
+                acc[oWo + idx] += v;
+            }
+            for (int f = tid; f < E; f += nt) {
+                float v = 0.f;
+                for (int i = 0; i < rc; ++i) v += dY[i * E + f];
+                acc[oBo + f] += v;
+            }
+            __syncthreads();
+            // dV += P^T dO (per head) ; dS = P * (dP - rowsum(P*dP)), dP = dO V^T   (dS overwrites P)
+            for (int idx = tid; idx < M * E; idx += nt) {
+                const int j = idx / E, f = idx - j * E, h = f / hd;
+                float v = 0.f;
+#pragma unroll 4
+                for (int i = 0; i < rc; ++i) v = fmaf(s.Pm[(h * rc + i) * M + j], dO[i * (E + 1) + f], v);
+                dV[idx] += v;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < H * rc; idx += nt) {
+                const int h = idx / rc, i = idx - h * rc;
+                float* prow = s.Pm + (h * rc + i) * M;
+                const float* go = dO + i * (E + 1) + h * hd;
+                float rowdot = 0.f;
+                for (int j = 0; j < M; ++j) {
+                    const float* vv = s.V + j * E + h * hd;
+                    float d = 0.f;
+                    for (int c = 0; c < hd; ++c) d = fmaf(go[c], vv[c], d);
+                    rowdot = fmaf(prow[j], d, rowdot);
+                }
+                for (int j = 0; j < M; ++j) {
+                    const float* vv = s.V + j * E + h * hd;
+                    float d = 0.f;
+                    for (int c = 0; c < hd; ++c) d = fmaf(go[c], vv[c], d);
+                    prow[j] = prow[j] * (d - rowdot) * scale;       // d loss / d (q.k), scale folded in
+                }
+            }
+            __syncthreads();
+            // dQ = dS K ; dK += dS^T Q
+            float* dQ = dY;
+            for (int idx = tid; idx < rc * E; idx += nt) {
+                const int i = idx / E, f = idx - i * E, h = f / hd;
+                const float* srow = s.Pm + (h * rc + i) * M;
+                float v = 0.f;
+#pragma unroll 4
+                for (int j = 0; j < M; ++j) v = fmaf(srow[j], s.K[j * E + f], v);
+                dQ[idx] = v;
+            }
+            for (int idx = tid; idx < M * E; idx += nt) {
+                const int j = idx / E, f = idx - j * E, h = f / hd;
+                float v = 0.f;
+#pragma unroll 4
+                for (int i = 0; i < rc; ++i) v = fmaf(s.Pm[(h * rc + i) * M + j], s.Q[i * (E + 1) + f], v);
+                dK[idx] += v;
+            }
+            __syncthreads();
+            // query-side input gradient and projection gradients of this chunk
+            float* dxb = a.dx + ((int64_t)b * R + r0) * E;
+            for (int idx = tid; idx < rc * E; idx += nt) {
+                const int i = idx / E, k = idx - i * E;
+                float v = 0.f;
 #pragma unroll 8
-            for (int f = 0; f < E; ++f) v = fmaf(dQ[i * E + f], WinO[f * E + k], v);
-            dxb[idx] = v;
+                for (int f = 0; f < E; ++f) v = fmaf(dQ[i * E + f], WinO[f * E + k], v);
+                dxb[idx] = v;
+            }
+            for (int idx = tid; idx < E * E; idx += nt) {
+                const int f = idx / E, k = idx - f * E;
+                float v = 0.f;
+#pragma unroll 4
+                for (int i = 0; i < rc; ++i) v = fmaf(dQ[i * E + f], s.X[i * E + k], v);
+                acc[idx] += v;
+            }
+            for (int f = tid; f < E; f += nt) {
+                float v = 0.f;
+                for (int i = 0; i < rc; ++i) v += dQ[i * E + f];
+                acc[oBin + f] += v;
+            }
+            __syncthreads();
         }
+        // key/value side: input gradient and projection gradients (after all row chunks)
         float* dab = a.da + (int64_t)b * M * E;
         for (int idx = tid; idx < M * E; idx += nt) {
             const int j = idx / E, k = idx - j * E;
             float v = 0.f;
+#pragma unroll 8
             for (int f = 0; f < E; ++f) {
                 v = fmaf(dK[j * E + f], WinO[(E + f) * E + k], v);
                 v = fmaf(dV[j * E + f], WinO[(2 * E + f) * E + k], v);
             }
             dab[idx] = v;
         }
-        // projection weight / bias gradients (per-CTA accumulators; every entry has one owner thread)
-        for (int idx = tid; idx < 3 * E * E; idx += nt) {
-            const int f3 = idx / E, k = idx - f3 * E;
+        for (int idx = tid; idx < 2 * E * E; idx += nt) {
+            const int f2 = idx / E, k = idx - f2 * E;
+            const float* dsrc = (f2 < E) ? dK + f2 : dV + (f2 - E);
             float v = 0.f;
-            if (f3 < E) {
 #pragma unroll 4
-                for (int i = 0; i < R; ++i) v = fmaf(dQ[i * E + f3], s.X[i * E + k], v);
-            } else if (f3 < 2 * E) {
-#pragma unroll 4
-                for (int j = 0; j < M; ++j) v = fmaf(dK[j * E + f3 - E], s.A[j * E + k], v);
-            } else {
-#pragma unroll 4
-                for (int j = 0; j < M; ++j) v = fmaf(dV[j * E + f3 - 2 * E], s.A[j * E + k], v);
-            }
-            acc[idx] += v;
+            for (int j = 0; j < M; ++j) v = fmaf(dsrc[j * E], s.A[j * E + k], v);
+            acc[E * E + idx] += v;
         }
-        for (int f3 = tid; f3 < 3 * E; f3 += nt) {
+        for (int f2 = tid; f2 < 2 * E; f2 += nt) {
+            const float* dsrc = (f2 < E) ? dK + f2 : dV + (f2 - E);
             float v = 0.f;
-            if (f3 < E) {
-                for (int i = 0; i < R; ++i) v += dQ[i * E + f3];
-            } else if (f3 < 2 * E) {
-                for (int j = 0; j < M; ++j) v += dK[j * E + f3 - E];
-            } else {
-                for (int j = 0; j < M; ++j) v += dV[j * E + f3 - 2 * E];
-            }
-            acc[oBin + f3] += v;
+            for (int j = 0; j < M; ++j) v += dsrc[j * E];
+            acc[oBin + E + f2] += v;
         }
         __syncthreads();
     }
@@ -290,9 +315,20 @@ __global__ void __launch_bounds__(512) cross_attn_bwd_kernel(AttnArgs a) {
     for (int i = tid; i < a.P; i += nt) prow[i] = acc[i];
 }
 
-static size_t attn_fwd_smem(int R, int M, int E, int H) { return 4 * attn_common_floats(R, M, E, H); }
-static size_t attn_bwd_smem(int R, int M, int E, int H, int P) {
-    return 4 * (attn_common_floats(R, M, E, H) + 2 * (size_t)R * E + R + 2 * (size_t)M * E + P + 4 * (size_t)E * E);
+// query rows per chunk: the whole graph when it fits, else the largest chunk that keeps the backward under ~200 KB
+static int attn_rows_per_chunk(int R, int M, int E, int H) {
+    int rc = R;
+    while (rc > 8) {
+        const size_t fl = attn_common_floats(rc, M, E, H) + 2 * (size_t)rc * E + rc + 2 * (size_t)M * E + (size_t)(4 * E * E + 4 * E) +
+                          4 * (size_t)E * E;
+        if (4 * fl <= 200 * 1024) break;
+        rc = (rc + 1) / 2;
+    }
+    return rc;
+}
+static size_t attn_fwd_smem(int Rc, int M, int E, int H) { return 4 * attn_common_floats(Rc, M, E, H); }
+static size_t attn_bwd_smem(int Rc, int M, int E, int H, int P) {
+    return 4 * (attn_common_floats(Rc, M, E, H) + 2 * (size_t)Rc * E + Rc + 2 * (size_t)M * E + P + 4 * (size_t)E * E);
 }
 static int attn_ctas(size_t smem, int64_t B, int nthreads = 256) {
     int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -310,6 +346,7 @@ static int attn_fill(AttnArgs& a, const char* who, const float* x, const float* 
     a.x = x; a.a = kv; a.Win = Win; a.bin = bin; a.Wo = Wo; a.bo = bo;
     a.B = (int)B; a.R = (int)R; a.M = (int)M; a.E = (int)E; a.heads = (int)heads; a.relu = relu ? 1 : 0;
     a.P = (int)(4 * E * E + 4 * E);
+    a.Rc = attn_rows_per_chunk((int)R, (int)M, (int)E, (int)heads);
     return IGCN_OK;
 }
 
@@ -319,7 +356,7 @@ using namespace igcn;
 
 extern "C" int64_t igcn_cross_attn_param_count(int64_t E) { return 4 * E * E + 4 * E; }
 extern "C" int64_t igcn_cross_attn_bwd_ctas(int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads) {
-    return attn_ctas(attn_bwd_smem((int)R, (int)M, (int)E, (int)heads, (int)(4 * E * E + 4 * E)), B, 512);
+    return attn_ctas(attn_bwd_smem(attn_rows_per_chunk((int)R, (int)M, (int)E, (int)heads), (int)M, (int)E, (int)heads, (int)(4 * E * E + 4 * E)), B, 512);
 }
 
 extern "C" int igcn_cross_attn_fwd(const float* q_in, const float* kv_in, const float* in_proj_weight, const float* in_proj_bias,
@@ -331,7 +368,7 @@ extern "C" int igcn_cross_attn_fwd(const float* q_in, const float* kv_in, const 
     IGCN_REQUIRE(out, IGCN_ERR_BAD_ARG, "cross_attn_fwd: null output");
     if (B == 0) return IGCN_OK;
     a.y = out;
-    size_t smem = attn_fwd_smem(a.R, a.M, a.E, a.heads);
+    size_t smem = attn_fwd_smem(a.Rc, a.M, a.E, a.heads);
     if ((rc = allow_smem(cross_attn_fwd_kernel, smem, "cross_attn_fwd"))) return rc;
     cross_attn_fwd_kernel<<<attn_ctas(smem, B), 256, smem, (cudaStream_t)stream>>>(a);
     IGCN_CHECK_LAUNCH("cross_attn_fwd");
@@ -354,7 +391,7 @@ extern "C" int igcn_cross_attn_bwd(const float* q_in, const float* kv_in, const 
     const int want = (int)igcn_cross_attn_bwd_ctas(B, R, M, E, heads);
     IGCN_REQUIRE(n_cta == want, IGCN_ERR_BAD_ARG, "cross_attn_bwd: n_cta=%lld, expected %d", (long long)n_cta, want);
     a.yout = out; a.gy = g_out; a.dx = d_q_in; a.da = d_kv_in; a.partials = partials;
-    size_t smem = attn_bwd_smem(a.R, a.M, a.E, a.heads, a.P);
+    size_t smem = attn_bwd_smem(a.Rc, a.M, a.E, a.heads, a.P);
     if ((rc = allow_smem(cross_attn_bwd_kernel, smem, "cross_attn_bwd"))) return rc;
     cross_attn_bwd_kernel<<<want, 512, smem, st>>>(a);   // one graph per CTA, 16 warps: the per-graph chain is latency bound
     IGCN_CHECK_LAUNCH("cross_attn_bwd");

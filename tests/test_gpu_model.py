@@ -264,3 +264,29 @@ def test_config1_sgcn_models_golden(kind):
     for k, v in H.sub_dict(g, "%s/grad/" % kind).items():
         if k != "x":
             H.assert_close(P[k].grad, v, rtol=2e-4, what="grad " + k)
+
+
+@pytest.mark.parametrize("B,R,M,E", [(5, 90, 19, 32), (3, 264, 60, 32), (4, 37, 7, 24)])
+def test_cross_attention_vs_torch_mha(B, R, M, E):
+    """Fused relu(MHA(q, kv, kv)) kernel vs nn.MultiheadAttention in fp64 (the checker); R=264 exercises row chunking."""
+    from igcn_b200 import ops
+    torch.manual_seed(0)
+    mha = torch.nn.MultiheadAttention(E, 2, batch_first=True).to(DEV)
+    with torch.no_grad():
+        mha.in_proj_bias.uniform_(-0.2, 0.2)
+        mha.out_proj.bias.uniform_(-0.2, 0.2)
+    ref = torch.nn.MultiheadAttention(E, 2, batch_first=True).to(DEV).double()
+    ref.load_state_dict({k: v.double() for k, v in mha.state_dict().items()})
+    q = torch.randn(B, R, E, device=DEV, requires_grad=True)
+    kv = torch.randn(B, M, E, device=DEV, requires_grad=True)
+    q64, kv64 = q.detach().double().requires_grad_(True), kv.detach().double().requires_grad_(True)
+    g = torch.randn(B, R, E, device=DEV)
+    out = ops.cross_attention(q, kv, mha, relu=True)
+    (out * g).sum().backward()
+    o64 = torch.relu(ref(q64, kv64, kv64, need_weights=False)[0])
+    (o64 * g.double()).sum().backward()
+    H.assert_close(out, o64, what="out")
+    H.assert_close(q.grad, q64.grad, what="dq")
+    H.assert_close(kv.grad, kv64.grad, what="dkv")
+    for (k, p), (_, p64) in zip(mha.named_parameters(), ref.named_parameters()):
+        H.assert_close(p.grad, p64.grad, rtol=2e-4, what="grad " + k)

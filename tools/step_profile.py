@@ -46,6 +46,16 @@ def main():
             agg[k][1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
             tot += e.device_time if hasattr(e, "device_time") else e.cuda_time
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=50))
+    ew = collections.defaultdict(lambda: [0, 0.0])
+    for e in prof.events():
+        if e.device_type == torch.autograd.DeviceType.CUDA and ("elementwise" in e.name or "reduce_kernel" in e.name):
+            m = re.search(r"(\w+Functor\w*|\w+_kernel_cuda\w*|\w+Ops?\b|\w+_cuda\w*)", e.name.split("elementwise_kernel")[-1] if "elementwise" in e.name else e.name)
+            k = (m.group(1) if m else e.name[-60:])
+            ew[k][0] += 1
+            ew[k][1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+    print("-- elementwise / reduce kernels by functor")
+    for k, (c, t) in sorted(ew.items(), key=lambda kv: -kv[1][1])[:25]:
+        print("%5d %9.1f us  %s" % (c, t, k))
     n = sum(c for c, _ in agg.values())
     print("kernels in one step: %d, summed device time %.1f us" % (n, tot))
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
