@@ -96,25 +96,6 @@ def build_problem(w, rank, dev):
     return model, sub, (adj, go_snps, pool_dim)
 
 
-def algorithmic_bytes(tag, w, E):
-    """SURVEY.md 8(d) per-unit figures x units per launch (pre-built i32 CSR; each compulsory tensor once)."""
-    B, R, LH, F0 = w["B"], w["R"], w["L"] * w["H"], 3
-    N = B * R
-    if tag.startswith("sgcn_encoder_fwd"):
-        L = int(tag.split("L=")[1].rstrip("]"))
-        b = N * F0 * 4 + E * 8 + (N + 1) * 4 + N * L * w["H"] * 4
-        if "explain" in tag:
-            b += E * 4 + R * F0 * 4
-        return b
-    if tag.startswith("sgcn_encoder_bwd"):
-        L = int(tag.split("L=")[1].rstrip("]"))
-        b = 2 * N * L * w["H"] * 4 + N * F0 * 4 + E * 8 + (N + 1) * 4 + E * 4 + (N + 1) * 4 + N * F0 * 4
-        if "explain" in tag:
-            b += E * 4
-        return b
-    return None
-
-
 def run_igcn(args, w):
     import torch.distributed as dist
     from igcn_b200 import _lib, train as T
@@ -216,11 +197,22 @@ def run_igcn(args, w):
         return
     peak, peak_src = peaks()
     # dominant igcn kernel by total device time inside the timed steps
-    kern = {k: dict(calls=c, ms_per_call=tot / max(c, 1), share_of_step=tot / n_prof / ms) for k, (c, tot) in prof.items()}
-    cand = [(v["calls"] * v["ms_per_call"], k) for k, v in kern.items() if algorithmic_bytes(k, w, E) is not None]
-    top = max(cand)[1]
-    ab = algorithmic_bytes(top, w, E)
-    ach = ab / (kern[top]["ms_per_call"] * 1e-3) / 1e9
+    traffic_db = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_%s.json" % args.workload)
+    if os.path.exists(tpath):
+        traffic_db = json.load(open(tpath))
+    kern = {}
+    for k, (c, tot, nb) in prof.items():
+        per = tot / max(c, 1)
+        kern[k] = dict(calls_per_step=c / n_prof, us_per_call=per * 1e3, share_of_step=tot / n_prof / ms,
+                       algorithmic_bytes=nb, achieved_GBs=(nb / (per * 1e-3) / 1e9 if nb else None),
+                       frac_of_peak=(nb / (per * 1e-3) / 1e9 / peak if nb else None),
+                       traffic=traffic_db.get(k.split("[")[0]))
+    # the dominant igcn kernel of the step = largest share of device time among the C-ABI calls
+    top = max((v["share_of_step"], k) for k, v in kern.items() if v["algorithmic_bytes"])[1]
+    ab = kern[top]["algorithmic_bytes"]
+    ach = kern[top]["achieved_GBs"]
+    sg = "sgcn_encoder_bwd[explain,L=%d]" % w["L"]
     out = dict(metric=METRIC, value=B * world / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                config=dict(workload=args.workload, description=w["desc"], graphs_per_gpu=B, rois=w["R"], layers=w["L"], hidden=w["H"],
@@ -231,8 +223,12 @@ def run_igcn(args, w):
                e2e=dict(value=B * world / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
                         ms_per_step=e2e_ms),
                gpu_launches=int(launches),
-               roofline=dict(bound="hbm", kernel=top, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
-                             peak_source=peak_src, algorithmic_bytes_per_launch=int(ab), us_per_launch=kern[top]["ms_per_call"] * 1e3),
+               roofline=dict(bound="hbm", kernel=top, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=kern[top]["traffic"],
+                             peak_source=peak_src, algorithmic_bytes_per_launch=int(ab), us_per_launch=kern[top]["us_per_call"],
+                             note="dominant igcn kernel of the step by device time; at this batch size every kernel of the path is "
+                                  "latency bound (<= 12 MB per launch), see roofline_sgcn and profiles/ for the same kernels at config-4 size"),
+               roofline_sgcn=(dict(kernel=sg, **{q: kern[sg][q] for q in ("us_per_call", "algorithmic_bytes", "achieved_GBs", "frac_of_peak", "traffic")})
+                              if sg in kern else None),
                kernels=kern, clocks=clocks, wall_s_timed_region=t_wall)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(w, steps=3, warmup=1)

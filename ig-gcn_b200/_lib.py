@@ -83,15 +83,16 @@ def profile_begin():
 
 
 def profile_end():
-    """Returns {name: (calls, total_ms)}; synchronises."""
+    """Returns {name: (calls, total_ms, algorithmic_bytes_per_call or None)}; synchronises."""
     global _profile
     prof, _profile = _profile, None
     torch.cuda.synchronize()
-    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (prof or {}).items()}
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b, _ in v), v[0][2]) for k, v in (prof or {}).items()}
 
 
-def call(name, *args, tag=None):
-    """Invoke one C-ABI entry point on the current stream; raises on a non-zero status."""
+def call(name, *args, tag=None, nbytes=None):
+    """Invoke one C-ABI entry point on the current stream; raises on a non-zero status.
+    `nbytes` = algorithmic bytes of the call (compulsory tensors once each), recorded for roofline reporting."""
     global launch_count
     fn = getattr(lib(), name)
     if _profile is not None:
@@ -99,7 +100,7 @@ def call(name, *args, tag=None):
         e0.record()
         rc = fn(*args)
         e1.record()
-        _profile.setdefault(tag or name, []).append((e0, e1))
+        _profile.setdefault(tag or name, []).append((e0, e1, nbytes))
     else:
         rc = fn(*args)
     launch_count += KERNELS_PER_CALL.get(name, 1)

@@ -49,7 +49,9 @@ class _GoSpmmFn(torch.autograd.Function):
         out = torch.empty((B, g["n_rows"], C), dtype=torch.float32, device=data.device)
         with torch.cuda.device(data.device):
             _lib.call("igcn_go_spmm_fwd", _lib.ptr(data), _lib.ptr(g["rowptr"]), _lib.ptr(g["col"]), _lib.ptr(vals), B, g["n_cols"],
-                                      g["n_rows"], g["nnz"], C, _lib.ptr(out), _lib.stream())
+                                      g["n_rows"], g["nnz"], C, _lib.ptr(out), _lib.stream(),
+                      tag="go_spmm_fwd[rows=%d,cols=%d,C=%d]" % (g["n_rows"], g["n_cols"], C),
+                      nbytes=4 * (B * g["n_cols"] + B * g["n_rows"] * C + g["nnz"] * (2 + C)))
         ctx.g = g
         ctx.need_in = data.requires_grad
         ctx.save_for_backward(data, vals)
@@ -66,7 +68,9 @@ class _GoSpmmFn(torch.autograd.Function):
         with torch.cuda.device(data.device):
             _lib.call("igcn_go_spmm_bwd", _lib.ptr(g_out), _lib.ptr(data), _lib.ptr(g["row_of"]), _lib.ptr(g["col"]), _lib.ptr(g["colptr"]),
                                       _lib.ptr(g["crow"]), _lib.ptr(g["cpos"]), _lib.ptr(vals), B, g["n_cols"], g["n_rows"], g["nnz"],
-                                      C, _lib.ptr(d_in), _lib.ptr(d_vals), _lib.stream())
+                                      C, _lib.ptr(d_in), _lib.ptr(d_vals), _lib.stream(),
+                      tag="go_spmm_bwd[rows=%d,cols=%d,C=%d]" % (g["n_rows"], g["n_cols"], C),
+                      nbytes=4 * (2 * B * g["n_cols"] + B * g["n_rows"] * C + g["nnz"] * (4 + 2 * C)))
         return d_in, d_vals, None
 
 
@@ -90,7 +94,8 @@ class _GoLayerFn(torch.autograd.Function):
             _lib.call("igcn_go_layer_fwd", _lib.ptr(x), _lib.ptr(Wa), _lib.ptr(Ws), _lib.ptr(u), _lib.ptr(v), _lib.ptr(gamma), _lib.ptr(beta),
                                        _lib.ptr(mask), _lib.ptr(g["rowptr"]), _lib.ptr(g["col"]), _lib.ptr(g["colptr"]), _lib.ptr(g["crow"]),
                                        _lib.ptr(g["cpos"]), B, m_in, m_row, g["nnz"], din, dout, int(attn), self_off, keep_from,
-                                       _lib.ptr(y), _lib.ptr(stats), _lib.stream(), tag="go_layer_fwd[%s,M=%d]" % ("attn" if attn else "dec", m_row))
+                                       _lib.ptr(y), _lib.ptr(stats), _lib.stream(), tag="go_layer_fwd[%s,M=%d]" % ("attn" if attn else "dec", m_row),
+                      nbytes=4 * (B * m_in * din + B * (m_row - keep_from) * dout + (B * m_row if mask is not None else 0) + 2 * B * dout))
         ctx.g, ctx.attn, ctx.self_off, ctx.keep_from = g, attn, self_off, keep_from
         ctx.save_for_backward(x, Wa, Ws, u, v, gamma, beta, mask, stats)
         return y
@@ -112,7 +117,8 @@ class _GoLayerFn(torch.autograd.Function):
                                        _lib.ptr(mask), _lib.ptr(g["rowptr"]), _lib.ptr(g["col"]), _lib.ptr(g["colptr"]), _lib.ptr(g["crow"]),
                                        _lib.ptr(g["cpos"]), B, m_in, m_row, g["nnz"], din, dout, int(attn), ctx.self_off, ctx.keep_from,
                                        _lib.ptr(stats), _lib.ptr(gy), _lib.ptr(dx), _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream(),
-                      tag="go_layer_bwd[%s,M=%d]" % ("attn" if attn else "dec", m_row))
+                      tag="go_layer_bwd[%s,M=%d]" % ("attn" if attn else "dec", m_row),
+                      nbytes=4 * (2 * B * m_in * din + B * (m_row - ctx.keep_from) * dout + (B * m_row if mask is not None else 0) + 2 * B * dout))
         n = dout * din
         dWa, dWs = grads[:n].view(dout, din), grads[n:2 * n].view(dout, din)
         du = grads[2 * n:2 * n + 2 * dout].view(1, 2 * dout) if attn else None

@@ -35,7 +35,8 @@ class _SGCNEncoderFn(torch.autograd.Function):
             _lib.call("igcn_sgcn_encoder_fwd", _lib.ptr(x), _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(csr.csr_w),
                                            _lib.ptr(probc), _lib.ptr(pbc), _lib.ptr(wbc), B, R, F0, H, L, csr.max_eg, int(relu),
                                            _lib.ptr(out), _lib.ptr(p_e), _lib.stream(),
-                      tag="sgcn_encoder_fwd[%s,L=%d]" % ("explain" if explain else "plain", L))
+                      tag="sgcn_encoder_fwd[%s,L=%d]" % ("explain" if explain else "plain", L),
+                      nbytes=4 * (B * R * F0 + 2 * csr.E + B * R + 1 + B * R * L * H + (csr.E + R * F0 if explain else 0)))
         ctx.csr, ctx.L, ctx.H, ctx.explain, ctx.relu = csr, L, H, explain, bool(relu)
         ctx.save_for_backward(x, probc, pbc, wbc, out)
         if p_e is None:
@@ -61,7 +62,8 @@ class _SGCNEncoderFn(torch.autograd.Function):
                                            _lib.ptr(csr.rowptr_s), _lib.ptr(csr.csc_pos), _lib.ptr(prob), _lib.ptr(pb),
                                            _lib.ptr(wb), _lib.ptr(out), _lib.ptr(g_out), _lib.ptr(gpe), B, R, F0, H, L,
                                            csr.max_eg, int(ctx.relu), _lib.ptr(dx), _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream(),
-                      tag="sgcn_encoder_bwd[%s,L=%d]" % ("explain" if ctx.explain else "plain", L))
+                      tag="sgcn_encoder_bwd[%s,L=%d]" % ("explain" if ctx.explain else "plain", L),
+                      nbytes=4 * (2 * B * R * L * H + 2 * B * R * F0 + 3 * csr.E + 2 * (B * R + 1) + (csr.E if gpe is not None else 0)))
         nwb = P - R * F0 - 2 * F0
         d_wb = grads[:nwb] if wb is not None else None
         d_prob = grads[nwb:nwb + R * F0].view(R, F0) if ctx.explain else None
@@ -96,7 +98,8 @@ class _GATConvFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             _lib.call("igcn_gat_layer_fwd", _lib.ptr(x), _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(ea), _lib.ptr(Wc),
                       _lib.ptr(a_s), _lib.ptr(a_d), _lib.ptr(le), _lib.ptr(ae), _lib.ptr(b), B, R, Fin, H, csr.max_eg, float(slope),
-                      _lib.ptr(out), _lib.stream())
+                      _lib.ptr(out), _lib.stream(), tag="gat_layer_fwd[Fin=%d,H=%d]" % (Fin, H),
+                      nbytes=4 * (B * R * Fin + 3 * csr.E + B * R + 1 + B * R * H))
         ctx.csr, ctx.slope = csr, float(slope)
         ctx.shapes = (att_src.shape, att_dst.shape, lin_edge.shape, att_edge.shape, bias.shape)
         ctx.save_for_backward(x, ea, Wc, a_s, a_d, le, ae, b)
@@ -116,7 +119,8 @@ class _GATConvFn(torch.autograd.Function):
             _lib.call("igcn_gat_layer_bwd", _lib.ptr(x), _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(ea),
                       _lib.ptr(csr.rowptr_s), _lib.ptr(csr.csc_pos), _lib.ptr(W), _lib.ptr(a_s), _lib.ptr(a_d), _lib.ptr(le), _lib.ptr(ae),
                       _lib.ptr(b), _lib.ptr(g_out.contiguous()), B, R, Fin, H, csr.max_eg, ctx.slope, _lib.ptr(dx), _lib.ptr(d_ea),
-                      _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream())
+                      _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream(), tag="gat_layer_bwd[Fin=%d,H=%d]" % (Fin, H),
+                      nbytes=4 * (2 * B * R * Fin + 5 * csr.E + 2 * (B * R + 1) + B * R * H))
         o = H * Fin
         sh = ctx.shapes
         return (dx, d_ea, grads[:o].view(H, Fin), grads[o:o + H].view(sh[0]), grads[o + H:o + 2 * H].view(sh[1]),
@@ -153,7 +157,7 @@ class _CatLinearFn(torch.autograd.Function):
         with torch.cuda.device(W.device):
             _lib.call("igcn_cat_linear_fwd", _lib_ptr_strided(cs[0]), _lib_ptr_strided(cs[1]), _lib_ptr_strided(cs[2]),
                       ctypes.addressof(hw), ctypes.addressof(hs), _lib.ptr(Wc), _lib.ptr(bc), M, N, K, int(relu), _lib.ptr(part), S,
-                      _lib.ptr(out), _lib.stream())
+                      _lib.ptr(out), _lib.stream(), tag="cat_linear_fwd[M=%d,N=%d,K=%d]" % (M, N, K), nbytes=4 * (M * K + N * K + M * N))
         ctx.relu, ctx.widths, ctx.strides = bool(relu), widths, strides
         ctx.need = [t is not None and t.requires_grad for t in srcs]
         ctx.save_for_backward(Wc, out, *[t for t in cs if t is not None])
@@ -178,7 +182,8 @@ class _CatLinearFn(torch.autograd.Function):
             _lib.call("igcn_cat_linear_bwd", _lib_ptr_strided(cs[0]), _lib_ptr_strided(cs[1]), _lib_ptr_strided(cs[2]),
                       ctypes.addressof(hw), ctypes.addressof(hs), _lib.ptr(W), _lib.ptr(out), _lib.ptr(g_out.contiguous()), M, N, K,
                       int(ctx.relu), _lib.ptr(dxs[0]), _lib.ptr(dxs[1]), _lib.ptr(dxs[2]), ctypes.addressof(hd), _lib.ptr(dW), _lib.ptr(db),
-                      _lib.stream())
+                      _lib.stream(), tag="cat_linear_bwd[M=%d,N=%d,K=%d]" % (M, N, K),
+                      nbytes=4 * (M * K + 2 * N * K + 2 * M * N + sum(M * w for w, d in zip(ctx.widths, dxs) if d is not None)))
         return dxs[0], dxs[1], dxs[2], dW, db, None
 
 
@@ -204,7 +209,8 @@ class _CrossAttnFn(torch.autograd.Function):
         out = torch.empty_like(q)
         with torch.cuda.device(q.device):
             _lib.call("igcn_cross_attn_fwd", _lib.ptr(q), _lib.ptr(kv), _lib.ptr(in_w), _lib.ptr(in_b), _lib.ptr(out_w), _lib.ptr(out_b),
-                      B, R, M, E, heads, int(relu), _lib.ptr(out), _lib.stream())
+                      B, R, M, E, heads, int(relu), _lib.ptr(out), _lib.stream(), tag="cross_attn_fwd[R=%d,M=%d,E=%d]" % (R, M, E),
+                      nbytes=4 * (2 * B * R * E + B * M * E + 4 * E * E + 4 * E))
         ctx.heads, ctx.relu = heads, bool(relu)
         ctx.save_for_backward(q, kv, in_w, in_b, out_w, out_b, out)
         return out
@@ -223,7 +229,8 @@ class _CrossAttnFn(torch.autograd.Function):
         with torch.cuda.device(q.device):
             _lib.call("igcn_cross_attn_bwd", _lib.ptr(q), _lib.ptr(kv), _lib.ptr(in_w), _lib.ptr(in_b), _lib.ptr(out_w), _lib.ptr(out_b),
                       _lib.ptr(out), _lib.ptr(g.contiguous()), B, R, M, E, ctx.heads, int(ctx.relu), _lib.ptr(dq), _lib.ptr(dkv),
-                      _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream())
+                      _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream(), tag="cross_attn_bwd[R=%d,M=%d,E=%d]" % (R, M, E),
+                      nbytes=4 * (4 * B * R * E + 2 * B * M * E + 2 * (4 * E * E + 4 * E)))
         o1, o2, o3 = 3 * E * E, 3 * E * E + 3 * E, 4 * E * E + 3 * E
         return dq, dkv, grads[:o1].view(3 * E, E), grads[o1:o2], grads[o2:o3].view(E, E), grads[o3:], None, None
 

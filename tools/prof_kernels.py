@@ -57,7 +57,7 @@ def main():
                 flush.zero_()
                 out.backward(go)
             prof = _lib.profile_end()
-            for k, (c, tot) in prof.items():
+            for k, (c, tot, _nb) in prof.items():
                 ms = tot / c
                 if "fwd" in k:
                     ab = N * 12 + E * 8 + (N + 1) * 4 + N * LH * 4 + (E * 4 if explain else 0)
@@ -79,7 +79,7 @@ def main():
             lat, xd, _, att = net(data)
             (lat.sum() + xd.sum() + att.sum()).backward()
         prof = _lib.profile_end()
-        for k, (c, tot) in prof.items():
+        for k, (c, tot, _nb) in prof.items():
             res[k] = dict(us=tot / c * 1e3)
     print(json.dumps(dict(B=a.B, R=a.R, L=a.L, H=a.H, peak_GBs=peak, kernels=res), indent=1))
 
