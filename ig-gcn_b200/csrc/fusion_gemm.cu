@@ -46,15 +46,29 @@ __global__ void __launch_bounds__(256) cat_linear_fwd_partial(CatSrc src, const 
     const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN, s = blockIdx.z;
     const int k_begin = s * kchunk, k_end = min(K, k_begin + kchunk);
     float acc[4][4] = {};
-    for (int k0 = k_begin; k0 < k_end; k0 += TK) {
-        for (int e = tid; e < TM * TK; e += 256) {
+    // register double buffering: the next tile's global loads are in flight while the current tile is multiplied
+    float ra[8], rb[8];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int e = tid + q * 256;
             const int r = e / TK, kk = e - r * TK;           // consecutive threads -> consecutive k (coalesced)
-            const int m = m0 + r, k = k0 + kk;
-            As[kk][r] = (m < M && k < k_end) ? cat_load(src, m, k) : 0.f;
-            const int n = n0 + r;
-            Bs[kk][r] = (n < N && k < k_end) ? W[(int64_t)n * K + k] : 0.f;
+            const int m = m0 + r, n = n0 + r, k = k0 + kk;
+            ra[q] = (m < M && k < k_end) ? cat_load(src, m, k) : 0.f;
+            rb[q] = (n < N && k < k_end) ? W[(int64_t)n * K + k] : 0.f;
+        }
+    };
+    if (k_begin < k_end) fetch(k_begin);
+    for (int k0 = k_begin; k0 < k_end; k0 += TK) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int e = tid + q * 256;
+            const int r = e / TK, kk = e - r * TK;
+            As[kk][r] = ra[q];
+            Bs[kk][r] = rb[q];
         }
         __syncthreads();
+        if (k0 + TK < k_end) fetch(k0 + TK);
         IGCN_TILE_MMA(As, Bs, acc)
         __syncthreads();
     }
@@ -93,8 +107,11 @@ __global__ void __launch_bounds__(256) cat_linear_bwd_w(CatSrc src, const float*
     const int n0 = blockIdx.y * TM, k0 = blockIdx.x * TN;
     float acc[4][4] = {};
     float dbacc = 0.f;
-    for (int m0 = 0; m0 < M; m0 += TK) {
-        for (int e = tid; e < TK * TM; e += 256) {
+    float ra[8], rb[8];
+    auto fetch = [&](int m0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int e = tid + q * 256;
             const int mm = e / TM, c = e - mm * TM;          // consecutive threads -> consecutive n / k (coalesced)
             const int m = m0 + mm;
             const int n = n0 + c, k = k0 + c;
@@ -103,10 +120,21 @@ __global__ void __launch_bounds__(256) cat_linear_bwd_w(CatSrc src, const float*
                 gz = gY[(int64_t)m * N + n];
                 if (relu && !(Y[(int64_t)m * N + n] > 0.f)) gz = 0.f;
             }
-            As[mm][c] = gz;
-            Bs[mm][c] = (m < M && k < K) ? cat_load(src, m, k) : 0.f;
+            ra[q] = gz;
+            rb[q] = (m < M && k < K) ? cat_load(src, m, k) : 0.f;
+        }
+    };
+    fetch(0);
+    for (int m0 = 0; m0 < M; m0 += TK) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int e = tid + q * 256;
+            const int mm = e / TM, c = e - mm * TM;
+            As[mm][c] = ra[q];
+            Bs[mm][c] = rb[q];
         }
         __syncthreads();
+        if (m0 + TK < M) fetch(m0 + TK);
         IGCN_TILE_MMA(As, Bs, acc)
         if (blockIdx.x == 0 && tid < TM) {                   // d bias: column sums of gZ, one thread per n, fixed order
 #pragma unroll 8
@@ -140,23 +168,38 @@ __global__ void __launch_bounds__(256) cat_linear_bwd_x(CatDst dst, const float*
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * TM, k0 = blockIdx.x * TN;
     float acc[4][4] = {};
-    for (int nb = 0; nb < N; nb += TK) {
-        for (int e = tid; e < TM * TK; e += 256) {
-            const int r = e / TK, nn = e - r * TK;           // gZ row-major (m, n): consecutive threads -> consecutive n
-            const int m = m0 + r, n = nb + nn;
-            float gz = 0.f;
-            if (m < M && n < N) {
-                gz = gY[(int64_t)m * N + n];
-                if (relu && !(Y[(int64_t)m * N + n] > 0.f)) gz = 0.f;
+    float ra[8], rb[8];
+    auto fetch = [&](int nb) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int e = tid + q * 256;
+            {
+                const int r = e / TK, nn = e - r * TK;       // gZ row-major (m, n): consecutive threads -> consecutive n
+                const int m = m0 + r, n = nb + nn;
+                float gz = 0.f;
+                if (m < M && n < N) {
+                    gz = gY[(int64_t)m * N + n];
+                    if (relu && !(Y[(int64_t)m * N + n] > 0.f)) gz = 0.f;
+                }
+                ra[q] = gz;
             }
-            As[nn][r] = gz;
+            {
+                const int nn = e / TN, c = e - nn * TN;      // W row-major (n, k): consecutive threads -> consecutive k
+                const int n = nb + nn, k = k0 + c;
+                rb[q] = (n < N && k < K) ? W[(int64_t)n * K + k] : 0.f;
+            }
         }
-        for (int e = tid; e < TK * TN; e += 256) {
-            const int nn = e / TN, c = e - nn * TN;          // W row-major (n, k): consecutive threads -> consecutive k
-            const int n = nb + nn, k = k0 + c;
-            Bs[nn][c] = (n < N && k < K) ? W[(int64_t)n * K + k] : 0.f;
+    };
+    fetch(0);
+    for (int nb = 0; nb < N; nb += TK) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int e = tid + q * 256;
+            As[e - (e / TK) * TK][e / TK] = ra[q];
+            Bs[e / TN][e - (e / TN) * TN] = rb[q];
         }
         __syncthreads();
+        if (nb + TK < N) fetch(nb + TK);
         IGCN_TILE_MMA(As, Bs, acc)
         __syncthreads();
     }
@@ -238,11 +281,13 @@ extern "C" int igcn_cat_linear_bwd(const float* x0, const float* x1, const float
     IGCN_REQUIRE(widths && strides, IGCN_ERR_BAD_ARG, "cat_linear_bwd: null host arrays");
     int rc = cat_check("cat_linear_bwd", xs, widths, strides, M, N, K, true);
     if (rc) return rc;
-    IGCN_REQUIRE(W && out && g_out && dW && db && dstrides, IGCN_ERR_BAD_ARG, "cat_linear_bwd: null pointer");
+    IGCN_REQUIRE(W && out && g_out && dstrides && ((dW == nullptr) == (db == nullptr)), IGCN_ERR_BAD_ARG, "cat_linear_bwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (M == 0) {
-        cudaMemsetAsync(dW, 0, sizeof(float) * N * K, st);
-        cudaMemsetAsync(db, 0, sizeof(float) * N, st);
+        if (dW) {
+            cudaMemsetAsync(dW, 0, sizeof(float) * N * K, st);
+            cudaMemsetAsync(db, 0, sizeof(float) * N, st);
+        }
         return IGCN_OK;
     }
     CatSrc src;
@@ -252,9 +297,11 @@ extern "C" int igcn_cat_linear_bwd(const float* x0, const float* x1, const float
         src.p[i] = xs[i]; src.w[i] = (int)widths[i]; src.ld[i] = (int)strides[i];
         dst.p[i] = dxs[i]; dst.w[i] = (int)widths[i]; dst.ld[i] = (int)dstrides[i];
     }
-    dim3 gw((unsigned)((K + TN - 1) / TN), (unsigned)((N + TM - 1) / TM));
-    cat_linear_bwd_w<<<gw, 256, 0, st>>>(src, g_out, out, (int)relu, (int)M, (int)N, (int)K, dW, db);
-    IGCN_CHECK_LAUNCH("cat_linear_bwd_w");
+    if (dW) {   // dW == db == NULL: weight gradient not wanted
+        dim3 gw((unsigned)((K + TN - 1) / TN), (unsigned)((N + TM - 1) / TM));
+        cat_linear_bwd_w<<<gw, 256, 0, st>>>(src, g_out, out, (int)relu, (int)M, (int)N, (int)K, dW, db);
+        IGCN_CHECK_LAUNCH("cat_linear_bwd_w");
+    }
     if (dx0 || dx1 || dx2) {
         dim3 gx((unsigned)((K + TN - 1) / TN), (unsigned)((M + TM - 1) / TM));
         cat_linear_bwd_x<<<gx, 256, 0, st>>>(dst, g_out, out, (int)relu, W, (int)M, (int)N, (int)K);

@@ -240,7 +240,7 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         if n == 0:
             return 0
         if s.is_cuda:
-            gram = ops.cat_linear([s], s, s.new_zeros(n), relu=False)
+            gram = ops.gram(s)
         else:
             gram = s @ s.t()
         W, d = self._similarity(n, tsne_result, s)

@@ -299,3 +299,46 @@ class MaskBank(object):
                     ends.append(tot)
                 self.plans[self.key] = (names, [r[1] for r in self.recording], ends, [r[2] for r in self.recording])
         self.active = False
+
+
+class _GramFn(torch.autograd.Function):
+    """G = S S^T (B x B) on the split-K tile kernels; backward dS = (gG + gG^T) S is ONE product (the generic
+    linear backward would spend a second, equally large one on the 'weight' side)."""
+
+    @staticmethod
+    def forward(ctx, s):
+        import ctypes
+        _lib.require_cuda(s)
+        lib = _lib.lib()
+        sc = s.contiguous().float()
+        M, K = sc.shape
+        S = lib.igcn_cat_linear_splits(M, M, K)
+        part = torch.empty((S, M, M), dtype=torch.float32, device=s.device)
+        out = torch.empty((M, M), dtype=torch.float32, device=s.device)
+        zero = torch.zeros(M, dtype=torch.float32, device=s.device)
+        hw, hs = (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0)
+        with torch.cuda.device(s.device):
+            _lib.call("igcn_cat_linear_fwd", _lib.ptr(sc), None, None, ctypes.addressof(hw), ctypes.addressof(hs), _lib.ptr(sc), _lib.ptr(zero),
+                      M, M, K, 0, _lib.ptr(part), S, _lib.ptr(out), _lib.stream(), tag="gram_fwd[B=%d,D=%d]" % (M, K),
+                      nbytes=4 * (M * K + M * M))
+        ctx.save_for_backward(sc, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes
+        sc, out = ctx.saved_tensors
+        M, K = sc.shape
+        gsym = (g + g.t()).contiguous()
+        ds = torch.empty_like(sc)
+        hw, hs, hd = (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0)
+        with torch.cuda.device(sc.device):
+            _lib.call("igcn_cat_linear_bwd", _lib.ptr(sc), None, None, ctypes.addressof(hw), ctypes.addressof(hs), _lib.ptr(sc), _lib.ptr(out),
+                      _lib.ptr(gsym), M, M, K, 0, _lib.ptr(ds), None, None, ctypes.addressof(hd), None, None, _lib.stream(),
+                      tag="gram_bwd[B=%d,D=%d]" % (M, K), nbytes=4 * (2 * M * K + M * M))
+        return ds
+
+
+def gram(s):
+    """s @ s.T for a (B, D) CUDA tensor."""
+    return _GramFn.apply(s)

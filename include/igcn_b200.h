@@ -186,7 +186,7 @@ int igcn_cross_attn_bwd(const float* q_in, const float* kv_in, const float* in_p
  *   bias (N); relu = 1 applies ReLU.  Split-K over S = igcn_cat_linear_splits(M,N,K) chunks: partials (S,M,N) workspace,
  *   reduced in a fixed order (deterministic).  host_* arrays are 3-element HOST arrays.
  *   bwd: g_out = dLoss/d out, `out` = the forward output (ReLU mask); dW (N,K), db (N), dx_i (M, width_i) with row
- *   stride host_dstrides[i] (NULL = not needed); all fully overwritten.
+ *   stride host_dstrides[i] (NULL = not needed); dW = db = NULL skips the weight gradient; outputs fully overwritten.
  */
 int64_t igcn_cat_linear_splits(int64_t M, int64_t N, int64_t K);
 int igcn_cat_linear_fwd(const float* x0, const float* x1, const float* x2, const int64_t* host_widths, const int64_t* host_strides,
