@@ -206,6 +206,7 @@ class Gene_ontology_network(nn.Module):
         self.classification = nn.Sequential(nn.BatchNorm1d(l_dim + S), nn.ReLU(), nn.Dropout(0.5), nn.Linear(l_dim + S, 16, bias=False),
                                             nn.ReLU(), nn.Dropout(0.3), nn.Linear(16, 1, bias=True), nn.Sigmoid())
         self._dev_graphs = {}
+        self._groups = 1
         self.dropout_masks = None     # test hook: dict name -> multiplicative scale tensor (oracle.GO_MASK_NAMES)
         self.mask_bank = MaskBank()   # all masks of a pass from one kernel launch (shared with the enclosing model)
 
@@ -231,9 +232,20 @@ class Gene_ontology_network(nn.Module):
         m = self._mask(name, t.shape, p, t.device)
         return t if m is None else t * m
 
-    def forward(self, data, T=None, device=None):
+    def _bn(self, bn, x):
+        """BatchNorm over the batch -- or, when two passes are stacked along the batch (`groups`=2), over each pass
+        separately and in order, so statistics and running buffers are exactly those of two separate forward calls."""
+        g = self._groups
+        if g == 1:
+            return bn(x)
+        h = x.shape[0] // g
+        return torch.cat([bn(x[i * h:(i + 1) * h]) for i in range(g)], 0)
+
+    def forward(self, data, T=None, device=None, groups=1):
+        """groups=2: `data` holds the plain pass and the explain pass stacked along the batch (train.step_loss)."""
         dev = data.device
         n_l, pool = self.n_l, self.pool
+        self._groups = groups
         own_pass = self.training and self.dropout_masks is None and not self.mask_bank.active
         if own_pass:
             self.mask_bank.begin_pass(data.shape[0], dev)
@@ -244,18 +256,18 @@ class Gene_ontology_network(nn.Module):
             mask = self._mask("go_enc%d" % j, (x.shape[0], g["n_rows"]), 0.4, dev)
             x = _GoLayerFn.apply(x, self.w_inc[j].weight, self.w_s_loop[j].weight, self.w_att_in[j].weight, self.w_att_s[j].weight,
                                  self.G_B[j].weight, self.G_B[j].bias, mask, g, True, 0, pool[j])
-        atten_out = self.conc_for_attention(x)
+        atten_out = F.relu(self._bn(self.conc_for_attention[1], self.conc_for_attention[0](x)))
         inp = self.conc(x).squeeze(-1)
-        inp_out = self._drop("go_B", F.relu(self.B[0](inp)), 0.5)
+        inp_out = self._drop("go_B", F.relu(self._bn(self.B[0], inp)), 0.5)
         for j in range(n_l):
             g = self._g("dec%d" % j, dev)
             mask = self._mask("go_dec%d" % j, (x.shape[0], g["n_rows"]), 0.4, dev)
             x = _GoLayerFn.apply(x, self.w_out[j].weight, self.w_s_loop_out[j].weight, None, None, self.G_B_D[j].weight,
                                  self.G_B_D[j].bias, mask, g, False, pool[n_l - j - 1], 0)
-        out_D = self._drop("go_BD", F.relu(self.B_D[0](self.conc_D(x).squeeze(-1))), 0.5)
+        out_D = self._drop("go_BD", F.relu(self._bn(self.B_D[0], self.conc_D(x).squeeze(-1))), 0.5)
         x_D = _GoSpmmFn.apply(out_D, self.t_D[0].unsqueeze(0), self._g("ag_t", dev)).squeeze(-1)
-        h = self._drop("go_latent", F.relu(self.latent[1](self.latent[0](inp_out))), 0.5)
-        latent = F.relu(self.latent[5](self.latent[4](h)))
+        h = self._drop("go_latent", F.relu(self._bn(self.latent[1], self.latent[0](inp_out))), 0.5)
+        latent = F.relu(self._bn(self.latent[5], self.latent[4](h)))
         if own_pass:
             self.mask_bank.end_pass()
         return latent, x_D, [torch.zeros(3, device=dev)], atten_out

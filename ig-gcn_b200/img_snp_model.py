@@ -328,5 +328,53 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             bank.end_pass()
         return F.log_softmax(logits, dim=-1), x_hat, out_z, out_lin, linear_outf, our_reg
 
+    def forward_pair(self, data, temperature=None, device=None):
+        """Plain pass and explain pass of ONE batch in a single sweep: everything downstream of the two encoder
+        launches (GO network, cross attention, fusion heads) runs once on the 2B stacked samples, with BatchNorm
+        applied per pass, so the results equal `forward(data)` followed by `forward(data, isExplain=True)` while every
+        parameter is used once (no gradient-accumulation kernels) and half as many kernels are launched.
+        Returns (plain 6-tuple, explain 6-tuple).  Default configuration only (cross attention, image + SNP fusion)."""
+        if not (self.isCrossAtten and not self.isImageOnly and not self.isSNPsOnly and not self.graph_pool):
+            return self.forward(data, temperature, device), self.forward(data, temperature, device, isExplain=True)
+        x, edge_index = data.x, data.edge_index
+        snps = data.snps_feat
+        if not x.requires_grad and x.is_leaf:
+            x.requires_grad = True
+        self.input = x
+        csr = self._csr_for(data, self.rois)
+        Ws, bs = self._conv_params()
+        B = csr.B
+        bank = self.go_network.mask_bank
+        use_bank = self.training and self.dropout_masks is None
+        if use_bank:
+            bank.begin_pass(("pair", B), x.device)
+        h_plain, _ = ops.sgcn_encoder(x, csr, Ws, bs)
+        h_expl, p_e = ops.sgcn_encoder(x, csr, Ws, bs, self.prob, self.prob_bias, want_pe=True)
+        self._pe_cache = ((x.data_ptr(), edge_index.data_ptr(), self.prob._version, self.prob_bias._version), p_e,
+                          torch.is_grad_enabled())
+        batch_x = torch.cat([h_plain, h_expl], 0)                                   # (2B, R, LH)
+        snps2 = torch.cat([snps, snps * torch.sigmoid(self.snps_prob)], 0)
+        go = self.go_network
+        go.dropout_masks = self.dropout_masks
+        latent, x_hat, _, atten_out = go(snps2, temperature, device, groups=2)
+        img_out = batch_x.view(2 * B, -1)
+        out_cross = ops.cross_attention(batch_x, atten_out, self.multihead_attn, relu=True).reshape(2 * B, -1)
+        out_z = (img_out + out_cross) / 2
+        parts = [out_z, latent]
+        out_lin = torch.cat(parts, -1).detach()
+        linear_outf = ops.cat_linear(parts, self.lin1.weight, self.lin1.bias, relu=True)
+        logits = self.lin2(self._mask("lin1", linear_outf, 0.5))
+        rparts = parts
+        if self.isuseProb4Regr:
+            img_feat = (x.view(B, self.rois, -1) * self.prob).reshape(B, -1)
+            rparts = parts + [torch.cat([img_feat, img_feat], 0)]
+        r = self._mask("lin1_regr", ops.cat_linear(rparts, self.lin1_regr.weight, self.lin1_regr.bias, relu=True), 0.3)
+        our_reg = self.lin2_regr(r)
+        if use_bank:
+            bank.end_pass()
+        logp = F.log_softmax(logits, dim=-1)
+        outs = (logp, x_hat, out_z, out_lin, linear_outf, our_reg)
+        return tuple(t[:B] for t in outs), tuple(t[B:] for t in outs)
+
     def __repr__(self):
         return self.__class__.__name__

@@ -15,13 +15,18 @@ hp = types.SimpleNamespace(lamda_x_l1=0.1, lamda_e_l1=0.1, lamda_x_ent=0.1, lamd
 DEFAULT_LAMBDA = [0.0, 1.0, 0.5, 0.0000015, 0.1, 0.0]      # main.py:73-78 -> main.py:204
 
 
-def step_loss(model, data, lambda_loss=None, isSoftSimilarity=True, temperature=None, num_cluster=2, hyper=hp):
+def step_loss(model, data, lambda_loss=None, isSoftSimilarity=True, temperature=None, num_cluster=2, hyper=hp, pair=True):
     """The scalar that train() back-propagates, term by term as in train_eval_sgcn_img_snps.py:521-544."""
     lam = DEFAULT_LAMBDA if lambda_loss is None else lambda_loss
     dev = data.x.device
     y = data.y.view(-1)
-    out, snps_hat, out_feat, out_lin, _, our_reg = model(data, temperature, dev)
-    out_p, snps_hat_p, out_feat_p, out_lin_p, _, our_reg_p = model(data, temperature, dev, isExplain=True)
+    if pair and hasattr(model, "forward_pair"):
+        # both passes in one sweep (identical results, half the launches; see SGCN_GCN_IMGSNP.forward_pair)
+        (out, snps_hat, out_feat, out_lin, _, our_reg), (out_p, snps_hat_p, out_feat_p, out_lin_p, _, our_reg_p) = \
+            model.forward_pair(data, temperature, dev)
+    else:
+        out, snps_hat, out_feat, out_lin, _, our_reg = model(data, temperature, dev)
+        out_p, snps_hat_p, out_feat_p, out_lin_p, _, our_reg_p = model(data, temperature, dev, isExplain=True)
     cs = data.clini_score.view(-1)
     loss_reg = lam[1] * (F.mse_loss(our_reg.view(-1), cs) + F.mse_loss(our_reg_p.view(-1), cs)) / 2
     loss_prob = lam[2] * model.loss_probability(data.x, data.edge_index, data.edge_attr, hyper)

@@ -157,19 +157,28 @@ def test_full_model_golden(case):
     mp = {k: torch.from_numpy(v) for k, v in H.sub_dict(g, "stepmask/plain/").items()}
     me = {k: torch.from_numpy(v) for k, v in H.sub_dict(g, "stepmask/explain/").items()}
     orig_forward = m.forward
-
-    def fwd(data, temperature=None, device=None, isExplain=False):
-        m.dropout_masks = me if isExplain else mp
-        return orig_forward(data, temperature, device, isExplain)
-    m.forward = fwd
-    b.x.grad = None
-    loss = T.step_loss(m, b, list(g["lambda_loss"]), True)
-    loss.backward()
-    H.assert_close(loss, g["step/loss"], what="step loss")
-    P = dict(m.named_parameters())
-    for k, v in H.sub_dict(g, "grad/").items():
-        assert P[k].grad is not None, k
-        H.assert_close(P[k].grad, v, rtol=3e-4, what="grad " + k)
+    params0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    for pair in (False, True):
+        m.load_state_dict(params0)
+        for p_ in m.parameters():
+            p_.grad = None
+        b.x.grad = None
+        if pair:
+            # both passes stacked along the batch (forward_pair): masks of the plain pass first, then the explain pass
+            m.forward = orig_forward
+            m.dropout_masks = {k: torch.cat([mp[k], me[k]], 0) for k in mp}
+        else:
+            def fwd(data, temperature=None, device=None, isExplain=False):
+                m.dropout_masks = me if isExplain else mp
+                return orig_forward(data, temperature, device, isExplain)
+            m.forward = fwd
+        loss = T.step_loss(m, b, list(g["lambda_loss"]), True, pair=pair)
+        loss.backward()
+        H.assert_close(loss, g["step/loss"], what="step loss (pair=%s)" % pair)
+        P = dict(m.named_parameters())
+        for k, v in H.sub_dict(g, "grad/").items():
+            assert P[k].grad is not None, k
+            H.assert_close(P[k].grad, v, rtol=3e-4, what="grad %s (pair=%s)" % (k, pair))
     for k, v in H.sub_dict(g, "bn_after/").items():
         if "classification" in k:      # unused head, sized for 54 SNPs in the reference
             continue
@@ -188,17 +197,11 @@ def test_adam_trajectory_golden_flat_adam_and_graph():
     m.train()
     opt = T.FlatAdam(m.parameters(), lr=1e-3)
     lam = list(g["lambda_loss"])
-    orig_forward = m.forward
-    state = {"s": 0}
-
-    def fwd(data, temperature=None, device=None, isExplain=False):
-        tag = "explain" if isExplain else "plain"
-        m.dropout_masks = {k: torch.from_numpy(v) for k, v in H.sub_dict(g, "adam/mask/%d/%s/" % (state["s"], tag)).items()}
-        return orig_forward(data, temperature, device, isExplain)
-    m.forward = fwd
     losses = []
     for s in range(len(g["adam/losses"])):
-        state["s"] = s
+        mp = H.sub_dict(g, "adam/mask/%d/plain/" % s)
+        me = H.sub_dict(g, "adam/mask/%d/explain/" % s)
+        m.dropout_masks = {k: torch.cat([torch.from_numpy(mp[k]), torch.from_numpy(me[k])], 0) for k in mp}
         losses.append(float(T.train_step(m, b, opt, lam)))
     H.assert_close(np.asarray(losses), g["adam/losses"], what="loss trajectory")
     P = dict(m.named_parameters())
