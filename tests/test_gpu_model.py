@@ -293,3 +293,57 @@ def test_cross_attention_vs_torch_mha(B, R, M, E):
     H.assert_close(kv.grad, kv64.grad, what="dkv")
     for (k, p), (_, p64) in zip(mha.named_parameters(), ref.named_parameters()):
         H.assert_close(p.grad, p64.grad, rtol=2e-4, what="grad " + k)
+
+
+def test_reference_training_loop_calling_convention():
+    """The call sequence of the reference's train() (kernel/train_eval_sgcn_img_snps.py:511-548) against the drop-in classes:
+    DataLoader over a list of Data objects, data.to(device), two model calls, the model's loss helpers, torch Adam."""
+    import types
+    import torch.nn.functional as F
+    from igcn_b200 import synthetic as syn
+    from igcn_b200.data import Data, DataLoader
+    from igcn_b200.img_snp_model import SGCN_GCN_IMGSNP
+    hp = types.SimpleNamespace(lamda_x_l1=0.1, lamda_e_l1=0.1, lamda_x_ent=0.1, lamda_e_ent=0.1, lamda_mi=1, lamda_ce=1)
+    device = torch.device(DEV)
+    sub = syn.make_subjects(10, rois=90, n_snps=54, seed=8)
+    ep = sub["edge_ptr"]
+    dataset = [Data(x=torch.from_numpy(sub["x"][i]),
+                    edge_index=torch.from_numpy(np.vstack([sub["edge_src"][ep[i]:ep[i + 1]], sub["edge_dst"][ep[i]:ep[i + 1]]])),
+                    edge_attr=torch.from_numpy(sub["edge_attr"][ep[i]:ep[i + 1]]), y=torch.tensor([sub["y"][i]]),
+                    clust_y=torch.tensor([sub["clust_y"][i]]), snps_feat=torch.from_numpy(sub["snps_feat"][i:i + 1]),
+                    sbjID=torch.tensor([sub["sbjID"][i]]), tsne_fdim=torch.from_numpy(sub["tsne_fdim"][i:i + 1]),
+                    clini_score=torch.from_numpy(sub["clini_score"][i])) for i in range(10)]
+    loader = DataLoader(dataset, 4, shuffle=True)
+    adj, go_snps, pool_dim = syn.make_go_hierarchy(None, 54, seed=0)
+    A = torch.tensor(adj).float().t().to_sparse().coalesce().to(device)
+    A_g = torch.tensor(go_snps).float().to_sparse().coalesce().to(device)
+    model = SGCN_GCN_IMGSNP(2, 16, A_g, A, pool_dim, 32, device, rois=90, H_0=3, num_classes=3, isSoftSimilarity=True, rbf_gamma=0.01,
+                            isCrossAtten=True, num_regr=3, model4eachregr=False, isuseProb4Regr=True, isImageOnly=False,
+                            isSNPsOnly=False, isMultiFusion=False).to(device)
+    optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0)
+    criterion_recon = torch.nn.MSELoss(reduction="none")
+    lam = [0.0, 1.0, 0.5, 0.0000015, 0.1, 0.0]
+    model.train()
+    total, seen = 0.0, 0
+    for data in loader:
+        optimizer.zero_grad()
+        data = data.to(device)
+        for param in model.parameters():
+            param.requires_grad = True
+        out, snps_hat, out_feat, out_lin, _, our_reg = model(data, 0.1, device)
+        out_prob, snps_hat_prob, out_feat_prob, out_lin_prob, _, our_reg_prob = model(data, 0.1, device, isExplain=True)
+        loss_reg = lam[1] * (F.mse_loss(our_reg.view(-1), data.clini_score.view(-1)) + F.mse_loss(our_reg_prob.view(-1), data.clini_score.view(-1))) / 2
+        loss_prob = lam[2] * model.loss_probability(data.x, data.edge_index, data.edge_attr, hp)
+        recon = lam[3] * (torch.sum(criterion_recon(snps_hat, data.snps_feat)) + torch.sum(criterion_recon(snps_hat_prob, data.snps_feat))) / 2
+        cluster = lam[4] * (model.consist_loss(out_feat, data.tsne_fdim) + model.consist_loss(out_feat_prob, data.tsne_fdim)) / 2
+        orth = lam[5] * model.OrthogonalConstraint(out_feat)
+        loss = loss_reg + loss_prob + recon + cluster + orth
+        loss.backward()
+        n = data.num_graphs if data.batch is not None else data.x.size(0)
+        total += loss.detach().cpu().item() * n
+        seen += n
+        optimizer.step()
+        assert out.shape == (n, 3) and out_lin.shape == (n, 90 * 32 + 32) and snps_hat.shape == (n, 54) and our_reg.shape == (n, 3)
+        assert data.batch.shape == (n * 90,) and int(data.batch[-1]) == n - 1
+    assert seen == len(loader.dataset) == 10 and np.isfinite(total)
+    assert model.prob.grad is not None and model.edge_prob.grad is None      # edge_prob is unused, as in the reference
