@@ -7,6 +7,8 @@
 // ReLU stay in shared memory (R*M <= 264*300 scores per head fit); projection-weight gradients are accumulated per CTA in shared
 // memory across its graphs and reduced in a fixed order afterwards (deterministic, no float atomics).
 // Shape-generic (runtime R, M, E, heads); fp32 FFMA.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace igcn {
@@ -28,29 +30,49 @@ struct AttnArgs {
     int Rc;             // query rows staged per chunk
 };
 
+// Register tiling: every thread produces 4 consecutive output features, so one broadcast LDS.32 + one LDS.128 feed 4 FMAs
+// (the first version had 2 LDS per FMA and was ~3x slower).  Row-walked arrays (Q, K, V, dO) use a row stride of E+4 floats:
+// 16-byte aligned for LDS.128 and bank-conflict free when consecutive threads read consecutive rows.
+__device__ __forceinline__ float4 ld4s(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4s(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void fma4(float s, float4 v, float4& acc) {
+    acc.x = fmaf(s, v.x, acc.x);
+    acc.y = fmaf(s, v.y, acc.y);
+    acc.z = fmaf(s, v.z, acc.z);
+    acc.w = fmaf(s, v.w, acc.w);
+}
+__device__ __forceinline__ float dot4s(float4 a, float4 b, float acc) {
+    acc = fmaf(a.x, b.x, acc);
+    acc = fmaf(a.y, b.y, acc);
+    acc = fmaf(a.z, b.z, acc);
+    return fmaf(a.w, b.w, acc);
+}
+
 struct AttnSmem {
     float *WinT, *WoT, *bin, *bo;   // WinT[k][3E] (k-major), WoT[k][E]
-    float *X, *A, *Q, *K, *V, *Pm, *O;   // X, Q, Pm, O hold ONE CHUNK of Rc query rows
+    float *X, *A, *Q, *K, *V, *Pm, *O;   // X, Q, Pm, O hold ONE CHUNK of Rc query rows; Q/K/V rows have stride E+4
     float* tail;
 };
 __device__ __forceinline__ AttnSmem attn_carve(float* p, int Rc, int M, int E, int heads) {
     AttnSmem s;
+    const int EP = E + 4;
     s.WinT = p;  p += 3 * E * E;
     s.WoT = p;   p += E * E;
     s.bin = p;   p += 3 * E;
     s.bo = p;    p += E;
     s.X = p;     p += Rc * E;
     s.A = p;     p += M * E;
-    s.Q = p;     p += Rc * (E + 1);   // row stride E+1: rows are walked by different threads at the same column
-    s.K = p;     p += M * E;
-    s.V = p;     p += M * E;
-    s.Pm = p;    p += heads * Rc * M;
+    s.Q = p;     p += Rc * EP;
+    s.K = p;     p += M * EP;
+    s.V = p;     p += M * EP;
     s.O = p;     p += Rc * E;
+    s.Pm = p;    p += (heads * Rc * M + 3) & ~3;
     s.tail = p;
     return s;
 }
 static size_t attn_common_floats(int Rc, int M, int E, int heads) {
-    return (size_t)4 * E * E + 4 * E + 3 * (size_t)Rc * E + Rc + 3 * (size_t)M * E + (size_t)heads * Rc * M;
+    return (size_t)4 * E * E + 4 * E + 2 * (size_t)Rc * E + (size_t)Rc * (E + 4) + (size_t)M * E + 2 * (size_t)M * (E + 4) +
+           (((size_t)heads * Rc * M + 3) & ~(size_t)3);
 }
 
 __device__ __forceinline__ void attn_load_params(const AttnArgs& a, const AttnSmem& s) {
@@ -68,55 +90,48 @@ __device__ __forceinline__ void attn_load_params(const AttnArgs& a, const AttnSm
     __syncthreads();
 }
 
+// out[r][4c..4c+3] = bias[4c..] + sum_k in[r*ldin + k] * Wt[k*ldw + 4c..]   for r < rows, c < E/4
+__device__ __forceinline__ void proj4(const float* in, int ldin, const float* Wt, int ldw, const float* bias, int rows, int E,
+                                      float* out, int ldout) {
+    const int E4 = E >> 2;
+    for (int idx = threadIdx.x; idx < rows * E4; idx += blockDim.x) {
+        const int r = idx / E4, c = idx - r * E4;
+        float4 acc = bias ? ld4s(bias + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* row = in + r * ldin;
+#pragma unroll 8
+        for (int k = 0; k < E; ++k) fma4(row[k], ld4s(Wt + k * ldw + 4 * c), acc);
+        st4s(out + r * ldout + 4 * c, acc);
+    }
+}
+
 // K, V of one graph (all M key/value tokens)
 __device__ __forceinline__ void attn_keys_values(const AttnArgs& a, const AttnSmem& s, int b) {
-    const int tid = threadIdx.x, nt = blockDim.x, M = a.M, E = a.E;
+    const int tid = threadIdx.x, nt = blockDim.x, M = a.M, E = a.E, EP = E + 4;
     const float* ab = a.a + (int64_t)b * M * E;
     for (int i = tid; i < M * E; i += nt) s.A[i] = ab[i];
     __syncthreads();
-    for (int idx = tid; idx < M * E; idx += nt) {
-        const int j = idx / E, f = idx - j * E;
-        float ak = s.bin[E + f], av = s.bin[2 * E + f];
-#pragma unroll 8
-        for (int k = 0; k < E; ++k) {
-            const float v = s.A[j * E + k];
-            ak = fmaf(v, s.WinT[k * 3 * E + E + f], ak);
-            av = fmaf(v, s.WinT[k * 3 * E + 2 * E + f], av);
-        }
-        s.K[idx] = ak;
-        s.V[idx] = av;
-    }
+    proj4(s.A, E, s.WinT + E, 3 * E, s.bin + E, M, E, s.K, EP);
+    proj4(s.A, E, s.WinT + 2 * E, 3 * E, s.bin + 2 * E, M, E, s.V, EP);
     __syncthreads();
 }
 
-// Q, P, O for the query rows [r0, r0+rc) of one graph
-__device__ __forceinline__ void attn_forward_chunk(const AttnArgs& a, const AttnSmem& s, int b, int r0, int rc) {
-    const int tid = threadIdx.x, nt = blockDim.x, R = a.R, M = a.M, E = a.E, H = a.heads, hd = E / H;
+// scores for one chunk: Pm[h][i][j] = scale * <Q_i^h, K_j^h>, one element per thread; then a row softmax per (h, i)
+__device__ __forceinline__ void attn_scores_softmax(const AttnSmem& s, int rc, int M, int E, int H) {
+    const int tid = threadIdx.x, nt = blockDim.x, hd = E / H, EP = E + 4;
     const float scale = rsqrtf((float)hd);
-    const float* xb = a.x + ((int64_t)b * R + r0) * E;
-    for (int i = tid; i < rc * E; i += nt) s.X[i] = xb[i];
-    __syncthreads();
-    for (int idx = tid; idx < rc * E; idx += nt) {
-        const int i = idx / E, f = idx - i * E;
-        float acc = s.bin[f];
-#pragma unroll 8
-        for (int k = 0; k < E; ++k) acc = fmaf(s.X[i * E + k], s.WinT[k * 3 * E + f], acc);
-        s.Q[i * (E + 1) + f] = acc;
+    for (int idx = tid; idx < H * rc * M; idx += nt) {
+        const int j = idx % M, hi = idx / M, h = hi / rc, i = hi - h * rc;
+        const float* q = s.Q + i * EP + h * hd;
+        const float* kk = s.K + j * EP + h * hd;
+        float d = 0.f;
+        for (int c = 0; c < hd; c += 4) d = dot4s(ld4s(q + c), ld4s(kk + c), d);
+        s.Pm[idx] = d * scale;
     }
     __syncthreads();
-    for (int idx = tid; idx < H * rc; idx += nt) {          // one (head, query) row per thread: scores, softmax
-        const int h = idx / rc, i = idx - h * rc;
-        float* prow = s.Pm + (h * rc + i) * M;
-        const float* q = s.Q + i * (E + 1) + h * hd;
+    for (int hi = tid; hi < H * rc; hi += nt) {
+        float* prow = s.Pm + hi * M;
         float mx = -INFINITY;
-        for (int j = 0; j < M; ++j) {
-            const float* kk = s.K + j * E + h * hd;
-            float d = 0.f;
-            for (int c = 0; c < hd; ++c) d = fmaf(q[c], kk[c], d);
-            d *= scale;
-            prow[j] = d;
-            mx = fmaxf(mx, d);
-        }
+        for (int j = 0; j < M; ++j) mx = fmaxf(mx, prow[j]);
         float den = 0.f;
         for (int j = 0; j < M; ++j) {
             const float e = __expf(prow[j] - mx);
@@ -127,20 +142,31 @@ __device__ __forceinline__ void attn_forward_chunk(const AttnArgs& a, const Attn
         for (int j = 0; j < M; ++j) prow[j] *= inv;
     }
     __syncthreads();
-    for (int idx = tid; idx < rc * E; idx += nt) {
-        const int i = idx / E, f = idx - i * E, h = f / hd;
+}
+
+// Q, P, O for the query rows [r0, r0+rc) of one graph
+__device__ __forceinline__ void attn_forward_chunk(const AttnArgs& a, const AttnSmem& s, int b, int r0, int rc) {
+    const int tid = threadIdx.x, nt = blockDim.x, R = a.R, M = a.M, E = a.E, H = a.heads, hd = E / H, EP = E + 4, E4 = E >> 2;
+    const float* xb = a.x + ((int64_t)b * R + r0) * E;
+    for (int i = tid; i < rc * E; i += nt) s.X[i] = xb[i];
+    __syncthreads();
+    proj4(s.X, E, s.WinT, 3 * E, s.bin, rc, E, s.Q, EP);
+    __syncthreads();
+    attn_scores_softmax(s, rc, M, E, H);
+    for (int idx = tid; idx < rc * E4; idx += nt) {          // O = P V
+        const int i = idx / E4, c = idx - i * E4, h = (4 * c) / hd;
         const float* prow = s.Pm + (h * rc + i) * M;
-        float acc = 0.f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-        for (int j = 0; j < M; ++j) acc = fmaf(prow[j], s.V[j * E + f], acc);
-        s.O[idx] = acc;
+        for (int j = 0; j < M; ++j) fma4(prow[j], ld4s(s.V + j * EP + 4 * c), acc);
+        st4s(s.O + i * E + 4 * c, acc);
     }
     __syncthreads();
 }
 
 __global__ void __launch_bounds__(256) cross_attn_fwd_kernel(AttnArgs a) {
-    extern __shared__ float smf[];
-    const int tid = threadIdx.x, nt = blockDim.x, R = a.R, E = a.E, Rc = a.Rc;
+    extern __shared__ __align__(16) float smf[];
+    const int tid = threadIdx.x, nt = blockDim.x, R = a.R, E = a.E, Rc = a.Rc, E4 = E >> 2;
     AttnSmem s = attn_carve(smf, Rc, a.M, E, a.heads);
     attn_load_params(a, s);
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
@@ -149,12 +175,16 @@ __global__ void __launch_bounds__(256) cross_attn_fwd_kernel(AttnArgs a) {
             const int rc = min(Rc, R - r0);
             attn_forward_chunk(a, s, b, r0, rc);
             float* yb = a.y + ((int64_t)b * R + r0) * E;
-            for (int idx = tid; idx < rc * E; idx += nt) {
-                const int i = idx / E, f = idx - i * E;
-                float acc = s.bo[f];
+            for (int idx = tid; idx < rc * E4; idx += nt) {
+                const int i = idx / E4, c = idx - i * E4;
+                float4 acc = ld4s(s.bo + 4 * c);
+                const float* orow = s.O + i * E;
 #pragma unroll 8
-                for (int k = 0; k < E; ++k) acc = fmaf(s.O[i * E + k], s.WoT[k * E + f], acc);
-                yb[idx] = a.relu ? fmaxf(acc, 0.f) : acc;
+                for (int k = 0; k < E; ++k) fma4(orow[k], ld4s(s.WoT + k * E + 4 * c), acc);
+                if (a.relu) {
+                    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+                }
+                *reinterpret_cast<float4*>(yb + i * E + 4 * c) = acc;
             }
             __syncthreads();
         }
@@ -162,18 +192,20 @@ __global__ void __launch_bounds__(256) cross_attn_fwd_kernel(AttnArgs a) {
 }
 
 __global__ void __launch_bounds__(512) cross_attn_bwd_kernel(AttnArgs a) {
-    extern __shared__ float smf[];
+    extern __shared__ __align__(16) float smf[];
     const int tid = threadIdx.x, nt = blockDim.x, R = a.R, M = a.M, E = a.E, H = a.heads, hd = E / H, Rc = a.Rc;
+    const int EP = E + 4, E4 = E >> 2;
     const float scale = rsqrtf((float)hd);
     AttnSmem s = attn_carve(smf, Rc, M, E, H);
     float* p = s.tail;
-    float* dY = p;   p += Rc * E;        // dY, later dQ
-    float* dO = p;   p += Rc * (E + 1);  // padded like Q
-    float* dK = p;   p += M * E;         // accumulated over the row chunks of a graph
+    float* dY = p;   p += Rc * E;           // dY, later dQ
+    float* dO = p;   p += Rc * EP;
+    float* dK = p;   p += M * E;            // accumulated over the row chunks of a graph
     float* dV = p;   p += M * E;
-    float* acc = p;  p += a.P;           // [dWin (3E,E) | dbin (3E) | dWo (E,E) | dbo (E)]
-    float* WinO = p; p += 3 * E * E;     // row-major copies [f][k] for the transposed products of the backward
+    float* dP = p;   p += (H * Rc * M + 3) & ~3;
+    float* WinO = p; p += 3 * E * E;        // row-major copies [f][k] for the transposed products of the backward
     float* WoO = p;  p += E * E;
+    float* acc = p;  p += a.P;              // [dWin (3E,E) | dbin (3E) | dWo (E,E) | dbo (E)]
     attn_load_params(a, s);
     for (int i = tid; i < 3 * E * E; i += nt) WinO[i] = a.Win[i];
     for (int i = tid; i < E * E; i += nt) WoO[i] = a.Wo[i];
@@ -194,19 +226,14 @@ __global__ void __launch_bounds__(512) cross_attn_bwd_kernel(AttnArgs a) {
             for (int i = tid; i < rc * E; i += nt) dY[i] = (!a.relu || yb[i] > 0.f) ? gb[i] : 0.f;
             __syncthreads();
             // out_proj: dO = dY Wo ; dWo += dY^T O ; dbo += colsum(dY)
-            for (int idx = tid; idx < rc * E; idx += nt) {
-                const int i = idx / E, k = idx - i * E;
-                float v = 0.f;
-#pragma unroll 8
-                for (int f = 0; f < E; ++f) v = fmaf(dY[i * E + f], WoO[f * E + k], v);
-                dO[i * (E + 1) + k] = v;
-            }
-            for (int idx = tid; idx < E * E; idx += nt) {
-                const int f = idx / E, k = idx - f * E;
-                float v = 0.f;
+            proj4(dY, E, WoO, E, nullptr, rc, E, dO, EP);
+            for (int idx = tid; idx < E * E4; idx += nt) {
+                const int f = idx / E4, c = idx - f * E4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-                for (int i = 0; i < rc; ++i) v = fmaf(dY[i * E + f], s.O[i * E + k], v);
-                acc[oWo + idx] += v;
+                for (int i = 0; i < rc; ++i) fma4(dY[i * E + f], ld4s(s.O + i * E + 4 * c), v);
+                float* d = acc + oWo + f * E + 4 * c;
+                d[0] += v.x; d[1] += v.y; d[2] += v.z; d[3] += v.w;
             }
             for (int f = tid; f < E; f += nt) {
                 float v = 0.f;
@@ -214,67 +241,69 @@ __global__ void __launch_bounds__(512) cross_attn_bwd_kernel(AttnArgs a) {
                 acc[oBo + f] += v;
             }
             __syncthreads();
-            // dV += P^T dO (per head) ; dS = P * (dP - rowsum(P*dP)), dP = dO V^T   (dS overwrites P)
-            for (int idx = tid; idx < M * E; idx += nt) {
-                const int j = idx / E, f = idx - j * E, h = f / hd;
-                float v = 0.f;
+            // dP = dO V^T (one element per thread) ; dV += P^T dO
+            for (int idx = tid; idx < H * rc * M; idx += nt) {
+                const int j = idx % M, hi = idx / M, h = hi / rc, i = hi - h * rc;
+                const float* go = dO + i * EP + h * hd;
+                const float* vv = s.V + j * EP + h * hd;
+                float d = 0.f;
+                for (int c = 0; c < hd; c += 4) d = dot4s(ld4s(go + c), ld4s(vv + c), d);
+                dP[idx] = d;
+            }
+            for (int idx = tid; idx < M * E4; idx += nt) {
+                const int j = idx / E4, c = idx - j * E4, h = (4 * c) / hd;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-                for (int i = 0; i < rc; ++i) v = fmaf(s.Pm[(h * rc + i) * M + j], dO[i * (E + 1) + f], v);
-                dV[idx] += v;
+                for (int i = 0; i < rc; ++i) fma4(s.Pm[(h * rc + i) * M + j], ld4s(dO + i * EP + 4 * c), v);
+                float* d = dV + j * E + 4 * c;
+                d[0] += v.x; d[1] += v.y; d[2] += v.z; d[3] += v.w;
             }
             __syncthreads();
-            for (int idx = tid; idx < H * rc; idx += nt) {
-                const int h = idx / rc, i = idx - h * rc;
-                float* prow = s.Pm + (h * rc + i) * M;
-                const float* go = dO + i * (E + 1) + h * hd;
+            // dS = P * (dP - rowsum(P * dP)) * scale   (overwrites P)
+            for (int hi = tid; hi < H * rc; hi += nt) {
+                float* prow = s.Pm + hi * M;
+                const float* dprow = dP + hi * M;
                 float rowdot = 0.f;
-                for (int j = 0; j < M; ++j) {
-                    const float* vv = s.V + j * E + h * hd;
-                    float d = 0.f;
-                    for (int c = 0; c < hd; ++c) d = fmaf(go[c], vv[c], d);
-                    rowdot = fmaf(prow[j], d, rowdot);
-                }
-                for (int j = 0; j < M; ++j) {
-                    const float* vv = s.V + j * E + h * hd;
-                    float d = 0.f;
-                    for (int c = 0; c < hd; ++c) d = fmaf(go[c], vv[c], d);
-                    prow[j] = prow[j] * (d - rowdot) * scale;       // d loss / d (q.k), scale folded in
-                }
+                for (int j = 0; j < M; ++j) rowdot = fmaf(prow[j], dprow[j], rowdot);
+                for (int j = 0; j < M; ++j) prow[j] = prow[j] * (dprow[j] - rowdot) * scale;
             }
             __syncthreads();
             // dQ = dS K ; dK += dS^T Q
             float* dQ = dY;
-            for (int idx = tid; idx < rc * E; idx += nt) {
-                const int i = idx / E, f = idx - i * E, h = f / hd;
+            for (int idx = tid; idx < rc * E4; idx += nt) {
+                const int i = idx / E4, c = idx - i * E4, h = (4 * c) / hd;
                 const float* srow = s.Pm + (h * rc + i) * M;
-                float v = 0.f;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-                for (int j = 0; j < M; ++j) v = fmaf(srow[j], s.K[j * E + f], v);
-                dQ[idx] = v;
+                for (int j = 0; j < M; ++j) fma4(srow[j], ld4s(s.K + j * EP + 4 * c), v);
+                st4s(dQ + i * E + 4 * c, v);
             }
-            for (int idx = tid; idx < M * E; idx += nt) {
-                const int j = idx / E, f = idx - j * E, h = f / hd;
-                float v = 0.f;
+            for (int idx = tid; idx < M * E4; idx += nt) {
+                const int j = idx / E4, c = idx - j * E4, h = (4 * c) / hd;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-                for (int i = 0; i < rc; ++i) v = fmaf(s.Pm[(h * rc + i) * M + j], s.Q[i * (E + 1) + f], v);
-                dK[idx] += v;
+                for (int i = 0; i < rc; ++i) fma4(s.Pm[(h * rc + i) * M + j], ld4s(s.Q + i * EP + 4 * c), v);
+                float* d = dK + j * E + 4 * c;
+                d[0] += v.x; d[1] += v.y; d[2] += v.z; d[3] += v.w;
             }
             __syncthreads();
             // query-side input gradient and projection gradients of this chunk
             float* dxb = a.dx + ((int64_t)b * R + r0) * E;
-            for (int idx = tid; idx < rc * E; idx += nt) {
-                const int i = idx / E, k = idx - i * E;
-                float v = 0.f;
+            for (int idx = tid; idx < rc * E4; idx += nt) {
+                const int i = idx / E4, c = idx - i * E4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float* row = dQ + i * E;
 #pragma unroll 8
-                for (int f = 0; f < E; ++f) v = fmaf(dQ[i * E + f], WinO[f * E + k], v);
-                dxb[idx] = v;
+                for (int f = 0; f < E; ++f) fma4(row[f], ld4s(WinO + f * E + 4 * c), v);
+                *reinterpret_cast<float4*>(dxb + i * E + 4 * c) = v;
             }
-            for (int idx = tid; idx < E * E; idx += nt) {
-                const int f = idx / E, k = idx - f * E;
-                float v = 0.f;
+            for (int idx = tid; idx < E * E4; idx += nt) {
+                const int f = idx / E4, c = idx - f * E4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-                for (int i = 0; i < rc; ++i) v = fmaf(dQ[i * E + f], s.X[i * E + k], v);
-                acc[idx] += v;
+                for (int i = 0; i < rc; ++i) fma4(dQ[i * E + f], ld4s(s.X + i * E + 4 * c), v);
+                float* d = acc + f * E + 4 * c;
+                d[0] += v.x; d[1] += v.y; d[2] += v.z; d[3] += v.w;
             }
             for (int f = tid; f < E; f += nt) {
                 float v = 0.f;
@@ -285,23 +314,24 @@ __global__ void __launch_bounds__(512) cross_attn_bwd_kernel(AttnArgs a) {
         }
         // key/value side: input gradient and projection gradients (after all row chunks)
         float* dab = a.da + (int64_t)b * M * E;
-        for (int idx = tid; idx < M * E; idx += nt) {
-            const int j = idx / E, k = idx - j * E;
-            float v = 0.f;
+        for (int idx = tid; idx < M * E4; idx += nt) {
+            const int j = idx / E4, c = idx - j * E4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
             for (int f = 0; f < E; ++f) {
-                v = fmaf(dK[j * E + f], WinO[(E + f) * E + k], v);
-                v = fmaf(dV[j * E + f], WinO[(2 * E + f) * E + k], v);
+                fma4(dK[j * E + f], ld4s(WinO + (E + f) * E + 4 * c), v);
+                fma4(dV[j * E + f], ld4s(WinO + (2 * E + f) * E + 4 * c), v);
             }
-            dab[idx] = v;
+            *reinterpret_cast<float4*>(dab + j * E + 4 * c) = v;
         }
-        for (int idx = tid; idx < 2 * E * E; idx += nt) {
-            const int f2 = idx / E, k = idx - f2 * E;
+        for (int idx = tid; idx < 2 * E * E4; idx += nt) {
+            const int f2 = idx / E4, c = idx - f2 * E4;
             const float* dsrc = (f2 < E) ? dK + f2 : dV + (f2 - E);
-            float v = 0.f;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-            for (int j = 0; j < M; ++j) v = fmaf(dsrc[j * E], s.A[j * E + k], v);
-            acc[E * E + idx] += v;
+            for (int j = 0; j < M; ++j) fma4(dsrc[j * E], ld4s(s.A + j * E + 4 * c), v);
+            float* d = acc + E * E + f2 * E + 4 * c;
+            d[0] += v.x; d[1] += v.y; d[2] += v.z; d[3] += v.w;
         }
         for (int f2 = tid; f2 < 2 * E; f2 += nt) {
             const float* dsrc = (f2 < E) ? dK + f2 : dV + (f2 - E);
@@ -318,17 +348,22 @@ __global__ void __launch_bounds__(512) cross_attn_bwd_kernel(AttnArgs a) {
 // query rows per chunk: the whole graph when it fits, else the largest chunk that keeps the backward under ~200 KB
 static int attn_rows_per_chunk(int R, int M, int E, int H) {
     int rc = R;
+    if (const char* e = getenv("IGCN_ATTN_RC")) {     // tuning hook
+        const int v = atoi(e);
+        if (v >= 8 && v < rc) rc = v;
+    }
     while (rc > 8) {
-        const size_t fl = attn_common_floats(rc, M, E, H) + 2 * (size_t)rc * E + rc + 2 * (size_t)M * E + (size_t)(4 * E * E + 4 * E) +
-                          4 * (size_t)E * E;
+        const size_t fl = attn_common_floats(rc, M, E, H) + (size_t)rc * E + (size_t)rc * (E + 4) + 2 * (size_t)M * E +
+                          (size_t)H * rc * M + 4 + (size_t)(4 * E * E + 4 * E) + 4 * (size_t)E * E;
         if (4 * fl <= 200 * 1024) break;
         rc = (rc + 1) / 2;
     }
     return rc;
 }
-static size_t attn_fwd_smem(int Rc, int M, int E, int H) { return 4 * attn_common_floats(Rc, M, E, H); }
+static size_t attn_fwd_smem(int Rc, int M, int E, int H) { return 4 * attn_common_floats(Rc, M, E, H) + 16; }
 static size_t attn_bwd_smem(int Rc, int M, int E, int H, int P) {
-    return 4 * (attn_common_floats(Rc, M, E, H) + 2 * (size_t)Rc * E + Rc + 2 * (size_t)M * E + P + 4 * (size_t)E * E);
+    return 4 * (attn_common_floats(Rc, M, E, H) + (size_t)Rc * E + (size_t)Rc * (E + 4) + 2 * (size_t)M * E + (size_t)H * Rc * M + 4 + P +
+                4 * (size_t)E * E) + 16;
 }
 static int attn_ctas(size_t smem, int64_t B, int nthreads = 256) {
     int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -341,7 +376,9 @@ static int attn_ctas(size_t smem, int64_t B, int nthreads = 256) {
 static int attn_fill(AttnArgs& a, const char* who, const float* x, const float* kv, const float* Win, const float* bin, const float* Wo,
                      const float* bo, int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads, int64_t relu) {
     IGCN_REQUIRE(B >= 0 && R > 0 && M > 0 && E > 0 && heads > 0 && E % heads == 0, IGCN_ERR_BAD_ARG, "%s: bad size", who);
-    IGCN_REQUIRE(E <= 128, IGCN_ERR_UNSUPPORTED, "%s: embed dim %lld > 128 not supported", who, (long long)E);
+    IGCN_REQUIRE(E <= 128 && E % 4 == 0 && (E / heads) % 4 == 0, IGCN_ERR_UNSUPPORTED,
+                 "%s: embed dim %lld / heads %lld: need E <= 128 and head_dim a multiple of 4", who, (long long)E, (long long)heads);
+    IGCN_REQUIRE(((uintptr_t)x | (uintptr_t)kv) % 16 == 0, IGCN_ERR_BAD_ARG, "%s: inputs must be 16-byte aligned", who);
     IGCN_REQUIRE(x && kv && Win && bin && Wo && bo, IGCN_ERR_BAD_ARG, "%s: null pointer", who);
     a.x = x; a.a = kv; a.Win = Win; a.bin = bin; a.Wo = Wo; a.bo = bo;
     a.B = (int)B; a.R = (int)R; a.M = (int)M; a.E = (int)E; a.heads = (int)heads; a.relu = relu ? 1 : 0;
