@@ -310,11 +310,11 @@ static size_t fwd_fast_smem(int R, int L, int maxEg) {
 }
 
 // threads per CTA: a multiple of 32 from {128..256} that wastes the fewest (node, feature-group) task slots
-static int fast_threads(int R) {
+static int fast_threads(int R, int max_threads = 256) {
     const int ntask = 4 * R;
     int best = 256;
     double best_u = 0.0;
-    for (int nt = 128; nt <= 256; nt += 32) {
+    for (int nt = 128; nt <= max_threads; nt += 32) {
         const int iters = (ntask + nt - 1) / nt;
         const double u = (double)ntask / ((double)iters * nt);
         if (u >= best_u - 1e-9) {
@@ -355,7 +355,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 }
 
 template <bool kExplain>
-__global__ void __launch_bounds__(256, 1) sgcn_bwd_h16_kernel(EncArgs a) {
+__global__ void __launch_bounds__(384, 1) sgcn_bwd_h16_kernel(EncArgs a) {
     extern __shared__ __align__(16) float smf[];
     const int R = a.R, maxEg = a.maxEg;
     constexpr int LH = 2 * kH;
@@ -364,8 +364,8 @@ __global__ void __launch_bounds__(256, 1) sgcn_bwd_h16_kernel(EncArgs a) {
     const int ntask = R * 4;
     // ---- carve ---------------------------------------------------------------------------------------------------
     const int WBc = wb_size(kF0, kH, 2);
-    float* red = smf;                    // 8 warps * WB : end-of-kernel reduction scratch
-    float* bufA = red + 8 * ((WBc + 3) & ~3);   // R*20  H^{1} (layer-2 input)
+    float* red = smf;                    // 12 warps * WB : end-of-kernel reduction scratch
+    float* bufA = red + 12 * ((WBc + 3) & ~3);   // R*20  H^{1} (layer-2 input)
     float* bufB = bufA + R * kHP;        // R*20  G_l
     float* bufC = bufB + R * kHP;        // R*20  Z, then dH
     float* bufD = bufC + R * kHP;        // R*20  dZ
@@ -430,9 +430,8 @@ __global__ void __launch_bounds__(256, 1) sgcn_bwd_h16_kernel(EncArgs a) {
     __syncthreads();
     const int off1 = layer_off(1, kF0, kH);
     // weights in registers: wt[f] = W2[f][4fg..4fg+3]  (columns for dZ = G W2) ; w1q[a][c] = W1[4fg+a][c]
-    float4 wt[16];
-#pragma unroll
-    for (int f = 0; f < 16; ++f) wt[f] = ld4(Wsm + off1 + f * kH + 4 * fg);
+    const float* wt_s = Wsm + off1 + 4 * fg;     // wt_s[f*16 .. +3] = W2[f][4fg..4fg+3]: read per use (LDS.128, 4 distinct
+                                                  // addresses per warp) -- keeping them in 64 registers forced one 7-warp CTA per SM
     float w1q[4][3];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -571,8 +570,8 @@ __global__ void __launch_bounds__(256, 1) sgcn_bwd_h16_kernel(EncArgs a) {
             const float4 zq = ld4(bufC + i * kHP + 4 * fg);
             const float4 gme = ld4(gr + 4 * fg);
             float4 dz = make_float4(0.f, 0.f, 0.f, 0.f);
-#define IGCN_BWD_STEP(GV, F)            \
-    axpy4(GV, wt[F], dz);               \
+#define IGCN_BWD_STEP(GV, F)                    \
+    axpy4(GV, ld4(wt_s + (F) * kH), dz);        \
     axpy4(GV, zq, acc2[F]);
             IGCN_BWD_STEP(g0.x, 0) IGCN_BWD_STEP(g0.y, 1) IGCN_BWD_STEP(g0.z, 2) IGCN_BWD_STEP(g0.w, 3)
             IGCN_BWD_STEP(g1.x, 4) IGCN_BWD_STEP(g1.y, 5) IGCN_BWD_STEP(g1.z, 6) IGCN_BWD_STEP(g1.w, 7)
@@ -797,11 +796,11 @@ __global__ void __launch_bounds__(256, 1) sgcn_bwd_h16_kernel(EncArgs a) {
 static size_t bwd_fast_smem(int R, int maxEg) {
     const int WB = wb_size(kF0, kH, 2);
     const size_t stage = (size_t)R * kF0 + 2 * ((size_t)R + 1) + 4 * (size_t)maxEg;
-    size_t fl = 8 * (size_t)((WB + 3) & ~3) + 4 * (size_t)R * kHP + ((WB + 3) & ~3) + 4 * (size_t)maxEg /* edges, tedges (int2) */ + 3 * (size_t)maxEg + 2 * (size_t)maxEg +
+    size_t fl = 12 * (size_t)((WB + 3) & ~3) + 4 * (size_t)R * kHP + ((WB + 3) & ~3) + 4 * (size_t)maxEg /* edges, tedges (int2) */ + 3 * (size_t)maxEg + 2 * (size_t)maxEg +
                 4 * (size_t)R * kF0 + 5 * (size_t)R + (size_t)R * kF0 + 8 + 2 * ((size_t)R + 1) + 2 * stage;
     return 4 * fl + 16;
 }
 
-static int fast_threads_bwd(int R) { return fast_threads(R); }
+static int fast_threads_bwd(int R) { return fast_threads(R, 384); }   // one CTA per SM: more warps hide more latency
 
 }  // namespace igcn
