@@ -39,6 +39,13 @@ SIGNATURES = {
     "igcn_cat_linear_bwd": (ctypes.c_int, [_P] * 8 + [_I] * 4 + [_P] * 7),
     "igcn_dropout_masks": (ctypes.c_int, [_P, _P, _P, _I, ctypes.c_uint64, _P, _P]),
     "igcn_adam_step": (ctypes.c_int, [_P] * 6 + [ctypes.c_double] * 4 + [_I, _P]),
+    "igcn_bn_act_fwd": (ctypes.c_int, [_P] * 4 + [_I] * 4 + [ctypes.c_double] * 2 + [_I] + [_P] * 6),
+    "igcn_bn_act_bwd": (ctypes.c_int, [_P] * 6 + [_I] * 5 + [_P] * 4),
+    "igcn_reduce_blocks": (_I, [_I]),
+    "igcn_mask_loss_fwd": (ctypes.c_int, [_P, _I, _P, _I, _P, _I, _P, ctypes.c_double, _P, _I, _P, _P]),
+    "igcn_mask_loss_bwd": (ctypes.c_int, [_P, _I, _P, _I, _P, _I, _P, ctypes.c_double, _P, _P, _P, _P, _P]),
+    "igcn_dot": (ctypes.c_int, [_P, _P, _I, ctypes.c_double, _P, _I, _P, _P]),
+    "igcn_scale_by_scalar": (ctypes.c_int, [_P, _P, ctypes.c_double, _I, _P, _P]),
     "igcn_go_spmm_fwd": (ctypes.c_int, [_P] * 4 + [_I] * 5 + [_P, _P]),
     "igcn_go_spmm_bwd": (ctypes.c_int, [_P] * 8 + [_I] * 5 + [_P, _P, _P]),
     "igcn_go_layer_param_count": (_I, [_I, _I, _I]),
@@ -66,12 +73,8 @@ def lib():
 # ---- launch accounting (bench.py: gpu_launches, per-kernel CUDA-event timing) -------------------------------
 KERNELS_PER_CALL = {
     "igcn_collate_csr": 1, "igcn_csr_from_edge_index": 2, "igcn_sgcn_encoder_fwd": 1, "igcn_sgcn_encoder_bwd": 2,
-    "igcn_gat_param_count": (_I, [_I, _I]),
-    "igcn_gat_bwd_ctas": (_I, [_I] * 5),
-    "igcn_gat_layer_fwd": (ctypes.c_int, [_P] * 10 + [_I] * 5 + [ctypes.c_double, _P, _P]),
-    "igcn_gat_layer_bwd": (ctypes.c_int, [_P] * 13 + [_I] * 5 + [ctypes.c_double, _P, _P, _P, _I, _P, _P]),
-    "igcn_adam_step": (ctypes.c_int, [_P] * 6 + [ctypes.c_double] * 4 + [_I, _P]),
     "igcn_go_spmm_fwd": 1, "igcn_go_spmm_bwd": 2, "igcn_go_layer_fwd": 1, "igcn_go_layer_bwd": 2, "igcn_adam_step": 1, "igcn_dropout_masks": 2, "igcn_cross_attn_fwd": 1, "igcn_cross_attn_bwd": 2, "igcn_cat_linear_fwd": 2, "igcn_cat_linear_bwd": 2, "igcn_gat_layer_fwd": 1, "igcn_gat_layer_bwd": 2,
+    "igcn_bn_act_fwd": 1, "igcn_bn_act_bwd": 1, "igcn_mask_loss_fwd": 2, "igcn_mask_loss_bwd": 1, "igcn_dot": 2, "igcn_scale_by_scalar": 1,
 }
 launch_count = 0          # number of igcn kernels launched by this process
 _profile = None           # None, or dict name -> list[(start_event, end_event)]

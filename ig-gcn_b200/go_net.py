@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib
+from . import _lib, ops
 from .ops import MaskBank
 
 
@@ -241,6 +241,14 @@ class Gene_ontology_network(nn.Module):
         h = x.shape[0] // g
         return torch.cat([bn(x[i * h:(i + 1) * h]) for i in range(g)], 0)
 
+    def _bn_act(self, bn, z, name=None, p=0.0):
+        """dropout(relu(bn(z))) -- one fused launch in training mode (ops.bn_act), the torch modules otherwise."""
+        if self.training and z.is_cuda and bn.track_running_stats:
+            mask = self._mask(name, z.shape, p, z.device) if name else None
+            return ops.bn_act(z, bn, mask, self._groups, relu=True)
+        y = F.relu(self._bn(bn, z))
+        return self._drop(name, y, p) if name else y
+
     def forward(self, data, T=None, device=None, groups=1):
         """groups=2: `data` holds the plain pass and the explain pass stacked along the batch (train.step_loss)."""
         dev = data.device
@@ -256,18 +264,18 @@ class Gene_ontology_network(nn.Module):
             mask = self._mask("go_enc%d" % j, (x.shape[0], g["n_rows"]), 0.4, dev)
             x = _GoLayerFn.apply(x, self.w_inc[j].weight, self.w_s_loop[j].weight, self.w_att_in[j].weight, self.w_att_s[j].weight,
                                  self.G_B[j].weight, self.G_B[j].bias, mask, g, True, 0, pool[j])
-        atten_out = F.relu(self._bn(self.conc_for_attention[1], self.conc_for_attention[0](x)))
+        atten_out = self._bn_act(self.conc_for_attention[1], self.conc_for_attention[0](x))
         inp = self.conc(x).squeeze(-1)
-        inp_out = self._drop("go_B", F.relu(self._bn(self.B[0], inp)), 0.5)
+        inp_out = self._bn_act(self.B[0], inp, "go_B", 0.5)
         for j in range(n_l):
             g = self._g("dec%d" % j, dev)
             mask = self._mask("go_dec%d" % j, (x.shape[0], g["n_rows"]), 0.4, dev)
             x = _GoLayerFn.apply(x, self.w_out[j].weight, self.w_s_loop_out[j].weight, None, None, self.G_B_D[j].weight,
                                  self.G_B_D[j].bias, mask, g, False, pool[n_l - j - 1], 0)
-        out_D = self._drop("go_BD", F.relu(self._bn(self.B_D[0], self.conc_D(x).squeeze(-1))), 0.5)
+        out_D = self._bn_act(self.B_D[0], self.conc_D(x).squeeze(-1), "go_BD", 0.5)
         x_D = _GoSpmmFn.apply(out_D, self.t_D[0].unsqueeze(0), self._g("ag_t", dev)).squeeze(-1)
-        h = self._drop("go_latent", F.relu(self._bn(self.latent[1], self.latent[0](inp_out))), 0.5)
-        latent = F.relu(self._bn(self.latent[5], self.latent[4](h)))
+        h = self._bn_act(self.latent[1], self.latent[0](inp_out), "go_latent", 0.5)
+        latent = self._bn_act(self.latent[5], self.latent[4](h))
         if own_pass:
             self.mask_bank.end_pass()
         return latent, x_D, [torch.zeros(3, device=dev)], atten_out

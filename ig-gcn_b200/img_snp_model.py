@@ -212,6 +212,8 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
     def loss_probability(self, x, edge_index, edge_weight, hp, eps=1e-6):
         """sgcn_img_snp.py:153-181 (sums over edges are order independent, so CSR-slot order is used as is)."""
         edge_prob = self._edge_prob(x, edge_index, edge_weight)
+        if self.prob.is_cuda:
+            return ops.mask_loss(self.prob, edge_prob, self.snps_prob, hp, eps)        # one fused reduction (glue.cu)
         f_l1, f_en = _l1_entropy(torch.sigmoid(self.prob), eps)
         e_l1, e_en = _l1_entropy(edge_prob, eps)
         s_l1, s_en = _l1_entropy(torch.sigmoid(self.snps_prob), eps)
@@ -219,32 +221,34 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         loss_entropy = hp.lamda_x_ent * f_en + hp.lamda_e_ent * e_en + hp.lamda_x_ent * s_en
         return loss_l1 + loss_entropy
 
-    def _similarity(self, n, tsne_result, like):
-        """W (n,n) and its row sums; depends on the data only, so the two passes of a step share it."""
-        if self.isSoftSimilarity and tsne_result is not None:
-            key = (tsne_result.data_ptr(), tsne_result._version, n)
-            c = getattr(self, "_w_cache", None)
-            if c is not None and c[0] == key:
-                return c[1], c[2]
-            W = torch.exp(-self.rbf_gamma * torch.cdist(tsne_result, tsne_result, p=2) ** 2)
-            d = W.sum(1)
-            self._w_cache = (key, W, d)
-            return W, d
-        W = torch.ones(n, n, device=like.device, dtype=like.dtype)
-        return W, W.sum(1)
+    def _laplacian(self, n, tsne_result, like):
+        """Lsym = D - (W + W^T)/2 with W the similarity matrix of the batch (RBF of tsne_fdim, or all ones) and D its row
+        sums; depends on the data only, so the two passes of a step share it."""
+        soft = self.isSoftSimilarity and tsne_result is not None
+        key = (tsne_result.data_ptr(), tsne_result._version, n) if soft else ("ones", n, str(like.device))
+        c = getattr(self, "_w_cache", None)
+        if c is not None and c[0] == key:
+            return c[1]
+        with torch.no_grad():
+            if soft:
+                W = torch.exp(-self.rbf_gamma * torch.cdist(tsne_result, tsne_result, p=2) ** 2)
+            else:
+                W = torch.ones(n, n, device=like.device, dtype=like.dtype)
+            lap = torch.diag(W.sum(1)) - 0.5 * (W + W.t())
+        self._w_cache = (key, lap)
+        return lap
 
     def consist_loss(self, s, tsne_result=None):
-        """tr(s^T (D-W) s)/B^2 (sgcn_img_snp.py:183-196) in Gram form: sum_i d_i |s_i|^2 - sum_ij W_ij <s_i,s_j>.
-        The B x B x D Gram product runs on the split-K tile kernels (cuBLAS picks a 16-CTA shape for it: 50 us at B=256)."""
+        """tr(s^T (D-W) s)/B^2 (sgcn_img_snp.py:183-196).  With L = D - W this is <s, L s>/B^2: one (B x B)(B x D) product
+        T = L s gives the value (a dot product) and the gradient 2 T / B^2 -- the reference's D x D intermediates
+        (8 448^2 at 264 ROIs) and a second product in the backward never exist."""
         n = s.shape[0]
         if n == 0:
             return 0
+        lap = self._laplacian(n, tsne_result, s)
         if s.is_cuda:
-            gram = ops.gram(s)
-        else:
-            gram = s @ s.t()
-        W, d = self._similarity(n, tsne_result, s)
-        return ((d * gram.diagonal()).sum() - (W * gram).sum()) / (n * n)
+            return ops.laplacian_quadratic(s, lap, 1.0 / (n * n))
+        return (s * (lap @ s)).sum() / (n * n)
 
     def OrthogonalConstraint(self, w):
         """||w^T w - I_D||_F^2 / B^2 with row-normalised w (sgcn_img_snp.py:198-205) = (||w w^T||_F^2 - 2B + D)/B^2."""

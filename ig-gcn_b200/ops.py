@@ -342,3 +342,130 @@ class _GramFn(torch.autograd.Function):
 def gram(s):
     """s @ s.T for a (B, D) CUDA tensor."""
     return _GramFn.apply(s)
+
+
+class _BnActFn(torch.autograd.Function):
+    """mask * relu(BatchNorm1d(z)) in training mode, statistics per `groups` consecutive batch slices (igcn_bn_act_*)."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, mask, bn, groups: int, relu: bool):
+        _lib.require_cuda(z, gamma, beta, mask)
+        zc = z.contiguous().float()
+        N, C = zc.shape[0], zc.shape[1]
+        L = zc.numel() // (N * C)
+        mc = None if mask is None else mask.expand_as(zc).contiguous().float()
+        y = torch.empty_like(zc)
+        stats = torch.empty((groups, C, 2), dtype=torch.float32, device=zc.device)
+        rm, rv, nbt = bn.running_mean, bn.running_var, bn.num_batches_tracked
+        mom = 0.1 if bn.momentum is None else float(bn.momentum)
+        with torch.cuda.device(zc.device):
+            _lib.call("igcn_bn_act_fwd", _lib.ptr(zc), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(mc), N, C, L, groups, float(bn.eps), mom,
+                      int(relu), _lib.ptr(rm), _lib.ptr(rv), _lib.ptr(nbt), _lib.ptr(y), _lib.ptr(stats), _lib.stream(),
+                      tag="bn_act_fwd[C=%d,L=%d]" % (C, L), nbytes=4 * zc.numel() * (2 + (mc is not None)))
+        ctx.dims, ctx.groups, ctx.relu = (N, C, L), groups, bool(relu)
+        ctx.save_for_backward(zc, gamma, beta, mc, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        zc, gamma, beta, mc, stats = ctx.saved_tensors
+        N, C, L = ctx.dims
+        dz = torch.empty_like(zc)
+        dg = torch.empty(C, dtype=torch.float32, device=zc.device) if gamma is not None else None
+        db = torch.empty(C, dtype=torch.float32, device=zc.device) if beta is not None else None
+        with torch.cuda.device(zc.device):
+            _lib.call("igcn_bn_act_bwd", _lib.ptr(zc), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(mc), _lib.ptr(stats), _lib.ptr(gy.contiguous()),
+                      N, C, L, ctx.groups, int(ctx.relu), _lib.ptr(dz), _lib.ptr(dg), _lib.ptr(db), _lib.stream(),
+                      tag="bn_act_bwd[C=%d,L=%d]" % (C, L), nbytes=4 * zc.numel() * (3 + (mc is not None)))
+        return dz, dg, db, None, None, None, None
+
+
+def bn_act(z, bn: torch.nn.BatchNorm1d, mask=None, groups=1, relu=True):
+    """mask * relu(bn(z)) for a TRAINING-mode BatchNorm1d over (N,C) or (N,C,L) CUDA input, one launch each way.
+    groups > 1: z stacks that many passes along the batch; each gets its own statistics and running-buffer update, in
+    order, exactly as `groups` successive module calls would (reference: kernel/go_model.py:117-146)."""
+    if not bn.training or not bn.track_running_stats:
+        raise RuntimeError("igcn_b200.bn_act is the training-mode path (use the module itself in eval mode)")
+    return _BnActFn.apply(z, bn.weight, bn.bias, mask, bn, groups, relu)
+
+
+class _MaskLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prob, p_e, snps_prob, coef, eps):
+        import ctypes
+        _lib.require_cuda(prob, p_e, snps_prob)
+        pc, ec, sc = prob.contiguous().float(), p_e.contiguous().float(), snps_prob.contiguous().float()
+        lib = _lib.lib()
+        nb = lib.igcn_reduce_blocks(max(pc.numel(), ec.numel(), sc.numel()))
+        part = torch.empty(nb, dtype=torch.float32, device=pc.device)
+        loss = torch.empty((), dtype=torch.float32, device=pc.device)
+        hc = (ctypes.c_float * 4)(*coef)
+        with torch.cuda.device(pc.device):
+            _lib.call("igcn_mask_loss_fwd", _lib.ptr(pc), pc.numel(), _lib.ptr(ec) if ec.numel() else None, ec.numel(), _lib.ptr(sc), sc.numel(),
+                      ctypes.addressof(hc), float(eps), _lib.ptr(part), nb, _lib.ptr(loss), _lib.stream(), tag="mask_loss_fwd",
+                      nbytes=4 * (pc.numel() + ec.numel() + sc.numel()))
+        ctx.coef, ctx.eps = tuple(coef), float(eps)
+        ctx.save_for_backward(pc, ec, sc)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes
+        pc, ec, sc = ctx.saved_tensors
+        dp = torch.empty_like(pc) if ctx.needs_input_grad[0] else None
+        de = torch.empty_like(ec) if ctx.needs_input_grad[1] else None
+        ds = torch.empty_like(sc) if ctx.needs_input_grad[2] else None
+        hc = (ctypes.c_float * 4)(*ctx.coef)
+        with torch.cuda.device(pc.device):
+            _lib.call("igcn_mask_loss_bwd", _lib.ptr(pc), pc.numel(), _lib.ptr(ec) if ec.numel() else None, ec.numel(), _lib.ptr(sc), sc.numel(),
+                      ctypes.addressof(hc), ctx.eps, _lib.ptr(g.contiguous().float()), _lib.ptr(dp), _lib.ptr(de), _lib.ptr(ds), _lib.stream(),
+                      tag="mask_loss_bwd", nbytes=8 * (pc.numel() + ec.numel() + sc.numel()))
+        return dp, de, ds, None, None
+
+
+def mask_loss(prob, p_e, snps_prob, hp, eps=1e-6):
+    """loss_probability (kernel/sgcn_img_snp.py:153-181) of the raw node mask `prob`, the edge probabilities `p_e` and the raw
+    SNP mask `snps_prob` as one fused reduction."""
+    return _MaskLossFn.apply(prob, p_e, snps_prob, (hp.lamda_x_l1, hp.lamda_e_l1, hp.lamda_x_ent, hp.lamda_e_ent), eps)
+
+
+class _LaplacianQuadFn(torch.autograd.Function):
+    """scale * <S, Lsym S> for a symmetric (B,B) matrix Lsym: ONE product T = Lsym S serves the value (a dot product) and
+    the gradient (2 * scale * T) -- the Gram formulation needs a B x B x D product each way."""
+
+    @staticmethod
+    def forward(ctx, s, lsym, scale: float):
+        import ctypes
+        _lib.require_cuda(s, lsym)
+        sc, lc = s.contiguous().float(), lsym.contiguous().float()
+        M, K = sc.shape
+        t = torch.empty_like(sc)
+        hw, hs, hd = (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0)
+        lib = _lib.lib()
+        nb = lib.igcn_reduce_blocks(sc.numel())
+        part = torch.empty(nb, dtype=torch.float32, device=sc.device)
+        out = torch.empty((), dtype=torch.float32, device=sc.device)
+        with torch.cuda.device(sc.device):
+            # T[i][d] = sum_j Lsym[i][j] S[j][d]: the "dX = gZ W" tile kernel with gZ = Lsym (M x M) and W = S (M x K)
+            _lib.call("igcn_cat_linear_bwd", _lib.ptr(sc), None, None, ctypes.addressof(hw), ctypes.addressof(hs), _lib.ptr(sc), _lib.ptr(lc),
+                      _lib.ptr(lc), M, M, K, 0, _lib.ptr(t), None, None, ctypes.addressof(hd), None, None, _lib.stream(),
+                      tag="laplacian_product[B=%d,D=%d]" % (M, K), nbytes=4 * (2 * M * K + M * M))
+            _lib.call("igcn_dot", _lib.ptr(sc), _lib.ptr(t), sc.numel(), float(scale), _lib.ptr(part), nb, _lib.ptr(out), _lib.stream(),
+                      tag="dot", nbytes=8 * sc.numel())
+        ctx.scale = float(scale)
+        ctx.save_for_backward(t)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (t,) = ctx.saved_tensors
+        ds = torch.empty_like(t)
+        with torch.cuda.device(t.device):
+            _lib.call("igcn_scale_by_scalar", _lib.ptr(t), _lib.ptr(g.contiguous().float()), 2.0 * ctx.scale, t.numel(), _lib.ptr(ds),
+                      _lib.stream(), tag="scale_by_scalar", nbytes=8 * t.numel())
+        return ds, None, None
+
+
+def laplacian_quadratic(s, lsym, scale=1.0):
+    """scale * tr(s^T Lsym s) for a (B, D) CUDA tensor and a SYMMETRIC (B, B) matrix (treated as a constant)."""
+    return _LaplacianQuadFn.apply(s, lsym, scale)

@@ -3,6 +3,7 @@ data-parallel form: one process per GPU, graphs sharded across ranks, ONE flat f
 """
 from __future__ import annotations
 
+import os
 import types
 
 import torch
@@ -134,7 +135,8 @@ class FlatAdam(object):
         from . import _lib
         self.gather_grads()
         scale = 1.0
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1 \
+                and not os.environ.get("IGCN_DIAG_NO_ALLREDUCE"):       # diagnostic switch: isolates the collective's cost
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
             scale = 1.0 / dist.get_world_size(self.group)
         self.step_t += 1.0

@@ -216,6 +216,45 @@ int igcn_dropout_masks(float* out, const int64_t* host_seg_end, const float* hos
 int igcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* step, const float* lr,
                    double beta1, double beta2, double eps, double grad_scale, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Read-out heads of the GO network: mask * relu(BatchNorm1d(z)) in TRAINING mode as one launch (forward) and one
+ * launch (backward).  Replaces nn.BatchNorm1d + nn.ReLU + nn.Dropout as chained in kernel/go_model.py:117-146
+ * (conc_for_attention[1:3], B, B_D, latent[1:4], latent[5:7]).
+ *   z (N, C, L) f32 contiguous (L = 1 for a 2-D input); statistics per channel c over the N/groups * L values of each
+ *   of `groups` consecutive slices of the batch, visited in order: running_mean / running_var (C, updated in place,
+ *   may be NULL) and num_batches_tracked (i64 device scalar, may be NULL) receive exactly the updates of `groups`
+ *   successive module calls.  gamma / beta / mask may be NULL; mask has z's shape (multiplicative, 0 or 1/keep).
+ *   stats (groups, C, 2) f32 receives (mean, rstd) for the backward.  relu != 0 applies max(.,0) before the mask.
+ *   bwd: dz (N,C,L), dgamma (C), dbeta (C) (either may be NULL) are fully overwritten.
+ */
+int igcn_bn_act_fwd(const float* z, const float* gamma, const float* beta, const float* mask, int64_t N, int64_t C, int64_t L,
+                    int64_t groups, double eps, double momentum, int64_t relu, float* running_mean, float* running_var,
+                    long long* num_batches_tracked, float* y, float* stats, void* stream);
+int igcn_bn_act_bwd(const float* z, const float* gamma, const float* beta, const float* mask, const float* stats, const float* g_y,
+                    int64_t N, int64_t C, int64_t L, int64_t groups, int64_t relu, float* dz, float* dgamma, float* dbeta,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * loss_probability (kernel/sgcn_img_snp.py:153-181): for p in {sigmoid(prob) (n_prob), p_e (n_e), sigmoid(snps_prob)
+ * (n_snps)}:  c_l1 * mean|p| + c_ent * mean(-(p log(p+eps) + (1-p) log(1-p+eps))), summed.
+ *   host_coef = {lamda_x_l1, lamda_e_l1, lamda_x_ent, lamda_e_ent} (sgcn_hyperparameters.py:18-21; the SNP mask uses
+ *   the x coefficients, :176-179).  prob / snps_prob are the RAW parameters (sigmoid applied inside), p_e is a
+ *   probability.  partials: workspace of n_partials = igcn_reduce_blocks(max n) floats; loss (1).  Fixed summation
+ *   order (two launches, no atomics).  bwd: g_loss (1) device scalar; d_* may be NULL.
+ */
+int64_t igcn_reduce_blocks(int64_t n);
+int igcn_mask_loss_fwd(const float* prob, int64_t n_prob, const float* p_e, int64_t n_e, const float* snps_prob, int64_t n_snps,
+                       const float* host_coef, double eps, float* partials, int64_t n_partials, float* loss, void* stream);
+int igcn_mask_loss_bwd(const float* prob, int64_t n_prob, const float* p_e, int64_t n_e, const float* snps_prob, int64_t n_snps,
+                       const float* host_coef, double eps, const float* g_loss, float* d_prob, float* d_pe, float* d_snps_prob,
+                       void* stream);
+
+/* out[0] = scale * <a, b> over n f32 values in a fixed order (partials: igcn_reduce_blocks(n) floats); and
+ * out[i] = a[i] * s[0] * scale with s a device scalar.  Together with one product T = Lsym S they are the consistency
+ * loss tr(s^T (D - W) s) / B^2 of kernel/sgcn_img_snp.py:183-196 and its gradient 2 T g / B^2. */
+int igcn_dot(const float* a, const float* b, int64_t n, double scale, float* partials, int64_t n_partials, float* out, void* stream);
+int igcn_scale_by_scalar(const float* a, const float* s, double scale, int64_t n, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
