@@ -3,6 +3,8 @@ from __future__ import annotations
 
 import torch
 
+import os
+
 from . import _lib
 from .data import GraphCSR
 
@@ -133,6 +135,59 @@ def gat_conv(x, csr: GraphCSR, edge_attr_csr, W, att_src, att_dst, lin_edge, att
     return _GATConvFn.apply(x, edge_attr_csr, W, att_src, att_dst, lin_edge, att_edge, bias, csr, negative_slope)
 
 
+# ---- tensor-core (tcgen05, 3xTF32) products: ops built on igcn_tc_split + igcn_tc_gemm ---------------------------------
+USE_TC = os.environ.get("IGCN_NO_TC", "") == ""     # IGCN_NO_TC=1 keeps the fp32 FFMA tile kernels (A/B comparison)
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+def _job(src, hi_lo, rows, cols, ld_src, row_off=0, col_off=0, transpose=False, mask=None):
+    """One operand-preparation job of igcn_tc_split; hi_lo is a (2, R, ld) buffer (hi = [0], lo = [1])."""
+    return [0 if src is None else src.data_ptr(), 0 if mask is None else mask.data_ptr(), hi_lo[0].data_ptr(), hi_lo[1].data_ptr(),
+            rows, cols, ld_src, hi_lo.shape[2], row_off, col_off, int(transpose)]
+
+
+def _tc_split(jobs, dev):
+    import ctypes
+    flat = [v for j in jobs for v in j]
+    arr = (ctypes.c_int64 * len(flat))(*flat)
+    with torch.cuda.device(dev):
+        _lib.call("igcn_tc_split", ctypes.addressof(arr), len(jobs), _lib.stream(), tag="tc_split[%d jobs]" % len(jobs))
+
+
+def _tc_gemm(a, b, M, N, K, dsts, widths, strides, bias=None, relu=False, tag="tc_gemm"):
+    """C[m][n] = act(sum_k A[m][k] B[n][k] + bias[n]); a, b: (2, rows, ld) hi/lo buffers; C columns go to `dsts`."""
+    import ctypes
+    lib = _lib.lib()
+    S = lib.igcn_tc_gemm_splits(M, N, K)
+    part = torch.empty((S, M, N), dtype=torch.float32, device=a.device) if S > 1 else None
+    dsts = list(dsts) + [None] * (3 - len(dsts))
+    hw = (ctypes.c_int64 * 3)(*(list(widths) + [0] * (3 - len(widths))))
+    hs = (ctypes.c_int64 * 3)(*(list(strides) + [0] * (3 - len(strides))))
+    with torch.cuda.device(a.device):
+        _lib.call("igcn_tc_gemm", a[0].data_ptr(), a[1].data_ptr(), a.shape[2], b[0].data_ptr(), b[1].data_ptr(), b.shape[2], M, N, K,
+                  _lib.ptr(bias), int(relu), _lib.ptr(dsts[0]), _lib.ptr(dsts[1]), _lib.ptr(dsts[2]), ctypes.addressof(hw),
+                  ctypes.addressof(hs), _lib.ptr(part), S, _lib.stream(), tag="%s[M=%d,N=%d,K=%d]" % (tag, M, N, K),
+                  nbytes=4 * (2 * M * K + 2 * N * K + M * N))
+
+
+def tc_matmul_nt(a, b, bias=None, relu=False):
+    """act(a @ b.T + bias) for CUDA fp32 matrices a (M,K), b (N,K) on the tcgen05 tensor cores with fp32-level accuracy
+    (3xTF32).  No autograd; the building block of cat_linear / laplacian_quadratic, exposed for tests."""
+    _lib.require_cuda(a, b, bias)
+    M, K = a.shape
+    N = b.shape[0]
+    a, b = a.contiguous().float(), b.contiguous().float()
+    A = torch.empty((2, M, _pad4(K)), dtype=torch.float32, device=a.device)
+    Bm = torch.empty((2, N, _pad4(K)), dtype=torch.float32, device=a.device)
+    _tc_split([_job(a, A, M, K, K), _job(b, Bm, N, K, K)], a.device)
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    _tc_gemm(A, Bm, M, N, K, [out], [N], [N], bias, relu)
+    return out
+
+
 class _CatLinearFn(torch.autograd.Function):
     """act([x0 | x1 | x2] W^T + b) via igcn_cat_linear_* (sources may be None)."""
 
@@ -150,6 +205,25 @@ class _CatLinearFn(torch.autograd.Function):
         if sum(widths) != K:
             raise RuntimeError("cat_linear: source widths %s do not add up to in_features=%d" % (widths, K))
         Wc, bc = W.contiguous().float(), bias.contiguous().float()
+        ctx.tc = USE_TC and M > 0
+        if ctx.tc:
+            # tensor cores: one split launch folds the concatenation, then one 3xTF32 product with bias + ReLU in its epilogue
+            A = torch.empty((2, M, _pad4(K)), dtype=torch.float32, device=W.device)
+            Bw = torch.empty((2, N, _pad4(K)), dtype=torch.float32, device=W.device)
+            jobs, off = [], 0
+            for t, w, ld in zip(cs, widths, strides):
+                if t is not None and w:
+                    jobs.append(_job(t, A, M, w, ld, col_off=off))
+                off += w
+            jobs.append(_job(Wc, Bw, N, K, K))
+            _tc_split(jobs, W.device)
+            out = torch.empty((M, N), dtype=torch.float32, device=W.device)
+            _tc_gemm(A, Bw, M, N, K, [out], [N], [N], bc, relu, tag="cat_linear_fwd_tc")
+            ctx.relu, ctx.widths, ctx.strides = bool(relu), widths, strides
+            ctx.need = [t is not None and t.requires_grad for t in srcs]
+            ctx.save_for_backward(Wc, out, *[t for t in cs if t is not None])
+            ctx.present = [t is not None for t in cs]
+            return out
         S = lib.igcn_cat_linear_splits(M, N, K)
         part = torch.empty((S, M, N), dtype=torch.float32, device=W.device)
         out = torch.empty((M, N), dtype=torch.float32, device=W.device)
@@ -176,6 +250,27 @@ class _CatLinearFn(torch.autograd.Function):
                for need, w in zip(ctx.need, ctx.widths)]
         dW = torch.empty_like(W)
         db = torch.empty(N, dtype=torch.float32, device=W.device)
+        if ctx.tc:
+            dev = W.device
+            g_out = g_out.contiguous()
+            mask = out if ctx.relu else None
+            gz = torch.empty((2, M, _pad4(N)), dtype=torch.float32, device=dev)          # gZ          (M, N): A of dX
+            gzt = torch.empty((2, N, _pad4(M)), dtype=torch.float32, device=dev)         # gZ^T        (N, M): A of dW
+            wt = torch.empty((2, K, _pad4(N)), dtype=torch.float32, device=dev)          # W^T         (K, N): B of dX
+            xt = torch.empty((2, K + 1, _pad4(M)), dtype=torch.float32, device=dev)      # [X | 1]^T (K+1, M): B of dW (ones row -> d bias)
+            jobs = [_job(g_out, gz, M, N, N, mask=mask), _job(g_out, gzt, M, N, N, transpose=True, mask=mask),
+                    _job(W, wt, N, K, K, transpose=True)]
+            off = 0
+            for t, w, ld in zip(cs, ctx.widths, ctx.strides):
+                if t is not None and w:
+                    jobs.append(_job(t, xt, M, w, ld, row_off=off, transpose=True))
+                off += w
+            jobs.append(_job(None, xt, M, 1, 1, row_off=K, transpose=True))
+            _tc_split(jobs, dev)
+            if any(d is not None for d in dxs):
+                _tc_gemm(gz, wt, M, K, N, dxs, ctx.widths, [0 if d is None else d.stride(0) for d in dxs], tag="cat_linear_bwd_x_tc")
+            _tc_gemm(gzt, xt, N, K + 1, M, [dW, db], [K, 1], [K, 1], tag="cat_linear_bwd_w_tc")
+            return dxs[0], dxs[1], dxs[2], dW, db, None
         hw, hs = (ctypes.c_int64 * 3)(*ctx.widths), (ctypes.c_int64 * 3)(*ctx.strides)
         hd = (ctypes.c_int64 * 3)(*[0 if t is None else t.stride(0) for t in dxs])
         with torch.cuda.device(W.device):
@@ -445,11 +540,18 @@ class _LaplacianQuadFn(torch.autograd.Function):
         nb = lib.igcn_reduce_blocks(sc.numel())
         part = torch.empty(nb, dtype=torch.float32, device=sc.device)
         out = torch.empty((), dtype=torch.float32, device=sc.device)
+        if USE_TC:
+            # T[i][d] = sum_j Lsym[i][j] S^T[d][j] on the tensor cores (3xTF32): A = Lsym (M x M), B = S^T (K x M)
+            la = torch.empty((2, M, _pad4(M)), dtype=torch.float32, device=sc.device)
+            st = torch.empty((2, K, _pad4(M)), dtype=torch.float32, device=sc.device)
+            _tc_split([_job(lc, la, M, M, M), _job(sc, st, M, K, K, transpose=True)], sc.device)
+            _tc_gemm(la, st, M, K, M, [t], [K], [K], tag="laplacian_product_tc")
         with torch.cuda.device(sc.device):
             # T[i][d] = sum_j Lsym[i][j] S[j][d]: the "dX = gZ W" tile kernel with gZ = Lsym (M x M) and W = S (M x K)
-            _lib.call("igcn_cat_linear_bwd", _lib.ptr(sc), None, None, ctypes.addressof(hw), ctypes.addressof(hs), _lib.ptr(sc), _lib.ptr(lc),
-                      _lib.ptr(lc), M, M, K, 0, _lib.ptr(t), None, None, ctypes.addressof(hd), None, None, _lib.stream(),
-                      tag="laplacian_product[B=%d,D=%d]" % (M, K), nbytes=4 * (2 * M * K + M * M))
+            if not USE_TC:
+                _lib.call("igcn_cat_linear_bwd", _lib.ptr(sc), None, None, ctypes.addressof(hw), ctypes.addressof(hs), _lib.ptr(sc), _lib.ptr(lc),
+                          _lib.ptr(lc), M, M, K, 0, _lib.ptr(t), None, None, ctypes.addressof(hd), None, None, _lib.stream(),
+                          tag="laplacian_product[B=%d,D=%d]" % (M, K), nbytes=4 * (2 * M * K + M * M))
             _lib.call("igcn_dot", _lib.ptr(sc), _lib.ptr(t), sc.numel(), float(scale), _lib.ptr(part), nb, _lib.ptr(out), _lib.stream(),
                       tag="dot", nbytes=8 * sc.numel())
         ctx.scale = float(scale)

@@ -255,6 +255,29 @@ int igcn_mask_loss_bwd(const float* prob, int64_t n_prob, const float* p_e, int6
 int igcn_dot(const float* a, const float* b, int64_t n, double scale, float* partials, int64_t n_partials, float* out, void* stream);
 int igcn_scale_by_scalar(const float* a, const float* s, double scale, int64_t n, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Dense products on the tcgen05 tensor cores, fp32-accurate ("3xTF32", accumulators in TMEM, operands by TMA).
+ * Used for the fusion heads lin1 / lin1_regr (kernel/sgcn_img_snp.py:286-305) forward and backward, and for the
+ * (B x B)(B x D) Laplacian product of consist_loss (kernel/sgcn_img_snp.py:183-196).
+ *
+ * igcn_tc_split: operand preparation, up to 8 jobs in one launch.  Job = 11 int64 in host memory:
+ *   {src, mask, hi, lo, rows, cols, ld_src, ld_dst, row_off, col_off, transpose}
+ *   src (rows, cols) f32 with row pitch ld_src (NULL = the constant 1.0); mask (same geometry, may be NULL): elements
+ *   whose mask value is not > 0 are taken as 0 (the ReLU mask of a backward pass); every element x is written as the
+ *   pair hi = rn_tf32(x), lo = rn_tf32(x - hi) to hi/lo[(row_off + r) * ld_dst + col_off + c], or transposed to
+ *   hi/lo[(row_off + c) * ld_dst + col_off + r].  This is also where cat(...) happens (column offsets).
+ * igcn_tc_gemm:  C[m][n] = act(sum_k A[m][k] * B[n][k] + bias[n]) with A = a_hi + a_lo (M, K; row pitch lda) and
+ *   B = b_hi + b_lo (N, K; row pitch ldb), pitches multiples of 4 floats, bases 16-byte aligned.  Column n of C goes to
+ *   up to three destination segments d0 | d1 | d2 (host_dst_widths add up to N, host_dst_strides = row pitches; a NULL
+ *   destination drops that segment).  S = igcn_tc_gemm_splits(M, N, K) K-splits; for S > 1 `partials` (S*M*N floats)
+ *   is required and the splits are summed in a fixed order.  bias may be NULL.
+ */
+int igcn_tc_split(const int64_t* host_jobs, int64_t njobs, void* stream);
+int64_t igcn_tc_gemm_splits(int64_t M, int64_t N, int64_t K);
+int igcn_tc_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb, int64_t M,
+                 int64_t N, int64_t K, const float* bias, int64_t relu, float* d0, float* d1, float* d2,
+                 const int64_t* host_dst_widths, const int64_t* host_dst_strides, float* partials, int64_t S, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
