@@ -389,10 +389,40 @@ static int attn_fill(AttnArgs& a, const char* who, const float* x, const float* 
 
 }  // namespace igcn
 
+#include "cross_attn_rows.cuh"
+
+namespace igcn {
+
+// the row-parallel kernels cover the reference's shape; everything else stays on the staged kernels above
+static bool use_rows(int64_t R, int64_t M, int64_t E, int64_t heads) {
+    if (getenv("IGCN_ATTN_STAGED")) return false;            // A/B hook
+    if (E != rows::kE || M < 1 || M > 32 || R > 288 || heads < 1 || (E % heads) != 0 || ((E / heads) % 4) != 0) return false;
+    return rows::fwd_geo((int)R, (int)M, (int)heads).smem <= 110 * 1024 && rows::bwd_geo((int)R, (int)M, (int)heads).smem <= 224 * 1024;
+}
+static int rows_ctas(const rows::Geo& g, int64_t B, int per_sm) {
+    const int64_t groups = (B + g.gpc - 1) / g.gpc;
+    int64_t n = (int64_t)sm_count() * per_sm;
+    if (n > groups) n = groups;
+    return (int)(n < 1 ? 1 : n);
+}
+template <int MC>
+static void launch_rows_fwd(const AttnArgs& a, const rows::Geo& g, int ctas, cudaStream_t st) {
+    cudaFuncSetAttribute(rows::attn_rows_fwd_kernel<MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    rows::attn_rows_fwd_kernel<MC><<<ctas, g.nthreads, g.smem, st>>>(a, g);
+}
+template <int MC>
+static void launch_rows_bwd(const AttnArgs& a, const rows::Geo& g, int ctas, cudaStream_t st) {
+    cudaFuncSetAttribute(rows::attn_rows_bwd_kernel<MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    rows::attn_rows_bwd_kernel<MC><<<ctas, g.nthreads, g.smem, st>>>(a, g);
+}
+
+}  // namespace igcn
+
 using namespace igcn;
 
 extern "C" int64_t igcn_cross_attn_param_count(int64_t E) { return 4 * E * E + 4 * E; }
 extern "C" int64_t igcn_cross_attn_bwd_ctas(int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads) {
+    if (use_rows(R, M, E, heads)) return rows_ctas(rows::bwd_geo((int)R, (int)M, (int)heads), B, 1);
     return attn_ctas(attn_bwd_smem(attn_rows_per_chunk((int)R, (int)M, (int)E, (int)heads), (int)M, (int)E, (int)heads, (int)(4 * E * E + 4 * E)), B, 512);
 }
 
@@ -405,6 +435,17 @@ extern "C" int igcn_cross_attn_fwd(const float* q_in, const float* kv_in, const 
     IGCN_REQUIRE(out, IGCN_ERR_BAD_ARG, "cross_attn_fwd: null output");
     if (B == 0) return IGCN_OK;
     a.y = out;
+    if (use_rows(R, M, E, heads)) {
+        const rows::Geo g = rows::fwd_geo((int)R, (int)M, (int)heads);
+        const int ctas = rows_ctas(g, B, 2);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (M <= 8) launch_rows_fwd<8>(a, g, ctas, st);
+        else if (M <= 16) launch_rows_fwd<16>(a, g, ctas, st);
+        else if (M <= 24) launch_rows_fwd<24>(a, g, ctas, st);
+        else launch_rows_fwd<32>(a, g, ctas, st);
+        IGCN_CHECK_LAUNCH("cross_attn_rows_fwd");
+        return IGCN_OK;
+    }
     size_t smem = attn_fwd_smem(a.Rc, a.M, a.E, a.heads);
     if ((rc = allow_smem(cross_attn_fwd_kernel, smem, "cross_attn_fwd"))) return rc;
     cross_attn_fwd_kernel<<<attn_ctas(smem, B), 256, smem, (cudaStream_t)stream>>>(a);
@@ -428,6 +469,18 @@ extern "C" int igcn_cross_attn_bwd(const float* q_in, const float* kv_in, const 
     const int want = (int)igcn_cross_attn_bwd_ctas(B, R, M, E, heads);
     IGCN_REQUIRE(n_cta == want, IGCN_ERR_BAD_ARG, "cross_attn_bwd: n_cta=%lld, expected %d", (long long)n_cta, want);
     a.yout = out; a.gy = g_out; a.dx = d_q_in; a.da = d_kv_in; a.partials = partials;
+    if (use_rows(R, M, E, heads)) {
+        IGCN_REQUIRE(((uintptr_t)out | (uintptr_t)g_out | (uintptr_t)d_q_in | (uintptr_t)d_kv_in) % 16 == 0, IGCN_ERR_BAD_ARG, "cross_attn_bwd: buffers must be 16-byte aligned");
+        const rows::Geo g = rows::bwd_geo((int)R, (int)M, (int)heads);
+        if (M <= 8) launch_rows_bwd<8>(a, g, want, st);
+        else if (M <= 16) launch_rows_bwd<16>(a, g, want, st);
+        else if (M <= 24) launch_rows_bwd<24>(a, g, want, st);
+        else launch_rows_bwd<32>(a, g, want, st);
+        IGCN_CHECK_LAUNCH("cross_attn_rows_bwd");
+        reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(partials, want, a.P, grads);
+        IGCN_CHECK_LAUNCH("cross_attn_reduce_partials");
+        return IGCN_OK;
+    }
     size_t smem = attn_bwd_smem(a.Rc, a.M, a.E, a.heads, a.P);
     if ((rc = allow_smem(cross_attn_bwd_kernel, smem, "cross_attn_bwd"))) return rc;
     cross_attn_bwd_kernel<<<want, 512, smem, st>>>(a);   // one graph per CTA, 16 warps: the per-graph chain is latency bound

@@ -269,7 +269,8 @@ def test_config1_sgcn_models_golden(kind):
             H.assert_close(P[k].grad, v, rtol=2e-4, what="grad " + k)
 
 
-@pytest.mark.parametrize("B,R,M,E", [(5, 90, 19, 32), (3, 264, 60, 32), (4, 37, 7, 24)])
+@pytest.mark.parametrize("B,R,M,E", [(5, 90, 19, 32), (3, 264, 60, 32), (4, 37, 7, 24), (3, 264, 19, 32), (150, 90, 19, 32),
+                                     (7, 37, 7, 32), (2, 50, 32, 32), (9, 200, 24, 32), (1, 288, 1, 32)])
 def test_cross_attention_vs_torch_mha(B, R, M, E):
     """Fused relu(MHA(q, kv, kv)) kernel vs nn.MultiheadAttention in fp64 (the checker); R=264 exercises row chunking."""
     from igcn_b200 import ops

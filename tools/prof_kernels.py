@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--what", default="sgcn")
     ap.add_argument("--pool", default="20,15,10,8,1")
     ap.add_argument("--S", type=int, default=54)
+    ap.add_argument("--compact", action="store_true")
     a = ap.parse_args()
     import __graft_entry__ as ge
     ge.build()
@@ -64,6 +65,23 @@ def main():
                 else:
                     ab = 2 * N * LH * 4 + N * 12 + E * 8 + (N + 1) * 8 + E * 4 + N * 12
                 res[k] = dict(us=ms * 1e3, alg_MB=ab / 1e6, GBs=ab / ms / 1e6, frac_of_measured_peak=ab / ms / 1e6 / peak)
+    if a.what in ("attn", "all"):
+        torch.manual_seed(0)
+        M = 19
+        mha = torch.nn.MultiheadAttention(32, 2, batch_first=True).to(dev)
+        q = torch.randn(a.B, a.R, 32, device=dev, requires_grad=True)
+        kv = torch.randn(a.B, M, 32, device=dev, requires_grad=True)
+        go = torch.randn(a.B, a.R, 32, device=dev)
+        for it in range(a.iters + 2):
+            flush.zero_()
+            if it == 2:
+                _lib.profile_begin()
+            out = ops.cross_attention(q, kv, mha, relu=True)
+            flush.zero_()
+            out.backward(go)
+        for k, (c, tot, nb) in _lib.profile_end().items():
+            ms = tot / c
+            res[k] = dict(us=ms * 1e3, alg_MB=nb / 1e6, GBs=nb / ms / 1e6, frac_of_measured_peak=nb / ms / 1e6 / peak)
     if a.what in ("go", "all"):
         from igcn_b200.go_net import Gene_ontology_network
         pool = [int(v) for v in a.pool.split(",")]
@@ -81,7 +99,11 @@ def main():
         prof = _lib.profile_end()
         for k, (c, tot, _nb) in prof.items():
             res[k] = dict(us=tot / c * 1e3)
-    print(json.dumps(dict(B=a.B, R=a.R, L=a.L, H=a.H, peak_GBs=peak, kernels=res), indent=1))
+    if a.compact:
+        for k, v in res.items():
+            print("%-44s %9.1f us  %s" % (k, v["us"], ("%.3f of peak" % v["frac_of_measured_peak"]) if "frac_of_measured_peak" in v else ""))
+    else:
+        print(json.dumps(dict(B=a.B, R=a.R, L=a.L, H=a.H, peak_GBs=peak, kernels=res), indent=1))
 
 
 if __name__ == "__main__":
