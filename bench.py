@@ -226,16 +226,56 @@ def run_igcn(args, w):
                roofline=dict(bound="hbm", kernel=top, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=kern[top]["traffic"],
                              peak_source=peak_src, algorithmic_bytes_per_launch=int(ab), us_per_launch=kern[top]["us_per_call"],
                              note="dominant igcn kernel of the step by device time; at this batch size every kernel of the path is "
-                                  "latency bound (<= 12 MB per launch), see roofline_sgcn and profiles/ for the same kernels at config-4 size"),
+                                  "latency bound (<= 26 MB per launch): roofline_sgcn is the SGCN encoder backward inside this step, "
+                                  "roofline_config4 the SGCN kernels at config-4 size, where the path can be bandwidth bound"),
                roofline_sgcn=(dict(kernel=sg, **{q: kern[sg][q] for q in ("us_per_call", "algorithmic_bytes", "achieved_GBs", "frac_of_peak", "traffic")})
                               if sg in kern else None),
                kernels=kern, clocks=clocks, wall_s_timed_region=t_wall)
+    if world == 1 and args.workload == "config2" and not args.no_config4_kernels:
+        out["roofline_config4"] = sgcn_kernels_at_config4(dev, peak, flush)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(w, steps=3, warmup=1)
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(out), flush=True)
     finish(world)
+
+
+def sgcn_kernels_at_config4(dev, peak, flush, iters=5):
+    """The SGCN encoder kernels alone at BASELINE.json configs[3] size (B=4096 graphs x 264 ROIs: 182-363 MB per launch, where the
+    path CAN be bandwidth bound; a config-2 launch moves < 8 MB).  Measured live: CUDA events on the launching stream, L2 flushed
+    before every launch, algorithmic bytes as defined in SURVEY.md section 8(d) with the pre-built i32 CSR."""
+    from igcn_b200 import _lib, ops, synthetic as syn
+    from igcn_b200.data import Batch, SubjectSet
+    w4 = WORKLOADS["config4"]
+    B, R, L, H = w4["B"], w4["R"], w4["L"], w4["H"]
+    sub = syn.make_subjects(256, rois=R, n_snps=w4["S"], seed=7)
+    b = Batch.collate(SubjectSet(sub), np.arange(B) % 256, dev)
+    g = torch.Generator().manual_seed(0)
+    Ws = [(torch.rand(H, 3 if l == 0 else H, generator=g) - 0.5).to(dev).requires_grad_(True) for l in range(L)]
+    bs = [((torch.rand(H, generator=g) - 0.5) * 0.1).to(dev).requires_grad_(True) for l in range(L)]
+    prob = (torch.rand(R, 3, generator=g) - 0.5).to(dev).requires_grad_(True)
+    pb = (torch.rand(6, 1, generator=g) - 0.5).to(dev).requires_grad_(True)
+    x = b.x.clone().requires_grad_(True)
+    res = {}
+    for explain in (False, True):
+        go = None
+        for it in range(iters + 2):
+            flush.zero_()
+            if it == 2:
+                _lib.profile_begin()
+            out, _ = ops.sgcn_encoder(x, b.csr, Ws, bs, prob if explain else None, pb if explain else None, want_pe=explain)
+            if go is None:
+                go = torch.randn_like(out)
+            flush.zero_()
+            out.backward(go)
+        for k, (c, tot, nb) in _lib.profile_end().items():
+            us = tot / c * 1e3
+            res[k] = dict(us_per_launch=us, algorithmic_bytes_per_launch=int(nb), achieved=nb / us / 1e3, peak=peak, unit="GB/s",
+                          frac=nb / us / 1e3 / peak)
+    del b, x
+    torch.cuda.empty_cache()
+    return dict(workload="SGCN encoder kernels alone, B=4096 graphs x 264 ROIs (configs[3] size), L2 flushed before every launch", kernels=res)
 
 
 def finish(world):
@@ -327,6 +367,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="igcn", choices=["igcn", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4-kernels", action="store_true", help="skip the side measurement of the SGCN kernels at config-4 size")
     ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying the CUDA graph")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
