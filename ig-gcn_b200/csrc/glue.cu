@@ -23,17 +23,29 @@ __device__ __forceinline__ float block_sum_256(float v, float* sm /* >= 9 floats
     for (int w = 0; w < 8; ++w) t += sm[w];
     return t;
 }
+// any block size that is a multiple of 32 (<= 1024); fixed order
+__device__ __forceinline__ float block_sum_any(float v, float* sm /* >= 32 floats */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += sm[w];
+    return t;
+}
 
 // ---- BatchNorm1d (training) + ReLU + multiplicative mask ------------------------------------------------------------------
 // z: (N, C, L) contiguous (L = 1 for a 2-D input).  One CTA per channel c; the groups are visited in order so the running
 // statistics receive exactly the updates of `groups` successive module calls.
-__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(1024) bn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, const float* __restrict__ mask,
                                                          int N, int C, int L, int groups, float eps, float momentum, int relu,
                                                          float* __restrict__ running_mean, float* __restrict__ running_var,
                                                          long long* __restrict__ num_batches_tracked,
                                                          float* __restrict__ y, float* __restrict__ stats /* (groups, C, 2) */) {
-    __shared__ float sm[9];
+    __shared__ float sm[33];
+    const int nthr = blockDim.x;
     const int c = blockIdx.x, tid = threadIdx.x;
     const int ng = N / groups;
     const int cnt = ng * L;
@@ -42,20 +54,20 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
     for (int g = 0; g < groups; ++g) {
         const int64_t base = ((int64_t)g * ng * C + c) * L;
         float s = 0.f;
-        for (int e = tid; e < cnt; e += 256) {
+        for (int e = tid; e < cnt; e += nthr) {
             const int n = e / L, l = e - n * L;
             s += z[base + (int64_t)n * C * L + l];
         }
-        const float mean = block_sum_256(s, sm) / (float)cnt;
+        const float mean = block_sum_any(s, sm) / (float)cnt;
         float q = 0.f;
-        for (int e = tid; e < cnt; e += 256) {
+        for (int e = tid; e < cnt; e += nthr) {
             const int n = e / L, l = e - n * L;
             const float d = z[base + (int64_t)n * C * L + l] - mean;
             q += d * d;
         }
-        const float var = block_sum_256(q, sm) / (float)cnt;
+        const float var = block_sum_any(q, sm) / (float)cnt;
         const float rstd = rsqrtf(var + eps);
-        for (int e = tid; e < cnt; e += 256) {
+        for (int e = tid; e < cnt; e += nthr) {
             const int n = e / L, l = e - n * L;
             const int64_t i = base + (int64_t)n * C * L + l;
             float v = (z[i] - mean) * rstd * ga + be;
@@ -77,12 +89,13 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
     }
 }
 
-__global__ void __launch_bounds__(256) bn_act_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(1024) bn_act_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, const float* __restrict__ mask,
                                                          const float* __restrict__ stats, const float* __restrict__ gy,
                                                          int N, int C, int L, int groups, int relu,
                                                          float* __restrict__ dz, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    __shared__ float sm[9];
+    __shared__ float sm[33];
+    const int nthr = blockDim.x;
     const int c = blockIdx.x, tid = threadIdx.x;
     const int ng = N / groups;
     const int cnt = ng * L;
@@ -92,7 +105,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const float* __restrict
         const int64_t base = ((int64_t)g * ng * C + c) * L;
         const float mean = stats[((int64_t)g * C + c) * 2 + 0], rstd = stats[((int64_t)g * C + c) * 2 + 1];
         float s1 = 0.f, s2 = 0.f;
-        for (int e = tid; e < cnt; e += 256) {
+        for (int e = tid; e < cnt; e += nthr) {
             const int n = e / L, l = e - n * L;
             const int64_t i = base + (int64_t)n * C * L + l;
             const float xh = (z[i] - mean) * rstd;
@@ -102,10 +115,10 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const float* __restrict
             s1 += d;
             s2 += d * xh;
         }
-        s1 = block_sum_256(s1, sm);
-        s2 = block_sum_256(s2, sm);
+        s1 = block_sum_any(s1, sm);
+        s2 = block_sum_any(s2, sm);
         const float m1 = s1 / (float)cnt, m2 = s2 / (float)cnt;
-        for (int e = tid; e < cnt; e += 256) {
+        for (int e = tid; e < cnt; e += nthr) {
             const int n = e / L, l = e - n * L;
             const int64_t i = base + (int64_t)n * C * L + l;
             const float xh = (z[i] - mean) * rstd;
@@ -210,6 +223,69 @@ __global__ void __launch_bounds__(256) scale_by_scalar_kernel(const float* __res
     if (blockIdx.x == 0 && threadIdx.x < (int)(n - n4)) out[n4 + threadIdx.x] = a[n4 + threadIdx.x] * f;
 }
 
+
+// ---- skinny linear: z[r][l] = sum_k x[r][k] W[l][k], Kin <= 8, Lout <= 64 (the per-node read-out projections of the GO
+//      network, kernel/go_model.py:117-131: 5 -> dim_snps_atten, 5 -> 1, 2 -> 1 over batch * nodes rows).  cuBLAS runs the weight
+//      gradient of these (Lout x rows)(rows x Kin) shapes on one CTA (35 us at 9 728 rows).
+constexpr int SK_MAXK = 8, SK_MAXL = 64, SK_ROWS = 64;
+
+__global__ void __launch_bounds__(256) skinny_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, int64_t rows, int Kin,
+                                                                int Lout, float* __restrict__ z) {
+    __shared__ float Ws[SK_MAXL * SK_MAXK];
+    for (int i = threadIdx.x; i < Lout * Kin; i += 256) Ws[i] = W[i];
+    __syncthreads();
+    const int64_t total = rows * Lout;
+    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+        const int64_t r = idx / Lout;
+        const int l = (int)(idx - r * Lout);
+        const float* xr = x + r * Kin;
+        float v = 0.f;
+        for (int k = 0; k < Kin; ++k) v = fmaf(xr[k], Ws[l * Kin + k], v);
+        z[idx] = v;
+    }
+}
+
+// dx[r][k] = sum_l dz[r][l] W[l][k] ; partial dW[l][k] of this CTA = sum over its rows of dz[r][l] x[r][k]
+__global__ void __launch_bounds__(256) skinny_linear_bwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                                const float* __restrict__ dz, int64_t rows, int Kin, int Lout,
+                                                                float* __restrict__ dx, float* __restrict__ partials) {
+    __shared__ float Ws[SK_MAXL * SK_MAXK];
+    __shared__ float dzs[SK_ROWS * SK_MAXL];
+    __shared__ float xs[SK_ROWS * SK_MAXK];
+    const int tid = threadIdx.x, LK = Lout * Kin;
+    for (int i = tid; i < LK; i += 256) Ws[i] = W[i];
+    float acc[2] = {0.f, 0.f};                               // dW entries tid and tid + 256 (LK <= 512)
+    for (int64_t r0 = (int64_t)blockIdx.x * SK_ROWS; r0 < rows; r0 += (int64_t)gridDim.x * SK_ROWS) {
+        const int nr = (int)min((int64_t)SK_ROWS, rows - r0);
+        __syncthreads();
+        for (int i = tid; i < nr * Lout; i += 256) dzs[i] = dz[r0 * Lout + i];
+        for (int i = tid; i < nr * Kin; i += 256) xs[i] = x[r0 * Kin + i];
+        __syncthreads();
+        if (dx)
+            for (int i = tid; i < nr * Kin; i += 256) {
+                const int r = i / Kin, k = i - r * Kin;
+                float v = 0.f;
+                for (int l = 0; l < Lout; ++l) v = fmaf(dzs[r * Lout + l], Ws[l * Kin + k], v);
+                dx[r0 * Kin + i] = v;
+            }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = tid + u * 256;
+            if (i < LK) {
+                const int l = i / Kin, k = i - l * Kin;
+                float v = acc[u];
+                for (int r = 0; r < nr; ++r) v = fmaf(dzs[r * Lout + l], xs[r * Kin + k], v);
+                acc[u] = v;
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int i = tid + u * 256;
+        if (i < LK) partials[(int64_t)blockIdx.x * LK + i] = acc[u];
+    }
+}
+
 static int blocks_for(int64_t n, int per_block) {
     int64_t b = (n + per_block - 1) / per_block;
     const int64_t cap = (int64_t)sm_count() * 4;
@@ -229,7 +305,9 @@ extern "C" int igcn_bn_act_fwd(const float* z, const float* gamma, const float* 
     IGCN_REQUIRE(N > 0 && C > 0 && L > 0 && groups > 0 && N % groups == 0, IGCN_ERR_BAD_ARG, "bn_act_fwd: bad sizes (N=%lld C=%lld L=%lld groups=%lld)",
                  (long long)N, (long long)C, (long long)L, (long long)groups);
     IGCN_REQUIRE((N / groups) * L > 1, IGCN_ERR_UNSUPPORTED, "bn_act_fwd: training-mode BatchNorm needs more than one value per channel");
-    bn_act_fwd_kernel<<<(unsigned)C, 256, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, (int)N, (int)C, (int)L, (int)groups, (float)eps,
+    const int64_t cnt = (N / groups) * L;
+    const int nthr = cnt >= 4096 ? 1024 : (cnt >= 1024 ? 512 : 256);
+    bn_act_fwd_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, (int)N, (int)C, (int)L, (int)groups, (float)eps,
                                                                      (float)momentum, (int)relu, running_mean, running_var,
                                                                      num_batches_tracked, y, stats);
     IGCN_CHECK_LAUNCH("bn_act_fwd");
@@ -241,7 +319,9 @@ extern "C" int igcn_bn_act_bwd(const float* z, const float* gamma, const float* 
                                void* stream) {
     IGCN_REQUIRE(z && stats && g_y && dz, IGCN_ERR_BAD_ARG, "bn_act_bwd: null pointer");
     IGCN_REQUIRE(N > 0 && C > 0 && L > 0 && groups > 0 && N % groups == 0, IGCN_ERR_BAD_ARG, "bn_act_bwd: bad sizes");
-    bn_act_bwd_kernel<<<(unsigned)C, 256, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L, (int)groups,
+    const int64_t cnt = (N / groups) * L;
+    const int nthr = cnt >= 4096 ? 1024 : (cnt >= 1024 ? 512 : 256);
+    bn_act_bwd_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L, (int)groups,
                                                                      (int)relu, dz, dgamma, dbeta);
     IGCN_CHECK_LAUNCH("bn_act_bwd");
     return IGCN_OK;
@@ -307,5 +387,48 @@ extern "C" int igcn_scale_by_scalar(const float* a, const float* s, double scale
     IGCN_REQUIRE((((uintptr_t)a | (uintptr_t)out) & 15) == 0, IGCN_ERR_BAD_ARG, "scale_by_scalar: operands must be 16-byte aligned");
     scale_by_scalar_kernel<<<blocks_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(a, s, (float)scale, n, out);
     IGCN_CHECK_LAUNCH("scale_by_scalar");
+    return IGCN_OK;
+}
+
+static int skinny_check(const char* who, int64_t rows, int64_t Kin, int64_t Lout) {
+    IGCN_REQUIRE(rows >= 0 && Kin >= 1 && Lout >= 1, IGCN_ERR_BAD_ARG, "%s: bad size", who);
+    IGCN_REQUIRE(Kin <= SK_MAXK && Lout <= SK_MAXL, IGCN_ERR_UNSUPPORTED, "%s: in_features <= %d and out_features <= %d only (got %lld, %lld)", who,
+                 SK_MAXK, SK_MAXL, (long long)Kin, (long long)Lout);
+    return IGCN_OK;
+}
+
+extern "C" int64_t igcn_skinny_linear_bwd_ctas(int64_t rows) {
+    int64_t n = (rows + SK_ROWS - 1) / SK_ROWS;
+    const int64_t cap = (int64_t)sm_count() * 2;
+    if (n > cap) n = cap;
+    return n < 1 ? 1 : n;
+}
+
+extern "C" int igcn_skinny_linear_fwd(const float* x, const float* W, int64_t rows, int64_t Kin, int64_t Lout, float* z, void* stream) {
+    int rc = skinny_check("skinny_linear_fwd", rows, Kin, Lout);
+    if (rc) return rc;
+    IGCN_REQUIRE(x && W && z, IGCN_ERR_BAD_ARG, "skinny_linear_fwd: null pointer");
+    if (rows == 0) return IGCN_OK;
+    skinny_linear_fwd_kernel<<<blocks_for(rows * Lout, 256 * 4), 256, 0, (cudaStream_t)stream>>>(x, W, rows, (int)Kin, (int)Lout, z);
+    IGCN_CHECK_LAUNCH("skinny_linear_fwd");
+    return IGCN_OK;
+}
+
+extern "C" int igcn_skinny_linear_bwd(const float* x, const float* W, const float* dz, int64_t rows, int64_t Kin, int64_t Lout, float* dx,
+                                      float* partials, int64_t n_cta, float* dW, void* stream) {
+    int rc = skinny_check("skinny_linear_bwd", rows, Kin, Lout);
+    if (rc) return rc;
+    IGCN_REQUIRE(x && W && dz && partials && dW, IGCN_ERR_BAD_ARG, "skinny_linear_bwd: null pointer");
+    IGCN_REQUIRE(n_cta == igcn_skinny_linear_bwd_ctas(rows), IGCN_ERR_BAD_ARG, "skinny_linear_bwd: n_cta must be igcn_skinny_linear_bwd_ctas()");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int LK = (int)(Lout * Kin);
+    if (rows == 0) {
+        cudaMemsetAsync(dW, 0, sizeof(float) * LK, st);
+        return IGCN_OK;
+    }
+    skinny_linear_bwd_kernel<<<(unsigned)n_cta, 256, 0, st>>>(x, W, dz, rows, (int)Kin, (int)Lout, dx, partials);
+    IGCN_CHECK_LAUNCH("skinny_linear_bwd");
+    reduce_partials_kernel<<<(LK + 31) / 32, 256, 0, st>>>(partials, (int)n_cta, LK, dW);
+    IGCN_CHECK_LAUNCH("skinny_linear_reduce");
     return IGCN_OK;
 }

@@ -249,6 +249,14 @@ class Gene_ontology_network(nn.Module):
         y = F.relu(self._bn(bn, z))
         return self._drop(name, y, p) if name else y
 
+    @staticmethod
+    def _lin(mod, x):
+        """Bias-free read-out projection; the skinny shapes (in <= 8, out <= 64) run on their own kernels (glue.cu)."""
+        w = mod.weight
+        if x.is_cuda and mod.bias is None and w.shape[1] <= 8 and w.shape[0] <= 64:
+            return ops.skinny_linear(x, w)
+        return mod(x)
+
     def forward(self, data, T=None, device=None, groups=1):
         """groups=2: `data` holds the plain pass and the explain pass stacked along the batch (train.step_loss)."""
         dev = data.device
@@ -264,15 +272,15 @@ class Gene_ontology_network(nn.Module):
             mask = self._mask("go_enc%d" % j, (x.shape[0], g["n_rows"]), 0.4, dev)
             x = _GoLayerFn.apply(x, self.w_inc[j].weight, self.w_s_loop[j].weight, self.w_att_in[j].weight, self.w_att_s[j].weight,
                                  self.G_B[j].weight, self.G_B[j].bias, mask, g, True, 0, pool[j])
-        atten_out = self._bn_act(self.conc_for_attention[1], self.conc_for_attention[0](x))
-        inp = self.conc(x).squeeze(-1)
+        atten_out = self._bn_act(self.conc_for_attention[1], self._lin(self.conc_for_attention[0], x))
+        inp = self._lin(self.conc, x).squeeze(-1)
         inp_out = self._bn_act(self.B[0], inp, "go_B", 0.5)
         for j in range(n_l):
             g = self._g("dec%d" % j, dev)
             mask = self._mask("go_dec%d" % j, (x.shape[0], g["n_rows"]), 0.4, dev)
             x = _GoLayerFn.apply(x, self.w_out[j].weight, self.w_s_loop_out[j].weight, None, None, self.G_B_D[j].weight,
                                  self.G_B_D[j].bias, mask, g, False, pool[n_l - j - 1], 0)
-        out_D = self._bn_act(self.B_D[0], self.conc_D(x).squeeze(-1), "go_BD", 0.5)
+        out_D = self._bn_act(self.B_D[0], self._lin(self.conc_D, x).squeeze(-1), "go_BD", 0.5)
         x_D = _GoSpmmFn.apply(out_D, self.t_D[0].unsqueeze(0), self._g("ag_t", dev)).squeeze(-1)
         h = self._bn_act(self.latent[1], self.latent[0](inp_out), "go_latent", 0.5)
         latent = self._bn_act(self.latent[5], self.latent[4](h))

@@ -250,6 +250,13 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             return ops.laplacian_quadratic(s, lap, 1.0 / (n * n))
         return (s * (lap @ s)).sum() / (n * n)
 
+    def consist_loss_pair(self, s2, tsne_result=None):
+        """consist_loss(s2[:B], t) + consist_loss(s2[B:], t) for the stacked plain / explain features of forward_pair: one
+        Laplacian product and one dot product for both passes, and no slice in the autograd graph."""
+        n = s2.shape[0] // 2
+        lap = self._laplacian(n, tsne_result, s2)
+        return ops.laplacian_quadratic(s2, lap, 1.0 / (n * n), halves=2)
+
     def OrthogonalConstraint(self, w):
         """||w^T w - I_D||_F^2 / B^2 with row-normalised w (sgcn_img_snp.py:198-205) = (||w w^T||_F^2 - 2B + D)/B^2."""
         wn = w / w.norm(dim=1)[:, None]
@@ -332,13 +339,15 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             bank.end_pass()
         return F.log_softmax(logits, dim=-1), x_hat, out_z, out_lin, linear_outf, our_reg
 
-    def forward_pair(self, data, temperature=None, device=None):
+    def forward_pair(self, data, temperature=None, device=None, stacked=False):
         """Plain pass and explain pass of ONE batch in a single sweep: everything downstream of the two encoder
         launches (GO network, cross attention, fusion heads) runs once on the 2B stacked samples, with BatchNorm
         applied per pass, so the results equal `forward(data)` followed by `forward(data, isExplain=True)` while every
         parameter is used once (no gradient-accumulation kernels) and half as many kernels are launched.
         Returns (plain 6-tuple, explain 6-tuple).  Default configuration only (cross attention, image + SNP fusion)."""
-        if not (self.isCrossAtten and not self.isImageOnly and not self.isSNPsOnly and not self.graph_pool):
+        if not self.supports_pair():
+            if stacked:
+                raise RuntimeError("forward_pair(stacked=True) needs the default configuration (see supports_pair())")
             return self.forward(data, temperature, device), self.forward(data, temperature, device, isExplain=True)
         x, edge_index = data.x, data.edge_index
         snps = data.snps_feat
@@ -378,7 +387,12 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             bank.end_pass()
         logp = F.log_softmax(logits, dim=-1)
         outs = (logp, x_hat, out_z, out_lin, linear_outf, our_reg)
+        if stacked:
+            return outs                # rows [0, B) = plain pass, rows [B, 2B) = explain pass
         return tuple(t[:B] for t in outs), tuple(t[B:] for t in outs)
+
+    def supports_pair(self):
+        return bool(self.isCrossAtten and not self.isImageOnly and not self.isSNPsOnly and not self.graph_pool)
 
     def __repr__(self):
         return self.__class__.__name__

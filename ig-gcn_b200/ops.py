@@ -525,33 +525,43 @@ def mask_loss(prob, p_e, snps_prob, hp, eps=1e-6):
 
 
 class _LaplacianQuadFn(torch.autograd.Function):
-    """scale * <S, Lsym S> for a symmetric (B,B) matrix Lsym: ONE product T = Lsym S serves the value (a dot product) and
-    the gradient (2 * scale * T) -- the Gram formulation needs a B x B x D product each way."""
+    """scale * sum_h <S_h, Lsym S_h> for a symmetric (B,B) matrix Lsym and `halves` row blocks S_h of s (halves*B, D):
+    ONE product T_h = Lsym S_h serves the value (a dot product) and the gradient (2 * scale * T) -- the Gram formulation needs a
+    B x B x D product each way.  All blocks go through one tensor-core product (N = halves * D, segmented epilogue)."""
 
     @staticmethod
-    def forward(ctx, s, lsym, scale: float):
+    def forward(ctx, s, lsym, scale: float, halves: int):
         import ctypes
         _lib.require_cuda(s, lsym)
         sc, lc = s.contiguous().float(), lsym.contiguous().float()
-        M, K = sc.shape
+        MB, K = sc.shape
+        M = MB // halves
+        if M * halves != MB or lc.shape != (M, M) or not 1 <= halves <= 3:
+            raise RuntimeError("laplacian_quadratic: s is (%d, %d), Lsym %s, halves=%d" % (MB, K, tuple(lc.shape), halves))
         t = torch.empty_like(sc)
-        hw, hs, hd = (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0)
         lib = _lib.lib()
         nb = lib.igcn_reduce_blocks(sc.numel())
         part = torch.empty(nb, dtype=torch.float32, device=sc.device)
         out = torch.empty((), dtype=torch.float32, device=sc.device)
         if USE_TC:
-            # T[i][d] = sum_j Lsym[i][j] S^T[d][j] on the tensor cores (3xTF32): A = Lsym (M x M), B = S^T (K x M)
+            # T_h[i][d] = sum_j Lsym[i][j] S_h^T[d][j] on the tensor cores (3xTF32): A = Lsym (M x M), B = [S_0^T ; S_1^T ...] (halves*K x M)
             la = torch.empty((2, M, _pad4(M)), dtype=torch.float32, device=sc.device)
-            st = torch.empty((2, K, _pad4(M)), dtype=torch.float32, device=sc.device)
-            _tc_split([_job(lc, la, M, M, M), _job(sc, st, M, K, K, transpose=True)], sc.device)
-            _tc_gemm(la, st, M, K, M, [t], [K], [K], tag="laplacian_product_tc")
+            st = torch.empty((2, halves * K, _pad4(M)), dtype=torch.float32, device=sc.device)
+            jobs = [_job(lc, la, M, M, M)]
+            for h in range(halves):
+                jobs.append(_job(sc[h * M:], st, M, K, K, row_off=h * K, transpose=True))
+            _tc_split(jobs, sc.device)
+            _tc_gemm(la, st, M, halves * K, M, [t[h * M:] for h in range(halves)], [K] * halves, [K] * halves, tag="laplacian_product_tc")
+        else:
+            hw, hs, hd = (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0)
+            with torch.cuda.device(sc.device):
+                for h in range(halves):
+                    # T[i][d] = sum_j Lsym[i][j] S[j][d]: the "dX = gZ W" tile kernel with gZ = Lsym (M x M) and W = S (M x K)
+                    _lib.call("igcn_cat_linear_bwd", _lib.ptr(sc[h * M:(h + 1) * M]), None, None, ctypes.addressof(hw), ctypes.addressof(hs),
+                              _lib.ptr(sc[h * M:(h + 1) * M]), _lib.ptr(lc), _lib.ptr(lc), M, M, K, 0, _lib.ptr(t[h * M:(h + 1) * M]), None, None,
+                              ctypes.addressof(hd), None, None, _lib.stream(), tag="laplacian_product[B=%d,D=%d]" % (M, K),
+                              nbytes=4 * (2 * M * K + M * M))
         with torch.cuda.device(sc.device):
-            # T[i][d] = sum_j Lsym[i][j] S[j][d]: the "dX = gZ W" tile kernel with gZ = Lsym (M x M) and W = S (M x K)
-            if not USE_TC:
-                _lib.call("igcn_cat_linear_bwd", _lib.ptr(sc), None, None, ctypes.addressof(hw), ctypes.addressof(hs), _lib.ptr(sc), _lib.ptr(lc),
-                          _lib.ptr(lc), M, M, K, 0, _lib.ptr(t), None, None, ctypes.addressof(hd), None, None, _lib.stream(),
-                          tag="laplacian_product[B=%d,D=%d]" % (M, K), nbytes=4 * (2 * M * K + M * M))
             _lib.call("igcn_dot", _lib.ptr(sc), _lib.ptr(t), sc.numel(), float(scale), _lib.ptr(part), nb, _lib.ptr(out), _lib.stream(),
                       tag="dot", nbytes=8 * sc.numel())
         ctx.scale = float(scale)
@@ -565,9 +575,45 @@ class _LaplacianQuadFn(torch.autograd.Function):
         with torch.cuda.device(t.device):
             _lib.call("igcn_scale_by_scalar", _lib.ptr(t), _lib.ptr(g.contiguous().float()), 2.0 * ctx.scale, t.numel(), _lib.ptr(ds),
                       _lib.stream(), tag="scale_by_scalar", nbytes=8 * t.numel())
-        return ds, None, None
+        return ds, None, None, None
 
 
-def laplacian_quadratic(s, lsym, scale=1.0):
-    """scale * tr(s^T Lsym s) for a (B, D) CUDA tensor and a SYMMETRIC (B, B) matrix (treated as a constant)."""
-    return _LaplacianQuadFn.apply(s, lsym, scale)
+def laplacian_quadratic(s, lsym, scale=1.0, halves=1):
+    """scale * sum_h tr(s_h^T Lsym s_h) over the `halves` row blocks s_h (B, D) of a (halves*B, D) CUDA tensor, for a SYMMETRIC
+    (B, B) matrix Lsym (treated as a constant)."""
+    return _LaplacianQuadFn.apply(s, lsym, scale, halves)
+
+
+class _SkinnyLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W):
+        _lib.require_cuda(x, W)
+        xc, Wc = x.contiguous().float(), W.contiguous().float()
+        Lout, Kin = Wc.shape
+        rows = xc.numel() // Kin
+        z = torch.empty(xc.shape[:-1] + (Lout,), dtype=torch.float32, device=xc.device)
+        with torch.cuda.device(xc.device):
+            _lib.call("igcn_skinny_linear_fwd", _lib.ptr(xc), _lib.ptr(Wc), rows, Kin, Lout, _lib.ptr(z), _lib.stream(),
+                      tag="skinny_linear_fwd[K=%d,L=%d]" % (Kin, Lout), nbytes=4 * (rows * (Kin + Lout)))
+        ctx.save_for_backward(xc, Wc)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        xc, Wc = ctx.saved_tensors
+        Lout, Kin = Wc.shape
+        rows = xc.numel() // Kin
+        n_cta = _lib.lib().igcn_skinny_linear_bwd_ctas(rows)
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        part = torch.empty((n_cta, Lout * Kin), dtype=torch.float32, device=xc.device)
+        dW = torch.empty_like(Wc)
+        with torch.cuda.device(xc.device):
+            _lib.call("igcn_skinny_linear_bwd", _lib.ptr(xc), _lib.ptr(Wc), _lib.ptr(gz.contiguous().float()), rows, Kin, Lout, _lib.ptr(dx),
+                      _lib.ptr(part), n_cta, _lib.ptr(dW), _lib.stream(), tag="skinny_linear_bwd[K=%d,L=%d]" % (Kin, Lout),
+                      nbytes=4 * (rows * (2 * Kin + Lout)))
+        return dx, dW
+
+
+def skinny_linear(x, weight):
+    """x @ weight.T for a bias-free Linear with in_features <= 8 and out_features <= 64 applied to the last dim of a CUDA tensor."""
+    return _SkinnyLinearFn.apply(x, weight)

@@ -21,25 +21,36 @@ def step_loss(model, data, lambda_loss=None, isSoftSimilarity=True, temperature=
     lam = DEFAULT_LAMBDA if lambda_loss is None else lambda_loss
     dev = data.x.device
     y = data.y.view(-1)
-    if pair and hasattr(model, "forward_pair"):
-        # both passes in one sweep (identical results, half the launches; see SGCN_GCN_IMGSNP.forward_pair)
-        (out, snps_hat, out_feat, out_lin, _, our_reg), (out_p, snps_hat_p, out_feat_p, out_lin_p, _, our_reg_p) = \
-            model.forward_pair(data, temperature, dev)
-    else:
-        out, snps_hat, out_feat, out_lin, _, our_reg = model(data, temperature, dev)
-        out_p, snps_hat_p, out_feat_p, out_lin_p, _, our_reg_p = model(data, temperature, dev, isExplain=True)
     cs = data.clini_score.view(-1)
-    loss_reg = lam[1] * (F.mse_loss(our_reg.view(-1), cs) + F.mse_loss(our_reg_p.view(-1), cs)) / 2
-    loss_prob = lam[2] * model.loss_probability(data.x, data.edge_index, data.edge_attr, hyper)
     snps = data.snps_feat
-    recon = lam[3] * (((snps_hat - snps) ** 2).sum() + ((snps_hat_p - snps) ** 2).sum()) / 2
-    cluster = 0
-    if isSoftSimilarity:
-        cluster = lam[4] * (model.consist_loss(out_feat, data.tsne_fdim) + model.consist_loss(out_feat_p, data.tsne_fdim)) / 2
+    if pair and isSoftSimilarity and getattr(model, "supports_pair", lambda: False)() and data.x.is_cuda:
+        # both passes in one sweep on 2B stacked samples (identical results, half the launches; SGCN_GCN_IMGSNP.forward_pair);
+        # every loss term of train() is the mean of its plain and explain values, so it is evaluated on the stacked tensors
+        # directly and no slicing enters the autograd graph
+        out2, snps_hat2, out_feat2, _, _, our_reg2 = model.forward_pair(data, temperature, dev, stacked=True)
+        B = data.snps_feat.shape[0]
+        loss_reg = lam[1] * F.mse_loss(our_reg2.view(2, -1), cs.view(1, -1).expand(2, -1))
+        loss_prob = lam[2] * model.loss_probability(data.x, data.edge_index, data.edge_attr, hyper)
+        recon = lam[3] * ((snps_hat2.view(2, B, -1) - snps.view(1, B, -1)) ** 2).sum() / 2
+        cluster = lam[4] * model.consist_loss_pair(out_feat2, data.tsne_fdim) / 2
+        out, out_p, out_feat = out2[:B], out2[B:], out_feat2[:B]
     else:
-        for c in range(num_cluster):
-            m = data.clust_y == c
-            cluster = cluster + lam[4] * (model.consist_loss(out_feat[m]) + model.consist_loss(out_feat_p[m])) / 2
+        if pair and hasattr(model, "forward_pair"):
+            (out, snps_hat, out_feat, out_lin, _, our_reg), (out_p, snps_hat_p, out_feat_p, out_lin_p, _, our_reg_p) = \
+                model.forward_pair(data, temperature, dev)
+        else:
+            out, snps_hat, out_feat, out_lin, _, our_reg = model(data, temperature, dev)
+            out_p, snps_hat_p, out_feat_p, out_lin_p, _, our_reg_p = model(data, temperature, dev, isExplain=True)
+        loss_reg = lam[1] * (F.mse_loss(our_reg.view(-1), cs) + F.mse_loss(our_reg_p.view(-1), cs)) / 2
+        loss_prob = lam[2] * model.loss_probability(data.x, data.edge_index, data.edge_attr, hyper)
+        recon = lam[3] * (((snps_hat - snps) ** 2).sum() + ((snps_hat_p - snps) ** 2).sum()) / 2
+        cluster = 0
+        if isSoftSimilarity:
+            cluster = lam[4] * (model.consist_loss(out_feat, data.tsne_fdim) + model.consist_loss(out_feat_p, data.tsne_fdim)) / 2
+        else:
+            for c in range(num_cluster):
+                m = data.clust_y == c
+                cluster = cluster + lam[4] * (model.consist_loss(out_feat[m]) + model.consist_loss(out_feat_p[m])) / 2
     # the reference evaluates OrthogonalConstraint even when its weight is 0 (train_eval...:538); skipping a
     # zero-weighted term changes neither the loss nor any gradient
     orth = lam[5] * model.OrthogonalConstraint(out_feat) if lam[5] != 0 else 0.0

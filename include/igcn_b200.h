@@ -278,6 +278,17 @@ int igcn_tc_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float*
                  int64_t N, int64_t K, const float* bias, int64_t relu, float* d0, float* d1, float* d2,
                  const int64_t* host_dst_widths, const int64_t* host_dst_strides, float* partials, int64_t S, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Skinny bias-free linear layers of the GO read-outs (kernel/go_model.py:117-131: Linear(5 -> dim_snps_atten), Linear(5 -> 1),
+ * Linear(2 -> 1) applied to every (subject, GO term) row): z (rows, Lout) = x (rows, Kin) W (Lout, Kin)^T with Kin <= 8,
+ * Lout <= 64.  bwd: dx (rows, Kin; may be NULL) and dW (Lout, Kin); partials = n_cta * Lout * Kin floats with
+ * n_cta = igcn_skinny_linear_bwd_ctas(rows); summed in CTA order (deterministic).
+ */
+int igcn_skinny_linear_fwd(const float* x, const float* W, int64_t rows, int64_t Kin, int64_t Lout, float* z, void* stream);
+int64_t igcn_skinny_linear_bwd_ctas(int64_t rows);
+int igcn_skinny_linear_bwd(const float* x, const float* W, const float* dz, int64_t rows, int64_t Kin, int64_t Lout, float* dx,
+                           float* partials, int64_t n_cta, float* dW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

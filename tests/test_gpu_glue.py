@@ -93,3 +93,40 @@ def test_laplacian_quadratic_vs_reference_form(B, D):
     (ref * 3.0).backward()
     H.assert_close(v, ref, what="quadratic form")
     H.assert_close(s1.grad, s2.grad, what="quadratic form gradient")
+
+
+def test_laplacian_quadratic_two_halves():
+    from igcn_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, D = 48, 320
+    s = torch.rand(2 * B, D, generator=g).to(DEV)
+    t = torch.rand(B, 30, generator=g).to(DEV)
+    W = torch.exp(-0.01 * torch.cdist(t, t) ** 2)
+    lap = torch.diag(W.sum(1)) - 0.5 * (W + W.t())
+    s1 = s.clone().requires_grad_(True)
+    v = ops.laplacian_quadratic(s1, lap, 1.0 / (B * B), halves=2)
+    v.backward()
+    s2 = s.double().clone().requires_grad_(True)
+    L = lap.double()
+    ref = (torch.trace(s2[:B].t() @ L @ s2[:B]) + torch.trace(s2[B:].t() @ L @ s2[B:])) / (B * B)
+    ref.backward()
+    H.assert_close(v, ref, what="paired quadratic form")
+    H.assert_close(s1.grad, s2.grad, what="paired quadratic form gradient")
+
+
+@pytest.mark.parametrize("rows_shape,Kin,Lout", [((512, 19), 5, 32), ((512, 19), 5, 1), ((64, 54), 2, 1), ((3, 7), 8, 64), ((1000,), 3, 20)])
+def test_skinny_linear_vs_torch(rows_shape, Kin, Lout):
+    from igcn_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(rows_shape + (Kin,), generator=g).to(DEV)
+    W = torch.randn(Lout, Kin, generator=g).to(DEV)
+    go = torch.randn(rows_shape + (Lout,), generator=g).to(DEV)
+    x1, W1 = x.clone().requires_grad_(True), W.clone().requires_grad_(True)
+    z = ops.skinny_linear(x1, W1)
+    (z * go).sum().backward()
+    x2, W2 = x.double().requires_grad_(True), W.double().requires_grad_(True)
+    zr = x2 @ W2.t()
+    (zr * go.double()).sum().backward()
+    H.assert_close(z, zr, what="skinny z")
+    H.assert_close(x1.grad, x2.grad, what="skinny dx")
+    H.assert_close(W1.grad, W2.grad, what="skinny dW")
