@@ -53,7 +53,7 @@ SIGNATURES = {
     "igcn_tc_gemm_splits": (_I, [_I, _I, _I]),
     "igcn_tc_gemm": (ctypes.c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
     "igcn_go_spmm_fwd": (ctypes.c_int, [_P] * 4 + [_I] * 5 + [_P, _P]),
-    "igcn_go_spmm_bwd": (ctypes.c_int, [_P] * 8 + [_I] * 5 + [_P, _P, _P]),
+    "igcn_go_spmm_bwd": (ctypes.c_int, [_P] * 8 + [_I] * 5 + [_P, _P, _P, _P]),
     "igcn_go_layer_param_count": (_I, [_I, _I, _I]),
     "igcn_go_layer_bwd_ctas": (_I, [_I] * 7),
     "igcn_go_layer_fwd": (ctypes.c_int, [_P] * 13 + [_I] * 9 + [_P, _P, _P]),

@@ -28,38 +28,73 @@ struct GoGraph {
 // ------------------------------------------------------------------------------------------------
 // SpMM with learnable per-nnz values, C value channels sharing one pattern.
 // ------------------------------------------------------------------------------------------------
+// Row lengths of the SNP <-> GO incidence are bimodal: a few entries per row (a SNP sits in ~3 terms, a term owns ~15 SNPs) and ONE
+// row with every SNP (the root term, snps_graph.py:247-248).  Short rows are walked by one thread each (32x the parallelism of a
+// warp per row: at G = 2 000 / S = 10 000 the warp-per-row version spent 770 us in dependent rowptr -> col -> x loads); rows longer
+// than kHeavy entries are queued in shared memory and summed by the whole CTA afterwards, in a fixed order.
+constexpr int kHeavy = 64, kMaxHeavy = 32;
+
 template <int C>
 __global__ void __launch_bounds__(256) go_spmm_fwd_kernel(const float* __restrict__ in, const int32_t* __restrict__ rowptr,
                                                           const int32_t* __restrict__ col, const float* __restrict__ vals,
                                                           int B, int Nin, int Nrow, int nnz, float* __restrict__ out) {
     extern __shared__ float smf[];
     float* xin = smf;  // Nin
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    __shared__ int heavy[kMaxHeavy];
+    __shared__ int n_heavy;
+    __shared__ float red[8 * C];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        if (tid == 0) n_heavy = 0;
         for (int i = tid; i < Nin; i += nt) xin[i] = in[(int64_t)b * Nin + i];
         __syncthreads();
-        // warp per row: rows are short except the root row (all SNPs), which a warp walks in 32-wide strides
-        for (int r = warp; r < Nrow; r += nw) {
+        for (int r = tid; r < Nrow; r += nt) {
+            const int k0 = rowptr[r], k1 = rowptr[r + 1];
+            if (k1 - k0 > kHeavy) {
+                const int slot = atomicAdd(&n_heavy, 1);
+                if (slot < kMaxHeavy) heavy[slot] = r;
+                if (slot < kMaxHeavy) continue;
+            }
             float acc[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) acc[c] = 0.f;
-            for (int k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) {
+            for (int k = k0; k < k1; ++k) {
                 const float xv = xin[col[k]];
 #pragma unroll
                 for (int c = 0; c < C; ++c) acc[c] = fmaf(vals[(int64_t)c * nnz + k], xv, acc[c]);
             }
 #pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] = warp_sum(acc[c]);
-            if (lane == 0) {
-#pragma unroll
-                for (int c = 0; c < C; ++c) out[((int64_t)b * Nrow + r) * C + c] = acc[c];
-            }
+            for (int c = 0; c < C; ++c) out[((int64_t)b * Nrow + r) * C + c] = acc[c];
         }
         __syncthreads();
+        const int nh = min(n_heavy, kMaxHeavy);
+        for (int hidx = 0; hidx < nh; ++hidx) {
+            const int r = heavy[hidx];
+            float acc[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = 0.f;
+            for (int k = rowptr[r] + tid; k < rowptr[r + 1]; k += nt) {
+                const float xv = xin[col[k]];
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[c] = fmaf(vals[(int64_t)c * nnz + k], xv, acc[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float s = warp_sum(acc[c]);
+                if (lane == 0) red[warp * C + c] = s;
+            }
+            __syncthreads();
+            if (tid < C) {
+                float t = 0.f;
+                for (int w = 0; w < (nt >> 5); ++w) t += red[w * C + tid];
+                out[((int64_t)b * Nrow + r) * C + tid] = t;
+            }
+            __syncthreads();
+        }
     }
 }
 
-// d_in[b,s] = sum_{q in col s} sum_c vals[c][cpos q] * g[b, crow q, c]
+// d_in[b,s] = sum_{q in col s} sum_c vals[c][cpos q] * g[b, crow q, c]      (same short / heavy split over the columns)
 template <int C>
 __global__ void __launch_bounds__(256) go_spmm_bwd_in_kernel(const float* __restrict__ g, const int32_t* __restrict__ colptr,
                                                              const int32_t* __restrict__ crow, const int32_t* __restrict__ cpos,
@@ -67,13 +102,23 @@ __global__ void __launch_bounds__(256) go_spmm_bwd_in_kernel(const float* __rest
                                                              float* __restrict__ d_in) {
     extern __shared__ float smf[];
     float* gs = smf;  // Nrow*C
-    const int tid = threadIdx.x, nt = blockDim.x;
+    __shared__ int heavy[kMaxHeavy];
+    __shared__ int n_heavy;
+    __shared__ float red[8];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        if (tid == 0) n_heavy = 0;
         for (int i = tid; i < Nrow * C; i += nt) gs[i] = g[(int64_t)b * Nrow * C + i];
         __syncthreads();
         for (int s = tid; s < Nin; s += nt) {
+            const int q0 = colptr[s], q1 = colptr[s + 1];
+            if (q1 - q0 > kHeavy) {
+                const int slot = atomicAdd(&n_heavy, 1);
+                if (slot < kMaxHeavy) heavy[slot] = s;
+                if (slot < kMaxHeavy) continue;
+            }
             float acc = 0.f;
-            for (int q = colptr[s]; q < colptr[s + 1]; ++q) {
+            for (int q = q0; q < q1; ++q) {
                 const int r = crow[q], k = cpos[q];
 #pragma unroll
                 for (int c = 0; c < C; ++c) acc = fmaf(vals[(int64_t)c * nnz + k], gs[r * C + c], acc);
@@ -81,6 +126,25 @@ __global__ void __launch_bounds__(256) go_spmm_bwd_in_kernel(const float* __rest
             d_in[(int64_t)b * Nin + s] = acc;
         }
         __syncthreads();
+        const int nh = min(n_heavy, kMaxHeavy);
+        for (int hidx = 0; hidx < nh; ++hidx) {
+            const int s = heavy[hidx];
+            float acc = 0.f;
+            for (int q = colptr[s] + tid; q < colptr[s + 1]; q += nt) {
+                const int r = crow[q], k = cpos[q];
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc = fmaf(vals[(int64_t)c * nnz + k], gs[r * C + c], acc);
+            }
+            const float ws = warp_sum(acc);
+            if (lane == 0) red[warp] = ws;
+            __syncthreads();
+            if (tid == 0) {
+                float t = 0.f;
+                for (int w = 0; w < (nt >> 5); ++w) t += red[w];
+                d_in[(int64_t)b * Nin + s] = t;
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -106,6 +170,61 @@ __global__ void __launch_bounds__(256) go_spmm_bwd_vals_kernel(const float* __re
     for (int c = 0; c < C; ++c) {
         const float t = warp_sum(acc[c]);
         if (lane == 0) d_vals[(int64_t)c * nnz + k] = t;
+    }
+}
+
+
+// ---- large-hierarchy path of d_vals: the batch-strided reads above cost one 32-byte sector per value (config 3: 40 K nnz x 256
+//      subjects x 2 operands = 650 MB of sector traffic, 890 us).  With g and in transposed once (batch contiguous) every nnz is a
+//      dot product of two contiguous B-vectors: coalesced, 10x less traffic.  Same lane partition and shuffle order as above, so
+//      the results are bit identical.
+__global__ void __launch_bounds__(256) transpose2_kernel(const float* __restrict__ a, int ra, int ca, float* __restrict__ at,
+                                                         const float* __restrict__ b, int rb, int cb, float* __restrict__ bt) {
+    __shared__ float tile[32][33];
+    const float* src = blockIdx.y ? b : a;
+    float* dst = blockIdx.y ? bt : at;
+    const int R0 = blockIdx.y ? rb : ra, C0 = blockIdx.y ? cb : ca;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tiles_c = (C0 + 31) / 32, tiles = tiles_c * ((R0 + 31) / 32);
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = r0 + ty + 8 * i, c = c0 + tx;
+            tile[ty + 8 * i][tx] = (r < R0 && c < C0) ? src[(int64_t)r * C0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = c0 + ty + 8 * i, r = r0 + tx;
+            if (r < R0 && c < C0) dst[(int64_t)c * R0 + r] = tile[tx][ty + 8 * i];
+        }
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) go_spmm_bwd_vals_t_kernel(const float* __restrict__ gT /* (Nrow*C, B) */,
+                                                                 const float* __restrict__ inT /* (Nin, B) */,
+                                                                 const int32_t* __restrict__ row_of, const int32_t* __restrict__ col, int B,
+                                                                 int nnz, float* __restrict__ d_vals) {
+    const int lane = threadIdx.x & 31;
+    for (int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < nnz; k += gridDim.x * (blockDim.x >> 5)) {
+        const int r = row_of[k], s = col[k];
+        const float* xi = inT + (int64_t)s * B;
+        float acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = 0.f;
+        for (int b = lane; b < B; b += 32) {
+            const float xv = xi[b];
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = fmaf(gT[((int64_t)r * C + c) * B + b], xv, acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float t = warp_sum(acc[c]);
+            if (lane == 0) d_vals[(int64_t)c * nnz + k] = t;
+        }
     }
 }
 
@@ -594,7 +713,7 @@ extern "C" int igcn_go_spmm_fwd(const float* in, const int32_t* rowptr, const in
 extern "C" int igcn_go_spmm_bwd(const float* g_out, const float* in, const int32_t* row_of, const int32_t* col,
                                 const int32_t* colptr, const int32_t* crow, const int32_t* cpos, const float* vals, int64_t B,
                                 int64_t n_in, int64_t n_row, int64_t nnz, int64_t channels, float* d_in, float* d_vals,
-                                void* stream) {
+                                float* workspace, void* stream) {
     IGCN_REQUIRE(B >= 0 && n_in > 0 && n_row > 0 && nnz >= 0, IGCN_ERR_BAD_ARG, "go_spmm_bwd: bad size");
     IGCN_REQUIRE(channels == 1 || channels == 2, IGCN_ERR_UNSUPPORTED, "go_spmm_bwd: channels=%lld (1 or 2 supported)", (long long)channels);
     IGCN_REQUIRE(d_vals && (B == 0 || (g_out && in && colptr)), IGCN_ERR_BAD_ARG, "go_spmm_bwd: null pointer");
@@ -611,13 +730,25 @@ extern "C" int igcn_go_spmm_bwd(const float* g_out, const float* in, const int32
             if ((rc = allow_smem(go_spmm_bwd_in_kernel<1>, smem, "go_spmm_bwd"))) return rc;
             go_spmm_bwd_in_kernel<1><<<grid, 256, smem, st>>>(g_out, colptr, crow, cpos, vals, (int)B, (int)n_in, (int)n_row, (int)nnz, d_in);
         }
-        if (nnz) go_spmm_bwd_vals_kernel<1><<<(int)((nnz + 7) / 8), 256, 0, st>>>(g_out, in, row_of, col, (int)B, (int)n_in, (int)n_row, (int)nnz, d_vals);
+        if (nnz && workspace) {
+            float* gT = workspace;
+            float* inT = workspace + (size_t)n_row * B;
+            transpose2_kernel<<<dim3(sm_count() * 4, 2), 256, 0, st>>>(g_out, (int)B, (int)n_row, gT, in, (int)B, (int)n_in, inT);
+            go_spmm_bwd_vals_t_kernel<1><<<sm_count() * 8, 256, 0, st>>>(gT, inT, row_of, col, (int)B, (int)nnz, d_vals);
+        } else if (nnz)
+            go_spmm_bwd_vals_kernel<1><<<(int)((nnz + 7) / 8), 256, 0, st>>>(g_out, in, row_of, col, (int)B, (int)n_in, (int)n_row, (int)nnz, d_vals);
     } else {
         if (d_in) {
             if ((rc = allow_smem(go_spmm_bwd_in_kernel<2>, smem, "go_spmm_bwd"))) return rc;
             go_spmm_bwd_in_kernel<2><<<grid, 256, smem, st>>>(g_out, colptr, crow, cpos, vals, (int)B, (int)n_in, (int)n_row, (int)nnz, d_in);
         }
-        if (nnz) go_spmm_bwd_vals_kernel<2><<<(int)((nnz + 7) / 8), 256, 0, st>>>(g_out, in, row_of, col, (int)B, (int)n_in, (int)n_row, (int)nnz, d_vals);
+        if (nnz && workspace) {
+            float* gT = workspace;
+            float* inT = workspace + (size_t)n_row * 2 * B;
+            transpose2_kernel<<<dim3(sm_count() * 4, 2), 256, 0, st>>>(g_out, (int)B, (int)n_row * 2, gT, in, (int)B, (int)n_in, inT);
+            go_spmm_bwd_vals_t_kernel<2><<<sm_count() * 8, 256, 0, st>>>(gT, inT, row_of, col, (int)B, (int)nnz, d_vals);
+        } else if (nnz)
+            go_spmm_bwd_vals_kernel<2><<<(int)((nnz + 7) / 8), 256, 0, st>>>(g_out, in, row_of, col, (int)B, (int)n_in, (int)n_row, (int)nnz, d_vals);
     }
     IGCN_CHECK_LAUNCH("go_spmm_bwd");
     return IGCN_OK;

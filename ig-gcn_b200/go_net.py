@@ -65,10 +65,12 @@ class _GoSpmmFn(torch.autograd.Function):
         g_out = g_out.contiguous()
         d_in = torch.empty_like(data) if ctx.need_in else None
         d_vals = torch.empty_like(vals)
+        # large hierarchies: transpose once, then coalesced dot products per nnz (see include/igcn_b200.h)
+        ws = torch.empty((g["n_rows"] * C + g["n_cols"]) * B, dtype=torch.float32, device=data.device) if g["nnz"] >= 4096 and B >= 8 else None
         with torch.cuda.device(data.device):
             _lib.call("igcn_go_spmm_bwd", _lib.ptr(g_out), _lib.ptr(data), _lib.ptr(g["row_of"]), _lib.ptr(g["col"]), _lib.ptr(g["colptr"]),
                                       _lib.ptr(g["crow"]), _lib.ptr(g["cpos"]), _lib.ptr(vals), B, g["n_cols"], g["n_rows"], g["nnz"],
-                                      C, _lib.ptr(d_in), _lib.ptr(d_vals), _lib.stream(),
+                                      C, _lib.ptr(d_in), _lib.ptr(d_vals), _lib.ptr(ws), _lib.stream(),
                       tag="go_spmm_bwd[rows=%d,cols=%d,C=%d]" % (g["n_rows"], g["n_cols"], C),
                       nbytes=4 * (2 * B * g["n_cols"] + B * g["n_rows"] * C + g["nnz"] * (4 + 2 * C)))
         return d_in, d_vals, None

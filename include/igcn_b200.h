@@ -104,14 +104,16 @@ int igcn_sgcn_encoder_bwd(const float* x, const int32_t* rowptr_t, const int32_t
  * (go_model.py:281-282; channels=1, values t_D[0]) with learnable per-nnz values:
  *     out[b,r,c] = sum_{k in row r} vals[c*nnz+k] * in[b, col[k]]
  *   in (B,n_in) f32, vals (channels,nnz) f32, out (B,n_row,channels) f32.
- *   bwd: d_in (B,n_in) or NULL, d_vals (channels,nnz) (summed over the batch in subject order).
+ *   bwd: d_in (B,n_in) or NULL, d_vals (channels,nnz) (summed over the batch in subject order).  workspace: NULL, or
+ *   (n_row*channels + n_in) * B floats -- then g_out and in are transposed once and every d_vals entry is a dot product of
+ *   two contiguous batch vectors (same summation order; the path for large hierarchies, nnz >= a few thousand).
  */
 int igcn_go_spmm_fwd(const float* in, const int32_t* rowptr, const int32_t* col, const float* vals,
                      int64_t B, int64_t n_in, int64_t n_row, int64_t nnz, int64_t channels, float* out, void* stream);
 int igcn_go_spmm_bwd(const float* g_out, const float* in, const int32_t* row_of, const int32_t* col,
                      const int32_t* colptr, const int32_t* crow, const int32_t* cpos, const float* vals,
                      int64_t B, int64_t n_in, int64_t n_row, int64_t nnz, int64_t channels,
-                     float* d_in, float* d_vals, void* stream);
+                     float* d_in, float* d_vals, float* workspace, void* stream);
 
 /* igcn_go_layer_*: one hierarchy layer, fused per subject.
  *   attn=1 (encoder, go_model.py:219-251): x_in = X Wa^T, x_s = X Ws^T, a_e = exp(tanh(u.[x_in_row|x_in_col])),
