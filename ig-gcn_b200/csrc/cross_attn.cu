@@ -422,7 +422,10 @@ using namespace igcn;
 
 extern "C" int64_t igcn_cross_attn_param_count(int64_t E) { return 4 * E * E + 4 * E; }
 extern "C" int64_t igcn_cross_attn_bwd_ctas(int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads) {
-    if (use_rows(R, M, E, heads)) return rows_ctas(rows::bwd_geo((int)R, (int)M, (int)heads), B, 1);
+    if (use_rows(R, M, E, heads)) {
+        const rows::Geo g = rows::bwd_geo((int)R, (int)M, (int)heads);
+        return rows_ctas(g, B, g.smem <= 110 * 1024 ? 2 : 1);
+    }
     return attn_ctas(attn_bwd_smem(attn_rows_per_chunk((int)R, (int)M, (int)E, (int)heads), (int)M, (int)E, (int)heads, (int)(4 * E * E + 4 * E)), B, 512);
 }
 

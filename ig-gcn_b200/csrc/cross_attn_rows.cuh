@@ -28,6 +28,7 @@ struct Geo {
     int nthreads;
     int per_sz;     // floats of per-graph tables
     int mcp;        // P / dS stage row stride (>= M + 1, multiple of 4)
+    int T;          // backward: thread groups that split the rows of a graph in the tile reductions (sized for a full pass)
     size_t smem;
 };
 
@@ -35,6 +36,7 @@ struct Geo {
 static Geo fwd_geo(int R, int M, int H) {
     Geo g;
     g.mcp = 0;
+    g.T = 1;
     g.per_sz = 3 * M * kE + 2 * H * M * kE + ((H * M + 3) & ~3);
     int gpc = 224 / R;
     if (gpc < 1) gpc = 1;
@@ -54,19 +56,35 @@ static Geo bwd_geo(int R, int M, int H) {
     Geo g;
     g.mcp = ((M + 1) + 3) & ~3;
     g.per_sz = bwd_per_sz(M, H, g.mcp);
+    auto threads_of = [&](int n) {
+        const int rows = n * R;
+        int nt = rows >= 288 ? 288 : ((rows + 31) / 32) * 32;
+        return nt < 128 ? 128 : nt;
+    };
+    auto split_of = [&](int n) {
+        const int tiles = n * (g.mcp / 4) * 17, nt = threads_of(n);
+        return tiles <= nt ? (nt / tiles < 3 ? nt / tiles : 3) : 1;
+    };
+    auto smem_of = [&](int n) {
+        const size_t rows = (size_t)n * R;
+        const int tiles = n * (g.mcp / 4) * 17;
+        const int T = split_of(n);
+        return (size_t)4 * (8 * kE * kE + 4 * kE + (size_t)n * g.per_sz + 2 * rows * XS + 2 * rows * g.mcp + (size_t)(T - 1) * tiles * 16) + 16;
+    };
     int gpc = 224 / R;
     if (gpc < 1) gpc = 1;
     if (gpc > 4) gpc = 4;
-    auto smem_of = [&](int n) {
-        const size_t rows = (size_t)n * R;
-        const size_t tiles = (size_t)n * (g.mcp / 4) * 17;
-        return (size_t)4 * (8 * kE * kE + 4 * kE + (size_t)n * g.per_sz + 2 * rows * XS + 2 * rows * g.mcp + 2 * tiles * 16) + 16;
-    };
     while (gpc > 1 && smem_of(gpc) > 216 * 1024) --gpc;
+    // two co-resident CTAs hide each other's barriers and fill a small batch in fewer waves: prefer the largest group that still
+    // leaves room for two CTAs per SM
+    for (int n = gpc; n >= 1; --n)
+        if (smem_of(n) <= 110 * 1024) {
+            gpc = n;
+            break;
+        }
     g.gpc = gpc;
-    int rows = gpc * R;
-    g.nthreads = rows >= 288 ? 288 : ((rows + 31) / 32) * 32;
-    if (g.nthreads < 128) g.nthreads = 128;
+    g.nthreads = threads_of(gpc);
+    g.T = split_of(gpc);
     g.smem = smem_of(gpc);
     return g;
 }
@@ -348,7 +366,7 @@ __global__ void __launch_bounds__(288) attn_rows_bwd_kernel(AttnArgs a, Geo geo)
             // groups and the partial tiles are added in group order; otherwise a thread walks several tiles.
             {
                 const int tiles = ng * tiles_g;
-                const int T = tiles <= nt ? min(3, nt / tiles) : 1;
+                const int T = geo.T;                        // sized for a full pass (a short last pass keeps the same split)
                 auto tile_sum = [&](int tl, int t, float (&acc)[4][4], int& gl2, int& jq, int& cq, bool& isV) {
                     gl2 = tl / tiles_g;
                     const int r = tl - gl2 * tiles_g;

@@ -82,6 +82,26 @@ def main():
         for k, (c, tot, nb) in _lib.profile_end().items():
             ms = tot / c
             res[k] = dict(us=ms * 1e3, alg_MB=nb / 1e6, GBs=nb / ms / 1e6, frac_of_measured_peak=nb / ms / 1e6 / peak)
+    if a.what in ("tc", "all"):
+        # the Laplacian product of consist_loss at the given batch (B x B)(B x D), D = R * L * H, both passes (N = 2D)
+        D = a.R * a.L * a.H
+        g = torch.Generator().manual_seed(0)
+        s2 = torch.rand(2 * a.B, D, generator=g).to(dev).requires_grad_(True)
+        t = torch.rand(a.B, a.R, generator=g).to(dev)
+        W = torch.exp(-0.01 * torch.cdist(t, t) ** 2)
+        lap = torch.diag(W.sum(1)) - 0.5 * (W + W.t())
+        for it in range(a.iters + 2):
+            flush.zero_()
+            if it == 2:
+                _lib.profile_begin()
+            v = ops.laplacian_quadratic(s2, lap, 1.0 / (a.B * a.B), halves=2)
+            v.backward()
+        for k, (c, tot, nb) in _lib.profile_end().items():
+            ms = tot / c
+            res[k] = dict(us=ms * 1e3)
+            if k.startswith("laplacian_product_tc"):
+                fl = 2.0 * a.B * a.B * 2 * D
+                res[k].update(fp32_equiv_TFLOPs=fl / ms / 1e9, tf32_TFLOPs=3 * fl / ms / 1e9)
     if a.what in ("go", "all"):
         from igcn_b200.go_net import Gene_ontology_network
         pool = [int(v) for v in a.pool.split(",")]
@@ -101,7 +121,10 @@ def main():
             res[k] = dict(us=tot / c * 1e3)
     if a.compact:
         for k, v in res.items():
-            print("%-44s %9.1f us  %s" % (k, v["us"], ("%.3f of peak" % v["frac_of_measured_peak"]) if "frac_of_measured_peak" in v else ""))
+            extra = ("%.3f of peak" % v["frac_of_measured_peak"]) if "frac_of_measured_peak" in v else ""
+            if "tf32_TFLOPs" in v:
+                extra = "%.0f TFLOP/s fp32-equivalent, %.0f TF32 TFLOP/s issued" % (v["fp32_equiv_TFLOPs"], v["tf32_TFLOPs"])
+            print("%-44s %9.1f us  %s" % (k, v["us"], extra))
     else:
         print(json.dumps(dict(B=a.B, R=a.R, L=a.L, H=a.H, peak_GBs=peak, kernels=res), indent=1))
 
