@@ -11,7 +11,7 @@ DEV = "cuda:0"
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 64, 64), (5, 3, 37), (512, 64, 2912), (256, 2880, 256), (64, 3183, 512),
-                                   (300, 200, 1000), (130, 129, 33)])
+                                   (300, 200, 1000), (130, 129, 33), (4096, 4900, 96)])
 def test_tc_matmul_vs_fp64(M, N, K):
     from igcn_b200 import ops
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
