@@ -49,6 +49,13 @@ SIGNATURES = {
     "igcn_skinny_linear_fwd": (ctypes.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "igcn_skinny_linear_bwd_ctas": (_I, [_I]),
     "igcn_skinny_linear_bwd": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P]),
+    "igcn_snp_mask_pair_fwd": (ctypes.c_int, [_P, _P, _I, _I, _P, _P]),
+    "igcn_snp_mask_pair_bwd": (ctypes.c_int, [_P, _P, _P, _I, _I, _P, _P]),
+    "igcn_heads_bwd_ctas": (_I, [_I]),
+    "igcn_heads_fwd": (ctypes.c_int, [_P] * 8 + [_I] * 4 + [_P, _P, _P]),
+    "igcn_heads_bwd": (ctypes.c_int, [_P] * 11 + [_I] * 4 + [_P, _P, _P, _I, _P, _P]),
+    "igcn_step_loss_fwd": (ctypes.c_int, [_P, _P, _I, _P, _P, _I, _P, _P] + [ctypes.c_double] * 4 + [_P, _P]),
+    "igcn_step_loss_bwd": (ctypes.c_int, [_P, _P, _I, _P, _P, _I, _P] + [ctypes.c_double] * 4 + [_P, _P, _P, _P, _P]),
     "igcn_tc_split": (ctypes.c_int, [_P, _I, _P]),
     "igcn_tc_gemm_splits": (_I, [_I, _I, _I]),
     "igcn_tc_gemm": (ctypes.c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
@@ -81,6 +88,7 @@ KERNELS_PER_CALL = {
     "igcn_collate_csr": 1, "igcn_csr_from_edge_index": 2, "igcn_sgcn_encoder_fwd": 1, "igcn_sgcn_encoder_bwd": 2,
     "igcn_go_spmm_fwd": 1, "igcn_go_spmm_bwd": 2, "igcn_go_layer_fwd": 1, "igcn_go_layer_bwd": 2, "igcn_adam_step": 1, "igcn_dropout_masks": 2, "igcn_cross_attn_fwd": 1, "igcn_cross_attn_bwd": 2, "igcn_cat_linear_fwd": 2, "igcn_cat_linear_bwd": 2, "igcn_gat_layer_fwd": 1, "igcn_gat_layer_bwd": 2,
     "igcn_bn_act_fwd": 1, "igcn_bn_act_bwd": 1, "igcn_mask_loss_fwd": 2, "igcn_mask_loss_bwd": 1, "igcn_dot": 2, "igcn_scale_by_scalar": 1, "igcn_tc_split": 1, "igcn_tc_gemm": 2, "igcn_skinny_linear_fwd": 1, "igcn_skinny_linear_bwd": 2,
+    "igcn_snp_mask_pair_fwd": 1, "igcn_snp_mask_pair_bwd": 1, "igcn_heads_fwd": 1, "igcn_heads_bwd": 2, "igcn_step_loss_fwd": 1, "igcn_step_loss_bwd": 1,
 }
 launch_count = 0          # number of igcn kernels launched by this process
 _profile = None           # None, or dict name -> list[(start_event, end_event)]

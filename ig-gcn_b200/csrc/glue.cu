@@ -432,3 +432,307 @@ extern "C" int igcn_skinny_linear_bwd(const float* x, const float* W, const floa
     IGCN_CHECK_LAUNCH("skinny_linear_reduce");
     return IGCN_OK;
 }
+
+// =============================================================================================================================
+// Tail of the training step (kernel/train_eval_sgcn_img_snps.py:521-544, kernel/sgcn_img_snp.py:286-305): three more fused pieces.
+// =============================================================================================================================
+namespace igcn {
+
+// ---- SNP mask of the stacked passes: rows [0,B) = snps, rows [B,2B) = snps * sigmoid(snps_prob)  (sgcn_img_snp.py:147-148) ----
+__global__ void __launch_bounds__(256) snp_mask_pair_fwd_kernel(const float* __restrict__ snps, const float* __restrict__ p, int B, int S,
+                                                                float* __restrict__ out) {
+    // grid.y strides the rows, threads walk the columns: no integer division per element
+    const int64_t n = (int64_t)B * S;
+    for (int s = blockIdx.x * 256 + threadIdx.x; s < S; s += gridDim.x * 256) {
+        const float sg = sigmoidf_(p[s]);
+        for (int b = blockIdx.y; b < B; b += gridDim.y) {
+            const float v = snps[(int64_t)b * S + s];
+            out[(int64_t)b * S + s] = v;
+            out[n + (int64_t)b * S + s] = v * sg;
+        }
+    }
+}
+// d p[s] = sig'(p[s]) * sum_b g[B + b][s] * snps[b][s]: 32 columns per CTA, 8 warps take every 8th row, warp partials added in order
+__global__ void __launch_bounds__(256) snp_mask_pair_bwd_kernel(const float* __restrict__ snps, const float* __restrict__ p,
+                                                                const float* __restrict__ g, int B, int S, float* __restrict__ dp) {
+    __shared__ float part[8][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.x * 32 + lane;
+    const float* g2 = g + (int64_t)B * S;
+    float acc = 0.f;
+    if (s < S)
+        for (int b = warp; b < B; b += 8) acc = fmaf(g2[(int64_t)b * S + s], snps[(int64_t)b * S + s], acc);
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && s < S) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += part[w][lane];
+        const float sg = sigmoidf_(p[s]);
+        dp[s] = t * sg * (1.f - sg);
+    }
+}
+
+// ---- output heads: logp = log_softmax(lin2(h1 * m1)), reg = lin2_regr(h2 * m2)  (sgcn_img_snp.py:290-291,300-301) -------------
+constexpr int HEAD_MAXC = 8;
+struct HeadArgs {
+    const float *h1, *m1, *h2, *m2;      // (rows, K); masks may be null
+    const float *W1, *b1, *W2, *b2;      // (C1, K), (C1), (C2, K), (C2)
+    int rows, K, C1, C2;
+};
+
+// warp per row: lane l owns features l and l + 32 (K <= 64), the C <= 8 outputs are warp sums
+__global__ void __launch_bounds__(256) heads_fwd_kernel(HeadArgs a, float* __restrict__ logp, float* __restrict__ reg) {
+    const int K = a.K, C1 = a.C1, C2 = a.C2, lane = threadIdx.x & 31;
+    const int warp_g = blockIdx.x * 8 + (threadIdx.x >> 5), nwarp = gridDim.x * 8;
+    float w1[HEAD_MAXC][2], w2[HEAD_MAXC][2];
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int k = lane + 32 * u;
+            w1[c][u] = (c < C1 && k < K) ? a.W1[c * K + k] : 0.f;
+            w2[c][u] = (c < C2 && k < K) ? a.W2[c * K + k] : 0.f;
+        }
+    for (int r = warp_g; r < a.rows; r += nwarp) {
+        float x1[2], x2[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int k = lane + 32 * u;
+            const int64_t i = (int64_t)r * K + k;
+            x1[u] = k < K ? (a.m1 ? a.h1[i] * a.m1[i] : a.h1[i]) : 0.f;
+            x2[u] = k < K ? (a.m2 ? a.h2[i] * a.m2[i] : a.h2[i]) : 0.f;
+        }
+        float z1[HEAD_MAXC], z2[HEAD_MAXC];
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) {
+            z1[c] = c < C1 ? warp_sum(fmaf(x1[1], w1[c][1], x1[0] * w1[c][0])) + a.b1[c] : 0.f;
+            z2[c] = c < C2 ? warp_sum(fmaf(x2[1], w2[c][1], x2[0] * w2[c][0])) + a.b2[c] : 0.f;
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c)
+            if (c < C1) mx = fmaxf(mx, z1[c]);
+        float den = 0.f;
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c)
+            if (c < C1) den += expf(z1[c] - mx);
+        const float lse = mx + logf(den);
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) {
+            if (c < C1 && lane == c) logp[(int64_t)r * C1 + c] = z1[c] - lse;
+            if (c < C2 && lane == c) reg[(int64_t)r * C2 + c] = z2[c];
+        }
+    }
+}
+
+// dz1 = g_logp - softmax * sum(g_logp) ; dz2 = g_reg ; dh = m * (dz W) ; per-CTA partial of [dW1 | db1 | dW2 | db2].
+// Warp per row; a lane accumulates d W[c][l], d W[c][l + 32] of the rows its warp sees, the 8 warps are added in order.
+__global__ void __launch_bounds__(256) heads_bwd_kernel(HeadArgs a, const float* __restrict__ logp, const float* __restrict__ g_logp,
+                                                        const float* __restrict__ g_reg, float* __restrict__ dh1, float* __restrict__ dh2,
+                                                        float* __restrict__ partials) {
+    __shared__ float red[8][2 * HEAD_MAXC * 64 + 2 * HEAD_MAXC];
+    const int K = a.K, C1 = a.C1, C2 = a.C2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp_g = blockIdx.x * 8 + warp, nwarp = gridDim.x * 8;
+    const int P = C1 * K + C1 + C2 * K + C2;
+    float w1[HEAD_MAXC][2], w2[HEAD_MAXC][2], aw1[HEAD_MAXC][2], aw2[HEAD_MAXC][2], ab1[HEAD_MAXC], ab2[HEAD_MAXC];
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c) {
+        ab1[c] = ab2[c] = 0.f;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int k = lane + 32 * u;
+            w1[c][u] = (c < C1 && k < K) ? a.W1[c * K + k] : 0.f;
+            w2[c][u] = (c < C2 && k < K) ? a.W2[c * K + k] : 0.f;
+            aw1[c][u] = aw2[c][u] = 0.f;
+        }
+    }
+    for (int r = warp_g; r < a.rows; r += nwarp) {
+        float dz1[HEAD_MAXC], dz2[HEAD_MAXC], gs = 0.f;
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) {
+            dz1[c] = (c < C1 && g_logp) ? g_logp[(int64_t)r * C1 + c] : 0.f;
+            dz2[c] = (c < C2 && g_reg) ? g_reg[(int64_t)r * C2 + c] : 0.f;
+            gs += dz1[c];
+        }
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c)
+            if (c < C1) dz1[c] -= expf(logp[(int64_t)r * C1 + c]) * gs;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int k = lane + 32 * u;
+            if (k >= K) continue;
+            const int64_t i = (int64_t)r * K + k;
+            const float m1 = a.m1 ? a.m1[i] : 1.f, m2 = a.m2 ? a.m2[i] : 1.f;
+            const float x1 = a.h1[i] * m1, x2 = a.h2[i] * m2;
+            float v1 = 0.f, v2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < HEAD_MAXC; ++c) {
+                v1 = fmaf(dz1[c], w1[c][u], v1);
+                v2 = fmaf(dz2[c], w2[c][u], v2);
+                aw1[c][u] = fmaf(dz1[c], x1, aw1[c][u]);
+                aw2[c][u] = fmaf(dz2[c], x2, aw2[c][u]);
+            }
+            if (dh1) dh1[i] = v1 * m1;
+            if (dh2) dh2[i] = v2 * m2;
+        }
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) {
+            ab1[c] += dz1[c];
+            ab2[c] += dz2[c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int k = lane + 32 * u;
+            if (c < C1 && k < K) red[warp][c * K + k] = aw1[c][u];
+            if (c < C2 && k < K) red[warp][C1 * K + C1 + c * K + k] = aw2[c][u];
+        }
+        if (lane == 0) {
+            if (c < C1) red[warp][C1 * K + c] = ab1[c];
+            if (c < C2) red[warp][C1 * K + C1 + C2 * K + c] = ab2[c];
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < P; e += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][e];
+        partials[(int64_t)blockIdx.x * P + e] = t;
+    }
+}
+
+// ---- the scalar train() back-propagates (its four data terms): ---------------------------------------------------------------
+// loss = c_reg * mean((reg - target)^2) + c_rec * sum((xhat - snps)^2) + c_prob * loss_prob + c_clu * quad
+// reg (2, n_reg), target (n_reg) broadcast over the two passes; xhat (2, n_rec), snps (n_rec) broadcast.  One CTA, fixed order.
+__global__ void __launch_bounds__(1024) step_loss_fwd_kernel(const float* __restrict__ reg, const float* __restrict__ target, int64_t n_reg,
+                                                             const float* __restrict__ xhat, const float* __restrict__ snps, int64_t n_rec,
+                                                             const float* __restrict__ loss_prob, const float* __restrict__ quad, float c_reg,
+                                                             float c_rec, float c_prob, float c_clu, float* __restrict__ out) {
+    __shared__ float sm[33];
+    float s1 = 0.f, s2 = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {
+        const float* r = reg + pass * n_reg;
+        const float* x = xhat + pass * n_rec;
+        for (int64_t i = threadIdx.x; i < n_reg; i += 1024) {
+            const float d = r[i] - target[i];
+            s1 = fmaf(d, d, s1);
+        }
+        for (int64_t i = threadIdx.x; i < n_rec; i += 1024) {
+            const float d = x[i] - snps[i];
+            s2 = fmaf(d, d, s2);
+        }
+    }
+    s1 = block_sum_any(s1, sm);
+    s2 = block_sum_any(s2, sm);
+    if (threadIdx.x == 0)
+        out[0] = c_reg * s1 / (float)(2 * n_reg) + c_rec * s2 + c_prob * (loss_prob ? loss_prob[0] : 0.f) + c_clu * (quad ? quad[0] : 0.f);
+}
+__global__ void __launch_bounds__(256) step_loss_bwd_kernel(const float* __restrict__ reg, const float* __restrict__ target, int64_t n_reg,
+                                                            const float* __restrict__ xhat, const float* __restrict__ snps, int64_t n_rec,
+                                                            const float* __restrict__ g, float c_reg, float c_rec, float c_prob, float c_clu,
+                                                            float* __restrict__ d_reg, float* __restrict__ d_xhat, float* __restrict__ d_prob,
+                                                            float* __restrict__ d_quad) {
+    const float gv = g[0];
+    const int64_t stride = (int64_t)gridDim.x * 256, t0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const float k1 = gv * c_reg * 2.f / (float)(2 * n_reg), k2 = gv * c_rec * 2.f;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int64_t i = t0; i < n_reg; i += stride) d_reg[pass * n_reg + i] = k1 * (reg[pass * n_reg + i] - target[i]);
+        for (int64_t i = t0; i < n_rec; i += stride) d_xhat[pass * n_rec + i] = k2 * (xhat[pass * n_rec + i] - snps[i]);
+    }
+    if (t0 == 0) {
+        if (d_prob) d_prob[0] = gv * c_prob;
+        if (d_quad) d_quad[0] = gv * c_clu;
+    }
+}
+
+}  // namespace igcn
+
+extern "C" int igcn_snp_mask_pair_fwd(const float* snps, const float* snps_prob, int64_t B, int64_t S, float* out, void* stream) {
+    IGCN_REQUIRE(snps && snps_prob && out && B >= 0 && S > 0, IGCN_ERR_BAD_ARG, "snp_mask_pair_fwd: bad argument");
+    if (B == 0) return IGCN_OK;
+    const unsigned gx = (unsigned)((S + 255) / 256);
+    unsigned gy = (unsigned)(sm_count() * 2 / gx);
+    if (gy < 1) gy = 1;
+    if (gy > (unsigned)B) gy = (unsigned)B;
+    snp_mask_pair_fwd_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(snps, snps_prob, (int)B, (int)S, out);
+    IGCN_CHECK_LAUNCH("snp_mask_pair_fwd");
+    return IGCN_OK;
+}
+extern "C" int igcn_snp_mask_pair_bwd(const float* snps, const float* snps_prob, const float* g_out, int64_t B, int64_t S, float* d_snps_prob,
+                                      void* stream) {
+    IGCN_REQUIRE(snps && snps_prob && g_out && d_snps_prob && B >= 0 && S > 0, IGCN_ERR_BAD_ARG, "snp_mask_pair_bwd: bad argument");
+    snp_mask_pair_bwd_kernel<<<(unsigned)((S + 31) / 32), 256, 0, (cudaStream_t)stream>>>(snps, snps_prob, g_out, (int)B, (int)S, d_snps_prob);
+    IGCN_CHECK_LAUNCH("snp_mask_pair_bwd");
+    return IGCN_OK;
+}
+
+static int heads_fill(HeadArgs& a, const char* who, const float* h1, const float* m1, const float* h2, const float* m2, const float* W1,
+                      const float* b1, const float* W2, const float* b2, int64_t rows, int64_t K, int64_t C1, int64_t C2) {
+    IGCN_REQUIRE(h1 && h2 && W1 && b1 && W2 && b2 && rows >= 0, IGCN_ERR_BAD_ARG, "%s: null pointer", who);
+    IGCN_REQUIRE(K >= 1 && K <= 64 && C1 >= 1 && C1 <= HEAD_MAXC && C2 >= 1 && C2 <= HEAD_MAXC, IGCN_ERR_UNSUPPORTED,
+                 "%s: hidden <= 64 and <= %d outputs per head only (K=%lld, C1=%lld, C2=%lld)", who, HEAD_MAXC, (long long)K, (long long)C1,
+                 (long long)C2);
+    a.h1 = h1; a.m1 = m1; a.h2 = h2; a.m2 = m2; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2;
+    a.rows = (int)rows; a.K = (int)K; a.C1 = (int)C1; a.C2 = (int)C2;
+    return IGCN_OK;
+}
+extern "C" int64_t igcn_heads_bwd_ctas(int64_t rows) {
+    int64_t n = (rows + 31) / 32;              // 8 warps per CTA, ~4 rows per warp
+    if (n > sm_count()) n = sm_count();
+    return n < 1 ? 1 : n;
+}
+extern "C" int igcn_heads_fwd(const float* h1, const float* m1, const float* h2, const float* m2, const float* W1, const float* b1,
+                              const float* W2, const float* b2, int64_t rows, int64_t K, int64_t C1, int64_t C2, float* logp, float* reg,
+                              void* stream) {
+    HeadArgs a;
+    int rc = heads_fill(a, "heads_fwd", h1, m1, h2, m2, W1, b1, W2, b2, rows, K, C1, C2);
+    if (rc) return rc;
+    IGCN_REQUIRE(logp && reg, IGCN_ERR_BAD_ARG, "heads_fwd: null output");
+    if (rows == 0) return IGCN_OK;
+    heads_fwd_kernel<<<(unsigned)igcn_heads_bwd_ctas(rows), 256, 0, (cudaStream_t)stream>>>(a, logp, reg);
+    IGCN_CHECK_LAUNCH("heads_fwd");
+    return IGCN_OK;
+}
+extern "C" int igcn_heads_bwd(const float* h1, const float* m1, const float* h2, const float* m2, const float* W1, const float* b1,
+                              const float* W2, const float* b2, const float* logp, const float* g_logp, const float* g_reg, int64_t rows,
+                              int64_t K, int64_t C1, int64_t C2, float* dh1, float* dh2, float* partials, int64_t n_cta, float* grads,
+                              void* stream) {
+    HeadArgs a;
+    int rc = heads_fill(a, "heads_bwd", h1, m1, h2, m2, W1, b1, W2, b2, rows, K, C1, C2);
+    if (rc) return rc;
+    IGCN_REQUIRE(logp && partials && grads, IGCN_ERR_BAD_ARG, "heads_bwd: null pointer");
+    IGCN_REQUIRE(n_cta == igcn_heads_bwd_ctas(rows), IGCN_ERR_BAD_ARG, "heads_bwd: n_cta must be igcn_heads_bwd_ctas()");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int P = (int)(C1 * K + C1 + C2 * K + C2);
+    if (rows == 0) {
+        cudaMemsetAsync(grads, 0, sizeof(float) * P, st);
+        return IGCN_OK;
+    }
+    heads_bwd_kernel<<<(unsigned)n_cta, 256, 0, st>>>(a, logp, g_logp, g_reg, dh1, dh2, partials);
+    IGCN_CHECK_LAUNCH("heads_bwd");
+    reduce_partials_kernel<<<(P + 31) / 32, 256, 0, st>>>(partials, (int)n_cta, P, grads);
+    IGCN_CHECK_LAUNCH("heads_reduce");
+    return IGCN_OK;
+}
+
+extern "C" int igcn_step_loss_fwd(const float* reg, const float* target, int64_t n_reg, const float* xhat, const float* snps, int64_t n_rec,
+                                  const float* loss_prob, const float* quad, double c_reg, double c_rec, double c_prob, double c_clu,
+                                  float* out, void* stream) {
+    IGCN_REQUIRE(reg && target && xhat && snps && out && n_reg > 0 && n_rec > 0, IGCN_ERR_BAD_ARG, "step_loss_fwd: bad argument");
+    step_loss_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(reg, target, n_reg, xhat, snps, n_rec, loss_prob, quad, (float)c_reg, (float)c_rec,
+                                                              (float)c_prob, (float)c_clu, out);
+    IGCN_CHECK_LAUNCH("step_loss_fwd");
+    return IGCN_OK;
+}
+extern "C" int igcn_step_loss_bwd(const float* reg, const float* target, int64_t n_reg, const float* xhat, const float* snps, int64_t n_rec,
+                                  const float* g_loss, double c_reg, double c_rec, double c_prob, double c_clu, float* d_reg, float* d_xhat,
+                                  float* d_loss_prob, float* d_quad, void* stream) {
+    IGCN_REQUIRE(reg && target && xhat && snps && g_loss && d_reg && d_xhat && n_reg > 0 && n_rec > 0, IGCN_ERR_BAD_ARG, "step_loss_bwd: bad argument");
+    step_loss_bwd_kernel<<<blocks_for(2 * (n_reg > n_rec ? n_reg : n_rec), 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+        reg, target, n_reg, xhat, snps, n_rec, g_loss, (float)c_reg, (float)c_rec, (float)c_prob, (float)c_clu, d_reg, d_xhat, d_loss_prob, d_quad);
+    IGCN_CHECK_LAUNCH("step_loss_bwd");
+    return IGCN_OK;
+}

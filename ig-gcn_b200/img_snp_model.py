@@ -272,6 +272,14 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             return t * self.dropout_masks[name].to(t.device).float()
         return t * self.go_network.mask_bank.get(name, t.shape, p)
 
+    def _mask_of(self, name, t, p):
+        """the multiplicative dropout scale `_mask` would apply (None in eval mode)"""
+        if not self.training:
+            return None
+        if self.dropout_masks is not None:
+            return self.dropout_masks[name].to(t.device).float().expand_as(t)
+        return self.go_network.mask_bank.get(name, t.shape, p)
+
     def forward(self, data, temperature=None, device=None, isExplain=False):
         x, edge_index, edge_weight = data.x, data.edge_index, data.edge_attr
         snps_feat = data.snps_feat
@@ -366,7 +374,7 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         self._pe_cache = ((x.data_ptr(), edge_index.data_ptr(), self.prob._version, self.prob_bias._version), p_e,
                           torch.is_grad_enabled())
         batch_x = torch.cat([h_plain, h_expl], 0)                                   # (2B, R, LH)
-        snps2 = torch.cat([snps, snps * torch.sigmoid(self.snps_prob)], 0)
+        snps2 = ops.snp_mask_pair(snps, self.snps_prob)                             # [snps ; snps * sigmoid(snps_prob)]
         go = self.go_network
         go.dropout_masks = self.dropout_masks
         latent, x_hat, _, atten_out = go(snps2, temperature, device, groups=2)
@@ -376,16 +384,16 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         parts = [out_z, latent]
         out_lin = torch.cat(parts, -1).detach()
         linear_outf = ops.cat_linear(parts, self.lin1.weight, self.lin1.bias, relu=True)
-        logits = self.lin2(self._mask("lin1", linear_outf, 0.5))
         rparts = parts
         if self.isuseProb4Regr:
             img_feat = (x.view(B, self.rois, -1) * self.prob).reshape(B, -1)
             rparts = parts + [torch.cat([img_feat, img_feat], 0)]
-        r = self._mask("lin1_regr", ops.cat_linear(rparts, self.lin1_regr.weight, self.lin1_regr.bias, relu=True), 0.3)
-        our_reg = self.lin2_regr(r)
+        r = ops.cat_linear(rparts, self.lin1_regr.weight, self.lin1_regr.bias, relu=True)
+        # dropout, lin2 + log_softmax and lin2_regr of both heads in one launch (glue.cu)
+        logp, our_reg = ops.output_heads(linear_outf, self._mask_of("lin1", linear_outf, 0.5), r, self._mask_of("lin1_regr", r, 0.3),
+                                         self.lin2, self.lin2_regr)
         if use_bank:
             bank.end_pass()
-        logp = F.log_softmax(logits, dim=-1)
         outs = (logp, x_hat, out_z, out_lin, linear_outf, our_reg)
         if stacked:
             return outs                # rows [0, B) = plain pass, rows [B, 2B) = explain pass

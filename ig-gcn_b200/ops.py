@@ -205,6 +205,7 @@ class _CatLinearFn(torch.autograd.Function):
         if sum(widths) != K:
             raise RuntimeError("cat_linear: source widths %s do not add up to in_features=%d" % (widths, K))
         Wc, bc = W.contiguous().float(), bias.contiguous().float()
+        ctx.set_materialize_grads(False)
         ctx.tc = USE_TC and M > 0
         if ctx.tc:
             # tensor cores: one split launch folds the concatenation, then one 3xTF32 product with bias + ReLU in its epilogue
@@ -241,6 +242,8 @@ class _CatLinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out):
         import ctypes
+        if g_out is None:                      # this head does not reach the loss
+            return None, None, None, None, None, None
         saved = ctx.saved_tensors
         W, out = saved[0], saved[1]
         it = iter(saved[2:])
@@ -617,3 +620,117 @@ class _SkinnyLinearFn(torch.autograd.Function):
 def skinny_linear(x, weight):
     """x @ weight.T for a bias-free Linear with in_features <= 8 and out_features <= 64 applied to the last dim of a CUDA tensor."""
     return _SkinnyLinearFn.apply(x, weight)
+
+
+class _SnpMaskPairFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, snps, snps_prob):
+        _lib.require_cuda(snps, snps_prob)
+        sc, pc = snps.contiguous().float(), snps_prob.contiguous().float().view(-1)
+        B, S = sc.shape
+        out = torch.empty((2 * B, S), dtype=torch.float32, device=sc.device)
+        with torch.cuda.device(sc.device):
+            _lib.call("igcn_snp_mask_pair_fwd", _lib.ptr(sc), _lib.ptr(pc), B, S, _lib.ptr(out), _lib.stream(), tag="snp_mask_pair_fwd",
+                      nbytes=12 * B * S)
+        ctx.save_for_backward(sc, pc)
+        ctx.pshape = snps_prob.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        sc, pc = ctx.saved_tensors
+        B, S = sc.shape
+        dp = torch.empty(S, dtype=torch.float32, device=sc.device)
+        with torch.cuda.device(sc.device):
+            _lib.call("igcn_snp_mask_pair_bwd", _lib.ptr(sc), _lib.ptr(pc), _lib.ptr(g.contiguous().float()), B, S, _lib.ptr(dp), _lib.stream(),
+                      tag="snp_mask_pair_bwd", nbytes=8 * B * S)
+        return None, dp.view(ctx.pshape)
+
+
+def snp_mask_pair(snps, snps_prob):
+    """cat([snps, snps * sigmoid(snps_prob)], 0): the SNP input of the stacked plain / explain passes (snps is data, no gradient)."""
+    return _SnpMaskPairFn.apply(snps, snps_prob)
+
+
+class _HeadsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h1, m1, h2, m2, W1, b1, W2, b2):
+        _lib.require_cuda(h1, h2, W1, b1, W2, b2, m1, m2)
+        c = lambda t: None if t is None else t.contiguous().float()
+        h1, m1, h2, m2, W1, b1, W2, b2 = c(h1), c(m1), c(h2), c(m2), c(W1), c(b1), c(W2), c(b2)
+        rows, K = h1.shape
+        C1, C2 = W1.shape[0], W2.shape[0]
+        logp = torch.empty((rows, C1), dtype=torch.float32, device=h1.device)
+        reg = torch.empty((rows, C2), dtype=torch.float32, device=h1.device)
+        with torch.cuda.device(h1.device):
+            _lib.call("igcn_heads_fwd", _lib.ptr(h1), _lib.ptr(m1), _lib.ptr(h2), _lib.ptr(m2), _lib.ptr(W1), _lib.ptr(b1), _lib.ptr(W2),
+                      _lib.ptr(b2), rows, K, C1, C2, _lib.ptr(logp), _lib.ptr(reg), _lib.stream(), tag="heads_fwd",
+                      nbytes=4 * rows * (2 * K * (1 + (m1 is not None)) + C1 + C2))
+        ctx.save_for_backward(h1, m1, h2, m2, W1, b1, W2, b2, logp)
+        ctx.set_materialize_grads(False)       # an unused head (e.g. the classifier when its loss weight is 0) costs nothing
+        return logp, reg
+
+    @staticmethod
+    def backward(ctx, g_logp, g_reg):
+        h1, m1, h2, m2, W1, b1, W2, b2, logp = ctx.saved_tensors
+        rows, K = h1.shape
+        C1, C2 = W1.shape[0], W2.shape[0]
+        n_cta = _lib.lib().igcn_heads_bwd_ctas(rows)
+        P = C1 * K + C1 + C2 * K + C2
+        if g_logp is None and g_reg is None:
+            return (None,) * 8
+        dh1 = torch.empty_like(h1) if g_logp is not None else None
+        dh2 = torch.empty_like(h2) if g_reg is not None else None
+        part = torch.empty((n_cta, P), dtype=torch.float32, device=h1.device)
+        grads = torch.empty(P, dtype=torch.float32, device=h1.device)
+        c = lambda t: None if t is None else t.contiguous().float()
+        with torch.cuda.device(h1.device):
+            _lib.call("igcn_heads_bwd", _lib.ptr(h1), _lib.ptr(m1), _lib.ptr(h2), _lib.ptr(m2), _lib.ptr(W1), _lib.ptr(b1), _lib.ptr(W2),
+                      _lib.ptr(b2), _lib.ptr(logp), _lib.ptr(c(g_logp)), _lib.ptr(c(g_reg)), rows, K, C1, C2, _lib.ptr(dh1), _lib.ptr(dh2),
+                      _lib.ptr(part), n_cta, _lib.ptr(grads), _lib.stream(), tag="heads_bwd", nbytes=4 * rows * (4 * K + C1 + C2))
+        o1, o2, o3 = C1 * K, C1 * K + C1, C1 * K + C1 + C2 * K
+        return (dh1, None, dh2, None, grads[:o1].view(C1, K) if g_logp is not None else None, grads[o1:o2] if g_logp is not None else None,
+                grads[o2:o3].view(C2, K) if g_reg is not None else None, grads[o3:] if g_reg is not None else None)
+
+
+def output_heads(h1, m1, h2, m2, lin2: torch.nn.Linear, lin2_regr: torch.nn.Linear):
+    """(log_softmax(lin2(h1 * m1)), lin2_regr(h2 * m2)) in one launch (kernel/sgcn_img_snp.py:290-291,300-301); the masks are the
+    dropout scales of F.dropout (None in eval mode)."""
+    return _HeadsFn.apply(h1, m1, h2, m2, lin2.weight, lin2.bias, lin2_regr.weight, lin2_regr.bias)
+
+
+class _StepLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, reg2, target, xhat2, snps, loss_prob, quad, c_reg, c_rec, c_prob, c_clu):
+        _lib.require_cuda(reg2, target, xhat2, snps, loss_prob, quad)
+        c = lambda t: None if t is None else t.contiguous().float()
+        reg2, target, xhat2, snps, loss_prob, quad = c(reg2), c(target), c(xhat2), c(snps), c(loss_prob), c(quad)
+        n_reg, n_rec = target.numel(), snps.numel()
+        if reg2.numel() != 2 * n_reg or xhat2.numel() != 2 * n_rec:
+            raise RuntimeError("step_loss: stacked tensors must hold exactly two passes")
+        out = torch.empty((), dtype=torch.float32, device=reg2.device)
+        with torch.cuda.device(reg2.device):
+            _lib.call("igcn_step_loss_fwd", _lib.ptr(reg2), _lib.ptr(target), n_reg, _lib.ptr(xhat2), _lib.ptr(snps), n_rec, _lib.ptr(loss_prob),
+                      _lib.ptr(quad), c_reg, c_rec, c_prob, c_clu, _lib.ptr(out), _lib.stream(), tag="step_loss_fwd",
+                      nbytes=4 * (3 * n_reg + 3 * n_rec))
+        ctx.coef = (c_reg, c_rec, c_prob, c_clu)
+        ctx.has = (loss_prob is not None, quad is not None)
+        ctx.save_for_backward(reg2, target, xhat2, snps)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        reg2, target, xhat2, snps = ctx.saved_tensors
+        d_reg, d_xhat = torch.empty_like(reg2), torch.empty_like(xhat2)
+        d_lp = torch.empty((), dtype=torch.float32, device=reg2.device) if ctx.has[0] else None
+        d_q = torch.empty((), dtype=torch.float32, device=reg2.device) if ctx.has[1] else None
+        with torch.cuda.device(reg2.device):
+            _lib.call("igcn_step_loss_bwd", _lib.ptr(reg2), _lib.ptr(target), target.numel(), _lib.ptr(xhat2), _lib.ptr(snps), snps.numel(),
+                      _lib.ptr(g.contiguous().float()), *ctx.coef, _lib.ptr(d_reg), _lib.ptr(d_xhat), _lib.ptr(d_lp), _lib.ptr(d_q),
+                      _lib.stream(), tag="step_loss_bwd", nbytes=4 * (5 * target.numel() + 5 * snps.numel()))
+        return d_reg, None, d_xhat, None, d_lp, d_q, None, None, None, None
+
+
+def step_loss_pair(reg2, target, xhat2, snps, loss_prob, quad, c_reg, c_rec, c_prob, c_clu):
+    """c_reg * mse(reg2 vs target, both passes) + c_rec * sum((xhat2 - snps)^2) + c_prob * loss_prob + c_clu * quad, one launch."""
+    return _StepLossFn.apply(reg2, target, xhat2, snps, loss_prob, quad, float(c_reg), float(c_rec), float(c_prob), float(c_clu))

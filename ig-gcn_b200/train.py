@@ -29,10 +29,12 @@ def step_loss(model, data, lambda_loss=None, isSoftSimilarity=True, temperature=
         # directly and no slicing enters the autograd graph
         out2, snps_hat2, out_feat2, _, _, our_reg2 = model.forward_pair(data, temperature, dev, stacked=True)
         B = data.snps_feat.shape[0]
-        loss_reg = lam[1] * F.mse_loss(our_reg2.view(2, -1), cs.view(1, -1).expand(2, -1))
-        loss_prob = lam[2] * model.loss_probability(data.x, data.edge_index, data.edge_attr, hyper)
-        recon = lam[3] * ((snps_hat2.view(2, B, -1) - snps.view(1, B, -1)) ** 2).sum() / 2
-        cluster = lam[4] * model.consist_loss_pair(out_feat2, data.tsne_fdim) / 2
+        from . import ops
+        lp = model.loss_probability(data.x, data.edge_index, data.edge_attr, hyper)
+        quad = model.consist_loss_pair(out_feat2, data.tsne_fdim)
+        # lam1 * (mse + mse_p)/2 + lam2 * loss_prob + lam3 * (recon + recon_p)/2 + lam4 * (cluster + cluster_p)/2 as one launch
+        loss_reg = ops.step_loss_pair(our_reg2, cs, snps_hat2, snps, lp, quad, lam[1], lam[3] / 2, lam[2], lam[4] / 2)
+        loss_prob = recon = cluster = 0.0
         out, out_p, out_feat = out2[:B], out2[B:], out_feat2[:B]
     else:
         if pair and hasattr(model, "forward_pair"):
@@ -54,7 +56,12 @@ def step_loss(model, data, lambda_loss=None, isSoftSimilarity=True, temperature=
     # the reference evaluates OrthogonalConstraint even when its weight is 0 (train_eval...:538); skipping a
     # zero-weighted term changes neither the loss nor any gradient
     orth = lam[5] * model.OrthogonalConstraint(out_feat) if lam[5] != 0 else 0.0
-    loss = loss_reg + loss_prob + recon + cluster + orth
+    loss = None
+    for term in (loss_reg, loss_prob, recon, cluster, orth):
+        if torch.is_tensor(term):                     # python zeros stand for terms that are absent or already folded in
+            loss = term if loss is None else loss + term
+    if loss is None:
+        loss = torch.zeros((), device=dev)
     if lam[0] != 0:
         loss = loss + hyper.lamda_ce * lam[0] * F.nll_loss(out, y) + hyper.lamda_mi * lam[0] * F.nll_loss(out_p, y)
     return loss

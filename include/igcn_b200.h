@@ -291,6 +291,36 @@ int64_t igcn_skinny_linear_bwd_ctas(int64_t rows);
 int igcn_skinny_linear_bwd(const float* x, const float* W, const float* dz, int64_t rows, int64_t Kin, int64_t Lout, float* dx,
                            float* partials, int64_t n_cta, float* dW, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Tail of the training step (kernel/sgcn_img_snp.py:147-148,290-291,300-301; kernel/train_eval_sgcn_img_snps.py:524-544).
+ *
+ * igcn_snp_mask_pair_*: the SNP input of the two stacked passes, out (2B, S): rows [0,B) = snps, rows [B,2B) =
+ *   snps * sigmoid(snps_prob) (cal_probability, :147-148).  bwd: d_snps_prob (S) from the gradient of out.
+ * igcn_heads_*: logp (rows, C1) = log_softmax(lin2(h1 * m1)), reg (rows, C2) = lin2_regr(h2 * m2) with h (rows, K <= 64),
+ *   dropout masks m (may be NULL), W (C, K), b (C), C <= 8.  bwd: g_logp / g_reg may be NULL (zero); dh1, dh2 (rows, K; may be NULL);
+ *   grads = [dW1 | db1 | dW2 | db2]; partials = igcn_heads_bwd_ctas(rows) * len(grads) floats (summed in CTA order).
+ * igcn_step_loss_*: c_reg * mean((reg - target)^2) + c_rec * sum((xhat - snps)^2) + c_prob * loss_prob + c_clu * quad, where
+ *   reg is (2, n_reg) and xhat (2, n_rec) -- the plain and explain passes -- with target (n_reg) / snps (n_rec) shared by both;
+ *   loss_prob / quad are device scalars (may be NULL).  One launch each way; d_loss_prob / d_quad receive the scalar gradients.
+ */
+int igcn_snp_mask_pair_fwd(const float* snps, const float* snps_prob, int64_t B, int64_t S, float* out, void* stream);
+int igcn_snp_mask_pair_bwd(const float* snps, const float* snps_prob, const float* g_out, int64_t B, int64_t S, float* d_snps_prob,
+                           void* stream);
+int64_t igcn_heads_bwd_ctas(int64_t rows);
+int igcn_heads_fwd(const float* h1, const float* m1, const float* h2, const float* m2, const float* W1, const float* b1,
+                   const float* W2, const float* b2, int64_t rows, int64_t K, int64_t C1, int64_t C2, float* logp, float* reg,
+                   void* stream);
+int igcn_heads_bwd(const float* h1, const float* m1, const float* h2, const float* m2, const float* W1, const float* b1,
+                   const float* W2, const float* b2, const float* logp, const float* g_logp, const float* g_reg, int64_t rows,
+                   int64_t K, int64_t C1, int64_t C2, float* dh1, float* dh2, float* partials, int64_t n_cta, float* grads,
+                   void* stream);
+int igcn_step_loss_fwd(const float* reg, const float* target, int64_t n_reg, const float* xhat, const float* snps, int64_t n_rec,
+                       const float* loss_prob, const float* quad, double c_reg, double c_rec, double c_prob, double c_clu,
+                       float* out, void* stream);
+int igcn_step_loss_bwd(const float* reg, const float* target, int64_t n_reg, const float* xhat, const float* snps, int64_t n_rec,
+                       const float* g_loss, double c_reg, double c_rec, double c_prob, double c_clu, float* d_reg, float* d_xhat,
+                       float* d_loss_prob, float* d_quad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

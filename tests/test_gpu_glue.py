@@ -130,3 +130,70 @@ def test_skinny_linear_vs_torch(rows_shape, Kin, Lout):
     H.assert_close(z, zr, what="skinny z")
     H.assert_close(x1.grad, x2.grad, what="skinny dx")
     H.assert_close(W1.grad, W2.grad, what="skinny dW")
+
+
+def test_snp_mask_pair_vs_torch():
+    from igcn_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    snps = (torch.randint(0, 3, (37, 54), generator=g).float() * 0.5).to(DEV)
+    p = torch.randn(1, 54, generator=g).to(DEV)
+    p1 = p.clone().requires_grad_(True)
+    out = ops.snp_mask_pair(snps, p1)
+    w = torch.randn(74, 54, generator=g).to(DEV)
+    (out * w).sum().backward()
+    p2 = p.double().clone().requires_grad_(True)
+    ref = torch.cat([snps.double(), snps.double() * torch.sigmoid(p2)], 0)
+    (ref * w.double()).sum().backward()
+    H.assert_close(out, ref, what="snp_mask_pair")
+    H.assert_close(p1.grad, p2.grad, what="d snps_prob")
+
+
+@pytest.mark.parametrize("rows,with_masks,use_logp", [(512, True, True), (300, False, True), (130, True, False)])
+def test_output_heads_vs_torch(rows, with_masks, use_logp):
+    from igcn_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    lin2, lin2r = torch.nn.Linear(64, 3).to(DEV), torch.nn.Linear(64, 3).to(DEV)
+    h1, h2 = torch.randn(rows, 64, generator=g).to(DEV), torch.randn(rows, 64, generator=g).to(DEV)
+    m1 = ((torch.rand(rows, 64, generator=g) > 0.5).float() * 2).to(DEV) if with_masks else None
+    m2 = ((torch.rand(rows, 64, generator=g) > 0.3).float() / 0.7).to(DEV) if with_masks else None
+    a1, a2 = h1.clone().requires_grad_(True), h2.clone().requires_grad_(True)
+    logp, reg = ops.output_heads(a1, m1, a2, m2, lin2, lin2r)
+    w1, w2 = torch.randn(rows, 3, generator=g).to(DEV), torch.randn(rows, 3, generator=g).to(DEV)
+    ((logp * w1).sum() * (1.0 if use_logp else 0.0) + (reg * w2).sum()).backward() if use_logp else (reg * w2).sum().backward()
+    r2, r2r = torch.nn.Linear(64, 3).to(DEV).double(), torch.nn.Linear(64, 3).to(DEV).double()
+    r2.load_state_dict({k: v.double() for k, v in lin2.state_dict().items()})
+    r2r.load_state_dict({k: v.double() for k, v in lin2r.state_dict().items()})
+    b1, b2 = h1.double().requires_grad_(True), h2.double().requires_grad_(True)
+    x1 = b1 * m1.double() if with_masks else b1
+    x2 = b2 * m2.double() if with_masks else b2
+    lr, rr = F.log_softmax(r2(x1), -1), r2r(x2)
+    ((lr * w1.double()).sum() * (1.0 if use_logp else 0.0) + (rr * w2.double()).sum()).backward()
+    H.assert_close(logp, lr, what="logp")
+    H.assert_close(reg, rr, what="reg")
+    H.assert_close(a2.grad, b2.grad, what="dh2")
+    H.assert_close(lin2r.weight.grad, r2r.weight.grad, what="dW2r")
+    H.assert_close(lin2r.bias.grad, r2r.bias.grad, what="db2r")
+    if use_logp:
+        H.assert_close(a1.grad, b1.grad, what="dh1")
+        H.assert_close(lin2.weight.grad, r2.weight.grad, what="dW2")
+        H.assert_close(lin2.bias.grad, r2.bias.grad, what="db2")
+
+
+def test_step_loss_pair_vs_torch():
+    from igcn_b200 import ops
+    g = torch.Generator().manual_seed(17)
+    B, S = 50, 54
+    reg2, cs = torch.randn(2 * B, 3, generator=g).to(DEV), torch.rand(B * 3, generator=g).to(DEV)
+    xh2, snps = torch.randn(2 * B, S, generator=g).to(DEV), torch.rand(B, S, generator=g).to(DEV)
+    lp, q = torch.rand((), generator=g).to(DEV), torch.rand((), generator=g).to(DEV)
+    a = [t.clone().requires_grad_(True) for t in (reg2, xh2, lp, q)]
+    loss = ops.step_loss_pair(a[0], cs, a[1], snps, a[2], a[3], 1.0, 1.5e-6 / 2, 0.5, 0.05)
+    (loss * 2.0).backward()
+    b = [t.double().clone().requires_grad_(True) for t in (reg2, xh2, lp, q)]
+    csd, sd = cs.double(), snps.double()
+    ref = 1.0 * (F.mse_loss(b[0][:B].reshape(-1), csd) + F.mse_loss(b[0][B:].reshape(-1), csd)) / 2 + 0.5 * b[2] \
+        + 1.5e-6 * (((b[1][:B] - sd) ** 2).sum() + ((b[1][B:] - sd) ** 2).sum()) / 2 + 0.05 * b[3]
+    (ref * 2.0).backward()
+    H.assert_close(loss, ref, what="step loss")
+    for x, y, n in zip(a, b, ("reg", "xhat", "loss_prob", "quad")):
+        H.assert_close(x.grad, y.grad, what="d " + n)
