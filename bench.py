@@ -165,26 +165,52 @@ def run_igcn(args, w):
     launches = launches_per_step * args.steps
     ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
     # ---- e2e: host arrays -> collate (H2D + kernel) -> step -> loss on the host, every step -----------------------------------
-    #      Software pipelined the way a training loop logs its loss: the loss of step i is copied to pinned host memory right after
-    #      step i and read (event wait) while step i+1 is already queued, so the host-side gather of the next batch overlaps the GPU.
-    staging = {}
+    #      The input pipeline of a training loop: two sets of device input buffers (each with its own captured graph of the same
+    #      step), the H2D copies + collation kernel of batch i+1 run on a copy stream while step i computes, and the loss of step i
+    #      is copied to pinned host memory and read while step i+1 is queued.  Every step's inputs start in pinned HOST memory
+    #      inside the timed region and every step's loss ends on the host.
     rng = np.random.default_rng(rank)
     loss_pin = torch.empty(2, dtype=torch.float32, pin_memory=True)
     loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    main_stream = torch.cuda.current_stream(dev)
+    if args.eager:
+        sets = [(None, eager_step)]
+    else:
+        batch_b = Batch.collate(ss, np.arange(B), dev)
+        graphed_b = T.GraphedTrainStep(model, opt, batch_b, LAMBDA, flat, True)
+        sets = [(batch, lambda d: graphed()), (batch_b, lambda d: graphed_b())]
+    copy_stream = torch.cuda.Stream(device=dev)
+    stagings = [{} for _ in sets]
+    ready = [torch.cuda.Event() for _ in sets]       # inputs of set k are on the device
+    done = [torch.cuda.Event() for _ in sets]        # the step that read set k has finished
+    for ev in done:
+        ev.record(main_stream)
+
+    def prefetch(k):
+        copy_stream.wait_event(done[k])              # do not overwrite inputs a running step still reads
+        with torch.cuda.stream(copy_stream):
+            b = Batch.collate(ss, rng.permutation(B), dev, stagings[k], out=sets[k][0])
+            ready[k].record(copy_stream)
+        return b
 
     def e2e_loop(n):
-        val = float("nan")
+        nxt = prefetch(0)
         for i in range(n):
-            loss = step(Batch.collate(ss, rng.permutation(B), dev, staging, out=collate_into))
+            k = i % len(sets)
+            cur = nxt
+            main_stream.wait_event(ready[k])
+            loss = sets[k][1](cur)
+            done[k].record(main_stream)
             loss_pin[i & 1:(i & 1) + 1].copy_(loss.view(1), non_blocking=True)
-            loss_ev[i & 1].record()
+            loss_ev[i & 1].record(main_stream)
+            if i + 1 < n:
+                nxt = prefetch((i + 1) % len(sets))  # overlaps step i
             if i > 0:
                 loss_ev[(i - 1) & 1].synchronize()
-                val = float(loss_pin[(i - 1) & 1])
         loss_ev[(n - 1) & 1].synchronize()
         return float(loss_pin[(n - 1) & 1])
 
-    e2e_loop(3)
+    e2e_loop(4)
     barrier()
     t0 = time.perf_counter()
     loss_host = e2e_loop(args.steps)
@@ -234,8 +260,8 @@ def run_igcn(args, w):
                            launch="eager" if args.eager else "whole step captured in one CUDA graph",
                            batchnorm="per-rank batch statistics", loss_last=float(loss_host)),
                e2e=dict(value=B * world / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
-                        ms_per_step=e2e_ms, path="pinned host arrays -> Batch.collate (H2D + igcn_collate_csr) -> graphed train step -> "
-                                                  "loss to pinned host memory; the loss of step i is read while step i+1 is queued"),
+                        ms_per_step=e2e_ms, path="pinned host arrays -> Batch.collate (H2D + igcn_collate_csr, copy stream, double-buffered inputs) -> "
+                                                  "graphed train step -> loss to pinned host memory, read while the next step is queued"),
                gpu_launches=int(launches),
                roofline=dict(bound="hbm", kernel=top, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=kern[top]["traffic"],
                              peak_source=peak_src, algorithmic_bytes_per_launch=int(ab), us_per_launch=kern[top]["us_per_call"],

@@ -224,10 +224,10 @@ __global__ void __launch_bounds__(256) scale_by_scalar_kernel(const float* __res
 }
 
 
-// ---- skinny linear: z[r][l] = sum_k x[r][k] W[l][k], Kin <= 8, Lout <= 64 (the per-node read-out projections of the GO
+// ---- skinny linear: z[r][l] = sum_k x[r][k] W[l][k], Kin <= 32, Lout <= 64 (the per-node read-out projections of the GO
 //      network, kernel/go_model.py:117-131: 5 -> dim_snps_atten, 5 -> 1, 2 -> 1 over batch * nodes rows).  cuBLAS runs the weight
 //      gradient of these (Lout x rows)(rows x Kin) shapes on one CTA (35 us at 9 728 rows).
-constexpr int SK_MAXK = 8, SK_MAXL = 64, SK_ROWS = 64;
+constexpr int SK_MAXK = 32, SK_MAXL = 64, SK_ROWS = 64, SK_ACC = (SK_MAXK * SK_MAXL + 255) / 256;
 
 __global__ void __launch_bounds__(256) skinny_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, int64_t rows, int Kin,
                                                                 int Lout, float* __restrict__ z) {
@@ -254,7 +254,9 @@ __global__ void __launch_bounds__(256) skinny_linear_bwd_kernel(const float* __r
     __shared__ float xs[SK_ROWS * SK_MAXK];
     const int tid = threadIdx.x, LK = Lout * Kin;
     for (int i = tid; i < LK; i += 256) Ws[i] = W[i];
-    float acc[2] = {0.f, 0.f};                               // dW entries tid and tid + 256 (LK <= 512)
+    float acc[SK_ACC];                                       // dW entries tid, tid + 256, ...
+#pragma unroll
+    for (int u = 0; u < SK_ACC; ++u) acc[u] = 0.f;
     for (int64_t r0 = (int64_t)blockIdx.x * SK_ROWS; r0 < rows; r0 += (int64_t)gridDim.x * SK_ROWS) {
         const int nr = (int)min((int64_t)SK_ROWS, rows - r0);
         __syncthreads();
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(256) skinny_linear_bwd_kernel(const float* __r
                 dx[r0 * Kin + i] = v;
             }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < SK_ACC; ++u) {
             const int i = tid + u * 256;
             if (i < LK) {
                 const int l = i / Kin, k = i - l * Kin;
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(256) skinny_linear_bwd_kernel(const float* __r
         }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < SK_ACC; ++u) {
         const int i = tid + u * 256;
         if (i < LK) partials[(int64_t)blockIdx.x * LK + i] = acc[u];
     }

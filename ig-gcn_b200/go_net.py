@@ -255,7 +255,7 @@ class Gene_ontology_network(nn.Module):
     def _lin(mod, x):
         """Bias-free read-out projection; the skinny shapes (in <= 8, out <= 64) run on their own kernels (glue.cu)."""
         w = mod.weight
-        if x.is_cuda and mod.bias is None and w.shape[1] <= 8 and w.shape[0] <= 64:
+        if x.is_cuda and mod.bias is None and w.shape[1] <= 32 and w.shape[0] <= 64:
             return ops.skinny_linear(x, w)
         return mod(x)
 
@@ -284,8 +284,8 @@ class Gene_ontology_network(nn.Module):
                                  self.G_B_D[j].bias, mask, g, False, pool[n_l - j - 1], 0)
         out_D = self._bn_act(self.B_D[0], self._lin(self.conc_D, x).squeeze(-1), "go_BD", 0.5)
         x_D = _GoSpmmFn.apply(out_D, self.t_D[0].unsqueeze(0), self._g("ag_t", dev)).squeeze(-1)
-        h = self._bn_act(self.latent[1], self.latent[0](inp_out), "go_latent", 0.5)
-        latent = self._bn_act(self.latent[5], self.latent[4](h))
+        h = self._bn_act(self.latent[1], self._lin(self.latent[0], inp_out), "go_latent", 0.5)
+        latent = self._bn_act(self.latent[5], self._lin(self.latent[4], h))
         if own_pass:
             self.mask_bank.end_pass()
         return latent, x_D, [torch.zeros(3, device=dev)], atten_out

@@ -618,7 +618,7 @@ class _SkinnyLinearFn(torch.autograd.Function):
 
 
 def skinny_linear(x, weight):
-    """x @ weight.T for a bias-free Linear with in_features <= 8 and out_features <= 64 applied to the last dim of a CUDA tensor."""
+    """x @ weight.T for a bias-free Linear with in_features <= 32 and out_features <= 64 applied to the last dim of a CUDA tensor."""
     return _SkinnyLinearFn.apply(x, weight)
 
 

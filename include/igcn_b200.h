@@ -282,7 +282,7 @@ int igcn_tc_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float*
 
 /* ------------------------------------------------------------------------------------------
  * Skinny bias-free linear layers of the GO read-outs (kernel/go_model.py:117-131: Linear(5 -> dim_snps_atten), Linear(5 -> 1),
- * Linear(2 -> 1) applied to every (subject, GO term) row): z (rows, Lout) = x (rows, Kin) W (Lout, Kin)^T with Kin <= 8,
+ * Linear(2 -> 1) applied to every (subject, GO term) row, and the two bias-free Linears of `latent`, :138-146): z (rows, Lout) = x (rows, Kin) W (Lout, Kin)^T with Kin <= 32,
  * Lout <= 64.  bwd: dx (rows, Kin; may be NULL) and dW (Lout, Kin); partials = n_cta * Lout * Kin floats with
  * n_cta = igcn_skinny_linear_bwd_ctas(rows); summed in CTA order (deterministic).
  */

@@ -114,7 +114,7 @@ def test_laplacian_quadratic_two_halves():
     H.assert_close(s1.grad, s2.grad, what="paired quadratic form gradient")
 
 
-@pytest.mark.parametrize("rows_shape,Kin,Lout", [((512, 19), 5, 32), ((512, 19), 5, 1), ((64, 54), 2, 1), ((3, 7), 8, 64), ((1000,), 3, 20)])
+@pytest.mark.parametrize("rows_shape,Kin,Lout", [((512, 19), 5, 32), ((512, 19), 5, 1), ((64, 54), 2, 1), ((3, 7), 8, 64), ((1000,), 3, 20), ((512,), 19, 32), ((512,), 32, 32), ((77,), 32, 64)])
 def test_skinny_linear_vs_torch(rows_shape, Kin, Lout):
     from igcn_b200 import ops
     g = torch.Generator().manual_seed(7)
