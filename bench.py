@@ -228,8 +228,15 @@ def run_igcn(args, w):
     h2d = sum(getattr(ss, k)[:1].element_size() * int(np.prod(getattr(ss, k).shape[1:])) * B for k in ss.FIELDS) + \
         E * (4 + 4 + 4) + (B + 1) * 8
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    replicas_identical = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # every rank must hold bit-identical parameters after all the steps above
+        chk = torch.stack([opt.flat_param.double().sum(), opt.flat_param.double().abs().sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        replicas_identical = bool(torch.equal(lo, hi))
     ms, e2e_ms = float(t[0]), float(t[1])
     if rank != 0:
         finish(world)
@@ -258,7 +265,11 @@ def run_igcn(args, w):
                            edges_per_batch=E, step="zero_grad + plain fwd + explain fwd + losses + bwd + grad all-reduce + Adam",
                            lambda_loss=LAMBDA, l2="flushed between timed steps (256 MB write)", parallelism="dp%d" % world,
                            launch="eager" if args.eager else "whole step captured in one CUDA graph",
-                           batchnorm="per-rank batch statistics", loss_last=float(loss_host)),
+                           batchnorm="per-rank batch statistics", loss_last=float(loss_host),
+                           grad_allreduce=("none (1 GPU)" if world == 1 else
+                                           ("fused with Adam in one kernel over NVLink peer memory (igcn_dp_allreduce_adam)"
+                                            if getattr(opt, "_peer", None) is not None else "ncclAllReduce + igcn_adam_step")),
+                           replicas_identical=replicas_identical),
                e2e=dict(value=B * world / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
                         ms_per_step=e2e_ms, path="pinned host arrays -> Batch.collate (H2D + igcn_collate_csr, copy stream, double-buffered inputs) -> "
                                                   "graphed train step -> loss to pinned host memory, read while the next step is queued"),

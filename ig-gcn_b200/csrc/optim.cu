@@ -64,3 +64,121 @@ extern "C" int igcn_adam_step(float* params, const float* grads, float* exp_avg,
     IGCN_CHECK_LAUNCH("adam_step");
     return IGCN_OK;
 }
+
+// =============================================================================================================================
+// Data-parallel step: gradient all-reduce + Adam as ONE kernel over NVLink peer memory.
+//
+// Every rank keeps its flat gradient buffer in symmetric (peer-mapped) memory.  The kernel of rank r
+//   1. signals every peer and waits for every peer, block by block (all gradient buffers are complete and visible),
+//   2. loads each 16-byte gradient chunk from ALL ranks (its own through L2, the others over NVLink / NVSwitch), adds them in rank
+//      order -- so every rank computes bit-identical sums and the replicas never drift -- scales by 1/world and applies the Adam
+//      update to its own parameter replica,
+//   3. signals / waits again so no rank starts overwriting its gradients while a peer still reads them.
+// This replaces ncclAllReduce + a separate optimizer launch (at 1.66 MB per rank the collective is latency bound: two device-side
+// flag exchanges and one pass over the data instead of a ring).  Flags are one 32-bit word per (block, peer) in each rank's signal
+// pad, set with a release CAS 0 -> 1 by the sender and cleared with an acquire CAS 1 -> 0 by the receiver, so they reset themselves
+// and the launch can be replayed inside a CUDA graph.  Waits are bounded: a missing peer traps instead of hanging the GPU.
+// =============================================================================================================================
+namespace igcn {
+
+constexpr int DP_MAX_WORLD = 16;
+struct DpPeers {
+    const float* grad[DP_MAX_WORLD];     // gradient buffer of every rank (peer pointers)
+    uint32_t* signal[DP_MAX_WORLD];      // signal pad of every rank
+};
+
+__device__ __forceinline__ uint32_t cas_release_sys(uint32_t* addr, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t cas_acquire_sys(uint32_t* addr, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+
+// all blocks with the same blockIdx.x on all ranks meet here; slot = which of the kernel's barriers (distinct flag words)
+__device__ __forceinline__ void dp_block_barrier(const DpPeers& peers, int rank, int world, int slot) {
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        const int peer = threadIdx.x;
+        const size_t base = ((size_t)slot * gridDim.x + blockIdx.x) * world;
+        uint32_t* put = peers.signal[peer] + base + rank;          // my flag in the peer's pad
+        uint32_t* get = peers.signal[rank] + base + peer;          // the peer's flag in my pad
+        const long long t0 = clock64();
+        while (cas_release_sys(put, 0u, 1u) != 0u)
+            if (clock64() - t0 > 4000000000LL) { printf("igcn dp_adam: signal to rank %d timed out\n", peer); __trap(); }
+        while (cas_acquire_sys(get, 1u, 0u) != 1u)
+            if (clock64() - t0 > 4000000000LL) { printf("igcn dp_adam: wait for rank %d timed out\n", peer); __trap(); }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(512) dp_allreduce_adam_kernel(DpPeers peers, int rank, int world, float* __restrict__ p,
+                                                                float* __restrict__ m, float* __restrict__ v,
+                                                                const float* __restrict__ step, const float* __restrict__ lr, float beta1,
+                                                                float beta2, float eps, int64_t n) {
+    dp_block_barrier(peers, rank, world, 0);
+    const float t = step[0];
+    const float bias1 = 1.f - powf(beta1, t), bias2 = 1.f - powf(beta2, t);
+    const float step_size = lr[0] / bias1, inv_sqrt_bias2 = rsqrtf(bias2), scale = 1.f / (float)world;
+    const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x;      // n is a multiple of 4 (FlatAdam pads every parameter)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < world; ++r) {                                      // rank order: identical sums on every rank
+            const float4 x = reinterpret_cast<const float4*>(peers.grad[r])[i];
+            g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+        }
+        float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+#define IGCN_ADAM1(C)                                                   \
+    {                                                                   \
+        const float gg = g.C * scale;                                   \
+        mv.C = beta1 * mv.C + (1.f - beta1) * gg;                       \
+        vv.C = beta2 * vv.C + (1.f - beta2) * gg * gg;                  \
+        pv.C -= step_size * mv.C / (sqrtf(vv.C) * inv_sqrt_bias2 + eps); \
+    }
+        IGCN_ADAM1(x) IGCN_ADAM1(y) IGCN_ADAM1(z) IGCN_ADAM1(w)
+#undef IGCN_ADAM1
+        reinterpret_cast<float4*>(p)[i] = pv;
+        reinterpret_cast<float4*>(m)[i] = mv;
+        reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    dp_block_barrier(peers, rank, world, 1);
+}
+
+}  // namespace igcn
+
+extern "C" int64_t igcn_dp_adam_blocks(int64_t n, int64_t world, int64_t signal_pad_bytes) {
+    using namespace igcn;
+    if (world < 1) world = 1;
+    int64_t blocks = (n / 4 + 511) / 512;
+    const int64_t by_pad = signal_pad_bytes / (2 * 4 * world);                 // two barriers x 4 bytes x world flags per block
+    if (blocks > by_pad) blocks = by_pad;
+    if (blocks > sm_count()) blocks = sm_count();                              // all blocks of all ranks must be co-resident
+    return blocks < 1 ? 0 : blocks;
+}
+
+extern "C" int igcn_dp_allreduce_adam(const int64_t* host_grad_ptrs, const int64_t* host_signal_ptrs, int64_t rank, int64_t world,
+                                      int64_t signal_pad_bytes, float* params, float* exp_avg, float* exp_avg_sq, const float* step,
+                                      const float* lr, double beta1, double beta2, double eps, int64_t n, void* stream) {
+    using namespace igcn;
+    IGCN_REQUIRE(host_grad_ptrs && host_signal_ptrs && params && exp_avg && exp_avg_sq && step && lr, IGCN_ERR_BAD_ARG, "dp_allreduce_adam: null pointer");
+    IGCN_REQUIRE(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, IGCN_ERR_BAD_ARG, "dp_allreduce_adam: rank %lld of %lld",
+                 (long long)rank, (long long)world);
+    IGCN_REQUIRE(n > 0 && (n & 3) == 0, IGCN_ERR_BAD_ARG, "dp_allreduce_adam: n must be a positive multiple of 4");
+    const int64_t blocks = igcn_dp_adam_blocks(n, world, signal_pad_bytes);
+    IGCN_REQUIRE(blocks >= 1, IGCN_ERR_UNSUPPORTED, "dp_allreduce_adam: signal pad of %lld bytes is too small for %lld ranks",
+                 (long long)signal_pad_bytes, (long long)world);
+    DpPeers peers;
+    for (int r = 0; r < DP_MAX_WORLD; ++r) {
+        peers.grad[r] = r < world ? reinterpret_cast<const float*>(host_grad_ptrs[r]) : nullptr;
+        peers.signal[r] = r < world ? reinterpret_cast<uint32_t*>(host_signal_ptrs[r]) : nullptr;
+        IGCN_REQUIRE(r >= world || (peers.grad[r] && peers.signal[r] && ((uintptr_t)peers.grad[r] & 15) == 0), IGCN_ERR_BAD_ARG,
+                     "dp_allreduce_adam: bad peer pointer for rank %d", r);
+    }
+    dp_allreduce_adam_kernel<<<(unsigned)blocks, 512, 0, (cudaStream_t)stream>>>(peers, (int)rank, (int)world, params, exp_avg, exp_avg_sq, step, lr,
+                                                                                (float)beta1, (float)beta2, (float)eps, n);
+    IGCN_CHECK_LAUNCH("dp_allreduce_adam");
+    return IGCN_OK;
+}

@@ -131,6 +131,45 @@ class FlatAdam(object):
         self.param_groups = [dict(params=self.params, lr=float(lr), betas=betas, eps=eps)]
         self._lr_seen = float(lr)
         self.group = process_group
+        self._peer = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1 \
+                and os.environ.get("IGCN_DP", "peer") != "nccl":
+            self._enable_peer_allreduce()
+
+    def _enable_peer_allreduce(self):
+        """Move the flat gradient buffer into symmetric (peer-mapped) memory so the gradient all-reduce and the Adam update run
+        as ONE kernel over NVLink (igcn_dp_allreduce_adam).  Falls back to ncclAllReduce + igcn_adam_step when the peer mapping
+        cannot be established (e.g. no P2P access between the ranks' devices)."""
+        import ctypes
+        import sys
+        from . import _lib
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = self.group if self.group is not None else dist.group.WORLD
+            dev = self.flat_param.device
+            buf = symm_mem.empty(self.n, dtype=torch.float32, device=dev)
+            hdl = symm_mem.rendezvous(buf, group)
+            world, rank = int(hdl.world_size), int(hdl.rank)
+            pad = int(hdl.signal_pad_size)
+            if _lib.lib().igcn_dp_adam_blocks(self.n, world, pad) < 1:
+                raise RuntimeError("signal pad of %d bytes too small for %d ranks" % (pad, world))
+            buf.zero_()
+            self.flat_grad = buf
+            self.grad_views = [buf[o:o + p.numel()].view_as(p) for p, o in zip(self.params, self.offsets)]
+            gp = (ctypes.c_int64 * world)(*[int(a) for a in hdl.buffer_ptrs])
+            sp = (ctypes.c_int64 * world)(*[int(a) for a in hdl.signal_pad_ptrs])
+            self._peer = dict(handle=hdl, grad_ptrs=gp, signal_ptrs=sp, world=world, rank=rank, pad=pad)
+            torch.cuda.synchronize(dev)
+        except Exception as e:                                     # noqa: BLE001 -- any failure means "use NCCL"
+            self._peer = None
+            sys.stderr.write("igcn_b200.FlatAdam: peer-memory all-reduce unavailable (%s: %s); using ncclAllReduce\n" % (type(e).__name__, e))
+        # all ranks must take the same path (a rank that fell back would never answer the others' flags)
+        ok = torch.tensor([1 if self._peer is not None else 0], dtype=torch.int32, device=self.flat_param.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0 and self._peer is not None:
+            self._peer = None
+            self.flat_grad = torch.zeros(self.n, dtype=torch.float32, device=self.flat_param.device)
+            self.grad_views = [self.flat_grad[o:o + p.numel()].view_as(p) for p, o in zip(self.params, self.offsets)]
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -151,7 +190,18 @@ class FlatAdam(object):
 
     def step(self):
         from . import _lib
+        import ctypes
         self.gather_grads()
+        if self._peer is not None:
+            # gradient all-reduce (sum in rank order, / world) + Adam in one kernel over peer memory
+            self.step_t += 1.0
+            g, pr = self.param_groups[0], self._peer
+            with torch.cuda.device(self.flat_param.device):
+                _lib.call("igcn_dp_allreduce_adam", ctypes.addressof(pr["grad_ptrs"]), ctypes.addressof(pr["signal_ptrs"]), pr["rank"], pr["world"],
+                          pr["pad"], _lib.ptr(self.flat_param), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(self.step_t),
+                          _lib.ptr(self.lr_t), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), self.n, _lib.stream(),
+                          tag="dp_allreduce_adam", nbytes=4 * self.n * (pr["world"] + 6))
+            return
         scale = 1.0
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1 \
                 and not os.environ.get("IGCN_DIAG_NO_ALLREDUCE"):       # diagnostic switch: isolates the collective's cost

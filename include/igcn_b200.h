@@ -321,6 +321,22 @@ int igcn_step_loss_bwd(const float* reg, const float* target, int64_t n_reg, con
                        const float* g_loss, double c_reg, double c_rec, double c_prob, double c_clu, float* d_reg, float* d_xhat,
                        float* d_loss_prob, float* d_quad, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel step: gradient all-reduce + Adam as ONE kernel over NVLink peer memory (replaces ncclAllReduce on the flat
+ * gradient buffer followed by igcn_adam_step; reference: one optimizer.step() per batch, kernel/train_eval_sgcn_img_snps.py:547,
+ * made data parallel over graphs).
+ *   host_grad_ptrs / host_signal_ptrs: HOST arrays of `world` device pointers -- the flat gradient buffer (n f32, 16-byte aligned)
+ *   and the signal pad (signal_pad_bytes, zero-initialised once) of every rank, all peer-mapped into this process (e.g. from
+ *   torch.distributed._symmetric_memory: buffer_ptrs / signal_pad_ptrs).  Every rank launches the same call on its own stream;
+ *   the kernel exchanges flags with all peers before and after reading their gradients (bounded waits: a missing peer traps),
+ *   sums the `world` gradients in rank order (bit-identical replicas), scales by 1/world and updates params / exp_avg / exp_avg_sq
+ *   exactly as igcn_adam_step does.  n must be a multiple of 4.  igcn_dp_adam_blocks = CTAs used (0: signal pad too small).
+ */
+int64_t igcn_dp_adam_blocks(int64_t n, int64_t world, int64_t signal_pad_bytes);
+int igcn_dp_allreduce_adam(const int64_t* host_grad_ptrs, const int64_t* host_signal_ptrs, int64_t rank, int64_t world,
+                           int64_t signal_pad_bytes, float* params, float* exp_avg, float* exp_avg_sq, const float* step,
+                           const float* lr, double beta1, double beta2, double eps, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
