@@ -197,3 +197,31 @@ def test_step_loss_pair_vs_torch():
     H.assert_close(loss, ref, what="step loss")
     for x, y, n in zip(a, b, ("reg", "xhat", "loss_prob", "quad")):
         H.assert_close(x.grad, y.grad, what="d " + n)
+
+
+def test_dp_allreduce_adam_single_rank_equals_adam_step():
+    """The fused all-reduce + Adam kernel with world = 1 (flags exchanged with itself) must equal igcn_adam_step bit for bit;
+    the multi-rank protocol is exercised by `bench.py --gpus N` (it reports `replicas_identical`)."""
+    import ctypes
+    from igcn_b200 import _lib
+    g = torch.Generator().manual_seed(23)
+    n = 4 * 1031
+    p0 = torch.randn(n, generator=g).to(DEV)
+    grad = torch.randn(n, generator=g).to(DEV)
+    m0, v0 = torch.rand(n, generator=g).to(DEV) * 0.1, torch.rand(n, generator=g).to(DEV) * 0.01
+    step = torch.full((1,), 3.0, device=DEV)
+    lr = torch.full((1,), 1e-3, device=DEV)
+    pad_bytes = 2048
+    pad = torch.zeros(pad_bytes // 4, dtype=torch.int32, device=DEV)
+    pa, ma, va = p0.clone(), m0.clone(), v0.clone()
+    pb, mb, vb = p0.clone(), m0.clone(), v0.clone()
+    gp, sp = (ctypes.c_int64 * 1)(grad.data_ptr()), (ctypes.c_int64 * 1)(pad.data_ptr())
+    for _ in range(3):                                   # replays: the flags must reset themselves
+        _lib.call("igcn_dp_allreduce_adam", ctypes.addressof(gp), ctypes.addressof(sp), 0, 1, pad_bytes, _lib.ptr(pa), _lib.ptr(ma),
+                  _lib.ptr(va), _lib.ptr(step), _lib.ptr(lr), 0.9, 0.999, 1e-8, n, _lib.stream())
+        _lib.call("igcn_adam_step", _lib.ptr(pb), _lib.ptr(grad), _lib.ptr(mb), _lib.ptr(vb), _lib.ptr(step), _lib.ptr(lr), 0.9, 0.999,
+                  1e-8, 1.0, n, _lib.stream())
+        step += 1.0
+    torch.cuda.synchronize()
+    assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)
+    assert int(pad.abs().sum()) == 0
