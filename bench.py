@@ -326,7 +326,39 @@ def sgcn_kernels_at_config4(dev, peak, flush, iters=5):
                           frac=nb / us / 1e3 / peak)
     del b, x
     torch.cuda.empty_cache()
-    return dict(workload="SGCN encoder kernels alone, B=4096 graphs x 264 ROIs (configs[3] size), L2 flushed before every launch", kernels=res)
+    # the dense contraction of the path at the same size: the Laplacian product of consist_loss for both passes,
+    # (B x B)(B x 2D) with D = R*L*H, on the tcgen05 kernel (3 TF32 MMAs per product, fp32-accurate)
+    tensor = None
+    try:
+        D = R * L * H
+        s2 = torch.rand(2 * B, D, generator=g).to(dev)
+        tt = torch.rand(B, R, generator=g).to(dev)
+        Wm = torch.exp(-0.01 * torch.cdist(tt, tt) ** 2)
+        lap = torch.diag(Wm.sum(1)) - 0.5 * (Wm + Wm.t())
+        for it in range(iters + 2):
+            flush.zero_()
+            if it == 2:
+                _lib.profile_begin()
+            ops.laplacian_quadratic(s2, lap, 1.0 / (B * B), halves=2)
+        for k, (c, tot, nb) in _lib.profile_end().items():
+            if k.startswith("laplacian_product_tc"):
+                us = tot / c * 1e3
+                flops = 2.0 * B * B * 2 * D
+                pk = None
+                try:
+                    pk = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2.0
+                except Exception:
+                    pass
+                issued = 3.0 * flops / us / 1e6
+                tensor = dict(bound="tensor", kernel=k, us_per_launch=us, achieved=issued, unit="TFLOP/s (TF32 issued; 3 MMAs per fp32-accurate product)",
+                              fp32_equivalent_tflops=flops / us / 1e6, peak=pk, frac=(issued / pk if pk else None),
+                              peak_source="MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate)" if pk else None)
+        del s2, lap, Wm
+        torch.cuda.empty_cache()
+    except Exception as e:                                           # noqa: BLE001 -- the side measurement must not break the bench line
+        tensor = dict(error="%s: %s" % (type(e).__name__, e))
+    return dict(workload="kernels alone at configs[3] size (B=4096 graphs x 264 ROIs), L2 flushed before every launch", kernels=res,
+                tensor=tensor)
 
 
 def run_config3(args):

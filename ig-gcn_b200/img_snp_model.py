@@ -16,6 +16,7 @@ What changed inside:
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -65,6 +66,10 @@ class GCNConv(nn.Module):
             csr = Batch.from_device_tensors(x.detach(), edge_index, w, x.shape[0]).csr      # one graph of N nodes
         out, _ = ops.sgcn_encoder(x, csr, [self.lin.weight], [self.bias], relu=False)
         return out.view(x.shape[0], self.out_channels)
+
+
+# IGCN_ONE_STREAM=1 keeps the whole step on one stream (A/B hook)
+_TWO_STREAMS = os.environ.get("IGCN_ONE_STREAM", "") == ""
 
 
 def get_csr(data):
@@ -369,15 +374,30 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         use_bank = self.training and self.dropout_masks is None
         if use_bank:
             bank.begin_pass(("pair", B), x.device)
+        # The GO network depends only on the SNPs, the SGCN encoders only on the brain graphs: they run on two streams (fork /
+        # join; inside a captured CUDA graph this becomes two parallel branches).  autograd replays every node on the stream of its
+        # forward, so the GO backward also overlaps the attention / encoder backward.
+        main = torch.cuda.current_stream(x.device)
+        side = self._go_stream(x.device) if _TWO_STREAMS else None
+        snps2 = ops.snp_mask_pair(snps, self.snps_prob)                             # [snps ; snps * sigmoid(snps_prob)]
+        go = self.go_network
+        go.dropout_masks = self.dropout_masks
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                latent, x_hat, _, atten_out = go(snps2, temperature, device, groups=2)
+            snps2.record_stream(side)
         h_plain, _ = ops.sgcn_encoder(x, csr, Ws, bs)
         h_expl, p_e = ops.sgcn_encoder(x, csr, Ws, bs, self.prob, self.prob_bias, want_pe=True)
         self._pe_cache = ((x.data_ptr(), edge_index.data_ptr(), self.prob._version, self.prob_bias._version), p_e,
                           torch.is_grad_enabled())
         batch_x = torch.cat([h_plain, h_expl], 0)                                   # (2B, R, LH)
-        snps2 = ops.snp_mask_pair(snps, self.snps_prob)                             # [snps ; snps * sigmoid(snps_prob)]
-        go = self.go_network
-        go.dropout_masks = self.dropout_masks
-        latent, x_hat, _, atten_out = go(snps2, temperature, device, groups=2)
+        if side is not None:
+            main.wait_stream(side)
+            for t in (latent, x_hat, atten_out):
+                t.record_stream(main)
+        else:
+            latent, x_hat, _, atten_out = go(snps2, temperature, device, groups=2)
         img_out = batch_x.view(2 * B, -1)
         out_cross = ops.cross_attention(batch_x, atten_out, self.multihead_attn, relu=True).reshape(2 * B, -1)
         out_z = (img_out + out_cross) / 2
@@ -398,6 +418,13 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         if stacked:
             return outs                # rows [0, B) = plain pass, rows [B, 2B) = explain pass
         return tuple(t[:B] for t in outs), tuple(t[B:] for t in outs)
+
+    def _go_stream(self, device):
+        st = getattr(self, "_side_stream", None)
+        if st is None or st.device != device:
+            st = torch.cuda.Stream(device=device)
+            self._side_stream = st
+        return st
 
     def supports_pair(self):
         return bool(self.isCrossAtten and not self.isImageOnly and not self.isSNPsOnly and not self.graph_pool)
