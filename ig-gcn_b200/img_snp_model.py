@@ -70,6 +70,10 @@ class GCNConv(nn.Module):
 
 # IGCN_ONE_STREAM=1 keeps the whole step on one stream (A/B hook)
 _TWO_STREAMS = os.environ.get("IGCN_ONE_STREAM", "") == ""
+if _TWO_STREAMS and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+    # parameters shared by nodes on different streams make autograd warn about the AccumulateGrad stream; the extra event wait it
+    # mentions is intended here
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
 
 
 def get_csr(data):
@@ -387,10 +391,19 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             with torch.cuda.stream(side):
                 latent, x_hat, _, atten_out = go(snps2, temperature, device, groups=2)
             snps2.record_stream(side)
-        h_plain, _ = ops.sgcn_encoder(x, csr, Ws, bs)
+        side2 = self._go_stream(x.device, 1) if _TWO_STREAMS and os.environ.get("IGCN_ENC_STREAM", "1") == "1" else None
+        if side2 is not None:                                                       # the plain pass on a third stream
+            side2.wait_stream(main)
+            with torch.cuda.stream(side2):
+                h_plain, _ = ops.sgcn_encoder(x, csr, Ws, bs)
+        else:
+            h_plain, _ = ops.sgcn_encoder(x, csr, Ws, bs)
         h_expl, p_e = ops.sgcn_encoder(x, csr, Ws, bs, self.prob, self.prob_bias, want_pe=True)
         self._pe_cache = ((x.data_ptr(), edge_index.data_ptr(), self.prob._version, self.prob_bias._version), p_e,
                           torch.is_grad_enabled())
+        if side2 is not None:
+            main.wait_stream(side2)
+            h_plain.record_stream(main)
         batch_x = torch.cat([h_plain, h_expl], 0)                                   # (2B, R, LH)
         if side is not None:
             main.wait_stream(side)
@@ -419,12 +432,12 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             return outs                # rows [0, B) = plain pass, rows [B, 2B) = explain pass
         return tuple(t[:B] for t in outs), tuple(t[B:] for t in outs)
 
-    def _go_stream(self, device):
-        st = getattr(self, "_side_stream", None)
-        if st is None or st.device != device:
-            st = torch.cuda.Stream(device=device)
-            self._side_stream = st
-        return st
+    def _go_stream(self, device, which=0):
+        sts = getattr(self, "_side_streams", None)
+        if sts is None or sts[0].device != device:
+            sts = [torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)]
+            self._side_streams = sts
+        return sts[which]
 
     def supports_pair(self):
         return bool(self.isCrossAtten and not self.isImageOnly and not self.isSNPsOnly and not self.graph_pool)
