@@ -460,7 +460,7 @@ def cpu_baseline(w, steps, warmup, threads=None):
                                        with_orth=True)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(warmup):
         one()
