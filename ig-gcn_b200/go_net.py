@@ -211,6 +211,7 @@ class Gene_ontology_network(nn.Module):
         self._groups = 1
         self.dropout_masks = None     # test hook: dict name -> multiplicative scale tensor (oracle.GO_MASK_NAMES)
         self.mask_bank = MaskBank()   # all masks of a pass from one kernel launch (shared with the enclosing model)
+        self.atten_ready = None       # optional torch.cuda.Event recorded as soon as atten_out is enqueued
 
     # graph index tensors follow the module's device lazily (they are not parameters / state_dict entries)
     def _g(self, name, dev):
@@ -275,6 +276,8 @@ class Gene_ontology_network(nn.Module):
             x = _GoLayerFn.apply(x, self.w_inc[j].weight, self.w_s_loop[j].weight, self.w_att_in[j].weight, self.w_att_s[j].weight,
                                  self.G_B[j].weight, self.G_B[j].bias, mask, g, True, 0, pool[j])
         atten_out = self._bn_act(self.conc_for_attention[1], self._lin(self.conc_for_attention[0], x))
+        if self.atten_ready is not None:          # lets a caller on another stream start the cross attention before the decoder is done
+            self.atten_ready.record(torch.cuda.current_stream(dev))
         inp = self._lin(self.conc, x).squeeze(-1)
         inp_out = self._bn_act(self.B[0], inp, "go_B", 0.5)
         for j in range(n_l):

@@ -386,11 +386,14 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         snps2 = ops.snp_mask_pair(snps, self.snps_prob)                             # [snps ; snps * sigmoid(snps_prob)]
         go = self.go_network
         go.dropout_masks = self.dropout_masks
+        early = side is not None and os.environ.get("IGCN_EARLY_ATTN", "1") == "1"
         if side is not None:
             side.wait_stream(main)
+            go.atten_ready = torch.cuda.Event() if early else None
             with torch.cuda.stream(side):
                 latent, x_hat, _, atten_out = go(snps2, temperature, device, groups=2)
             snps2.record_stream(side)
+            atten_ev, go.atten_ready = go.atten_ready, None
         side2 = self._go_stream(x.device, 1) if _TWO_STREAMS and os.environ.get("IGCN_ENC_STREAM", "1") == "1" else None
         if side2 is not None:                                                       # the plain pass on a third stream
             side2.wait_stream(main)
@@ -406,14 +409,22 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             h_plain.record_stream(main)
         batch_x = torch.cat([h_plain, h_expl], 0)                                   # (2B, R, LH)
         if side is not None:
-            main.wait_stream(side)
-            for t in (latent, x_hat, atten_out):
-                t.record_stream(main)
+            if early:
+                main.wait_event(atten_ev)        # the attention needs only atten_out; decoder and latent MLP keep running on `side`
+                atten_out.record_stream(main)
+            else:
+                main.wait_stream(side)
+                for t in (latent, x_hat, atten_out):
+                    t.record_stream(main)
         else:
             latent, x_hat, _, atten_out = go(snps2, temperature, device, groups=2)
         img_out = batch_x.view(2 * B, -1)
         out_cross = ops.cross_attention(batch_x, atten_out, self.multihead_attn, relu=True).reshape(2 * B, -1)
         out_z = (img_out + out_cross) / 2
+        if side is not None and early:
+            main.wait_stream(side)               # latent (fusion heads) and x_hat (reconstruction loss) are needed from here on
+            for t in (latent, x_hat):
+                t.record_stream(main)
         parts = [out_z, latent]
         out_lin = torch.cat(parts, -1).detach()
         linear_outf = ops.cat_linear(parts, self.lin1.weight, self.lin1.bias, relu=True)
