@@ -70,6 +70,7 @@ class GCNConv(nn.Module):
 
 # IGCN_ONE_STREAM=1 keeps the whole step on one stream (A/B hook)
 _TWO_STREAMS = os.environ.get("IGCN_ONE_STREAM", "") == ""
+_PREFETCH_CONSIST = os.environ.get("IGCN_NO_PREFETCH_CONSIST", "") == ""
 if _TWO_STREAMS and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
     # parameters shared by nodes on different streams make autograd warn about the AccumulateGrad stream; the extra event wait it
     # mentions is intended here
@@ -262,6 +263,14 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
     def consist_loss_pair(self, s2, tsne_result=None):
         """consist_loss(s2[:B], t) + consist_loss(s2[B:], t) for the stacked plain / explain features of forward_pair: one
         Laplacian product and one dot product for both passes, and no slice in the autograd graph."""
+        c = getattr(self, "_quad_cache", None)
+        if c is not None:
+            self._quad_cache = None
+            if c[0] is s2 and c[1] is tsne_result:       # already queued on the third stream by forward_pair(consist=True)
+                cur = torch.cuda.current_stream(s2.device)
+                cur.wait_stream(c[3])
+                c[2].record_stream(cur)
+                return c[2]
         n = s2.shape[0] // 2
         lap = self._laplacian(n, tsne_result, s2)
         return ops.laplacian_quadratic(s2, lap, 1.0 / (n * n), halves=2)
@@ -356,7 +365,7 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             bank.end_pass()
         return F.log_softmax(logits, dim=-1), x_hat, out_z, out_lin, linear_outf, our_reg
 
-    def forward_pair(self, data, temperature=None, device=None, stacked=False):
+    def forward_pair(self, data, temperature=None, device=None, stacked=False, consist=False):
         """Plain pass and explain pass of ONE batch in a single sweep: everything downstream of the two encoder
         launches (GO network, cross attention, fusion heads) runs once on the 2B stacked samples, with BatchNorm
         applied per pass, so the results equal `forward(data)` followed by `forward(data, isExplain=True)` while every
@@ -421,6 +430,14 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         img_out = batch_x.view(2 * B, -1)
         out_cross = ops.cross_attention(batch_x, atten_out, self.multihead_attn, relu=True).reshape(2 * B, -1)
         out_z = (img_out + out_cross) / 2
+        if consist and stacked and side2 is not None and self.isSoftSimilarity and _PREFETCH_CONSIST:
+            # the consistency loss needs only out_z: its Laplacian product starts now on the third stream, beside the fusion heads
+            tsne = data.tsne_fdim
+            side2.wait_stream(main)
+            with torch.cuda.stream(side2):
+                quad = self.consist_loss_pair(out_z, tsne)
+            out_z.record_stream(side2)
+            self._quad_cache = (out_z, tsne, quad, side2)
         if side is not None and early:
             main.wait_stream(side)               # latent (fusion heads) and x_hat (reconstruction loss) are needed from here on
             for t in (latent, x_hat):

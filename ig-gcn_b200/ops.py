@@ -143,6 +143,18 @@ def _pad4(n):
     return (n + 3) // 4 * 4
 
 
+_AUX_STREAM = os.environ.get("IGCN_NO_AUX_STREAM", "") == ""
+_aux_streams = {}
+
+
+def _aux_stream(dev):
+    st = _aux_streams.get(str(dev))
+    if st is None:
+        st = torch.cuda.Stream(device=dev)
+        _aux_streams[str(dev)] = st
+    return st
+
+
 def _job(src, hi_lo, rows, cols, ld_src, row_off=0, col_off=0, transpose=False, mask=None):
     """One operand-preparation job of igcn_tc_split; hi_lo is a (2, R, ld) buffer (hi = [0], lo = [1])."""
     return [0 if src is None else src.data_ptr(), 0 if mask is None else mask.data_ptr(), hi_lo[0].data_ptr(), hi_lo[1].data_ptr(),
@@ -270,9 +282,22 @@ class _CatLinearFn(torch.autograd.Function):
                 off += w
             jobs.append(_job(None, xt, M, 1, 1, row_off=K, transpose=True))
             _tc_split(jobs, dev)
+            # the two products are independent: the weight gradient runs on an auxiliary stream, so the input gradient -- which the
+            # rest of the backward waits for -- is not queued behind it
+            cur = torch.cuda.current_stream(dev)
+            aux = _aux_stream(dev) if _AUX_STREAM else None
+            if aux is not None:
+                aux.wait_stream(cur)
+                with torch.cuda.stream(aux):
+                    _tc_gemm(gzt, xt, N, K + 1, M, [dW, db], [K, 1], [K, 1], tag="cat_linear_bwd_w_tc")
+                for t in (gzt, xt, dW, db):
+                    t.record_stream(aux)
             if any(d is not None for d in dxs):
                 _tc_gemm(gz, wt, M, K, N, dxs, ctx.widths, [0 if d is None else d.stride(0) for d in dxs], tag="cat_linear_bwd_x_tc")
-            _tc_gemm(gzt, xt, N, K + 1, M, [dW, db], [K, 1], [K, 1], tag="cat_linear_bwd_w_tc")
+            if aux is not None:
+                cur.wait_stream(aux)
+            else:
+                _tc_gemm(gzt, xt, N, K + 1, M, [dW, db], [K, 1], [K, 1], tag="cat_linear_bwd_w_tc")
             return dxs[0], dxs[1], dxs[2], dW, db, None
         hw, hs = (ctypes.c_int64 * 3)(*ctx.widths), (ctypes.c_int64 * 3)(*ctx.strides)
         hd = (ctypes.c_int64 * 3)(*[0 if t is None else t.stride(0) for t in dxs])

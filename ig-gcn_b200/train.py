@@ -27,7 +27,7 @@ def step_loss(model, data, lambda_loss=None, isSoftSimilarity=True, temperature=
         # both passes in one sweep on 2B stacked samples (identical results, half the launches; SGCN_GCN_IMGSNP.forward_pair);
         # every loss term of train() is the mean of its plain and explain values, so it is evaluated on the stacked tensors
         # directly and no slicing enters the autograd graph
-        out2, snps_hat2, out_feat2, _, _, our_reg2 = model.forward_pair(data, temperature, dev, stacked=True)
+        out2, snps_hat2, out_feat2, _, _, our_reg2 = model.forward_pair(data, temperature, dev, stacked=True, consist=True)
         B = data.snps_feat.shape[0]
         from . import ops
         lp = model.loss_probability(data.x, data.edge_index, data.edge_attr, hyper)
