@@ -42,6 +42,26 @@ def test_no_cpu_fallback():
         Batch.collate(SubjectSet(sub, pin=False), np.arange(2), "cpu")
     with pytest.raises(RuntimeError):
         ops.sgcn_encoder(torch.zeros(20, 3), None, [torch.zeros(4, 3)], [torch.zeros(4)])
+    # every operator added on top of the encoder refuses host tensors as well (north star: no CPU fallback)
+    import types
+    hp = types.SimpleNamespace(lamda_x_l1=0.1, lamda_e_l1=0.1, lamda_x_ent=0.1, lamda_e_ent=0.1)
+    bn = torch.nn.BatchNorm1d(4).train()
+    lin = torch.nn.Linear(8, 3)
+    calls = [
+        lambda: ops.cat_linear([torch.zeros(2, 8)], torch.zeros(4, 8), torch.zeros(4)),
+        lambda: ops.tc_matmul_nt(torch.zeros(2, 8), torch.zeros(4, 8)),
+        lambda: ops.bn_act(torch.zeros(6, 4), bn),
+        lambda: ops.mask_loss(torch.zeros(5, 3), torch.zeros(7), torch.zeros(1, 4), hp),
+        lambda: ops.laplacian_quadratic(torch.zeros(4, 8), torch.zeros(4, 4)),
+        lambda: ops.skinny_linear(torch.zeros(6, 5), torch.zeros(3, 5)),
+        lambda: ops.snp_mask_pair(torch.zeros(3, 4), torch.zeros(1, 4)),
+        lambda: ops.output_heads(torch.zeros(2, 8), None, torch.zeros(2, 8), None, lin, lin),
+        lambda: ops.step_loss_pair(torch.zeros(4, 3), torch.zeros(6), torch.zeros(4, 5), torch.zeros(2, 5), None, None, 1, 1, 1, 1),
+        lambda: ops.cross_attention(torch.zeros(1, 4, 8), torch.zeros(1, 3, 8), torch.nn.MultiheadAttention(8, 2, batch_first=True)),
+    ]
+    for f in calls:
+        with pytest.raises(RuntimeError):
+            f()
 
 
 def test_subjectset_packing_roundtrip():
