@@ -176,3 +176,40 @@ def test_flat_grad_allreduce_world2_gloo():
     ref = torch.cat([torch.zeros(3)] + [p.grad.reshape(-1) for p in model.parameters()]).numpy()   # `unused` is listed first
     assert np.allclose(res[0], res[1])
     assert np.allclose(res[0], ref, atol=1e-6)
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
+    """Error convention of include/igcn_b200.h: non-zero status + igcn_last_error(), never an exception or a crash.  Only
+    argument validation is exercised (it runs before any CUDA call), so this is safe on a machine without a GPU."""
+    import ctypes
+    from igcn_b200 import _lib
+    l = _lib.lib()
+    BAD_ARG, UNSUPPORTED = 1, 2
+    three = (ctypes.c_int64 * 3)(4, 0, 0)
+
+    def err():
+        return l.igcn_last_error().decode()
+
+    assert l.igcn_tc_gemm(None, None, 8, None, None, 8, 4, 4, 8, None, 0, None, None, None, None, None, None, 1, None) == BAD_ARG
+    assert "null" in err()
+    # operands present but a row pitch that TMA cannot address (not a multiple of 4 floats)
+    fake = ctypes.c_void_p(256)
+    assert l.igcn_tc_gemm(fake, fake, 9, fake, fake, 9, 4, 4, 9, None, 0, fake, None, None, ctypes.addressof(three),
+                          ctypes.addressof(three), None, 1, None) == BAD_ARG
+    assert "pitch" in err()
+    assert l.igcn_tc_split(None, 1, None) == BAD_ARG
+    assert l.igcn_bn_act_fwd(None, None, None, None, 4, 4, 1, 1, 1e-5, 0.1, 1, None, None, None, None, None, None) == BAD_ARG
+    assert l.igcn_bn_act_fwd(fake, None, None, None, 5, 4, 1, 2, 1e-5, 0.1, 1, None, None, None, fake, fake, None) == BAD_ARG   # N % groups
+    assert l.igcn_skinny_linear_fwd(fake, fake, 10, 100, 4, fake, None) == UNSUPPORTED
+    assert "in_features" in err()
+    assert l.igcn_heads_fwd(fake, None, fake, None, fake, fake, fake, fake, 4, 100, 3, 3, fake, fake, None) == UNSUPPORTED
+    assert l.igcn_heads_fwd(None, None, None, None, None, None, None, None, 4, 8, 3, 3, None, None, None) == BAD_ARG
+    assert l.igcn_dp_allreduce_adam(None, None, 0, 2, 2048, None, None, None, None, None, 0.9, 0.999, 1e-8, 16, None) == BAD_ARG
+    assert l.igcn_mask_loss_fwd(None, 3, None, 0, None, 0, None, 1e-6, None, 1, None, None) == BAD_ARG
+    assert l.igcn_dot(None, None, 4, 1.0, None, 1, None, None) == BAD_ARG
+    assert l.igcn_step_loss_fwd(None, None, 3, None, None, 3, None, None, 1.0, 1.0, 1.0, 1.0, None, None) == BAD_ARG
+    assert l.igcn_cross_attn_fwd(fake, fake, fake, fake, fake, fake, 2, 10, 3, 30, 2, 1, fake, None) == UNSUPPORTED      # head_dim 15
+    # pure host queries
+    assert l.igcn_tc_gemm_splits(512, 64, 2912) >= 1
+    assert l.igcn_dp_adam_blocks(415000, 8, 2048) == 2048 // (2 * 4 * 8)
+    assert l.igcn_dp_adam_blocks(415000, 8, 16) == 0
