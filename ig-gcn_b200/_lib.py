@@ -57,7 +57,7 @@ SIGNATURES = {
     "igcn_step_loss_fwd": (ctypes.c_int, [_P, _P, _I, _P, _P, _I, _P, _P] + [ctypes.c_double] * 4 + [_P, _P]),
     "igcn_step_loss_bwd": (ctypes.c_int, [_P, _P, _I, _P, _P, _I, _P] + [ctypes.c_double] * 4 + [_P, _P, _P, _P, _P]),
     "igcn_dp_adam_blocks": (_I, [_I, _I, _I]),
-    "igcn_dp_allreduce_adam": (ctypes.c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P] + [ctypes.c_double] * 3 + [_I, _P]),
+    "igcn_dp_allreduce_adam": (ctypes.c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P] + [ctypes.c_double] * 3 + [_I, _I, _P, _P]),
     "igcn_tc_split": (ctypes.c_int, [_P, _I, _P]),
     "igcn_tc_gemm_splits": (_I, [_I, _I, _I]),
     "igcn_tc_gemm": (ctypes.c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P]),

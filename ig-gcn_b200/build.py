@@ -27,7 +27,7 @@ def _stamp():
     h = hashlib.sha256()
     for p in _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
             sorted(glob.glob(os.path.join(os.path.dirname(HERE), "include", "*.h"))):
-        h.update(p.encode())
+        h.update(os.path.relpath(p, os.path.dirname(HERE)).encode())      # relative: a relocated checkout keeps its stamp
         with open(p, "rb") as f:
             h.update(f.read())
     h.update(" ".join(FLAGS).encode())

@@ -25,6 +25,19 @@ int sm_count() {
     }
     return cached[dev];
 }
+
+// SM clock in kHz (= cycles per millisecond of clock64()); used to turn timeouts into cycle budgets.
+long long sm_clock_khz() {
+    static long long cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1965000;
+    if (cached[dev] == 0) {
+        int khz = 0;
+        if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 1965000;
+        cached[dev] = khz;
+    }
+    return cached[dev];
+}
 }  // namespace igcn
 
 extern "C" const char* igcn_last_error(void) { return igcn::g_err; }

@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(256) collate_kernel(EdgeIn<IdxT> in, const flo
                 edge_index[e0 + k] = node0 + s;
                 edge_index[E + e0 + k] = node0 + t;
             }
+            // host contract (validated in SubjectSet / Batch.from_device_tensors): every edge stays inside its graph
+            if ((unsigned)s >= (unsigned)R || (unsigned)t >= (unsigned)R) __trap();
             key_t[k] = t;
             key_s[k] = s;
             atomicAdd(&cnt_t[t], 1);   // integer atomics: the counts are order independent

@@ -10,6 +10,7 @@ namespace igcn {
 
 void set_error(const char* fmt, ...);
 int sm_count();
+long long sm_clock_khz();
 
 #define IGCN_REQUIRE(cond, code, ...)          \
     do {                                       \

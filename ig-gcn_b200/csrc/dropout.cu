@@ -1,8 +1,9 @@
 // All dropout masks of one forward pass in ONE launch (reference: nn.Dropout2d(0.4) x4 and nn.Dropout(0.5) x3 inside
 // kernel/go_model.py:104,113,127,135,142 plus F.dropout p=0.5 / 0.3 at kernel/sgcn_img_snp.py:290,300 -- nine masks per pass;
 // drawn with torch that is ~3 launches per mask).  Masks are multiplicative scale tensors: 0 or 1/keep.
-// Philox4x32-10 (curand device API): subsequence = thread id, offset = a device-resident call counter, so the launch is
-// replayable inside a captured CUDA graph and still draws fresh numbers on every replay.
+// Philox4x32-10 (curand device API): subsequence = thread id, offset = 4 x a device-resident call counter (the offset counts
+// single 32-bit outputs and every thread consumes four per call, so consecutive calls use disjoint counter blocks), so the
+// launch is replayable inside a captured CUDA graph and still draws fresh, uncorrelated numbers on every replay.
 #include <curand_kernel.h>
 
 #include "common.cuh"
@@ -22,7 +23,7 @@ __global__ void __launch_bounds__(256) dropout_masks_kernel(float* __restrict__ 
     const int64_t i0 = t * 4;
     if (i0 >= total) return;
     curandStatePhilox4_32_10_t st;
-    curand_init((unsigned long long)seed, (unsigned long long)t, counter[0], &st);
+    curand_init((unsigned long long)seed, (unsigned long long)t, counter[0] * 4ull, &st);
     const float4 u = curand_uniform4(&st);          // (0, 1]
     const float uv[4] = {u.x, u.y, u.z, u.w};
     int seg = 0;

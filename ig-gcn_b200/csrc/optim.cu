@@ -77,7 +77,10 @@ extern "C" int igcn_adam_step(float* params, const float* grads, float* exp_avg,
 // This replaces ncclAllReduce + a separate optimizer launch (at 1.66 MB per rank the collective is latency bound: two device-side
 // flag exchanges and one pass over the data instead of a ring).  Flags are one 32-bit word per (block, peer) in each rank's signal
 // pad, set with a release CAS 0 -> 1 by the sender and cleared with an acquire CAS 1 -> 0 by the receiver, so they reset themselves
-// and the launch can be replayed inside a CUDA graph.  Waits are bounded: a missing peer traps instead of hanging the GPU.
+// and the launch can be replayed inside a CUDA graph.  Waits are bounded by a caller-chosen timeout (minutes by default: ranks may
+// legitimately be seconds apart -- logging, evaluation, lazy module loads); on expiry the kernel records the peer in a
+// host-checked error flag and leaves the wait (the step's result is then invalid but the CUDA context survives and the host
+// can raise); without a flag it traps.  All ranks must issue their steps in lock-step, one fused launch per rank per step.
 // =============================================================================================================================
 namespace igcn {
 
@@ -99,18 +102,30 @@ __device__ __forceinline__ uint32_t cas_acquire_sys(uint32_t* addr, uint32_t cmp
 }
 
 // all blocks with the same blockIdx.x on all ranks meet here; slot = which of the kernel's barriers (distinct flag words)
-__device__ __forceinline__ void dp_block_barrier(const DpPeers& peers, int rank, int world, int slot) {
+__device__ __forceinline__ void dp_timeout(int* error_flag, int peer, int what) {
+    if (error_flag) {
+        atomicExch(error_flag, (what << 8) | (peer + 1));           // host side: FlatAdam.check_dp_error()
+        __threadfence_system();
+    } else {
+        printf("igcn dp_adam: %s rank %d timed out\n", what == 1 ? "signal to" : "wait for", peer);
+        __trap();
+    }
+}
+
+__device__ __forceinline__ void dp_block_barrier(const DpPeers& peers, int rank, int world, int slot, long long timeout_cycles,
+                                                 int* error_flag) {
     __syncthreads();
     if ((int)threadIdx.x < world) {
         const int peer = threadIdx.x;
         const size_t base = ((size_t)slot * gridDim.x + blockIdx.x) * world;
         uint32_t* put = peers.signal[peer] + base + rank;          // my flag in the peer's pad
         uint32_t* get = peers.signal[rank] + base + peer;          // the peer's flag in my pad
-        const long long t0 = clock64();
+        long long t0 = clock64();
         while (cas_release_sys(put, 0u, 1u) != 0u)
-            if (clock64() - t0 > 4000000000LL) { printf("igcn dp_adam: signal to rank %d timed out\n", peer); __trap(); }
+            if (clock64() - t0 > timeout_cycles) { dp_timeout(error_flag, peer, 1); break; }
+        t0 = clock64();                                             // each phase gets the full budget
         while (cas_acquire_sys(get, 1u, 0u) != 1u)
-            if (clock64() - t0 > 4000000000LL) { printf("igcn dp_adam: wait for rank %d timed out\n", peer); __trap(); }
+            if (clock64() - t0 > timeout_cycles) { dp_timeout(error_flag, peer, 2); break; }
     }
     __syncthreads();
 }
@@ -118,8 +133,9 @@ __device__ __forceinline__ void dp_block_barrier(const DpPeers& peers, int rank,
 __global__ void __launch_bounds__(512) dp_allreduce_adam_kernel(DpPeers peers, int rank, int world, float* __restrict__ p,
                                                                 float* __restrict__ m, float* __restrict__ v,
                                                                 const float* __restrict__ step, const float* __restrict__ lr, float beta1,
-                                                                float beta2, float eps, int64_t n) {
-    dp_block_barrier(peers, rank, world, 0);
+                                                                float beta2, float eps, int64_t n, long long timeout_cycles,
+                                                                int* error_flag) {
+    dp_block_barrier(peers, rank, world, 0, timeout_cycles, error_flag);
     const float t = step[0];
     const float bias1 = 1.f - powf(beta1, t), bias2 = 1.f - powf(beta2, t);
     const float step_size = lr[0] / bias1, inv_sqrt_bias2 = rsqrtf(bias2), scale = 1.f / (float)world;
@@ -144,7 +160,7 @@ __global__ void __launch_bounds__(512) dp_allreduce_adam_kernel(DpPeers peers, i
         reinterpret_cast<float4*>(m)[i] = mv;
         reinterpret_cast<float4*>(v)[i] = vv;
     }
-    dp_block_barrier(peers, rank, world, 1);
+    dp_block_barrier(peers, rank, world, 1, timeout_cycles, error_flag);
 }
 
 }  // namespace igcn
@@ -161,8 +177,10 @@ extern "C" int64_t igcn_dp_adam_blocks(int64_t n, int64_t world, int64_t signal_
 
 extern "C" int igcn_dp_allreduce_adam(const int64_t* host_grad_ptrs, const int64_t* host_signal_ptrs, int64_t rank, int64_t world,
                                       int64_t signal_pad_bytes, float* params, float* exp_avg, float* exp_avg_sq, const float* step,
-                                      const float* lr, double beta1, double beta2, double eps, int64_t n, void* stream) {
+                                      const float* lr, double beta1, double beta2, double eps, int64_t n, int64_t timeout_ms,
+                                      int* error_flag, void* stream) {
     using namespace igcn;
+    IGCN_REQUIRE(timeout_ms > 0, IGCN_ERR_BAD_ARG, "dp_allreduce_adam: timeout_ms must be positive");
     IGCN_REQUIRE(host_grad_ptrs && host_signal_ptrs && params && exp_avg && exp_avg_sq && step && lr, IGCN_ERR_BAD_ARG, "dp_allreduce_adam: null pointer");
     IGCN_REQUIRE(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, IGCN_ERR_BAD_ARG, "dp_allreduce_adam: rank %lld of %lld",
                  (long long)rank, (long long)world);
@@ -178,7 +196,8 @@ extern "C" int igcn_dp_allreduce_adam(const int64_t* host_grad_ptrs, const int64
                      "dp_allreduce_adam: bad peer pointer for rank %d", r);
     }
     dp_allreduce_adam_kernel<<<(unsigned)blocks, 512, 0, (cudaStream_t)stream>>>(peers, (int)rank, (int)world, params, exp_avg, exp_avg_sq, step, lr,
-                                                                                (float)beta1, (float)beta2, (float)eps, n);
+                                                                                (float)beta1, (float)beta2, (float)eps, n,
+                                                                                (long long)timeout_ms * sm_clock_khz(), error_flag);
     IGCN_CHECK_LAUNCH("dp_allreduce_adam");
     return IGCN_OK;
 }

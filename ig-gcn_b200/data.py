@@ -87,6 +87,17 @@ class SubjectSet(object):
         self.edge_src = t(packed["edge_src"], torch.int32)      # LOCAL ids; i32 halves the H2D bytes
         self.edge_dst = t(packed["edge_dst"], torch.int32)
         self.edge_attr = t(packed["edge_attr"], torch.float32)
+        # host contract of igcn_collate_csr (validated once here; the kernel indexes shared memory with these ids)
+        if self.x.dim() != 3:
+            raise ValueError("SubjectSet: x must be (subjects, rois, features), got %s" % (tuple(self.x.shape),))
+        ne = int(self.edge_ptr[-1]) if self.edge_ptr.numel() else 0
+        if self.edge_ptr.numel() != self.n + 1 or int(self.edge_ptr[0]) != 0 or bool((self.edge_ptr[1:] < self.edge_ptr[:-1]).any()) \
+                or not (self.edge_src.numel() == self.edge_dst.numel() == self.edge_attr.numel() == ne):
+            raise ValueError("SubjectSet: edge_ptr must be a non-decreasing prefix over %d subjects covering all %d edges"
+                             % (self.n, self.edge_src.numel()))
+        if ne and (int(self.edge_src.min()) < 0 or int(self.edge_src.max()) >= self.rois or
+                   int(self.edge_dst.min()) < 0 or int(self.edge_dst.max()) >= self.rois):
+            raise ValueError("SubjectSet: edge endpoints must be LOCAL node ids in [0, %d)" % self.rois)
         counts = self.edge_ptr[1:] - self.edge_ptr[:-1]
         self.edge_counts = counts
         self.max_eg = int(counts.max()) if self.n else 0
@@ -140,6 +151,8 @@ class Batch(Data):
 
     def to(self, device, non_blocking=False):
         dev = torch.device(device)
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())       # 'cuda' means the current device, as in torch
         if self.x is not None and self.x.device == dev:
             return self
         raise RuntimeError("igcn_b200.Batch is collated on its CUDA device; it cannot be moved to %s" % dev)
@@ -263,8 +276,21 @@ class Batch(Data):
         B = N // rois
         i32 = dict(dtype=torch.int32, device=dev)
         ei = edge_index.contiguous()
+        if N != B * rois:
+            raise ValueError("from_device_tensors: %d nodes is not a multiple of rois=%d" % (N, rois))
         gid = torch.div(ei[0], rois, rounding_mode="floor")
-        max_eg = int(torch.bincount(gid, minlength=B).max()) if E else 0
+        if E:
+            # one host read validates the kernel's contract (edges grouped by graph, no cross-graph edge, ids in range) together
+            # with the maximum per-graph edge count the launch needs anyway
+            gd = torch.div(ei[1], rois, rounding_mode="floor")
+            bad = (gid != gd).any() | (gid[1:] < gid[:-1]).any() | (ei.min() < 0) | (ei.max() >= N)
+            stats = torch.stack([torch.bincount(gid.clamp(0, max(B - 1, 0)), minlength=B).max(), bad.to(torch.int64)]).tolist()
+            if stats[1]:
+                raise ValueError("from_device_tensors: edge_index must be a collated batch of %d-node graphs (edges grouped by graph, "
+                                 "no edge between graphs, ids in [0, %d))" % (rois, N))
+            max_eg = int(stats[0])
+        else:
+            max_eg = 0
         eptr = torch.empty(B + 1, **i32)
         csr = GraphCSR(rowptr_t=torch.empty(N + 1, **i32), csr_src=torch.empty(E, **i32), csr_perm=torch.empty(E, **i32),
                        csr_w=torch.empty(E, dtype=torch.float32, device=dev), rowptr_s=torch.empty(N + 1, **i32),

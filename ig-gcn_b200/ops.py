@@ -376,7 +376,16 @@ class MaskBank(object):
         self.plans = {}
         self.active = False
         self.seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
+        self._rank_mixed = seed is not None          # an explicit seed is used as given (tests replay it)
         self.counter = None
+
+    def _mix_rank(self):
+        """Data-parallel ranks start from the same torch seed (identical replicas); their dropout masks must still differ."""
+        if not self._rank_mixed:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.seed = (self.seed ^ ((dist.get_rank() + 1) * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
+            self._rank_mixed = True
 
     def begin_pass(self, key, device):
         import ctypes
@@ -387,6 +396,7 @@ class MaskBank(object):
             return
         if self.counter is None or self.counter.device != device:
             self.counter = torch.zeros(1, dtype=torch.int64, device=device)
+            self._mix_rank()
         names, shapes, ends, keeps = plan
         out = torch.empty(ends[-1], dtype=torch.float32, device=device)
         he, hk = (ctypes.c_int64 * len(ends))(*ends), (ctypes.c_float * len(keeps))(*keeps)

@@ -158,7 +158,9 @@ class FlatAdam(object):
             self.grad_views = [buf[o:o + p.numel()].view_as(p) for p, o in zip(self.params, self.offsets)]
             gp = (ctypes.c_int64 * world)(*[int(a) for a in hdl.buffer_ptrs])
             sp = (ctypes.c_int64 * world)(*[int(a) for a in hdl.signal_pad_ptrs])
-            self._peer = dict(handle=hdl, grad_ptrs=gp, signal_ptrs=sp, world=world, rank=rank, pad=pad)
+            self._peer = dict(handle=hdl, grad_ptrs=gp, signal_ptrs=sp, world=world, rank=rank, pad=pad,
+                              timeout_ms=int(float(os.environ.get("IGCN_DP_TIMEOUT_S", "300")) * 1000),
+                              error=torch.zeros(1, dtype=torch.int32, device=dev))
             torch.cuda.synchronize(dev)
         except Exception as e:                                     # noqa: BLE001 -- any failure means "use NCCL"
             self._peer = None
@@ -175,8 +177,25 @@ class FlatAdam(object):
         for p in self.params:
             p.grad = None
 
+    def rendezvous(self):
+        """Host barrier for all ranks: call before the first fused step and after long rank-local host phases (evaluation,
+        checkpointing) so the device-side flag waits of igcn_dp_allreduce_adam start within their timeout of each other."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            torch.cuda.synchronize(self.flat_param.device)
+            dist.barrier(group=self.group)
+
+    def check_dp_error(self):
+        """Raises if a device-side wait of the fused all-reduce timed out (synchronises)."""
+        if self._peer is not None:
+            code = int(self._peer["error"].item())
+            if code:
+                raise RuntimeError("igcn_dp_allreduce_adam: %s rank %d timed out after %d ms; parameters are no longer in sync"
+                                   % ("signal to" if (code >> 8) == 1 else "wait for", (code & 255) - 1, self._peer["timeout_ms"]))
+
     def sync_lr(self):
-        """Call outside a captured graph after changing param_groups[0]['lr']."""
+        """Push param_groups[0]['lr'] (the reference decays it in place, train_eval_sgcn_img_snps.py:169-171) into the device
+        scalar the kernels read.  step() calls it whenever the stream is not capturing and GraphedTrainStep calls it before every
+        replay, so a changed learning rate is honoured by the eager and by the graphed step (the graph reads the device scalar)."""
         lr = float(self.param_groups[0]["lr"])
         if lr != self._lr_seen:
             self.lr_t.fill_(lr)
@@ -191,6 +210,8 @@ class FlatAdam(object):
     def step(self):
         from . import _lib
         import ctypes
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
         self.gather_grads()
         if self._peer is not None:
             # gradient all-reduce (sum in rank order, / world) + Adam in one kernel over peer memory
@@ -199,7 +220,8 @@ class FlatAdam(object):
             with torch.cuda.device(self.flat_param.device):
                 _lib.call("igcn_dp_allreduce_adam", ctypes.addressof(pr["grad_ptrs"]), ctypes.addressof(pr["signal_ptrs"]), pr["rank"], pr["world"],
                           pr["pad"], _lib.ptr(self.flat_param), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(self.step_t),
-                          _lib.ptr(self.lr_t), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), self.n, _lib.stream(),
+                          _lib.ptr(self.lr_t), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), self.n, pr["timeout_ms"],
+                          _lib.ptr(pr["error"]), _lib.stream(),
                           tag="dp_allreduce_adam", nbytes=4 * self.n * (pr["world"] + 6))
             return
         scale = 1.0
@@ -250,10 +272,16 @@ class GraphedTrainStep(object):
                  isSoftSimilarity=True, warmup=3):
         if isinstance(optimizer, FlatAdam):
             optimizer.sync_lr()
+            optimizer.rendezvous()                # ranks may arrive here seconds apart (lazy loads, data set-up)
         self.model, self.opt, self.batch, self.flat = model, optimizer, static_batch, flat
         self.lambda_loss, self.soft = lambda_loss, isSoftSimilarity
         dev = static_batch.x.device
         model._pe_cache = None
+        # The warm-up steps below are real training steps (they must be: lazy initialisation, the dropout-mask plan and the
+        # allocator's pools have to be in their steady state before capture).  Their effect is undone: parameters, BatchNorm
+        # buffers, Adam moments / step count and the dropout counter are snapshotted here and restored IN PLACE after capture,
+        # so building the graph leaves the training trajectory exactly where it was.
+        snap = self._snapshot()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -265,7 +293,53 @@ class GraphedTrainStep(object):
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = train_step(model, static_batch, optimizer, lambda_loss, flat, isSoftSimilarity)
+        self._restore(snap)
+        torch.cuda.synchronize(dev)
+
+    def _mask_bank(self):
+        go = getattr(self.model, "go_network", None)
+        return getattr(go, "mask_bank", None)
+
+    def _snapshot(self):
+        import copy
+        snap = dict(model={k: v.detach().clone() for k, v in self.model.state_dict().items()})
+        if isinstance(self.opt, FlatAdam):
+            o = self.opt
+            snap["adam"] = (o.exp_avg.clone(), o.exp_avg_sq.clone(), o.step_t.clone())
+        elif self.opt is not None:
+            snap["opt"] = copy.deepcopy(self.opt.state_dict())
+        bank = self._mask_bank()
+        snap["counter"] = None if bank is None or bank.counter is None else bank.counter.clone()
+        return snap
+
+    def _restore(self, snap):
+        with torch.no_grad():
+            for k, v in self.model.state_dict().items():
+                v.copy_(snap["model"][k])                      # in place: the captured graph holds these addresses
+            if "adam" in snap:
+                o = self.opt
+                o.exp_avg.copy_(snap["adam"][0])
+                o.exp_avg_sq.copy_(snap["adam"][1])
+                o.step_t.copy_(snap["adam"][2])
+            elif "opt" in snap:
+                cur = self.opt.state_dict()
+                old = snap["opt"]
+                for pid, st in cur["state"].items():           # in place as well (capturable optimizers keep device state)
+                    for name, val in st.items():
+                        if torch.is_tensor(val):
+                            if pid in old["state"] and name in old["state"][pid]:
+                                val.copy_(old["state"][pid][name])
+                            else:
+                                val.zero_()
+            bank = self._mask_bank()
+            if bank is not None and bank.counter is not None:
+                if snap["counter"] is not None:
+                    bank.counter.copy_(snap["counter"])
+                else:
+                    bank.counter.zero_()
 
     def __call__(self):
+        if isinstance(self.opt, FlatAdam):
+            self.opt.sync_lr()                    # lr_t.fill_ outside the graph; the replay reads the device scalar
         self.graph.replay()
         return self.loss

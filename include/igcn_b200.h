@@ -328,14 +328,18 @@ int igcn_step_loss_bwd(const float* reg, const float* target, int64_t n_reg, con
  *   host_grad_ptrs / host_signal_ptrs: HOST arrays of `world` device pointers -- the flat gradient buffer (n f32, 16-byte aligned)
  *   and the signal pad (signal_pad_bytes, zero-initialised once) of every rank, all peer-mapped into this process (e.g. from
  *   torch.distributed._symmetric_memory: buffer_ptrs / signal_pad_ptrs).  Every rank launches the same call on its own stream;
- *   the kernel exchanges flags with all peers before and after reading their gradients (bounded waits: a missing peer traps),
+ *   the kernel exchanges flags with all peers before and after reading their gradients.  Waits are bounded by `timeout_ms` per
+ *   phase (choose minutes: ranks may be seconds apart); on expiry the kernel stores ((phase << 8) | (peer + 1)) into `error_flag`
+ *   (a device or mapped-host int the caller polls; the step's result is then invalid) or, when error_flag is NULL, traps.  All
+ *   ranks must issue their steps in lock-step and should meet at a host barrier before the first fused launch.  The kernel
  *   sums the `world` gradients in rank order (bit-identical replicas), scales by 1/world and updates params / exp_avg / exp_avg_sq
  *   exactly as igcn_adam_step does.  n must be a multiple of 4.  igcn_dp_adam_blocks = CTAs used (0: signal pad too small).
  */
 int64_t igcn_dp_adam_blocks(int64_t n, int64_t world, int64_t signal_pad_bytes);
 int igcn_dp_allreduce_adam(const int64_t* host_grad_ptrs, const int64_t* host_signal_ptrs, int64_t rank, int64_t world,
                            int64_t signal_pad_bytes, float* params, float* exp_avg, float* exp_avg_sq, const float* step,
-                           const float* lr, double beta1, double beta2, double eps, int64_t n, void* stream);
+                           const float* lr, double beta1, double beta2, double eps, int64_t n, int64_t timeout_ms, int* error_flag,
+                           void* stream);
 
 #ifdef __cplusplus
 }

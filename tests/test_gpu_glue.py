@@ -216,12 +216,13 @@ def test_dp_allreduce_adam_single_rank_equals_adam_step():
     pa, ma, va = p0.clone(), m0.clone(), v0.clone()
     pb, mb, vb = p0.clone(), m0.clone(), v0.clone()
     gp, sp = (ctypes.c_int64 * 1)(grad.data_ptr()), (ctypes.c_int64 * 1)(pad.data_ptr())
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
     for _ in range(3):                                   # replays: the flags must reset themselves
         _lib.call("igcn_dp_allreduce_adam", ctypes.addressof(gp), ctypes.addressof(sp), 0, 1, pad_bytes, _lib.ptr(pa), _lib.ptr(ma),
-                  _lib.ptr(va), _lib.ptr(step), _lib.ptr(lr), 0.9, 0.999, 1e-8, n, _lib.stream())
+                  _lib.ptr(va), _lib.ptr(step), _lib.ptr(lr), 0.9, 0.999, 1e-8, n, 1000, _lib.ptr(err), _lib.stream())
         _lib.call("igcn_adam_step", _lib.ptr(pb), _lib.ptr(grad), _lib.ptr(mb), _lib.ptr(vb), _lib.ptr(step), _lib.ptr(lr), 0.9, 0.999,
                   1e-8, 1.0, n, _lib.stream())
         step += 1.0
     torch.cuda.synchronize()
     assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)
-    assert int(pad.abs().sum()) == 0
+    assert int(pad.abs().sum()) == 0 and int(err) == 0

@@ -210,3 +210,23 @@ def test_dropout_mask_bank_statistics_and_replay():
     assert not torch.equal(o[1][0], o[2][0]) and not torch.equal(o[2][1], o[3][1])
     o2 = run(MaskBank(seed=123), 4)
     assert torch.equal(o[2][0], o2[2][0]) and torch.equal(o[3][1], o2[3][1])
+
+
+def test_dropout_masks_of_consecutive_calls_are_uncorrelated():
+    """Consecutive launches must use disjoint Philox counter blocks: the mask of call c+1 is not a shifted copy of call c
+    (the offset counts 32-bit outputs and every thread consumes four per call)."""
+    from igcn_b200.ops import MaskBank
+    dev = _dev()
+    bank = MaskBank(seed=7)
+    outs = []
+    for _ in range(6):
+        bank.begin_pass(0, dev)
+        outs.append(bank.get("m", (1 << 16,), 0.5).clone())
+        bank.end_pass()
+    for a, b in zip(outs[1:-1], outs[2:]):          # outs[0] is the torch-drawn recording pass
+        ka, kb = (a > 0).float(), (b > 0).float()
+        for shift in range(0, 4):
+            n = ka.numel() - shift
+            agree = (ka[shift:shift + n] == kb[:n]).float().mean().item()
+            agree2 = (kb[shift:shift + n] == ka[:n]).float().mean().item()
+            assert abs(agree - 0.5) < 0.02 and abs(agree2 - 0.5) < 0.02, (shift, agree, agree2)

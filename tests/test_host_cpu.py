@@ -204,7 +204,7 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     assert "in_features" in err()
     assert l.igcn_heads_fwd(fake, None, fake, None, fake, fake, fake, fake, 4, 100, 3, 3, fake, fake, None) == UNSUPPORTED
     assert l.igcn_heads_fwd(None, None, None, None, None, None, None, None, 4, 8, 3, 3, None, None, None) == BAD_ARG
-    assert l.igcn_dp_allreduce_adam(None, None, 0, 2, 2048, None, None, None, None, None, 0.9, 0.999, 1e-8, 16, None) == BAD_ARG
+    assert l.igcn_dp_allreduce_adam(None, None, 0, 2, 2048, None, None, None, None, None, 0.9, 0.999, 1e-8, 16, 1000, None, None) == BAD_ARG
     assert l.igcn_mask_loss_fwd(None, 3, None, 0, None, 0, None, 1e-6, None, 1, None, None) == BAD_ARG
     assert l.igcn_dot(None, None, 4, 1.0, None, 1, None, None) == BAD_ARG
     assert l.igcn_step_loss_fwd(None, None, 3, None, None, 3, None, None, 1.0, 1.0, 1.0, 1.0, None, None) == BAD_ARG
