@@ -24,3 +24,20 @@ def pytest_collection_modifyitems(config, items):
         for it in items:
             if "gpu" in it.keywords:
                 it.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Which tolerance rule admitted each tensor (tests/helpers.py) -> gpurun_out/parity_report.json."""
+    try:
+        import json
+        from tests import helpers as H
+        if H.PARITY_LOG:
+            d = os.path.join(ROOT, "gpurun_out")
+            os.makedirs(d, exist_ok=True)
+            nb = sum(1 for r in H.PARITY_LOG if r["rule"] == "B")
+            with open(os.path.join(d, "parity_report.json"), "w") as f:
+                json.dump(dict(rtol=H.RTOL, tensors=len(H.PARITY_LOG), rule_B=nb,
+                               worst_rule_A=max([r["err32"] for r in H.PARITY_LOG if r["rule"] == "A"] or [0.0]),
+                               rule_B_tensors=[r for r in H.PARITY_LOG if r["rule"] == "B"]), f, indent=1)
+    except Exception:
+        pass

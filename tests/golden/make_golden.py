@@ -91,8 +91,26 @@ def go_graph(pool, S, seed):
     return adj, go_snps, pool_dim, A, A_g
 
 
-def sd_np(model, prefix="P/"):
-    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+def sd_np(model, prefix="P/", seeded=False):
+    """state_dict as arrays.  seeded=True: parameters with more than 50 000 elements are first OVERWRITTEN with values drawn
+    from a seeded torch CPU generator and stored as the recipe `Pseed/<name>` = [seed, bound, *shape] instead of the values
+    (tests/helpers.seeded_param regenerates them), which keeps the R=264 / H=16 fixtures small."""
+    out = {}
+    for i, (k, v) in enumerate(model.state_dict().items()):
+        if seeded and v.is_floating_point() and v.numel() > 50000:
+            bound = 1.0 / np.sqrt(v.shape[-1])
+            seed = 9000 + i
+            with torch.no_grad():
+                v.copy_(seeded_param(seed, bound, tuple(v.shape)))
+            out[prefix.rstrip("/") + "seed/" + k] = np.asarray([seed, bound] + list(v.shape), dtype=np.float64)
+        else:
+            out[prefix + k] = v.detach().cpu().numpy().copy()
+    return out
+
+
+def seeded_param(seed, bound, shape):
+    g = torch.Generator().manual_seed(int(seed))
+    return (torch.rand(shape, generator=g, dtype=torch.float32) * 2.0 - 1.0) * float(bound)
 
 
 def save(name, d):
@@ -148,14 +166,16 @@ def build_model(L, H, R, pool, S, num_regr=3, num_classes=3, seed=0):
     return m, adj, go_snps, pool_dim
 
 
-def case_model(name, L, H, R, B, pool, S, seed, skip_big_grads=False, steps=0):
-    """a2-a13: full SGCN_GCN_IMGSNP fwd (plain + explain), every loss, grads of one train() step."""
+def case_model(name, L, H, R, B, pool, S, seed, skip_big_grads=False, steps=0, compact=False):
+    """a2-a13: full SGCN_GCN_IMGSNP fwd (plain + explain), every loss, grads of one train() step.
+    compact=True (the R=264 case): big parameters are seeded recipes, out_lin is stored as its latent tail only (the rest is
+    out_z), and gradients of big parameters are stored as their row / column sums."""
     m, adj, go_snps, pool_dim = build_model(L, H, R, pool, S, seed=seed)
     sub = syn.make_subjects(B, rois=R, n_snps=S, seed=seed + 100)
     dl = data_list(sub)
     loader = REF.dataloader.DataLoader(dl, batch_size=B, shuffle=False)
     (b,) = list(loader)
-    out = sd_np(m)
+    out = sd_np(m, seeded=compact)
     out.update({"sub/" + k: np.asarray(v) for k, v in sub.items()})
     out.update(adj=adj, go_snps=go_snps, pool=np.asarray(pool_dim[0]),
                cfg=np.asarray([L, H, R, B, S]))
@@ -172,7 +192,7 @@ def case_model(name, L, H, R, B, pool, S, seed, skip_big_grads=False, steps=0):
         for tag, ex in (("plain", False), ("explain", True)):
             o = m(b, 0.1, "cpu", isExplain=ex)
             for n, t in zip(names, o):
-                out["eval/%s/%s" % (tag, n)] = t.numpy()
+                out["eval/%s/%s" % (tag, n)] = t.numpy()[:, -32:] if (compact and n == "out_lin") else t.numpy()
     b.x.requires_grad_(False)
 
     # train-mode forwards with recorded dropout
@@ -186,9 +206,9 @@ def case_model(name, L, H, R, B, pool, S, seed, skip_big_grads=False, steps=0):
         q = m(b, 0.1, "cpu", isExplain=True)
         masks_explain = list(rec.masks)
     for n, t in zip(names, o):
-        out["train/plain/%s" % n] = t.detach().numpy()
+        out["train/plain/%s" % n] = t.detach().numpy()[:, -32:] if (compact and n == "out_lin") else t.detach().numpy()
     for n, t in zip(names, q):
-        out["train/explain/%s" % n] = t.detach().numpy()
+        out["train/explain/%s" % n] = t.detach().numpy()[:, -32:] if (compact and n == "out_lin") else t.detach().numpy()
     from oracle.igcn_oracle import MODEL_MASK_NAMES
     assert len(masks_plain) == len(MODEL_MASK_NAMES) == len(masks_explain)
     for n, mp, me in zip(MODEL_MASK_NAMES, masks_plain, masks_explain):
@@ -221,13 +241,17 @@ def case_model(name, L, H, R, B, pool, S, seed, skip_big_grads=False, steps=0):
     for n, p in m.named_parameters():
         if p.grad is None:
             continue
-        if skip_big_grads and p.numel() > 50000:
+        if (skip_big_grads or compact) and p.numel() > 50000:
+            if compact:
+                out["gradsum/rows/" + n] = p.grad.sum(1).numpy().copy()
+                out["gradsum/cols/" + n] = p.grad.sum(0).numpy().copy()
             continue
         out["grad/" + n] = p.grad.numpy().copy()
     out.update({"bn_after/" + k: v.numpy().copy() for k, v in m.state_dict().items() if "running" in k})
 
     if steps:
         # loop-level: `steps` reference train() epochs with Adam, masks recorded per step
+        assert not compact
         m.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in out.items() if k.startswith("P/")})
         opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=0)
         losses = []
@@ -283,7 +307,7 @@ def case_go(name, pool, S, B, C, seed):
     save(name, out)
 
 
-def case_sgcn(name, R, B, L, H, seed):
+def case_sgcn(name, R, B, L, H, seed, seeded=False):
     """config 1: kernel/sgcn.py SGCN_GCN (GCNConv stack) and SGCN_GAT (GATConv edge_dim=1), 3-term step."""
     sub = syn.make_subjects(B, rois=R, n_snps=4, seed=seed, num_classes=2)
     dl = data_list(sub)
@@ -305,7 +329,7 @@ def case_sgcn(name, R, B, L, H, seed):
             for n, p in m.named_parameters():
                 if n.endswith("bias") and p.abs().sum() == 0:
                     p.uniform_(-0.1, 0.1)
-        out.update(sd_np(m, "P_%s/" % tag))
+        out.update(sd_np(m, "P_%s/" % tag, seeded=seeded))
         m.eval()
         b.x.requires_grad_(False)
         b.x.grad = None
@@ -320,12 +344,23 @@ def case_sgcn(name, R, B, L, H, seed):
         for n, p in m.named_parameters():
             if p.grad is not None and p.numel() <= 50000:
                 out["%s/grad/%s" % (tag, n)] = p.grad.numpy().copy()
+            elif p.grad is not None and seeded:
+                out["%s/gradsum/rows/%s" % (tag, n)] = p.grad.sum(1).numpy().copy()
+                out["%s/gradsum/cols/%s" % (tag, n)] = p.grad.sum(0).numpy().copy()
     save(name, out)
 
 
+CASES = {
+    "collate_r30": case_collate,
+    "imgsnp_small": lambda: case_model("imgsnp_small", L=3, H=8, R=30, B=6, pool=[9, 6, 4, 3, 1], S=20, seed=1, steps=3),
+    "imgsnp_adni": lambda: case_model("imgsnp_adni", L=2, H=16, R=90, B=4, pool=syn.ADNI_POOL, S=54, seed=2, skip_big_grads=True),
+    "go_mid": lambda: case_go("go_mid", pool=[40, 20, 10, 5, 1], S=150, B=5, C=7, seed=3),
+    "sgcn_cfg1": lambda: case_sgcn("sgcn_cfg1", R=90, B=4, L=2, H=8, seed=4),
+    # BASELINE config 4's graph size (264 ROIs) through the full model, and BASELINE config 1 exactly (B=32, H=16, 90 ROIs)
+    "imgsnp_r264": lambda: case_model("imgsnp_r264", L=2, H=16, R=264, B=8, pool=syn.ADNI_POOL, S=54, seed=6, compact=True),
+    "sgcn_cfg1_b32": lambda: case_sgcn("sgcn_cfg1_b32", R=90, B=32, L=2, H=16, seed=7, seeded=True),
+}
+
 if __name__ == "__main__":
-    case_collate()
-    case_model("imgsnp_small", L=3, H=8, R=30, B=6, pool=[9, 6, 4, 3, 1], S=20, seed=1, steps=3)
-    case_model("imgsnp_adni", L=2, H=16, R=90, B=4, pool=syn.ADNI_POOL, S=54, seed=2, skip_big_grads=True)
-    case_go("go_mid", pool=[40, 20, 10, 5, 1], S=150, B=5, C=7, seed=3)
-    case_sgcn("sgcn_cfg1", R=90, B=4, L=2, H=8, seed=4)
+    for name in (sys.argv[1:] or list(CASES)):
+        CASES[name]()

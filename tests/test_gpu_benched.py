@@ -1,0 +1,125 @@
+"""Parity of the thing that is BENCHMARKED, at the benchmarked size: BASELINE configs[1] exactly as bench.py runs it -- B=256
+graphs of 90 ROIs, `forward_pair` (plain + explain pass stacked), three streams, the whole step (zero_grad, forwards, losses,
+backward, fused Adam) captured in one CUDA graph and replayed -- against the oracle's `train_step_loss` + torch Adam on the CPU,
+in fp32 (what the reference would print) and fp64 (the truth).  Dropout is replayed from fixed masks on both sides.
+
+BatchNorm batch statistics, the B x B consistency loss, the per-CTA partial-sum reductions and the split-K choices all depend on
+the batch size, so the small golden fixtures do not cover this; the vectorised oracle runs B=256 in seconds.
+Reference: kernel/train_eval_sgcn_img_snps.py:511-548, kernel/sgcn_img_snp.py:207-307.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import igcn_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _mask_shapes(B, pool):
+    G, top = sum(pool), sum(pool[2:])
+    shapes = dict(go_enc0=(B, G, 1), go_enc1=(B, G - pool[0], 1), go_B=(B, top), go_dec0=(B, G - pool[0], 1), go_dec1=(B, G, 1),
+                  go_BD=(B, G), go_latent=(B, 32), lin1=(B, 64), lin1_regr=(B, 64))
+    ps = dict(go_enc0=0.4, go_enc1=0.4, go_B=0.5, go_dec0=0.4, go_dec1=0.4, go_BD=0.5, go_latent=0.5, lin1=0.5, lin1_regr=0.3)
+    return shapes, ps
+
+
+def _oracle_run(P0, prep, c, w, lam, masks_p, masks_e, dtype, steps):
+    P = {k: v.detach().clone().to(dtype).requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v.clone()
+         for k, v in P0.items()}
+    b = {k: torch.from_numpy(v) for k, v in c.items()}
+    for k in ("x", "edge_attr", "snps_feat", "clini_score", "tsne_fdim"):
+        b[k] = b[k].to(dtype)
+    leaves = [v for v in P.values() if v.requires_grad]
+    opt = torch.optim.Adam(leaves, lr=1e-3)
+    mp = {k: v.to(dtype) for k, v in masks_p.items()}
+    me = {k: v.to(dtype) for k, v in masks_e.items()}
+    losses, grads1 = [], None
+    for s in range(steps):
+        opt.zero_grad()
+        b["x"] = b["x"].detach().requires_grad_(True)
+        loss, _, _ = O.train_step_loss(P, prep, b, w["L"], w["R"], lam, 0.01, True, mp, me, with_orth=False)
+        loss.backward()
+        if s == 0:
+            grads1 = {k: v.grad.detach().clone() for k, v in P.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
+        opt.step()
+        losses.append(float(loss.detach()))
+    return losses, grads1, {k: v.detach() for k, v in P.items()}
+
+
+@pytest.mark.parametrize("workload,B", [("config2", 256), ("config4", 24)])
+def test_benched_graphed_step_vs_oracle(workload, B):
+    """config2: the benchmarked configuration exactly (B=256, R=90).  config4: the same step at 264 ROIs (BASELINE configs[3]'s
+    graph size) on a batch the CPU oracle finishes in seconds."""
+    import bench
+    from igcn_b200 import train as T
+    from igcn_b200.data import Batch, SubjectSet
+    w = dict(bench.WORKLOADS[workload], B=B)
+    lam = list(bench.LAMBDA)
+    dev = torch.device(DEV)
+    model, sub, (adj, go_snps, pool_dim) = bench.build_problem(w, 0, dev)
+    model = model.to(dev).train()
+    P0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    shapes, ps = _mask_shapes(B, w["pool"])
+    gen = torch.Generator().manual_seed(17)
+    masks_p = {k: (torch.rand(s, generator=gen) >= ps[k]).float() / (1 - ps[k]) for k, s in shapes.items()}
+    masks_e = {k: (torch.rand(s, generator=gen) >= ps[k]).float() / (1 - ps[k]) for k, s in shapes.items()}
+    model.dropout_masks = {k: torch.cat([masks_p[k], masks_e[k]], 0).to(dev) for k in shapes}     # rows [0,B) plain, [B,2B) explain
+    steps = 3
+    # ---- the benchmarked path: FlatAdam + GraphedTrainStep (forward_pair, 3 streams, one CUDA graph) -------------------------
+    opt = T.FlatAdam(model.parameters(), lr=1e-3)
+    batch = Batch.collate(SubjectSet(sub), np.arange(B), dev)
+    gs = T.GraphedTrainStep(model, opt, batch, lam, None, True)
+    names = [n for n, _ in model.named_parameters()]
+    losses, grads1 = [], None
+    for s in range(steps):
+        losses.append(float(gs()))
+        if s == 0:
+            torch.cuda.synchronize()
+            grads1 = {n: v.detach().cpu().clone() for n, v in zip(names, opt.grad_views)}
+    torch.cuda.synchronize()
+    final = {n: p.detach().cpu() for n, p in model.named_parameters()}
+    # ---- the oracle, fp32 and fp64 ---------------------------------------------------------------------------------------------
+    prep = O.go_index_prep(adj.T, go_snps, w["pool"])
+    c = O.collate(sub, np.arange(B))
+    l32, g32, p32 = _oracle_run(P0, prep, c, w, lam, masks_p, masks_e, torch.float32, steps)
+    l64, g64, p64 = _oracle_run(P0, prep, c, w, lam, masks_p, masks_e, torch.float64, steps)
+    tag = "%s B=%d graphed: " % (workload, B)
+    H.assert_parity(np.asarray(losses), np.asarray(l32), np.asarray(l64), what=tag + "loss trajectory")
+    checked = 0
+    for k, g in g64.items():
+        H.assert_parity(grads1[k], g32[k], g, what=tag + "step-1 grad " + k)
+        checked += 1
+    assert checked >= 40, checked
+    for k in g64:                       # every parameter that receives a gradient, after 3 fused Adam updates
+        H.assert_parity(final[k], p32[k], p64[k], what=tag + "after %d Adam steps: %s" % (steps, k))
+    for k, v in final.items():          # ... and the others did not move
+        if k not in g64:
+            assert torch.equal(v, P0[k]), k
+
+
+def test_lr_decay_is_honoured_by_eager_and_graphed_steps():
+    """The reference halves param_groups[0]['lr'] in place (train_eval_sgcn_img_snps.py:169-171); both step forms must follow."""
+    import bench
+    from igcn_b200 import train as T
+    from igcn_b200.data import Batch, SubjectSet
+    w = dict(bench.WORKLOADS["config2"], B=8)
+    dev = torch.device(DEV)
+    model, sub, _ = bench.build_problem(w, 0, dev)
+    model = model.to(dev).train()
+    model.dropout_masks = {k: torch.ones(1, device=dev) for k in O.MODEL_MASK_NAMES}
+    opt = T.FlatAdam(model.parameters(), lr=1e-3)
+    batch = Batch.collate(SubjectSet(sub), np.arange(8), dev)
+    for graphed in (False, True):
+        step = T.GraphedTrainStep(model, opt, batch, bench.LAMBDA, None, True) if graphed else \
+            (lambda: T.train_step(model, batch, opt, bench.LAMBDA, None, True))
+        moved = []
+        for lr in (1e-3, 0.0):
+            opt.param_groups[0]["lr"] = lr
+            before = opt.flat_param.clone()
+            step()
+            torch.cuda.synchronize()
+            moved.append(float((opt.flat_param - before).abs().max()))
+        assert moved[0] > 0.0 and moved[1] == 0.0, (graphed, moved)

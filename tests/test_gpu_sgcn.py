@@ -181,6 +181,23 @@ def test_sgcn_encoder_deterministic_and_full_size_properties():
     assert torch.equal(outs[0], outs[1])
     for a, c in zip(*grads):
         assert torch.equal(a, c)
+    # ... and the values themselves against the oracle at this size: fp32 oracle = reference, fp64 oracle = truth (rule A / B)
+    c = O.collate(sub, np.arange(n))
+    ei = torch.from_numpy(c["edge_index"])
+    res = {}
+    for dt in (torch.float32, torch.float64):
+        Po = {k: v.to(dt).clone().requires_grad_(True) for k, v in P.items()}
+        for k in list(Po):
+            if k.endswith(".bias"):
+                Po[k] = torch.zeros_like(Po[k]).requires_grad_(True)
+        xo = torch.from_numpy(c["x"]).to(dt).requires_grad_(True)
+        mm = O.cal_probability(Po, xo, ei, torch.from_numpy(c["edge_attr"]).to(dt), R)
+        ref = O.sgcn_encoder(Po, mm["x"], ei, mm["w"], L, R)
+        (ref.sum() + mm["p_e"].sum()).backward()
+        res[dt] = (ref.detach(), xo.grad, Po["prob"].grad, Po["conv1.lin.weight"].grad, Po["convs.0.lin.weight"].grad)
+    got = [outs[0]] + grads[0]
+    for nm, a, r32, r64 in zip(["out", "dx", "d prob", "dW1", "dW2"], got, res[torch.float32], res[torch.float64]):
+        H.assert_parity(a, r32, r64, what="encoder n=512 R=264 " + nm)
     o1, _ = ops.sgcn_encoder(b.x, b.csr, Ws, bs)
     o2, _ = ops.sgcn_encoder(b.x * 3.0, b.csr, Ws, bs)
     H.assert_close(o2, o1 * 3.0, what="homogeneity")

@@ -67,7 +67,12 @@ def test_go_network(loop):
         H.assert_close(P["go_network." + k].grad, v, what="grad " + k)
 
 
-@pytest.mark.parametrize("case", ["imgsnp_small", "imgsnp_adni"])
+def _lin_tail(case, t, n):
+    """the compact R=264 fixture stores out_lin as its latent tail (the leading part is out_z)"""
+    return t[:, -32:] if (case == "imgsnp_r264" and n == "out_lin") else t
+
+
+@pytest.mark.parametrize("case", ["imgsnp_small", "imgsnp_adni", "imgsnp_r264"])
 def test_full_model(case):
     g = H.load(case)
     L, Hd, R, B, S = [int(v) for v in g["cfg"]]
@@ -79,12 +84,12 @@ def test_full_model(case):
         for tag, ex in (("plain", False), ("explain", True)):
             o = O.model_forward(P, prep, b, L, R, ex, training=False)
             for n, t in zip(names, o):
-                H.assert_close(t, g["eval/%s/%s" % (tag, n)], what="eval %s %s" % (tag, n))
+                H.assert_close(_lin_tail(case, t, n), g["eval/%s/%s" % (tag, n)], what="eval %s %s" % (tag, n))
         for tag, ex in (("plain", False), ("explain", True)):
             masks = {k: torch.from_numpy(v) for k, v in H.sub_dict(g, "mask/%s/" % tag).items()}
             o = O.model_forward(P, prep, b, L, R, ex, training=True, masks=masks)
             for n, t in zip(names, o):
-                H.assert_close(t, g["train/%s/%s" % (tag, n)], what="train %s %s" % (tag, n))
+                H.assert_close(_lin_tail(case, t, n), g["train/%s/%s" % (tag, n)], what="train %s %s" % (tag, n))
             if tag == "plain":
                 H.assert_close(O.consist_loss(o[2], b["tsne_fdim"], 0.01), g["consist_loss"], what="consist")
                 H.assert_close(O.consist_loss(o[2]), g["consist_loss_ones"], what="consist ones")
@@ -102,13 +107,30 @@ def test_full_model(case):
     loss, _, _ = O.train_step_loss(P, prep, b, L, R, list(g["lambda_loss"]), 0.01, True, mp, me)
     loss.backward()
     H.assert_close(loss, g["step/loss"], what="step loss")
+    truth = _fp64_step_grads(g, prep, L, R, mp, me)
     for k, v in H.sub_dict(g, "grad/").items():
         assert P[k].grad is not None, k
-        H.assert_close(P[k].grad, v, rtol=2e-4, what="grad " + k)
+        H.assert_parity(P[k].grad, v, truth[k], what="grad " + k)
+    for k, v in H.sub_dict(g, "gradsum/rows/").items():
+        H.assert_parity(P[k].grad.sum(1), v, truth[k].sum(1), what="grad row sums " + k)
+    for k, v in H.sub_dict(g, "gradsum/cols/").items():
+        H.assert_parity(P[k].grad.sum(0), v, truth[k].sum(0), what="grad column sums " + k)
 
 
-def test_config1_sgcn_gcn():
-    g = H.load("sgcn_cfg1")
+def _fp64_step_grads(g, prep, L, R, mp, me):
+    """fp64 truth of the train() step's gradients (the oracle in double precision on the same inputs and masks)."""
+    P64 = H.params(g, dtype=torch.float64, grad=True)
+    b64 = _batch(H.subjects(g), dtype=torch.float64)
+    b64["x"].requires_grad_(True)
+    d = lambda m: {k: v.double() for k, v in m.items()}
+    loss, _, _ = O.train_step_loss(P64, prep, b64, L, R, list(g["lambda_loss"]), 0.01, True, d(mp), d(me))
+    loss.backward()
+    return {k: v.grad for k, v in P64.items() if v.grad is not None}
+
+
+@pytest.mark.parametrize("case", ["sgcn_cfg1", "sgcn_cfg1_b32"])
+def test_config1_sgcn_gcn(case):
+    g = H.load(case)
     L, Hd, R, B = [int(v) for v in g["cfg"]]
     b = _batch(H.subjects(g))
     P = H.params(g, "P_gcn/", grad=True)
@@ -126,11 +148,14 @@ def test_config1_sgcn_gcn():
     for k, v in H.sub_dict(g, "gcn/grad/").items():
         if k != "x":
             H.assert_close(P[k].grad, v, what="grad " + k)
+    for k, v in H.sub_dict(g, "gcn/gradsum/rows/").items():
+        H.assert_close(P[k].grad.sum(1), v, what="grad row sums " + k)
 
 
-def test_config1_gat_conv():
+@pytest.mark.parametrize("case", ["sgcn_cfg1", "sgcn_cfg1_b32"])
+def test_config1_gat_conv(case):
     """GATConv(edge_dim=1) layer stack of SGCN_GAT (kernel/sgcn.py:154-270) through the oracle's gat_conv."""
-    g = H.load("sgcn_cfg1")
+    g = H.load(case)
     L, Hd, R, B = [int(v) for v in g["cfg"]]
     b = _batch(H.subjects(g))
     P = H.params(g, "P_gat/", grad=True)
