@@ -56,22 +56,24 @@ __device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + __ex
 
 // grads[j] = sum over rows of partials[row][j], in a FIXED order (deterministic, no float atomics):
 // a block owns 32 consecutive columns; warp w adds rows w, w+8, ... (coalesced 128 B reads), then the 8 warp
-// sums are added in warp order.  Launch: <<<ceil(P/32), 256>>>.
+// sums are added in warp order.  The accumulation runs in fp64: with hundreds to thousands of per-CTA partials of mixed sign
+// (one per subject in the GO layers) an fp32 running sum loses ~1e-4 of a gradient to cancellation (measured at B=256 against
+// the fp64 oracle); the kernel reads n_rows * P floats once, so the fp64 adds are free.  Launch: <<<ceil(P/32), 256>>>.
 static __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int n_rows, int P,
                                                                      float* __restrict__ grads) {
-    __shared__ float sm[8][33];
+    __shared__ double sm[8][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + lane;
-    float s = 0.f;
+    double s = 0.0;
     if (j < P)
-        for (int r = warp; r < n_rows; r += 8) s += partials[(int64_t)r * P + j];
+        for (int r = warp; r < n_rows; r += 8) s += (double)partials[(int64_t)r * P + j];
     sm[warp][lane] = s;
     __syncthreads();
     if (warp == 0 && j < P) {
-        float t = 0.f;
+        double t = 0.0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) t += sm[w][lane];
-        grads[j] = t;
+        grads[j] = (float)t;
     }
 }
 

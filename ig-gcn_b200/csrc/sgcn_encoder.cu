@@ -425,7 +425,16 @@ __global__ void __launch_bounds__(256) sgcn_encoder_bwd_kernel(EncArgs a) {
 
 }  // namespace igcn
 #include "sgcn_fast.cuh"
+#include "sgcn_mma.cuh"
 namespace igcn {
+
+// second-generation kernels (sgcn_mma.cuh): reference shape only; IGCN_SGCN_MMA=0 keeps the register-tiled kernels (A/B hook)
+static bool use_mma(int64_t R, int64_t F0, int64_t H, int64_t L, int64_t relu) {
+    const char* e = getenv("IGCN_SGCN_MMA");
+    if (e && e[0] == '0') return false;
+    return F0 == kF0 && H == kH && L == 2 && relu && R <= mma::kMaxThreads;
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static bool use_fast(int64_t F0, int64_t H, int64_t L) {
     const char* e = getenv("IGCN_FORCE_GENERIC");   // test hook: exercise the shape-generic kernels
@@ -475,9 +484,14 @@ static int ctas_for(size_t smem, int64_t B) {
 static bool use_fast_bwd(int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg) {
     return use_fast(F0, H, L) && L == 2 && bwd_fast_smem((int)R, (int)max_eg) <= 227 * 1024;
 }
+// tensor-core backward (sgcn_mma.cuh): also one CTA per SM, so igcn_sgcn_bwd_ctas() is the same for both L == 2 paths
+static bool use_mma_bwd(int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg, bool explain) {
+    return use_fast(F0, H, L) && use_mma(R, F0, H, L, 1) &&
+           mma::bwd_mma_smem((int)R, (int)max_eg, mma::mma_bwd_threads((int)R), explain) <= 227 * 1024;
+}
 
 extern "C" int64_t igcn_sgcn_bwd_ctas(int64_t B, int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg) {
-    if (use_fast_bwd(R, F0, H, L, max_eg)) {
+    if (use_fast_bwd(R, F0, H, L, max_eg) || use_mma_bwd(R, F0, H, L, max_eg, true)) {
         int64_t n = sm_count();
         if (n > B) n = B;
         return n < 1 ? 1 : n;
@@ -499,6 +513,30 @@ extern "C" int igcn_sgcn_encoder_fwd(const float* x, const int32_t* rowptr_t, co
     EncArgs a{};
     a.x = x; a.rowptr_t = rowptr_t; a.csr_src = csr_src; a.csr_w = csr_w; a.prob = prob; a.prob_bias = prob_bias; a.wb = wb;
     a.out_w = out; a.pe_w = p_e; a.relu = relu ? 1 : 0; a.B = (int)B; a.R = (int)R; a.F0 = (int)F0; a.H = (int)H; a.L = (int)L; a.maxEg = (int)max_eg;
+    if (use_fast(F0, H, L) && use_mma(R, F0, H, L, relu) && aligned16(x) && aligned16(rowptr_t) && aligned16(csr_src) && aligned16(csr_w)) {
+        const int nthr = mma::mma_threads(a.R);
+        const size_t smem = mma::fwd_mma_smem(a.R, a.maxEg, nthr);
+        if (smem <= 227 * 1024) {
+            // CTAs per SM the register budget is compiled for: 3 (72 registers) or 2 (112); IGCN_SGCN_FWD_OCC=2|3 is the A/B hook
+            const char* occ = getenv("IGCN_SGCN_FWD_OCC");
+            const bool occ2 = occ && occ[0] == '2';
+            auto kern = prob ? (occ2 ? mma::sgcn_fwd_mma_kernel<true, 2> : mma::sgcn_fwd_mma_kernel<true, 3>)
+                             : (occ2 ? mma::sgcn_fwd_mma_kernel<false, 2> : mma::sgcn_fwd_mma_kernel<false, 3>);
+            rc = allow_smem(kern, smem, "sgcn_fwd_mma");
+            if (rc) return rc;
+            int per_sm = (int)((227 * 1024) / (smem + 1024));
+            if (occ2 && per_sm > 2 && nthr > 192) per_sm = 2;
+            const int by_threads = 2048 / nthr;
+            if (per_sm > by_threads) per_sm = by_threads;
+            if (per_sm > 8) per_sm = 8;
+            if (per_sm < 1) per_sm = 1;
+            int64_t grid = (int64_t)sm_count() * per_sm;
+            if (grid > B) grid = B;
+            kern<<<(int)grid, nthr, smem, (cudaStream_t)stream>>>(a);
+            IGCN_CHECK_LAUNCH("sgcn_fwd_mma");
+            return IGCN_OK;
+        }
+    }
     if (use_fast(F0, H, L)) {
         size_t smem = fwd_fast_smem(a.R, a.L, a.maxEg);
         if (smem <= 227 * 1024) {
@@ -551,7 +589,17 @@ extern "C" int igcn_sgcn_encoder_bwd(const float* x, const int32_t* rowptr_t, co
         cudaMemsetAsync(grads, 0, sizeof(float) * a.P, st);
         return IGCN_OK;
     }
-    if (use_fast_bwd(R, F0, H, L, max_eg)) {
+    const bool al = aligned16(x) && aligned16(rowptr_t) && aligned16(csr_src) && aligned16(csr_w) && aligned16(rowptr_s) &&
+                    aligned16(csc_pos) && aligned16(out) && aligned16(g_out) && (g_pe == nullptr || aligned16(g_pe));
+    if (relu && al && use_mma_bwd(R, F0, H, L, max_eg, prob != nullptr)) {
+        const int nthr = mma::mma_bwd_threads(a.R);
+        size_t smem = mma::bwd_mma_smem(a.R, a.maxEg, nthr, prob != nullptr);
+        auto kern = prob ? mma::sgcn_bwd_mma_kernel<true> : mma::sgcn_bwd_mma_kernel<false>;
+        rc = allow_smem(kern, smem, "sgcn_bwd_mma");
+        if (rc) return rc;
+        kern<<<want, nthr, smem, st>>>(a);
+        IGCN_CHECK_LAUNCH("sgcn_bwd_mma");
+    } else if (use_fast_bwd(R, F0, H, L, max_eg)) {
         size_t smem = bwd_fast_smem(a.R, a.maxEg);
         auto kern = prob ? sgcn_bwd_h16_kernel<true> : sgcn_bwd_h16_kernel<false>;
         rc = allow_smem(kern, smem, "sgcn_bwd_h16");

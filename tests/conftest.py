@@ -38,6 +38,8 @@ def pytest_sessionfinish(session, exitstatus):
             with open(os.path.join(d, "parity_report.json"), "w") as f:
                 json.dump(dict(rtol=H.RTOL, tensors=len(H.PARITY_LOG), rule_B=nb,
                                worst_rule_A=max([r["err32"] for r in H.PARITY_LOG if r["rule"] == "A"] or [0.0]),
-                               rule_B_tensors=[r for r in H.PARITY_LOG if r["rule"] == "B"]), f, indent=1)
+                               rule_B_tensors=[r for r in H.PARITY_LOG if r["rule"] == "B"],
+                               worst_rule_A_tensors=sorted([r for r in H.PARITY_LOG if r["rule"] == "A"],
+                                                           key=lambda r: -r["err32"])[:12]), f, indent=1)
     except Exception:
         pass

@@ -89,6 +89,34 @@ def assert_close(a, b, rtol=RTOL, what=""):
     return e
 
 
+class Collector(object):
+    """Collects parity failures so one GPU run reports every offending tensor, then fails once: `with Collector() as c:
+    c.parity(...)`."""
+
+    def __init__(self):
+        self.failures = []
+
+    def __enter__(self):
+        return self
+
+    def parity(self, *a, **kw):
+        try:
+            return assert_parity(*a, **kw)
+        except AssertionError as e:
+            self.failures.append(str(e))
+
+    def close(self, *a, **kw):
+        try:
+            return assert_close(*a, **kw)
+        except AssertionError as e:
+            self.failures.append(str(e))
+
+    def __exit__(self, et, ev, tb):
+        if et is None and self.failures:
+            raise AssertionError("%d tensors out of tolerance:\n  " % len(self.failures) + "\n  ".join(self.failures))
+        return False
+
+
 def assert_parity(got, ref32, truth64, what="", rtol=RTOL):
     """Rule A against ref32, else rule B against the fp64 truth (see the module docstring).  Returns the rule that applied."""
     e32 = rel_err(got, ref32)

@@ -49,6 +49,32 @@ def _oracle_run(P0, prep, c, w, lam, masks_p, masks_e, dtype, steps):
     return losses, grads1, {k: v.detach() for k, v in P.items()}
 
 
+def _adam_params_close(got, p32, p64, g64, steps, lr):
+    """Parameters after `steps` Adam updates.  Adam divides every coordinate by the root of its own second moment, so each live
+    coordinate moves ~lr per step whatever its gradient's size, and a coordinate whose gradient g_i is small against the tensor
+    inherits the RELATIVE error of g_i.  A gradient that meets the parity bar (|dg_i| <= RTOL (|g_i| + rms g), tests/helpers.py)
+    therefore admits a displacement error of steps * lr * min(1, c * RTOL (|g_i| + rms g) / |g_i|) on coordinate i -- up to a full
+    step where g_i vanishes (e.g. the attention's key bias, whose gradient is identically zero and whose update follows the sign of
+    rounding noise, in the reference as much as here).  c = 4 covers the m / sqrt(v) ratio over the steps.  On top of that the
+    usual rule A / rule B applies to the parameter values themselves.  Returns None or a failure message."""
+    got, p32, p64, g = got.double(), p32.double(), p64.double(), g64.double().abs()
+    rms_g = float(torch.sqrt((g * g).mean()))
+    sens = H.RTOL * (g + rms_g) / g.clamp_min(1e-300)
+    slack = steps * lr * torch.clamp(4.0 * sens, max=1.0)
+    rms_p = float(torch.sqrt((p32 * p32).mean()))
+    tol = slack + H.RTOL * (p32.abs() + rms_p)
+    bad32 = (got - p32).abs() > tol
+    if not bool(bad32.any()):
+        return None
+    # rule B on the offending coordinates: not further from the fp64 run than the fp32 reference is, by more than 2x
+    eg, er = (got - p64).abs()[bad32], (p32 - p64).abs()[bad32]
+    if bool((eg <= 2.0 * er + tol[bad32]).all()):
+        return None
+    i = int(((got - p32).abs() - tol).argmax())
+    return "coordinate %d: |got - ref32| = %.3e > %.3e (|g_i| / rms g = %.2e)" % (
+        i, float((got - p32).abs().flatten()[i]), float(tol.flatten()[i]), float(g.flatten()[i]) / max(rms_g, 1e-300))
+
+
 @pytest.mark.parametrize("workload,B", [("config2", 256), ("config4", 24)])
 def test_benched_graphed_step_vs_oracle(workload, B):
     """config2: the benchmarked configuration exactly (B=256, R=90).  config4: the same step at 264 ROIs (BASELINE configs[3]'s
@@ -87,14 +113,15 @@ def test_benched_graphed_step_vs_oracle(workload, B):
     l32, g32, p32 = _oracle_run(P0, prep, c, w, lam, masks_p, masks_e, torch.float32, steps)
     l64, g64, p64 = _oracle_run(P0, prep, c, w, lam, masks_p, masks_e, torch.float64, steps)
     tag = "%s B=%d graphed: " % (workload, B)
-    H.assert_parity(np.asarray(losses), np.asarray(l32), np.asarray(l64), what=tag + "loss trajectory")
-    checked = 0
-    for k, g in g64.items():
-        H.assert_parity(grads1[k], g32[k], g, what=tag + "step-1 grad " + k)
-        checked += 1
-    assert checked >= 40, checked
-    for k in g64:                       # every parameter that receives a gradient, after 3 fused Adam updates
-        H.assert_parity(final[k], p32[k], p64[k], what=tag + "after %d Adam steps: %s" % (steps, k))
+    with H.Collector() as col:
+        col.parity(np.asarray(losses), np.asarray(l32), np.asarray(l64), what=tag + "loss trajectory")
+        assert len(g64) >= 40, len(g64)
+        for k, g in g64.items():
+            col.parity(grads1[k], g32[k], g, what=tag + "step-1 grad " + k)
+        for k in g64:                   # every parameter that receives a gradient, after 3 fused Adam updates
+            msg = _adam_params_close(final[k], p32[k], p64[k], g64[k], steps, 1e-3)
+            if msg:
+                col.failures.append(tag + "after %d Adam steps: %s: %s" % (steps, k, msg))
     for k, v in final.items():          # ... and the others did not move
         if k not in g64:
             assert torch.equal(v, P0[k]), k

@@ -176,7 +176,8 @@ def test_full_model_golden(case):
                 # 180.392 on imgsnp_adni); the Gram form is compared with the fp64 oracle on the golden out_z
                 truth = O.orthogonal_constraint(torch.from_numpy(g["train/plain/out_z"]).double())
                 H.assert_close(m.OrthogonalConstraint(o[2]), truth, what="orth (fp64 truth)")
-                assert abs(float(truth) - float(g["orthogonal"])) / float(truth) < 5e-3
+                # (5.4e-3 at 264 ROIs: the reference's own fp32 error grows with D = R*L*H)
+                assert abs(float(truth) - float(g["orthogonal"])) / float(truth) < 2e-2
         H.assert_close(m.loss_probability(b.x, b.edge_index, b.edge_attr, T.hp), g["loss_probability"], what="loss_prob")
         cp = m.cal_probability(b.x, b.edge_index, b.edge_attr, b.snps_feat)
         for n, t in zip(["x_feat_prob", "edge_weight_prob", "x_prob", "edge_prob", "snps_feat_prob", "snps_prob"], cp):

@@ -93,7 +93,8 @@ def _enc_params(L, Hd, R, F0, seed, dtype):
 
 
 @pytest.mark.parametrize("n,R,L,Hd,ragged", [(6, 30, 3, 8, True), (16, 90, 2, 16, False), (5, 264, 2, 16, True),
-                                               (9, 90, 4, 5, False), (7, 90, 2, 10, True), (4, 90, 1, 16, False)])
+                                               (9, 90, 4, 5, False), (7, 90, 2, 10, True), (4, 90, 1, 16, False),
+                                               (11, 33, 2, 16, True), (3, 288, 2, 16, False), (40, 7, 2, 16, True)])
 @pytest.mark.parametrize("explain", [False, True])
 def test_sgcn_encoder_fwd_bwd(n, R, L, Hd, ragged, explain):
     from igcn_b200 import ops
@@ -144,6 +145,14 @@ def test_sgcn_encoder_fwd_bwd(n, R, L, Hd, ragged, explain):
         H.assert_close(Pc[k].grad, P64[k].grad, what="grad " + k)
     if not explain:
         assert Pc["prob"].grad is None
+
+
+def test_register_tiled_kernels_on_default_shape(monkeypatch):
+    """F0=3/H=16/L=2 takes the tensor-core kernels (sgcn_mma.cuh); IGCN_SGCN_MMA=0 sends the same shape through the register-tiled
+    kernels of sgcn_fast.cuh (the path of L != 2), so both stay covered."""
+    monkeypatch.setenv("IGCN_SGCN_MMA", "0")
+    test_sgcn_encoder_fwd_bwd(6, 90, 2, 16, True, True)
+    test_sgcn_encoder_fwd_bwd(5, 264, 2, 16, True, False)
 
 
 def test_generic_kernels_on_default_shape(monkeypatch):
