@@ -390,6 +390,7 @@ static int attn_fill(AttnArgs& a, const char* who, const float* x, const float* 
 }  // namespace igcn
 
 #include "cross_attn_rows.cuh"
+#include "cross_attn_mma.cuh"
 
 namespace igcn {
 
@@ -398,6 +399,25 @@ static bool use_rows(int64_t R, int64_t M, int64_t E, int64_t heads) {
     if (getenv("IGCN_ATTN_STAGED")) return false;            // A/B hook
     if (E != rows::kE || M < 1 || M > 32 || R > 288 || heads < 1 || (E % heads) != 0 || ((E / heads) % 4) != 0) return false;
     return rows::fwd_geo((int)R, (int)M, (int)heads).smem <= 110 * 1024 && rows::bwd_geo((int)R, (int)M, (int)heads).smem <= 224 * 1024;
+}
+// tensor-core kernels (cross_attn_mma.cuh): same shapes as the row kernels; IGCN_ATTN_ROWS=1 keeps the FFMA row kernels (A/B hook)
+static bool use_mma_fwd(int64_t R, int64_t M, int64_t E, int64_t heads) {
+    if (getenv("IGCN_ATTN_ROWS")) return false;
+    return use_rows(R, M, E, heads) && amma::fwd_geo((int)R, (int)M, (int)heads).smem <= 110 * 1024;
+}
+static bool use_mma_bwd(int64_t R, int64_t M, int64_t E, int64_t heads) {
+    if (getenv("IGCN_ATTN_ROWS")) return false;
+    return use_rows(R, M, E, heads) && amma::bwd_geo((int)R, (int)M, (int)heads).smem <= 227 * 1024;
+}
+template <int NT>
+static void launch_mma_bwd(const AttnArgs& a, const amma::GeoB& g, int ctas, cudaStream_t st) {
+    cudaFuncSetAttribute(amma::attn_mma_bwd_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    amma::attn_mma_bwd_kernel<NT><<<ctas, g.nthreads, g.smem, st>>>(a, g);
+}
+template <int NT>
+static void launch_mma_fwd(const AttnArgs& a, const amma::Geo& g, int ctas, cudaStream_t st) {
+    cudaFuncSetAttribute(amma::attn_mma_fwd_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    amma::attn_mma_fwd_kernel<NT><<<ctas, amma::kThreads, g.smem, st>>>(a, g);
 }
 static int rows_ctas(const rows::Geo& g, int64_t B, int per_sm) {
     const int64_t groups = (B + g.gpc - 1) / g.gpc;
@@ -422,6 +442,11 @@ using namespace igcn;
 
 extern "C" int64_t igcn_cross_attn_param_count(int64_t E) { return 4 * E * E + 4 * E; }
 extern "C" int64_t igcn_cross_attn_bwd_ctas(int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads) {
+    if (use_mma_bwd(R, M, E, heads)) {                       // one graph per pass, one CTA per SM
+        int64_t n = sm_count();
+        if (n > B) n = B;
+        return n < 1 ? 1 : n;
+    }
     if (use_rows(R, M, E, heads)) {
         const rows::Geo g = rows::bwd_geo((int)R, (int)M, (int)heads);
         return rows_ctas(g, B, g.smem <= 110 * 1024 ? 2 : 1);
@@ -438,6 +463,22 @@ extern "C" int igcn_cross_attn_fwd(const float* q_in, const float* kv_in, const 
     IGCN_REQUIRE(out, IGCN_ERR_BAD_ARG, "cross_attn_fwd: null output");
     if (B == 0) return IGCN_OK;
     a.y = out;
+    if (use_mma_fwd(R, M, E, heads)) {
+        IGCN_REQUIRE(((uintptr_t)q_in | (uintptr_t)out) % 16 == 0, IGCN_ERR_BAD_ARG, "cross_attn_fwd: buffers must be 16-byte aligned");
+        const amma::Geo g = amma::fwd_geo((int)R, (int)M, (int)heads);
+        const int64_t groups = (B + g.gpc - 1) / g.gpc;
+        int64_t ctas = (int64_t)sm_count() * 2;
+        if (ctas > groups) ctas = groups;
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (g.MP / 8) {
+            case 1: launch_mma_fwd<1>(a, g, (int)ctas, st); break;
+            case 2: launch_mma_fwd<2>(a, g, (int)ctas, st); break;
+            case 3: launch_mma_fwd<3>(a, g, (int)ctas, st); break;
+            default: launch_mma_fwd<4>(a, g, (int)ctas, st); break;
+        }
+        IGCN_CHECK_LAUNCH("cross_attn_mma_fwd");
+        return IGCN_OK;
+    }
     if (use_rows(R, M, E, heads)) {
         const rows::Geo g = rows::fwd_geo((int)R, (int)M, (int)heads);
         const int ctas = rows_ctas(g, B, 2);
@@ -472,6 +513,21 @@ extern "C" int igcn_cross_attn_bwd(const float* q_in, const float* kv_in, const 
     const int want = (int)igcn_cross_attn_bwd_ctas(B, R, M, E, heads);
     IGCN_REQUIRE(n_cta == want, IGCN_ERR_BAD_ARG, "cross_attn_bwd: n_cta=%lld, expected %d", (long long)n_cta, want);
     a.yout = out; a.gy = g_out; a.dx = d_q_in; a.da = d_kv_in; a.partials = partials;
+    if (use_mma_bwd(R, M, E, heads)) {
+        IGCN_REQUIRE(((uintptr_t)q_in | (uintptr_t)out | (uintptr_t)g_out | (uintptr_t)d_q_in | (uintptr_t)d_kv_in) % 16 == 0, IGCN_ERR_BAD_ARG,
+                     "cross_attn_bwd: buffers must be 16-byte aligned");
+        const amma::GeoB g = amma::bwd_geo((int)R, (int)M, (int)heads);
+        switch (g.MP / 8) {
+            case 1: launch_mma_bwd<1>(a, g, want, st); break;
+            case 2: launch_mma_bwd<2>(a, g, want, st); break;
+            case 3: launch_mma_bwd<3>(a, g, want, st); break;
+            default: launch_mma_bwd<4>(a, g, want, st); break;
+        }
+        IGCN_CHECK_LAUNCH("cross_attn_mma_bwd");
+        reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(partials, want, a.P, grads);
+        IGCN_CHECK_LAUNCH("cross_attn_reduce_partials");
+        return IGCN_OK;
+    }
     if (use_rows(R, M, E, heads)) {
         IGCN_REQUIRE(((uintptr_t)out | (uintptr_t)g_out | (uintptr_t)d_q_in | (uintptr_t)d_kv_in) % 16 == 0, IGCN_ERR_BAD_ARG, "cross_attn_bwd: buffers must be 16-byte aligned");
         const rows::Geo g = rows::bwd_geo((int)R, (int)M, (int)heads);
