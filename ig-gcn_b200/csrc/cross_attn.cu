@@ -27,6 +27,7 @@ struct AttnArgs {
     float* da;          // (B, M, E)
     float* partials;    // (n_cta, P)  P = 3E*E + 3E + E*E + E : [dWin | dbin | dWo | dbo]
     int B, R, M, E, heads, relu, P;
+    int mix;            // 1: y = (x + relu(attn(x))) / 2 in one pass (kernel/sgcn_img_snp.py:239-242 + the fusion average); tensor-core kernels only
     int Rc;             // query rows staged per chunk
 };
 
@@ -381,7 +382,7 @@ static int attn_fill(AttnArgs& a, const char* who, const float* x, const float* 
     IGCN_REQUIRE(((uintptr_t)x | (uintptr_t)kv) % 16 == 0, IGCN_ERR_BAD_ARG, "%s: inputs must be 16-byte aligned", who);
     IGCN_REQUIRE(x && kv && Win && bin && Wo && bo, IGCN_ERR_BAD_ARG, "%s: null pointer", who);
     a.x = x; a.a = kv; a.Win = Win; a.bin = bin; a.Wo = Wo; a.bo = bo;
-    a.B = (int)B; a.R = (int)R; a.M = (int)M; a.E = (int)E; a.heads = (int)heads; a.relu = relu ? 1 : 0;
+    a.B = (int)B; a.R = (int)R; a.M = (int)M; a.E = (int)E; a.heads = (int)heads; a.relu = relu ? 1 : 0; a.mix = relu == 2 ? 1 : 0;
     a.P = (int)(4 * E * E + 4 * E);
     a.Rc = attn_rows_per_chunk((int)R, (int)M, (int)E, (int)heads);
     return IGCN_OK;
@@ -441,6 +442,9 @@ static void launch_rows_bwd(const AttnArgs& a, const rows::Geo& g, int ctas, cud
 using namespace igcn;
 
 extern "C" int64_t igcn_cross_attn_param_count(int64_t E) { return 4 * E * E + 4 * E; }
+extern "C" int64_t igcn_cross_attn_fused_average(int64_t R, int64_t M, int64_t E, int64_t heads) {
+    return (use_mma_fwd(R, M, E, heads) && use_mma_bwd(R, M, E, heads)) ? 1 : 0;
+}
 extern "C" int64_t igcn_cross_attn_bwd_ctas(int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads) {
     if (use_mma_bwd(R, M, E, heads)) {                       // one graph per pass, one CTA per SM
         int64_t n = sm_count();
@@ -463,6 +467,7 @@ extern "C" int igcn_cross_attn_fwd(const float* q_in, const float* kv_in, const 
     IGCN_REQUIRE(out, IGCN_ERR_BAD_ARG, "cross_attn_fwd: null output");
     if (B == 0) return IGCN_OK;
     a.y = out;
+    IGCN_REQUIRE(!a.mix || use_mma_fwd(R, M, E, heads), IGCN_ERR_UNSUPPORTED, "cross_attn_fwd: relu=2 (fused average) needs the tensor-core shape");
     if (use_mma_fwd(R, M, E, heads)) {
         IGCN_REQUIRE(((uintptr_t)q_in | (uintptr_t)out) % 16 == 0, IGCN_ERR_BAD_ARG, "cross_attn_fwd: buffers must be 16-byte aligned");
         const amma::Geo g = amma::fwd_geo((int)R, (int)M, (int)heads);
@@ -513,6 +518,7 @@ extern "C" int igcn_cross_attn_bwd(const float* q_in, const float* kv_in, const 
     const int want = (int)igcn_cross_attn_bwd_ctas(B, R, M, E, heads);
     IGCN_REQUIRE(n_cta == want, IGCN_ERR_BAD_ARG, "cross_attn_bwd: n_cta=%lld, expected %d", (long long)n_cta, want);
     a.yout = out; a.gy = g_out; a.dx = d_q_in; a.da = d_kv_in; a.partials = partials;
+    IGCN_REQUIRE(!a.mix || use_mma_bwd(R, M, E, heads), IGCN_ERR_UNSUPPORTED, "cross_attn_bwd: relu=2 (fused average) needs the tensor-core shape");
     if (use_mma_bwd(R, M, E, heads)) {
         IGCN_REQUIRE(((uintptr_t)q_in | (uintptr_t)out | (uintptr_t)g_out | (uintptr_t)d_q_in | (uintptr_t)d_kv_in) % 16 == 0, IGCN_ERR_BAD_ARG,
                      "cross_attn_bwd: buffers must be 16-byte aligned");

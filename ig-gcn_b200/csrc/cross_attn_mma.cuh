@@ -235,6 +235,12 @@ __global__ void __launch_bounds__(kThreads, 2) attn_mma_fwd_kernel(AttnArgs a, G
                 if (a.relu) {
                     v0.x = fmaxf(v0.x, 0.f); v0.y = fmaxf(v0.y, 0.f); v1.x = fmaxf(v1.x, 0.f); v1.y = fmaxf(v1.y, 0.f);
                 }
+                if (a.mix) {                                 // out_z = (img + relu(attn)) / 2: the query row is in the staged tile
+                    const float2 x0 = *reinterpret_cast<const float2*>(Xs + (gl * R + r0) * TS + 8 * n2 + 2 * tq);
+                    const float2 x1 = *reinterpret_cast<const float2*>(Xs + (gl * R + r1) * TS + 8 * n2 + 2 * tq);
+                    v0.x = 0.5f * (x0.x + v0.x); v0.y = 0.5f * (x0.y + v0.y);
+                    v1.x = 0.5f * (x1.x + v1.x); v1.y = 0.5f * (x1.y + v1.y);
+                }
                 if (r0 < R) *reinterpret_cast<float2*>(yg + r0 * kE + 8 * n2 + 2 * tq) = v0;
                 if (r1 < R) *reinterpret_cast<float2*>(yg + r1 * kE + 8 * n2 + 2 * tq) = v1;
             }
@@ -361,7 +367,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_mma_bwd_kernel(AttnArgs a, G
                 xv = ld4s(xg + (int64_t)idx * 4);
                 g = ld4s(gg + (int64_t)idx * 4);
                 if (a.relu) {
-                    const float4 yv = ld4s(yg + (int64_t)idx * 4);
+                    float4 yv = ld4s(yg + (int64_t)idx * 4);
+                    if (a.mix) {        // saved output is (x + relu(y)) / 2: relu(y) = 2 out - x ; the attention branch sees half the gradient
+                        yv.x = 2.f * yv.x - xv.x; yv.y = 2.f * yv.y - xv.y; yv.z = 2.f * yv.z - xv.z; yv.w = 2.f * yv.w - xv.w;
+                        g.x *= 0.5f; g.y *= 0.5f; g.z *= 0.5f; g.w *= 0.5f;
+                    }
                     if (!(yv.x > 0.f)) g.x = 0.f;
                     if (!(yv.y > 0.f)) g.y = 0.f;
                     if (!(yv.z > 0.f)) g.z = 0.f;
@@ -456,11 +466,19 @@ __global__ void __launch_bounds__(kThreads, 1) attn_mma_bwd_kernel(AttnArgs a, G
                         if (r0 < R) {
                             float2 v = make_float2(dx[n2][0], dx[n2][1]);
                             if (h > 0) { const float2 o = *d0; v.x += o.x; v.y += o.y; }
+                            else if (a.mix) {                  // the direct half of the average: d out / d x = 1/2
+                                const float2 o = *reinterpret_cast<const float2*>(gg + r0 * kE + 8 * n2 + 2 * tq);
+                                v.x = fmaf(0.5f, o.x, v.x); v.y = fmaf(0.5f, o.y, v.y);
+                            }
                             *d0 = v;
                         }
                         if (r1 < R) {
                             float2 v = make_float2(dx[n2][2], dx[n2][3]);
                             if (h > 0) { const float2 o = *d1; v.x += o.x; v.y += o.y; }
+                            else if (a.mix) {
+                                const float2 o = *reinterpret_cast<const float2*>(gg + r1 * kE + 8 * n2 + 2 * tq);
+                                v.x = fmaf(0.5f, o.x, v.x); v.y = fmaf(0.5f, o.y, v.y);
+                            }
                             *d1 = v;
                         }
                     }

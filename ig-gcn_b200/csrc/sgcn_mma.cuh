@@ -538,6 +538,10 @@ __global__ void __launch_bounds__(kBwdMaxThreads, 1) sgcn_bwd_mma_kernel(EncArgs
         if (has_gpe) issue_window(a.g_pe, ws, sb.gpe, bar);
     };
     auto issue_tile = [&](const float* src, float* dst, uint32_t bar) {
+        // the tile buffers were read -- and the layer-2 half of the gradient tile WRITTEN (dZ2 in place) -- through the generic
+        // proxy; the block barrier in front of every call ordered those accesses among the threads, this fence orders them
+        // before the async-proxy write of the refill (without it a late generic store can land on top of the new tile)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(bar, tile_bytes);
         bulk_g2s(smem_u32(dst), src, tile_bytes, bar);
     };

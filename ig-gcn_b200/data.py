@@ -65,6 +65,24 @@ class GraphCSR(object):
             setattr(self, k, v)
 
 
+# ---- batch-structure registry: lets the PyG-signature operators (pyg.py), which receive bare `edge_index` / `batch` tensors, find
+#      the structure of a collation this package produced (graphs of R nodes, CSR already built) without a host round trip -------------
+_structures = {}
+
+
+def register_structure(csr, *tensors):
+    for t in tensors:
+        if t is not None:
+            _structures[(t.data_ptr(), tuple(t.shape), str(t.device))] = csr
+    while len(_structures) > 64:
+        _structures.pop(next(iter(_structures)))
+
+
+def lookup_structure(t):
+    """GraphCSR registered for this `edge_index` / `batch` tensor by Batch (same storage and shape), or None."""
+    return None if t is None else _structures.get((t.data_ptr(), tuple(t.shape), str(t.device)))
+
+
 class SubjectSet(object):
     """A dataset of equally-sized brain graphs as packed host arrays (see synthetic.make_subjects for the
     field list).  Arrays are converted once to torch tensors in pinned memory when CUDA is available."""
@@ -257,6 +275,7 @@ class Batch(Data):
         b.clust_y = d["clust_y"]
         b.sbjID = d["sbjID"]
         b._num_graphs, b._csr, b.rois = B, csr, R
+        register_structure(csr, b.edge_index, b.batch)
         return b
 
     @staticmethod
@@ -306,6 +325,7 @@ class Batch(Data):
         for k, v in extra.items():
             setattr(b, k, v)
         b._num_graphs, b._csr, b.rois = B, csr, rois
+        register_structure(csr, b.edge_index, b.batch)
         return b
 
 

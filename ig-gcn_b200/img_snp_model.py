@@ -27,45 +27,7 @@ from torch.nn.parameter import Parameter
 from . import ops
 from .data import Batch
 from .go_net import Gene_ontology_network
-
-
-class _Lin(nn.Module):
-    """Holds `weight` so the GCN weight sits at `<conv>.lin.weight` as in PyG 2.0.2."""
-
-    def __init__(self, cin, cout):
-        super().__init__()
-        self.weight = Parameter(torch.empty(cout, cin))
-
-    def reset_parameters(self):
-        a = math.sqrt(6.0 / (self.weight.size(0) + self.weight.size(1)))     # PyG glorot
-        with torch.no_grad():
-            self.weight.uniform_(-a, a)
-
-
-class GCNConv(nn.Module):
-    """Parameter container with PyG's GCNConv names (`lin.weight` (out,in), `bias` (out,)).  The SGCN models
-    run all their GCNConv layers through one fused kernel; see ops.sgcn_encoder."""
-
-    def __init__(self, in_channels, out_channels):
-        super().__init__()
-        self.in_channels, self.out_channels = in_channels, out_channels
-        self.lin = _Lin(in_channels, out_channels)
-        self.bias = Parameter(torch.zeros(out_channels))
-        self.reset_parameters()
-
-    def reset_parameters(self):
-        self.lin.reset_parameters()
-        init.zeros_(self.bias)
-
-    def forward(self, x, edge_index, edge_weight=None, csr=None):
-        if edge_weight is not None and edge_weight.requires_grad:
-            raise RuntimeError("igcn_b200.GCNConv: gradients w.r.t. edge_weight are produced by the fused encoder "
-                               "(ops.sgcn_encoder with prob/prob_bias), not by the single-layer operator")
-        if csr is None:
-            w = edge_weight if edge_weight is not None else torch.ones(edge_index.shape[1], device=x.device)
-            csr = Batch.from_device_tensors(x.detach(), edge_index, w, x.shape[0]).csr      # one graph of N nodes
-        out, _ = ops.sgcn_encoder(x, csr, [self.lin.weight], [self.bias], relu=False)
-        return out.view(x.shape[0], self.out_channels)
+from .pyg import GCNConv            # PyG-signature operator; here the holder of `conv*.lin.weight` / `conv*.bias` (the stack runs fused)
 
 
 # IGCN_ONE_STREAM=1 keeps the whole step on one stream (A/B hook)
@@ -325,15 +287,20 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         go = self.go_network
         go.dropout_masks = self.dropout_masks
         latent, x_hat, _, atten_out = go(snps_feat_prob, temperature, device)
-        if self.isCrossAtten:
+        fused_avg = self.isCrossAtten and not self.graph_pool and not self.isImageOnly and not self.isSNPsOnly
+        if fused_avg:
+            # out_z = (img_out + relu(MHA(q = ROI tokens, k = v = GO tokens))) / 2 as one kernel each way (cross_attn_mma.cuh)
+            out_cross = None
+        elif self.isCrossAtten:
             # relu(MHA(q = ROI tokens, k = v = GO tokens)) as one kernel (cross_attn.cu)
             out_cross = ops.cross_attention(batch_x, atten_out, self.multihead_attn, relu=True)
         else:
             out_cross = torch.cat((img_out, latent), -1)
-        if self.graph_pool:
-            out_cross = torch.cat([out_cross.mean(1), out_cross.max(1)[0], out_cross.sum(1)], 1)
-        else:
-            out_cross = out_cross.reshape(B, -1)
+        if out_cross is not None:
+            if self.graph_pool:
+                out_cross = torch.cat([out_cross.mean(1), out_cross.max(1)[0], out_cross.sum(1)], 1)
+            else:
+                out_cross = out_cross.reshape(B, -1)
 
         def regr_head(parts):
             if self.isuseProb4Regr:
@@ -350,7 +317,8 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             out_z = latent
             parts = [snps_feat_prob, latent]
         else:
-            out_z = (img_out + out_cross) / 2
+            out_z = ops.cross_attention_average(batch_x, atten_out, self.multihead_attn).reshape(B, -1) if fused_avg \
+                else (img_out + out_cross) / 2
             parts = [out_z, latent]
         # out_lin is part of the returned tuple (eval_scores collects it, train_eval...:626); the heads read its parts in place
         out_lin = parts[0] if len(parts) == 1 else torch.cat(parts, -1).detach()
@@ -427,9 +395,8 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
                     t.record_stream(main)
         else:
             latent, x_hat, _, atten_out = go(snps2, temperature, device, groups=2)
-        img_out = batch_x.view(2 * B, -1)
-        out_cross = ops.cross_attention(batch_x, atten_out, self.multihead_attn, relu=True).reshape(2 * B, -1)
-        out_z = (img_out + out_cross) / 2
+        # out_z = (img_out + relu(attention)) / 2 in ONE kernel each way (the average is the attention kernels' epilogue)
+        out_z = ops.cross_attention_average(batch_x, atten_out, self.multihead_attn).reshape(2 * B, -1)
         if consist and stacked and side2 is not None and self.isSoftSimilarity and _PREFETCH_CONSIST:
             # the consistency loss needs only out_z: its Laplacian product starts now on the third stream, beside the fusion heads
             tsne = data.tsne_fdim
@@ -443,12 +410,14 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             for t in (latent, x_hat):
                 t.record_stream(main)
         parts = [out_z, latent]
-        out_lin = torch.cat(parts, -1).detach()
+        # out_lin is a RETURNED tensor only (eval_scores collects it, train() never reads it): the stacked fast path of
+        # train.step_loss does not materialise the concatenation
+        out_lin = None if stacked else torch.cat(parts, -1).detach()
         linear_outf = ops.cat_linear(parts, self.lin1.weight, self.lin1.bias, relu=True)
         rparts = parts
         if self.isuseProb4Regr:
             img_feat = (x.view(B, self.rois, -1) * self.prob).reshape(B, -1)
-            rparts = parts + [torch.cat([img_feat, img_feat], 0)]
+            rparts = parts + [img_feat]                      # B rows: cat_linear reads it for both stacked passes
         r = ops.cat_linear(rparts, self.lin1_regr.weight, self.lin1_regr.bias, relu=True)
         # dropout, lin2 + log_softmax and lin2_regr of both heads in one launch (glue.cu)
         logp, our_reg = ops.output_heads(linear_outf, self._mask_of("lin1", linear_outf, 0.5), r, self._mask_of("lin1_regr", r, 0.3),
@@ -457,7 +426,7 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             bank.end_pass()
         outs = (logp, x_hat, out_z, out_lin, linear_outf, our_reg)
         if stacked:
-            return outs                # rows [0, B) = plain pass, rows [B, 2B) = explain pass
+            return outs                # rows [0, B) = plain pass, rows [B, 2B) = explain pass (out_lin: None, see above)
         return tuple(t[:B] for t in outs), tuple(t[B:] for t in outs)
 
     def _go_stream(self, device, which=0):

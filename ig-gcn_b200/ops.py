@@ -18,6 +18,49 @@ def pack_layer_params(weights, biases):
     return torch.cat(parts) if parts else None
 
 
+def _adjacent_view(tensors):
+    """If the tensors sit back to back in one storage (train.FlatAdam lays the parameters out in registration order, which for
+    the SGCN layers IS the wb order), return a zero-copy 1-D view over all of them; else None."""
+    if not tensors:
+        return None
+    t0 = tensors[0]
+    if not t0.is_contiguous():
+        return None
+    ptr, n = t0.data_ptr(), 0
+    for t in tensors:
+        if not t.is_contiguous() or t.dtype != torch.float32 or t.data_ptr() != ptr + 4 * n or t.device != t0.device:
+            return None
+        n += t.numel()
+    try:
+        return torch.as_strided(t0.detach(), (n,), (1,), t0.storage_offset())
+    except RuntimeError:
+        return None
+
+
+class _SplitGradFn(torch.autograd.Function):
+    """wb = concatenation of the layer parameters WITHOUT a copy when they are adjacent in memory (one cat kernel per encoder call
+    and its split in the backward disappear; the gradients come back as views of the kernel's gradient buffer)."""
+
+    @staticmethod
+    def forward(ctx, *tensors):
+        ctx.shapes = [t.shape for t in tensors]
+        v = _adjacent_view(list(tensors))
+        if v is None:
+            v = torch.cat([t.reshape(-1) for t in tensors])
+        return v
+
+    @staticmethod
+    def backward(ctx, g):
+        out, off = [], 0
+        for sh in ctx.shapes:
+            n = 1
+            for d in sh:
+                n *= d
+            out.append(g[off:off + n].view(sh))
+            off += n
+        return tuple(out)
+
+
 class _SGCNEncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, prob, prob_bias, wb, csr: GraphCSR, L: int, H: int, want_pe: bool, relu: bool = True):
@@ -77,7 +120,7 @@ def sgcn_encoder(x, csr: GraphCSR, weights, biases, prob=None, prob_bias=None, w
     """Fused SGCN encoder. Returns (out (B,R,L*H), p_e (E,) in CSR-slot order or empty)."""
     L = len(weights)
     H = weights[0].shape[0] if L else 0
-    wb = pack_layer_params(weights, biases)
+    wb = _SplitGradFn.apply(*[t for w, b in zip(weights, biases) for t in (w, b)]) if L else None
     return _SGCNEncoderFn.apply(x, prob, prob_bias, wb, csr, L, H, want_pe, relu)
 
 
@@ -209,7 +252,15 @@ class _CatLinearFn(torch.autograd.Function):
         srcs = [x0, x1, x2]
         _lib.require_cuda(W, bias, *[t for t in srcs if t is not None])
         lib = _lib.lib()
-        M = next(t.shape[0] for t in srcs if t is not None)
+        M = max(t.shape[0] for t in srcs if t is not None)
+        # a source with M / k rows is read k times (rows i, i + M/k, ...): the stacked plain / explain passes share `img_feat`
+        reps = [1 if t is None else M // t.shape[0] for t in srcs]
+        if any(t is not None and t.shape[0] * r != M for t, r in zip(srcs, reps)):
+            raise RuntimeError("cat_linear: source row counts %s do not divide %d" % ([None if t is None else t.shape[0] for t in srcs], M))
+        if not (USE_TC and M > 0) and any(r > 1 for r in reps):
+            srcs = [t if r == 1 else torch.cat([t] * r, 0) for t, r in zip(srcs, reps)]
+            reps = [1, 1, 1]
+        ctx.reps = reps
         cs = [None if t is None else (t.float() if t.stride(-1) == 1 else t.contiguous().float()) for t in srcs]
         widths = [0 if t is None else t.shape[1] for t in cs]
         strides = [0 if t is None else t.stride(0) for t in cs]
@@ -224,9 +275,10 @@ class _CatLinearFn(torch.autograd.Function):
             A = torch.empty((2, M, _pad4(K)), dtype=torch.float32, device=W.device)
             Bw = torch.empty((2, N, _pad4(K)), dtype=torch.float32, device=W.device)
             jobs, off = [], 0
-            for t, w, ld in zip(cs, widths, strides):
+            for t, w, ld, rp in zip(cs, widths, strides, reps):
                 if t is not None and w:
-                    jobs.append(_job(t, A, M, w, ld, col_off=off))
+                    for k in range(rp):
+                        jobs.append(_job(t, A, M // rp, w, ld, row_off=k * (M // rp), col_off=off))
                 off += w
             jobs.append(_job(Wc, Bw, N, K, K))
             _tc_split(jobs, W.device)
@@ -276,12 +328,14 @@ class _CatLinearFn(torch.autograd.Function):
             jobs = [_job(g_out, gz, M, N, N, mask=mask), _job(g_out, gzt, M, N, N, transpose=True, mask=mask),
                     _job(W, wt, N, K, K, transpose=True)]
             off = 0
-            for t, w, ld in zip(cs, ctx.widths, ctx.strides):
+            for t, w, ld, rp in zip(cs, ctx.widths, ctx.strides, ctx.reps):
                 if t is not None and w:
-                    jobs.append(_job(t, xt, M, w, ld, row_off=off, transpose=True))
+                    for k in range(rp):
+                        jobs.append(_job(t, xt, M // rp, w, ld, row_off=off, col_off=k * (M // rp), transpose=True))
                 off += w
             jobs.append(_job(None, xt, M, 1, 1, row_off=K, transpose=True))
-            _tc_split(jobs, dev)
+            for i in range(0, len(jobs), 8):                 # igcn_tc_split takes up to 8 jobs per launch
+                _tc_split(jobs[i:i + 8], dev)
             # the two products are independent: the weight gradient runs on an auxiliary stream, so the input gradient -- which the
             # rest of the backward waits for -- is not queued behind it
             cur = torch.cuda.current_stream(dev)
@@ -298,6 +352,13 @@ class _CatLinearFn(torch.autograd.Function):
                 cur.wait_stream(aux)
             else:
                 _tc_gemm(gzt, xt, N, K + 1, M, [dW, db], [K, 1], [K, 1], tag="cat_linear_bwd_w_tc")
+            for i, rp in enumerate(ctx.reps):                # a repeated source collects the gradient of every repetition
+                if rp > 1 and dxs[i] is not None:
+                    h = M // rp
+                    acc = dxs[i][:h]
+                    for k in range(1, rp):
+                        acc = acc + dxs[i][k * h:(k + 1) * h]
+                    dxs[i] = acc
             return dxs[0], dxs[1], dxs[2], dW, db, None
         hw, hs = (ctypes.c_int64 * 3)(*ctx.widths), (ctypes.c_int64 * 3)(*ctx.strides)
         hd = (ctypes.c_int64 * 3)(*[0 if t is None else t.stride(0) for t in dxs])
@@ -322,8 +383,10 @@ def cat_linear(xs, weight, bias, relu=True):
 
 
 class _CrossAttnFn(torch.autograd.Function):
+    """relu: 0 = raw attention output, 1 = relu(attn), 2 = (q + relu(attn)) / 2 (the fusion average, tensor-core kernels only)."""
+
     @staticmethod
-    def forward(ctx, q, kv, in_w, in_b, out_w, out_b, heads: int, relu: bool):
+    def forward(ctx, q, kv, in_w, in_b, out_w, out_b, heads: int, relu: int):
         _lib.require_cuda(q, kv, in_w, in_b, out_w, out_b)
         c = lambda t: t.contiguous().float()
         q, kv, in_w, in_b, out_w, out_b = c(q), c(kv), c(in_w), c(in_b), c(out_w), c(out_b)
@@ -334,7 +397,7 @@ class _CrossAttnFn(torch.autograd.Function):
             _lib.call("igcn_cross_attn_fwd", _lib.ptr(q), _lib.ptr(kv), _lib.ptr(in_w), _lib.ptr(in_b), _lib.ptr(out_w), _lib.ptr(out_b),
                       B, R, M, E, heads, int(relu), _lib.ptr(out), _lib.stream(), tag="cross_attn_fwd[R=%d,M=%d,E=%d]" % (R, M, E),
                       nbytes=4 * (2 * B * R * E + B * M * E + 4 * E * E + 4 * E))
-        ctx.heads, ctx.relu = heads, bool(relu)
+        ctx.heads, ctx.relu = heads, int(relu)
         ctx.save_for_backward(q, kv, in_w, in_b, out_w, out_b, out)
         return out
 
@@ -358,12 +421,28 @@ class _CrossAttnFn(torch.autograd.Function):
         return dq, dkv, grads[:o1].view(3 * E, E), grads[o1:o2], grads[o2:o3].view(E, E), grads[o3:], None, None
 
 
-def cross_attention(q, kv, mha: torch.nn.MultiheadAttention, relu=True):
-    """relu(mha(q, kv, kv)[0]) for a batch_first nn.MultiheadAttention with packed in_proj (the reference's use)."""
+def _check_mha(mha):
     if mha.in_proj_weight is None or mha.in_proj_bias is None or mha.bias_k is not None or mha.dropout != 0.0 or not mha.batch_first:
         raise RuntimeError("igcn_b200.cross_attention supports the reference configuration only "
                            "(packed in_proj with bias, no bias_kv, dropout 0, batch_first)")
-    return _CrossAttnFn.apply(q, kv, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, mha.num_heads, relu)
+
+
+def cross_attention(q, kv, mha: torch.nn.MultiheadAttention, relu=True):
+    """relu(mha(q, kv, kv)[0]) for a batch_first nn.MultiheadAttention with packed in_proj (the reference's use)."""
+    _check_mha(mha)
+    return _CrossAttnFn.apply(q, kv, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, mha.num_heads,
+                              1 if relu else 0)
+
+
+def cross_attention_average(q, kv, mha: torch.nn.MultiheadAttention):
+    """(q + relu(mha(q, kv, kv)[0])) / 2 -- the image/SNP fusion `out_z = (img_out + out_cross) / 2` of kernel/sgcn_img_snp.py
+    folded into the attention epilogue (one kernel each way, the attention output itself is never materialised).  Falls back to
+    the two-step form for shapes outside the tensor-core kernels."""
+    _check_mha(mha)
+    B, R, E = q.shape
+    if q.is_cuda and _lib.lib().igcn_cross_attn_fused_average(R, kv.shape[1], E, mha.num_heads):
+        return _CrossAttnFn.apply(q, kv, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, mha.num_heads, 2)
+    return (q + cross_attention(q, kv, mha, relu=True)) * 0.5
 
 
 class MaskBank(object):

@@ -12,44 +12,8 @@ from torch.nn import init
 from torch.nn.parameter import Parameter
 
 from . import ops
-from .img_snp_model import GCNConv, MaskedEncoderMixin, _Lin, _l1_entropy
-
-
-def _glorot(t):
-    a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
-    with torch.no_grad():
-        t.uniform_(-a, a)
-
-
-class GATConv(nn.Module):
-    """PyG 2.0.2 GATConv(in, out, heads=1, edge_dim=1) parameter names: lin_src/lin_dst (shared) .weight, att_src, att_dst,
-    lin_edge.weight, att_edge, bias.  forward(x, edge_index, edge_attr, csr=...) runs the fused kernel."""
-
-    def __init__(self, in_channels, out_channels, edge_dim=1, negative_slope=0.2):
-        super().__init__()
-        if edge_dim != 1:
-            raise RuntimeError("igcn_b200.GATConv supports edge_dim=1 (the reference's use) only")
-        self.in_channels, self.out_channels, self.negative_slope = in_channels, out_channels, negative_slope
-        self.lin_src = _Lin(in_channels, out_channels)
-        self.lin_dst = self.lin_src
-        self.att_src = Parameter(torch.empty(1, 1, out_channels))
-        self.att_dst = Parameter(torch.empty(1, 1, out_channels))
-        self.lin_edge = _Lin(1, out_channels)
-        self.att_edge = Parameter(torch.empty(1, 1, out_channels))
-        self.bias = Parameter(torch.zeros(out_channels))
-        self.reset_parameters()
-
-    def reset_parameters(self):
-        self.lin_src.reset_parameters()
-        self.lin_edge.reset_parameters()
-        for t in (self.att_src, self.att_dst, self.att_edge):
-            _glorot(t)
-        init.zeros_(self.bias)
-
-    def forward(self, x, edge_index, edge_attr, csr):
-        ea = edge_attr.index_select(0, csr.csr_perm.long())          # per CSR slot; differentiable w.r.t. edge_attr
-        return ops.gat_conv(x, csr, ea, self.lin_src.weight, self.att_src, self.att_dst, self.lin_edge.weight, self.att_edge,
-                            self.bias, self.negative_slope)
+from .img_snp_model import MaskedEncoderMixin, _l1_entropy
+from .pyg import GATConv, GCNConv          # the PyG-signature operators (parameter containers here: the models fuse the stack)
 
 
 class _SGCNBase(nn.Module, MaskedEncoderMixin):

@@ -172,6 +172,10 @@ int igcn_gat_layer_bwd(const float* x, const int32_t* rowptr_t, const int32_t* c
  *   partials (n_cta,P) workspace, n_cta = igcn_cross_attn_bwd_ctas(...).  Deterministic.
  */
 int64_t igcn_cross_attn_param_count(int64_t E);
+/* 1 when relu = 2 is available for this shape: out = (q_in + relu(attn)) / 2, the fusion average of kernel/sgcn_img_snp.py
+ * (out_z = (img_out + out_cross) / 2) folded into the attention epilogue; the backward then takes that tensor as `out` and
+ * returns d q_in including the direct half. */
+int64_t igcn_cross_attn_fused_average(int64_t R, int64_t M, int64_t E, int64_t heads);
 int64_t igcn_cross_attn_bwd_ctas(int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads);
 int igcn_cross_attn_fwd(const float* q_in, const float* kv_in, const float* in_proj_weight, const float* in_proj_bias,
                         const float* out_proj_weight, const float* out_proj_bias,
@@ -340,6 +344,33 @@ int igcn_dp_allreduce_adam(const int64_t* host_grad_ptrs, const int64_t* host_si
                            int64_t signal_pad_bytes, float* params, float* exp_avg, float* exp_avg_sq, const float* step,
                            const float* lr, double beta1, double beta2, double eps, int64_t n, int64_t timeout_ms, int* error_flag,
                            void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GCNConv for ARBITRARY graphs: the operator the reference's model files call,
+ * torch_geometric.nn.GCNConv(in, out)(x, edge_index, edge_weight) (kernel/sgcn_img_snp.py:218-221, kernel/sgcn.py:281-284; PyG 2.0.2:
+ * add_remaining_self_loops with fill 1, D^-1/2 A D^-1/2, X W^T, scatter-add over targets, + bias), differentiable with respect
+ * to x, edge_weight, weight and bias.  One graph of N nodes in global memory (no size limit, no equal-size requirement).
+ *   igcn_graph_csr: int64 COO (2,E) -> in-edges grouped by target (rowptr_t, csr_src, csr_perm = original edge id per slot) and
+ *     out-edges grouped by source (rowptr_s, csc_pos = CSR slot of the q-th out-edge); stable order.  work: igcn_graph_csr_work_ints
+ *     int32s; its LAST entry is set to 1 when an endpoint lies outside [0, N).
+ *   igcn_gcn_conv_fwd: edge_weight (E, original edge order) or NULL (= ones); weight (O,C); bias (O) or NULL; out (N,O);
+ *     saved: igcn_gcn_conv_saved_floats floats the backward needs.
+ *   igcn_gcn_conv_bwd: dx (N,C) or NULL; d_edge_weight (E, original order) or NULL; grads (O*C + O) = [d weight | d bias];
+ *     work: igcn_gcn_conv_bwd_work_floats floats; partials (n_cta, O*C+O), n_cta = igcn_gcn_conv_bwd_ctas(N).  Deterministic.
+ */
+int64_t igcn_graph_csr_work_ints(int64_t N, int64_t E);
+int igcn_graph_csr(const int64_t* edge_index, int64_t N, int64_t E, int32_t* rowptr_t, int32_t* csr_src, int32_t* csr_perm,
+                   int32_t* rowptr_s, int32_t* csc_pos, int32_t* work, void* stream);
+int64_t igcn_gcn_conv_saved_floats(int64_t N, int64_t E, int64_t O);
+int igcn_gcn_conv_fwd(const float* x, const int32_t* rowptr_t, const int32_t* csr_src, const int32_t* csr_perm,
+                      const float* edge_weight, const float* weight, const float* bias, int64_t N, int64_t E, int64_t C, int64_t O,
+                      float* saved, float* out, void* stream);
+int64_t igcn_gcn_conv_bwd_ctas(int64_t N);
+int64_t igcn_gcn_conv_bwd_work_floats(int64_t N, int64_t E, int64_t O);
+int igcn_gcn_conv_bwd(const float* x, const int32_t* rowptr_t, const int32_t* csr_src, const int32_t* csr_perm,
+                      const int32_t* rowptr_s, const int32_t* csc_pos, const float* weight, const float* saved, const float* g_out,
+                      int64_t N, int64_t E, int64_t C, int64_t O, float* work, float* dx, float* d_edge_weight, float* partials,
+                      int64_t n_cta, float* grads, void* stream);
 
 #ifdef __cplusplus
 }

@@ -213,3 +213,44 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     assert l.igcn_tc_gemm_splits(512, 64, 2912) >= 1
     assert l.igcn_dp_adam_blocks(415000, 8, 2048) == 2048 // (2 * 4 * 8)
     assert l.igcn_dp_adam_blocks(415000, 8, 16) == 0
+
+
+def test_reference_model_files_import_on_the_shadow_modules():
+    """The UNMODIFIED reference model files resolve their torch_geometric / torch_scatter imports to integration/shims (= the
+    igcn_b200 operators) and build: same parameter names as the drop-in classes.  Construction only -- the operators are CUDA
+    kernels and this container has no GPU; the operator-level GPU test is tests/test_gpu_pyg.py.  Skipped where /root/reference
+    does not exist (the GPU box)."""
+    import subprocess
+    import sys
+    import pytest
+    if not os.path.isdir("/root/reference/kernel"):
+        pytest.skip("reference checkout not present")
+    code = r'''
+import sys, types
+root = %r
+sys.path[:0] = [root + "/integration/shims", root, root + "/oracle/shim", "/root/reference"]
+import torch, torch_geometric, torch_scatter
+assert torch_geometric.nn.GCNConv.__module__.endswith("pyg") and torch_scatter.scatter.__module__.endswith("pyg")
+import importlib.util
+def load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path); m = importlib.util.module_from_spec(spec); sys.modules[name] = m
+    spec.loader.exec_module(m); return m
+pkg = types.ModuleType("refkernel"); pkg.__path__ = ["/root/reference/kernel"]; sys.modules["refkernel"] = pkg
+go = load("refkernel.go_model", "/root/reference/kernel/go_model.py")
+sys.modules["kernel"] = types.ModuleType("kernel"); sys.modules["kernel"].__path__ = ["/root/reference/kernel"]; sys.modules["kernel.go_model"] = go
+ref = load("refkernel.sgcn_img_snp", "/root/reference/kernel/sgcn_img_snp.py")
+from igcn_b200 import synthetic as syn
+from igcn_b200.img_snp_model import SGCN_GCN_IMGSNP
+adj, go_snps, pool_dim = syn.make_go_hierarchy(None, 54, seed=0)
+A = torch.tensor(adj).float().t().to_sparse().coalesce(); A_g = torch.tensor(go_snps).float().to_sparse().coalesce()
+kw = dict(rois=90, H_0=3, num_classes=3, isCrossAtten=True, isSoftSimilarity=True, rbf_gamma=0.01, isuseProb4Regr=True, num_regr=3,
+          isImageOnly=False, isSNPsOnly=False)
+m_ref = ref.SGCN_GCN_IMGSNP(2, 16, A_g, A, pool_dim, 32, "cpu", **kw)
+m_own = SGCN_GCN_IMGSNP(2, 16, A_g, A, pool_dim, 32, "cpu", **kw)
+assert type(m_ref.conv1).__module__.endswith("pyg")
+a, b = {k: tuple(v.shape) for k, v in m_ref.state_dict().items()}, {k: tuple(v.shape) for k, v in m_own.state_dict().items()}
+assert a == b, sorted(set(a.items()) ^ set(b.items()))[:6]
+print("OK", len(a))
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
