@@ -42,10 +42,14 @@ SIGNATURES = {
     "igcn_adam_step": (ctypes.c_int, [_P] * 6 + [ctypes.c_double] * 4 + [_I, _P]),
     "igcn_bn_act_fwd": (ctypes.c_int, [_P] * 4 + [_I] * 4 + [ctypes.c_double] * 2 + [_I] + [_P] * 6),
     "igcn_bn_act_bwd": (ctypes.c_int, [_P] * 6 + [_I] * 5 + [_P] * 4),
+    "igcn_bn_eval_act": (ctypes.c_int, [_P] * 5 + [_I] * 3 + [ctypes.c_double, _I, _P, _P, _P]),
     "igcn_reduce_blocks": (_I, [_I]),
     "igcn_mask_loss_fwd": (ctypes.c_int, [_P, _I, _P, _I, _P, _I, _P, ctypes.c_double, _P, _I, _P, _P]),
     "igcn_mask_loss_bwd": (ctypes.c_int, [_P, _I, _P, _I, _P, _I, _P, ctypes.c_double, _P, _P, _P, _P, _P]),
     "igcn_dot": (ctypes.c_int, [_P, _P, _I, ctypes.c_double, _P, _I, _P, _P]),
+    "igcn_rbf_similarity": (ctypes.c_int, [_P, _I, _I, ctypes.c_double, _P, _P, _P]),
+    "igcn_col_mean": (ctypes.c_int, [_P, _I, _I, _I, _P, _P]),
+    "igcn_laplacian_finish": (ctypes.c_int, [_P, _P, _P, _P, _I, _I, _I, ctypes.c_double, ctypes.c_double, _P, _P, _I, _P, _P]),
     "igcn_scale_by_scalar": (ctypes.c_int, [_P, _P, ctypes.c_double, _I, _P, _P]),
     "igcn_skinny_linear_fwd": (ctypes.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "igcn_skinny_linear_bwd_ctas": (_I, [_I]),
@@ -106,6 +110,7 @@ KERNELS_PER_CALL = {
     "igcn_go_spmm_fwd": 1, "igcn_go_spmm_bwd": 2, "igcn_go_layer_fwd": 1, "igcn_go_layer_bwd": 2, "igcn_adam_step": 1, "igcn_dropout_masks": 2, "igcn_cross_attn_fwd": 1, "igcn_cross_attn_bwd": 2, "igcn_cat_linear_fwd": 2, "igcn_cat_linear_bwd": 2, "igcn_gat_layer_fwd": 1, "igcn_gat_layer_bwd": 2,
     "igcn_bn_act_fwd": 1, "igcn_bn_act_bwd": 1, "igcn_mask_loss_fwd": 2, "igcn_mask_loss_bwd": 1, "igcn_dot": 2, "igcn_scale_by_scalar": 1, "igcn_tc_split": 1, "igcn_tc_gemm": 2, "igcn_skinny_linear_fwd": 1, "igcn_skinny_linear_bwd": 2,
     "igcn_snp_mask_pair_fwd": 1, "igcn_snp_mask_pair_bwd": 1, "igcn_heads_fwd": 1, "igcn_heads_bwd": 2, "igcn_step_loss_fwd": 1, "igcn_step_loss_bwd": 1,
+    "igcn_rbf_similarity": 2, "igcn_col_mean": 1, "igcn_laplacian_finish": 2,
     "igcn_graph_csr": 5, "igcn_gcn_conv_fwd": 4, "igcn_gcn_conv_bwd": 7,
 }
 launch_count = 0          # number of igcn kernels launched by this process

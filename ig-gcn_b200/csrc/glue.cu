@@ -298,7 +298,39 @@ static int blocks_for(int64_t n, int per_block) {
 
 }  // namespace igcn
 
+namespace igcn {
+// ---- BatchNorm1d in EVAL mode (+ ReLU): a per-channel affine map with the running statistics -- the inference path of the read-out
+//      heads (kernel/go_model.py:117-146 under model.eval(), as eval_acc / eval_loss / eval_scores run it) ------------------------
+__global__ void __launch_bounds__(256) bn_eval_act_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, const float* __restrict__ rm,
+                                                         const float* __restrict__ rv, int64_t total, int C, int L, float eps, int relu,
+                                                         const float* __restrict__ gy, float* __restrict__ y) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int c = (int)((i / L) % C);
+        const float sc = (gamma ? gamma[c] : 1.f) * rsqrtf(rv[c] + eps);
+        const float v = fmaf(z[i] - rm[c], sc, beta ? beta[c] : 0.f);
+        if (gy)                                   // backward: d z = g * scale where the unit is active
+            y[i] = (!relu || v > 0.f) ? gy[i] * sc : 0.f;
+        else
+            y[i] = relu ? fmaxf(v, 0.f) : v;
+    }
+}
+}  // namespace igcn
+
 using namespace igcn;
+
+/* y = act((z - running_mean) / sqrt(running_var + eps) * gamma + beta) for z (N, C, L); with g_y given, y receives d z instead. */
+extern "C" int igcn_bn_eval_act(const float* z, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                                int64_t N, int64_t C, int64_t L, double eps, int64_t relu, const float* g_y, float* y, void* stream) {
+    IGCN_REQUIRE(N >= 0 && C > 0 && L > 0, IGCN_ERR_BAD_ARG, "bn_eval_act: bad sizes");
+    if (N == 0) return IGCN_OK;
+    IGCN_REQUIRE(z && running_mean && running_var && y, IGCN_ERR_BAD_ARG, "bn_eval_act: null pointer");
+    const int64_t total = N * C * L;
+    bn_eval_act_kernel<<<(unsigned)blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(z, gamma, beta, running_mean, running_var, total,
+                                                                                          (int)C, (int)L, (float)eps, (int)relu, g_y, y);
+    IGCN_CHECK_LAUNCH("bn_eval_act");
+    return IGCN_OK;
+}
 
 extern "C" int igcn_bn_act_fwd(const float* z, const float* gamma, const float* beta, const float* mask, int64_t N, int64_t C, int64_t L,
                                int64_t groups, double eps, double momentum, int64_t relu, float* running_mean, float* running_var,

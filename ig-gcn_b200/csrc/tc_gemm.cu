@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(const float* __restrict_
 struct SplitJob {
     const float* src;     // (rows, cols), row stride ld_src; NULL = constant 1.0
     const float* mask;    // same geometry as src, or NULL
+    const float* sub;     // per source column, or NULL: x <- x - sub[c] (the centring of the Laplacian product)
     float *hi, *lo;       // destination matrices, row stride ld_dst
     int rows, cols, ld_src, ld_dst, row_off, col_off, transpose;
 };
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(256) tc_split_kernel(SplitJobs jobs) {
                 if (r < J.rows && c < J.cols) {
                     float x = J.src ? J.src[(int64_t)r * J.ld_src + c] : 1.f;
                     if (J.mask && !(J.mask[(int64_t)r * J.ld_src + c] > 0.f)) x = 0.f;
+                    if (J.sub) x -= J.sub[c];
                     float h, l;
                     split_tf32(x, h, l);
                     const int64_t o = (int64_t)(J.row_off + r) * J.ld_dst + J.col_off + c;
@@ -310,6 +312,7 @@ __global__ void __launch_bounds__(256) tc_split_kernel(SplitJobs jobs) {
                 if (r < J.rows && c < J.cols) {
                     x = J.src ? J.src[(int64_t)r * J.ld_src + c] : 1.f;
                     if (J.mask && !(J.mask[(int64_t)r * J.ld_src + c] > 0.f)) x = 0.f;
+                    if (J.sub) x -= J.sub[c];
                 }
                 tile[ty + i * 8][tx] = x;
             }
@@ -435,7 +438,7 @@ extern "C" int igcn_tc_split(const int64_t* host_jobs, int64_t njobs, void* stre
     tc::SplitJobs jobs;
     int64_t max_tiles = 1;
     for (int i = 0; i < njobs; ++i) {
-        const int64_t* h = host_jobs + 11 * i;
+        const int64_t* h = host_jobs + 12 * i;
         tc::SplitJob& J = jobs.j[i];
         J.src = reinterpret_cast<const float*>(h[0]);
         J.mask = reinterpret_cast<const float*>(h[1]);
@@ -443,6 +446,7 @@ extern "C" int igcn_tc_split(const int64_t* host_jobs, int64_t njobs, void* stre
         J.lo = reinterpret_cast<float*>(h[3]);
         J.rows = (int)h[4]; J.cols = (int)h[5]; J.ld_src = (int)h[6]; J.ld_dst = (int)h[7];
         J.row_off = (int)h[8]; J.col_off = (int)h[9]; J.transpose = (int)h[10];
+        J.sub = reinterpret_cast<const float*>(h[11]);
         IGCN_REQUIRE(J.hi && J.lo && J.rows >= 0 && J.cols >= 0 && J.ld_dst > 0, IGCN_ERR_BAD_ARG, "tc_split: bad job %d", i);
         IGCN_REQUIRE(!J.mask || J.src, IGCN_ERR_BAD_ARG, "tc_split: job %d has a mask but no source", i);
         const int64_t t = (int64_t)((J.rows + 31) / 32) * ((J.cols + 31) / 32);

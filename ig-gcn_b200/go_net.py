@@ -235,28 +235,18 @@ class Gene_ontology_network(nn.Module):
         m = self._mask(name, t.shape, p, t.device)
         return t if m is None else t * m
 
-    def _bn(self, bn, x):
-        """BatchNorm over the batch -- or, when two passes are stacked along the batch (`groups`=2), over each pass
-        separately and in order, so statistics and running buffers are exactly those of two separate forward calls."""
-        g = self._groups
-        if g == 1:
-            return bn(x)
-        h = x.shape[0] // g
-        return torch.cat([bn(x[i * h:(i + 1) * h]) for i in range(g)], 0)
-
     def _bn_act(self, bn, z, name=None, p=0.0):
-        """dropout(relu(bn(z))) -- one fused launch in training mode (ops.bn_act), the torch modules otherwise."""
-        if self.training and z.is_cuda and bn.track_running_stats:
-            mask = self._mask(name, z.shape, p, z.device) if name else None
-            return ops.bn_act(z, bn, mask, self._groups, relu=True)
-        y = F.relu(self._bn(bn, z))
-        return self._drop(name, y, p) if name else y
+        """dropout(relu(bn(z))) as one fused launch (ops.bn_act): batch statistics + mask in training mode, the running statistics
+        in eval mode (the inference path of eval_acc / eval_loss / eval_scores)."""
+        mask = self._mask(name, z.shape, p, z.device) if (name and self.training) else None
+        return ops.bn_act(z, bn, mask, self._groups, relu=True)
 
     @staticmethod
     def _lin(mod, x):
-        """Bias-free read-out projection; the skinny shapes (in <= 8, out <= 64) run on their own kernels (glue.cu)."""
+        """Bias-free read-out projection; the skinny shapes (in <= 32, out <= 64) run on their own kernels (glue.cu); anything larger
+        is a plain library GEMM (nn.Linear)."""
         w = mod.weight
-        if x.is_cuda and mod.bias is None and w.shape[1] <= 32 and w.shape[0] <= 64:
+        if mod.bias is None and w.shape[1] <= 32 and w.shape[0] <= 64:
             return ops.skinny_linear(x, w)
         return mod(x)
 

@@ -184,47 +184,35 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
     def loss_probability(self, x, edge_index, edge_weight, hp, eps=1e-6):
         """sgcn_img_snp.py:153-181 (sums over edges are order independent, so CSR-slot order is used as is)."""
         edge_prob = self._edge_prob(x, edge_index, edge_weight)
-        if self.prob.is_cuda:
-            return ops.mask_loss(self.prob, edge_prob, self.snps_prob, hp, eps)        # one fused reduction (glue.cu)
-        f_l1, f_en = _l1_entropy(torch.sigmoid(self.prob), eps)
-        e_l1, e_en = _l1_entropy(edge_prob, eps)
-        s_l1, s_en = _l1_entropy(torch.sigmoid(self.snps_prob), eps)
-        loss_l1 = hp.lamda_x_l1 * f_l1 + hp.lamda_e_l1 * e_l1 + hp.lamda_x_l1 * s_l1
-        loss_entropy = hp.lamda_x_ent * f_en + hp.lamda_e_ent * e_en + hp.lamda_x_ent * s_en
-        return loss_l1 + loss_entropy
+        return ops.mask_loss(self.prob, edge_prob, self.snps_prob, hp, eps)        # one fused reduction (glue.cu); CUDA only
 
-    def _laplacian(self, n, tsne_result, like):
-        """Lsym = D - (W + W^T)/2 with W the similarity matrix of the batch (RBF of tsne_fdim, or all ones) and D its row
-        sums; depends on the data only, so the two passes of a step share it."""
+    def _similarity(self, n, tsne_result, like):
+        """(W, d): the similarity matrix of the batch (RBF of tsne_fdim; None = all ones) and its row sums; depends on the data
+        only, so the two passes of a step share it."""
         soft = self.isSoftSimilarity and tsne_result is not None
-        key = (tsne_result.data_ptr(), tsne_result._version, n) if soft else ("ones", n, str(like.device))
+        if not soft:
+            return None, None
+        key = (tsne_result.data_ptr(), tsne_result._version, n)
         c = getattr(self, "_w_cache", None)
         if c is not None and c[0] == key:
             return c[1]
-        with torch.no_grad():
-            if soft:
-                W = torch.exp(-self.rbf_gamma * torch.cdist(tsne_result, tsne_result, p=2) ** 2)
-            else:
-                W = torch.ones(n, n, device=like.device, dtype=like.dtype)
-            lap = torch.diag(W.sum(1)) - 0.5 * (W + W.t())
-        self._w_cache = (key, lap)
-        return lap
+        wd = ops.rbf_similarity(tsne_result, self.rbf_gamma)
+        self._w_cache = (key, wd)
+        return wd
 
     def consist_loss(self, s, tsne_result=None):
-        """tr(s^T (D-W) s)/B^2 (sgcn_img_snp.py:183-196).  With L = D - W this is <s, L s>/B^2: one (B x B)(B x D) product
-        T = L s gives the value (a dot product) and the gradient 2 T / B^2 -- the reference's D x D intermediates
-        (8 448^2 at 264 ROIs) and a second product in the backward never exist."""
+        """tr(s^T (D-W) s)/B^2 (sgcn_img_snp.py:183-196).  With L = D - W this is <s, L s>/B^2: one (B x B)(B x D) product gives the
+        value (a dot product) and the gradient 2 L s / B^2 -- the reference's D x D intermediates (8 448^2 at 264 ROIs) and a second
+        product in the backward never exist; ops.laplacian_quadratic centres the columns first so the product does not cancel."""
         n = s.shape[0]
         if n == 0:
             return 0
-        lap = self._laplacian(n, tsne_result, s)
-        if s.is_cuda:
-            return ops.laplacian_quadratic(s, lap, 1.0 / (n * n))
-        return (s * (lap @ s)).sum() / (n * n)
+        W, d = self._similarity(n, tsne_result, s)
+        return ops.laplacian_quadratic(s, W, d, 1.0 / (n * n))
 
     def consist_loss_pair(self, s2, tsne_result=None):
         """consist_loss(s2[:B], t) + consist_loss(s2[B:], t) for the stacked plain / explain features of forward_pair: one
-        Laplacian product and one dot product for both passes, and no slice in the autograd graph."""
+        product and one dot product for both passes, and no slice in the autograd graph."""
         c = getattr(self, "_quad_cache", None)
         if c is not None:
             self._quad_cache = None
@@ -234,15 +222,16 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
                 c[2].record_stream(cur)
                 return c[2]
         n = s2.shape[0] // 2
-        lap = self._laplacian(n, tsne_result, s2)
-        return ops.laplacian_quadratic(s2, lap, 1.0 / (n * n), halves=2)
+        W, d = self._similarity(n, tsne_result, s2)
+        return ops.laplacian_quadratic(s2, W, d, 1.0 / (n * n), halves=2)
 
     def OrthogonalConstraint(self, w):
-        """||w^T w - I_D||_F^2 / B^2 with row-normalised w (sgcn_img_snp.py:198-205) = (||w w^T||_F^2 - 2B + D)/B^2."""
+        """||w^T w - I_D||_F^2 / B^2 with row-normalised w (sgcn_img_snp.py:198-205) = (||w w^T||_F^2 - 2B + D)/B^2: the B x B Gram
+        matrix instead of the reference's D x D product (8 448^2 at 264 ROIs), on the tensor cores (ops.gram)."""
         wn = w / w.norm(dim=1)[:, None]
-        gram = wn @ wn.t()
+        g = ops.gram(wn)
         n, d = wn.shape
-        return ((gram * gram).sum() - 2.0 * gram.diagonal().sum() + d) / (n * n)
+        return ((g * g).sum() - 2.0 * g.diagonal().sum() + d) / (n * n)
 
     # --------------------------------------------------------------------------------------------------
     def _mask(self, name, t, p):
@@ -302,14 +291,6 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             else:
                 out_cross = out_cross.reshape(B, -1)
 
-        def regr_head(parts):
-            if self.isuseProb4Regr:
-                img_feat = (x.view(B, self.rois, -1) * self.prob).reshape(B, -1)       # data.x (unmasked) * prob (:293-297)
-                parts = parts + [img_feat]
-            # relu(lin1_regr(cat(parts))) without building the concatenation (fusion_gemm.cu)
-            r = self._mask("lin1_regr", ops.cat_linear(parts, self.lin1_regr.weight, self.lin1_regr.bias, relu=True), 0.3)
-            return self.lin2_regr(r)
-
         if self.isImageOnly:
             out_z = img_out
             parts = [out_z]
@@ -323,15 +304,18 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         # out_lin is part of the returned tuple (eval_scores collects it, train_eval...:626); the heads read its parts in place
         out_lin = parts[0] if len(parts) == 1 else torch.cat(parts, -1).detach()
         linear_outf = ops.cat_linear(parts, self.lin1.weight, self.lin1.bias, relu=True)
-        logits = self.lin2(self._mask("lin1", linear_outf, 0.5))
-        if self.isSNPsOnly:
-            r = self._mask("lin1_regr", ops.cat_linear(parts, self.lin1_regr.weight, self.lin1_regr.bias, relu=True), 0.3)
-            our_reg = self.lin2_regr(r)
-        else:
-            our_reg = regr_head(parts)
+        rparts = parts
+        if self.isuseProb4Regr and not self.isSNPsOnly:
+            img_feat = (x.view(B, self.rois, -1) * self.prob).reshape(B, -1)       # data.x (unmasked) * prob (:293-297)
+            rparts = parts + [img_feat]
+        # relu(lin1_regr(cat(parts))) without building the concatenation; then dropout, lin2 + log_softmax and lin2_regr of both
+        # heads in ONE launch (glue.cu), in training and in eval mode (masks None)
+        r = ops.cat_linear(rparts, self.lin1_regr.weight, self.lin1_regr.bias, relu=True)
+        logp, our_reg = ops.output_heads(linear_outf, self._mask_of("lin1", linear_outf, 0.5), r, self._mask_of("lin1_regr", r, 0.3),
+                                         self.lin2, self.lin2_regr)
         if use_bank:
             bank.end_pass()
-        return F.log_softmax(logits, dim=-1), x_hat, out_z, out_lin, linear_outf, our_reg
+        return logp, x_hat, out_z, out_lin, linear_outf, our_reg
 
     def forward_pair(self, data, temperature=None, device=None, stacked=False, consist=False):
         """Plain pass and explain pass of ONE batch in a single sweep: everything downstream of the two encoder

@@ -198,10 +198,10 @@ def _aux_stream(dev):
     return st
 
 
-def _job(src, hi_lo, rows, cols, ld_src, row_off=0, col_off=0, transpose=False, mask=None):
+def _job(src, hi_lo, rows, cols, ld_src, row_off=0, col_off=0, transpose=False, mask=None, sub=None):
     """One operand-preparation job of igcn_tc_split; hi_lo is a (2, R, ld) buffer (hi = [0], lo = [1])."""
     return [0 if src is None else src.data_ptr(), 0 if mask is None else mask.data_ptr(), hi_lo[0].data_ptr(), hi_lo[1].data_ptr(),
-            rows, cols, ld_src, hi_lo.shape[2], row_off, col_off, int(transpose)]
+            rows, cols, ld_src, hi_lo.shape[2], row_off, col_off, int(transpose), 0 if sub is None else sub.data_ptr()]
 
 
 def _tc_split(jobs, dev):
@@ -514,25 +514,31 @@ class MaskBank(object):
 
 
 class _GramFn(torch.autograd.Function):
-    """G = S S^T (B x B) on the split-K tile kernels; backward dS = (gG + gG^T) S is ONE product (the generic
-    linear backward would spend a second, equally large one on the 'weight' side)."""
+    """G = S S^T (B x B) on the tensor cores (igcn_tc_gemm, 3xTF32); backward dS = (gG + gG^T) S is ONE product (the generic
+    linear backward would spend a second, equally large one on the 'weight' side).  The dense contraction of
+    OrthogonalConstraint (kernel/sgcn_img_snp.py:198-205) in its B x B form."""
 
     @staticmethod
     def forward(ctx, s):
-        import ctypes
         _lib.require_cuda(s)
-        lib = _lib.lib()
         sc = s.contiguous().float()
         M, K = sc.shape
-        S = lib.igcn_cat_linear_splits(M, M, K)
-        part = torch.empty((S, M, M), dtype=torch.float32, device=s.device)
         out = torch.empty((M, M), dtype=torch.float32, device=s.device)
-        zero = torch.zeros(M, dtype=torch.float32, device=s.device)
-        hw, hs = (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0)
-        with torch.cuda.device(s.device):
-            _lib.call("igcn_cat_linear_fwd", _lib.ptr(sc), None, None, ctypes.addressof(hw), ctypes.addressof(hs), _lib.ptr(sc), _lib.ptr(zero),
-                      M, M, K, 0, _lib.ptr(part), S, _lib.ptr(out), _lib.stream(), tag="gram_fwd[B=%d,D=%d]" % (M, K),
-                      nbytes=4 * (M * K + M * M))
+        if USE_TC:
+            A = torch.empty((2, M, _pad4(K)), dtype=torch.float32, device=s.device)
+            _tc_split([_job(sc, A, M, K, K)], s.device)
+            _tc_gemm(A, A, M, M, K, [out], [M], [M], tag="gram_fwd_tc")
+        else:
+            import ctypes
+            lib = _lib.lib()
+            S = lib.igcn_cat_linear_splits(M, M, K)
+            part = torch.empty((S, M, M), dtype=torch.float32, device=s.device)
+            zero = torch.zeros(M, dtype=torch.float32, device=s.device)
+            hw, hs = (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0)
+            with torch.cuda.device(s.device):
+                _lib.call("igcn_cat_linear_fwd", _lib.ptr(sc), None, None, ctypes.addressof(hw), ctypes.addressof(hs), _lib.ptr(sc), _lib.ptr(zero),
+                          M, M, K, 0, _lib.ptr(part), S, _lib.ptr(out), _lib.stream(), tag="gram_fwd[B=%d,D=%d]" % (M, K),
+                          nbytes=4 * (M * K + M * M))
         ctx.save_for_backward(sc, out)
         return out
 
@@ -543,6 +549,13 @@ class _GramFn(torch.autograd.Function):
         M, K = sc.shape
         gsym = (g + g.t()).contiguous()
         ds = torch.empty_like(sc)
+        if USE_TC:
+            # dS[i][c] = sum_j gsym[i][j] S^T[c][j]: A = gsym (M x M), B = S^T (K x M) straight out of the split pass
+            ga = torch.empty((2, M, _pad4(M)), dtype=torch.float32, device=sc.device)
+            st = torch.empty((2, K, _pad4(M)), dtype=torch.float32, device=sc.device)
+            _tc_split([_job(gsym, ga, M, M, M), _job(sc, st, M, K, K, transpose=True)], sc.device)
+            _tc_gemm(ga, st, M, K, M, [ds], [K], [K], tag="gram_bwd_tc")
+            return ds
         hw, hs, hd = (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0)
         with torch.cuda.device(sc.device):
             _lib.call("igcn_cat_linear_bwd", _lib.ptr(sc), None, None, ctypes.addressof(hw), ctypes.addressof(hs), _lib.ptr(sc), _lib.ptr(out),
@@ -592,12 +605,45 @@ class _BnActFn(torch.autograd.Function):
         return dz, dg, db, None, None, None, None
 
 
+class _BnEvalActFn(torch.autograd.Function):
+    """relu(BatchNorm1d(z)) with the running statistics (model.eval()): one elementwise launch each way (igcn_bn_eval_act)."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, rm, rv, eps: float, relu: bool):
+        _lib.require_cuda(z, gamma, beta, rm, rv)
+        zc = z.contiguous().float()
+        N, C = zc.shape[0], zc.shape[1]
+        L = zc.numel() // max(N * C, 1)
+        y = torch.empty_like(zc)
+        with torch.cuda.device(zc.device):
+            _lib.call("igcn_bn_eval_act", _lib.ptr(zc), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(rm), _lib.ptr(rv), N, C, L, float(eps), int(relu),
+                      None, _lib.ptr(y), _lib.stream(), tag="bn_eval_act[C=%d,L=%d]" % (C, L), nbytes=8 * zc.numel())
+        ctx.dims, ctx.eps, ctx.relu = (N, C, L), float(eps), bool(relu)
+        ctx.save_for_backward(zc, gamma, beta, rm, rv)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        zc, gamma, beta, rm, rv = ctx.saved_tensors
+        N, C, L = ctx.dims
+        dz = torch.empty_like(zc)
+        with torch.cuda.device(zc.device):
+            _lib.call("igcn_bn_eval_act", _lib.ptr(zc), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(rm), _lib.ptr(rv), N, C, L, ctx.eps, int(ctx.relu),
+                      _lib.ptr(gy.contiguous().float()), _lib.ptr(dz), _lib.stream(), tag="bn_eval_act_bwd", nbytes=12 * zc.numel())
+        return dz, None, None, None, None, None, None          # eval mode: the affine parameters are constants
+
+
 def bn_act(z, bn: torch.nn.BatchNorm1d, mask=None, groups=1, relu=True):
-    """mask * relu(bn(z)) for a TRAINING-mode BatchNorm1d over (N,C) or (N,C,L) CUDA input, one launch each way.
-    groups > 1: z stacks that many passes along the batch; each gets its own statistics and running-buffer update, in
-    order, exactly as `groups` successive module calls would (reference: kernel/go_model.py:117-146)."""
-    if not bn.training or not bn.track_running_stats:
-        raise RuntimeError("igcn_b200.bn_act is the training-mode path (use the module itself in eval mode)")
+    """mask * relu(bn(z)) for a BatchNorm1d over (N,C) or (N,C,L) CUDA input, one launch each way.
+    Training mode: batch statistics; groups > 1: z stacks that many passes along the batch, each gets its own statistics and
+    running-buffer update, in order, exactly as `groups` successive module calls would (reference: kernel/go_model.py:117-146).
+    Eval mode: the running statistics (no dropout mask): a per-channel affine map (the inference path)."""
+    if not bn.track_running_stats:
+        raise RuntimeError("igcn_b200.bn_act needs a BatchNorm1d that tracks running statistics")
+    if not bn.training:
+        if mask is not None:
+            raise RuntimeError("igcn_b200.bn_act: a dropout mask in eval mode")
+        return _BnEvalActFn.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, relu)
     return _BnActFn.apply(z, bn.weight, bn.bias, mask, bn, groups, relu)
 
 
@@ -642,45 +688,46 @@ def mask_loss(prob, p_e, snps_prob, hp, eps=1e-6):
 
 
 class _LaplacianQuadFn(torch.autograd.Function):
-    """scale * sum_h <S_h, Lsym S_h> for a symmetric (B,B) matrix Lsym and `halves` row blocks S_h of s (halves*B, D):
-    ONE product T_h = Lsym S_h serves the value (a dot product) and the gradient (2 * scale * T) -- the Gram formulation needs a
-    B x B x D product each way.  All blocks go through one tensor-core product (N = halves * D, segmented epilogue)."""
+    """scale * sum_h <S_h, (D - W) S_h> for a SYMMETRIC similarity W (B,B) with row sums d and `halves` row blocks S_h of s
+    (halves*B, D).  csrc/laplacian.cu: because (D - W) 1 = 0 the columns of every block are centred first, s' = s - mean, and
+    T = d .* s' - W s' -- the large diagonal term is exact fp32 and the tensor-core product W s' (ONE product for all blocks,
+    N = halves * D) only carries a small correction, so the cancellation that cost ~1e-4 in round 1 is gone.  T serves the value
+    (<s', T>) and the gradient (2 * scale * T; the centring needs no backward since (D - W) 1 = 0).  W = None: all ones
+    (isSoftSimilarity=False): W s' = 0, d = B, no product at all."""
 
     @staticmethod
-    def forward(ctx, s, lsym, scale: float, halves: int):
-        import ctypes
-        _lib.require_cuda(s, lsym)
-        sc, lc = s.contiguous().float(), lsym.contiguous().float()
+    def forward(ctx, s, W, d, scale: float, halves: int):
+        _lib.require_cuda(s, W, d)
+        sc = s.contiguous().float()
         MB, K = sc.shape
         M = MB // halves
-        if M * halves != MB or lc.shape != (M, M) or not 1 <= halves <= 3:
-            raise RuntimeError("laplacian_quadratic: s is (%d, %d), Lsym %s, halves=%d" % (MB, K, tuple(lc.shape), halves))
-        t = torch.empty_like(sc)
+        if M * halves != MB or not 1 <= halves <= 3 or (W is not None and (tuple(W.shape) != (M, M) or d.numel() != M)):
+            raise RuntimeError("laplacian_quadratic: s is (%d, %d), W %s, halves=%d" % (MB, K, None if W is None else tuple(W.shape), halves))
         lib = _lib.lib()
+        dev = sc.device
+        t = torch.empty_like(sc)
+        m = torch.empty((halves, K), dtype=torch.float32, device=dev)
         nb = lib.igcn_reduce_blocks(sc.numel())
-        part = torch.empty(nb, dtype=torch.float32, device=sc.device)
-        out = torch.empty((), dtype=torch.float32, device=sc.device)
-        if USE_TC:
-            # T_h[i][d] = sum_j Lsym[i][j] S_h^T[d][j] on the tensor cores (3xTF32): A = Lsym (M x M), B = [S_0^T ; S_1^T ...] (halves*K x M)
-            la = torch.empty((2, M, _pad4(M)), dtype=torch.float32, device=sc.device)
-            st = torch.empty((2, halves * K, _pad4(M)), dtype=torch.float32, device=sc.device)
-            jobs = [_job(lc, la, M, M, M)]
+        part = torch.empty(nb, dtype=torch.float32, device=dev)
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("igcn_col_mean", _lib.ptr(sc), M, K, halves, _lib.ptr(m), _lib.stream(), tag="col_mean", nbytes=4 * sc.numel())
+        u = None
+        if W is not None:
+            Wc, dc = W.contiguous().float(), d.contiguous().float()
+            u = torch.empty_like(sc)
+            # U_h[i][c] = sum_j W[i][j] S'_h^T[c][j] on the tensor cores (3xTF32): A = W (M x M), B = [S'_0^T ; S'_1^T ...] (halves*K x M)
+            la = torch.empty((2, M, _pad4(M)), dtype=torch.float32, device=dev)
+            st = torch.empty((2, halves * K, _pad4(M)), dtype=torch.float32, device=dev)
+            jobs = [_job(Wc, la, M, M, M)]
             for h in range(halves):
-                jobs.append(_job(sc[h * M:], st, M, K, K, row_off=h * K, transpose=True))
-            _tc_split(jobs, sc.device)
-            _tc_gemm(la, st, M, halves * K, M, [t[h * M:] for h in range(halves)], [K] * halves, [K] * halves, tag="laplacian_product_tc")
-        else:
-            hw, hs, hd = (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0), (ctypes.c_int64 * 3)(K, 0, 0)
-            with torch.cuda.device(sc.device):
-                for h in range(halves):
-                    # T[i][d] = sum_j Lsym[i][j] S[j][d]: the "dX = gZ W" tile kernel with gZ = Lsym (M x M) and W = S (M x K)
-                    _lib.call("igcn_cat_linear_bwd", _lib.ptr(sc[h * M:(h + 1) * M]), None, None, ctypes.addressof(hw), ctypes.addressof(hs),
-                              _lib.ptr(sc[h * M:(h + 1) * M]), _lib.ptr(lc), _lib.ptr(lc), M, M, K, 0, _lib.ptr(t[h * M:(h + 1) * M]), None, None,
-                              ctypes.addressof(hd), None, None, _lib.stream(), tag="laplacian_product[B=%d,D=%d]" % (M, K),
-                              nbytes=4 * (2 * M * K + M * M))
-        with torch.cuda.device(sc.device):
-            _lib.call("igcn_dot", _lib.ptr(sc), _lib.ptr(t), sc.numel(), float(scale), _lib.ptr(part), nb, _lib.ptr(out), _lib.stream(),
-                      tag="dot", nbytes=8 * sc.numel())
+                jobs.append(_job(sc[h * M:], st, M, K, K, row_off=h * K, transpose=True, sub=m[h]))
+            _tc_split(jobs, dev)
+            _tc_gemm(la, st, M, halves * K, M, [u[h * M:] for h in range(halves)], [K] * halves, [K] * halves, tag="laplacian_product_tc")
+        with torch.cuda.device(dev):
+            _lib.call("igcn_laplacian_finish", _lib.ptr(sc), _lib.ptr(m), _lib.ptr(dc) if W is not None else None, _lib.ptr(u), M, K, halves,
+                      float(M), float(scale), _lib.ptr(t), _lib.ptr(part), nb, _lib.ptr(out), _lib.stream(), tag="laplacian_finish",
+                      nbytes=4 * sc.numel() * (3 if u is not None else 2))
         ctx.scale = float(scale)
         ctx.save_for_backward(t)
         return out
@@ -692,13 +739,27 @@ class _LaplacianQuadFn(torch.autograd.Function):
         with torch.cuda.device(t.device):
             _lib.call("igcn_scale_by_scalar", _lib.ptr(t), _lib.ptr(g.contiguous().float()), 2.0 * ctx.scale, t.numel(), _lib.ptr(ds),
                       _lib.stream(), tag="scale_by_scalar", nbytes=8 * t.numel())
-        return ds, None, None, None
+        return ds, None, None, None, None
 
 
-def laplacian_quadratic(s, lsym, scale=1.0, halves=1):
-    """scale * sum_h tr(s_h^T Lsym s_h) over the `halves` row blocks s_h (B, D) of a (halves*B, D) CUDA tensor, for a SYMMETRIC
-    (B, B) matrix Lsym (treated as a constant)."""
-    return _LaplacianQuadFn.apply(s, lsym, scale, halves)
+def laplacian_quadratic(s, W, d, scale=1.0, halves=1):
+    """scale * sum_h tr(s_h^T (diag(d) - W) s_h) over the `halves` row blocks s_h (B, D) of a (halves*B, D) CUDA tensor, for a
+    SYMMETRIC (B, B) similarity W with row sums d (constants); W = d = None means the all-ones similarity."""
+    return _LaplacianQuadFn.apply(s, W, d, scale, halves)
+
+
+def rbf_similarity(t, gamma):
+    """(W, d): W[i][j] = exp(-gamma ||t_i - t_j||^2) for the rows of t (B, R) -- rbf_kernel_torch of util/image_cluster.py:15-31 as
+    kernel/sgcn_img_snp.py:188 calls it -- and its row sums, in one kernel pair (no cdist / exp / sum launches)."""
+    _lib.require_cuda(t)
+    tc = t.detach().contiguous().float()
+    B, R = tc.shape
+    W = torch.empty((B, B), dtype=torch.float32, device=tc.device)
+    d = torch.empty(B, dtype=torch.float32, device=tc.device)
+    with torch.cuda.device(tc.device):
+        _lib.call("igcn_rbf_similarity", _lib.ptr(tc), B, R, float(gamma), _lib.ptr(W), _lib.ptr(d), _lib.stream(), tag="rbf_similarity",
+                  nbytes=4 * (B * R + B * B + B))
+    return W, d
 
 
 class _SkinnyLinearFn(torch.autograd.Function):

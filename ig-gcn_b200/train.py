@@ -16,8 +16,10 @@ hp = types.SimpleNamespace(lamda_x_l1=0.1, lamda_e_l1=0.1, lamda_x_ent=0.1, lamd
 DEFAULT_LAMBDA = [0.0, 1.0, 0.5, 0.0000015, 0.1, 0.0]      # main.py:73-78 -> main.py:204
 
 
-def step_loss(model, data, lambda_loss=None, isSoftSimilarity=True, temperature=None, num_cluster=2, hyper=hp, pair=True):
-    """The scalar that train() back-propagates, term by term as in train_eval_sgcn_img_snps.py:521-544."""
+def step_loss(model, data, lambda_loss=None, isSoftSimilarity=True, temperature=None, num_cluster=2, hyper=hp, pair=True,
+              return_logp=False):
+    """The scalar that train() back-propagates, term by term as in train_eval_sgcn_img_snps.py:521-544 (eval_loss evaluates the same
+    expression, :564-598).  return_logp: also return the plain pass's log-probabilities (B, C)."""
     lam = DEFAULT_LAMBDA if lambda_loss is None else lambda_loss
     dev = data.x.device
     y = data.y.view(-1)
@@ -64,7 +66,35 @@ def step_loss(model, data, lambda_loss=None, isSoftSimilarity=True, temperature=
         loss = torch.zeros((), device=dev)
     if lam[0] != 0:
         loss = loss + hyper.lamda_ce * lam[0] * F.nll_loss(out, y) + hyper.lamda_mi * lam[0] * F.nll_loss(out_p, y)
-    return loss
+    return (loss, out) if return_logp else loss
+
+
+def evaluate(model, loader, lambda_loss=None, isSoftSimilarity=True, temperature=None, hyper=hp):
+    """eval_loss and eval_acc of the reference (kernel/train_eval_sgcn_img_snps.py:551-600) in ONE sweep over `loader`.
+
+    The reference runs them as separate loops (plus eval_scores): five eval-mode forwards per batch and a `.cpu().item()` per batch.
+    Here a batch is one stacked plain + explain inference pass (forward_pair under model.eval(): running-statistics BatchNorm as a
+    fused affine kernel, no dropout), the weighted loss and the number of correct predictions accumulate ON THE DEVICE, and the
+    host reads two scalars at the end.  Returns (mean loss per graph, accuracy).  Leaves the model in eval mode, as the reference."""
+    model.eval()
+    dev = next(model.parameters()).device
+    loss_sum = torch.zeros((), dtype=torch.float64, device=dev)
+    correct = torch.zeros((), dtype=torch.int64, device=dev)
+    n = 0
+    with torch.no_grad():
+        for data in loader:
+            data = data.to(dev)
+            loss, logp = step_loss(model, data, lambda_loss, isSoftSimilarity, temperature, hyper=hyper, return_logp=True)
+            b = int(data.num_graphs)
+            loss_sum += loss.double() * b
+            correct += (logp.argmax(1) == data.y.view(-1)).sum()
+            n += b
+            model._pe_cache = None
+            model._w_cache = None
+    if n == 0:
+        return 0.0, 0.0
+    host = torch.stack([loss_sum, correct.double()]).cpu()
+    return float(host[0]) / n, float(host[1]) / n
 
 
 class FlatGradAllReduce(object):

@@ -239,6 +239,11 @@ int igcn_bn_act_fwd(const float* z, const float* gamma, const float* beta, const
 int igcn_bn_act_bwd(const float* z, const float* gamma, const float* beta, const float* mask, const float* stats, const float* g_y,
                     int64_t N, int64_t C, int64_t L, int64_t groups, int64_t relu, float* dz, float* dgamma, float* dbeta,
                     void* stream);
+/* Eval-mode form of the same heads (model.eval(): running statistics, no dropout) -- the inference path that eval_acc / eval_loss /
+ * eval_scores of kernel/train_eval_sgcn_img_snps.py:551-671 run five times per epoch:
+ *   y = act((z - running_mean) / sqrt(running_var + eps) * gamma + beta), z (N, C, L);  with g_y != NULL, y receives d z instead. */
+int igcn_bn_eval_act(const float* z, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                     int64_t N, int64_t C, int64_t L, double eps, int64_t relu, const float* g_y, float* y, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * loss_probability (kernel/sgcn_img_snp.py:153-181): for p in {sigmoid(prob) (n_prob), p_e (n_e), sigmoid(snps_prob)
@@ -261,13 +266,25 @@ int igcn_mask_loss_bwd(const float* prob, int64_t n_prob, const float* p_e, int6
 int igcn_dot(const float* a, const float* b, int64_t n, double scale, float* partials, int64_t n_partials, float* out, void* stream);
 int igcn_scale_by_scalar(const float* a, const float* s, double scale, int64_t n, float* out, void* stream);
 
+/* The consistency loss without its cancellation (csrc/laplacian.cu): with L = D - W and L 1 = 0,
+ *   <s, L s> = <s', T>,  T = L s = d .* s' - W s',  s' = s - column means,  d = row sums of W.
+ * igcn_rbf_similarity: W (B,B) = exp(-gamma ||t_i - t_j||^2) (util/image_cluster.py:15-31 via kernel/sgcn_img_snp.py:188) and d (B).
+ * igcn_col_mean: m (groups,D) = column means of each group of B rows of s (groups*B, D).
+ * igcn_laplacian_finish: T = d .* (s - m) - U (U = W (s - m), e.g. from igcn_tc_gemm; NULL = 0, the all-ones similarity) and
+ *   out[0] = scale * <s - m, T>; d NULL = the constant d_const; partials: n_partials = igcn_reduce_blocks(groups*B*D) floats. */
+int igcn_rbf_similarity(const float* t, int64_t B, int64_t R, double gamma, float* W, float* d, void* stream);
+int igcn_col_mean(const float* s, int64_t B, int64_t D, int64_t groups, float* m, void* stream);
+int igcn_laplacian_finish(const float* s, const float* m, const float* d, const float* U, int64_t B, int64_t D, int64_t groups,
+                          double d_const, double scale, float* T, float* partials, int64_t n_partials, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Dense products on the tcgen05 tensor cores, fp32-accurate ("3xTF32", accumulators in TMEM, operands by TMA).
  * Used for the fusion heads lin1 / lin1_regr (kernel/sgcn_img_snp.py:286-305) forward and backward, and for the
  * (B x B)(B x D) Laplacian product of consist_loss (kernel/sgcn_img_snp.py:183-196).
  *
- * igcn_tc_split: operand preparation, up to 8 jobs in one launch.  Job = 11 int64 in host memory:
- *   {src, mask, hi, lo, rows, cols, ld_src, ld_dst, row_off, col_off, transpose}
+ * igcn_tc_split: operand preparation, up to 8 jobs in one launch.  Job = 12 int64 in host memory:
+ *   {src, mask, hi, lo, rows, cols, ld_src, ld_dst, row_off, col_off, transpose, sub}
+ *   sub (cols f32, may be NULL): subtracted per source column before the split (column centring);
  *   src (rows, cols) f32 with row pitch ld_src (NULL = the constant 1.0); mask (same geometry, may be NULL): elements
  *   whose mask value is not > 0 are taken as 0 (the ReLU mask of a backward pass); every element x is written as the
  *   pair hi = rn_tf32(x), lo = rn_tf32(x - hi) to hi/lo[(row_off + r) * ld_dst + col_off + c], or transposed to

@@ -93,18 +93,29 @@ def test_laplacian_quadratic_vs_reference_form(B, D):
     g = torch.Generator().manual_seed(2)
     s = torch.rand(B, D, generator=g).to(DEV)
     t = torch.rand(B, 30, generator=g).to(DEV)
-    W = torch.exp(-0.01 * torch.cdist(t, t) ** 2)
-    lap = torch.diag(W.sum(1)) - 0.5 * (W + W.t())
+    W, d = ops.rbf_similarity(t, 0.01)                    # own kernels (csrc/laplacian.cu) vs torch in fp64
+    Wd = torch.exp(-0.01 * torch.cdist(t.double(), t.double()) ** 2)
+    H.assert_close(W, Wd, what="rbf similarity")
+    H.assert_close(d, Wd.sum(1), what="rbf row sums")
     s1 = s.clone().requires_grad_(True)
-    v = ops.laplacian_quadratic(s1, lap, 1.0 / (B * B))
+    v = ops.laplacian_quadratic(s1, W, d, 1.0 / (B * B))
     (v * 3.0).backward()
     s2 = s.double().clone().requires_grad_(True)
-    Wd = W.double()
     L = torch.eye(B, device=DEV, dtype=torch.float64) * Wd.sum(1) - Wd
     ref = torch.trace(s2.t() @ L @ s2) / (B * B)
     (ref * 3.0).backward()
     H.assert_close(v, ref, what="quadratic form")
     H.assert_close(s1.grad, s2.grad, what="quadratic form gradient")
+    # the all-ones similarity of isSoftSimilarity=False (kernel/sgcn_img_snp.py:190): no product at all
+    s3 = s.clone().requires_grad_(True)
+    v1 = ops.laplacian_quadratic(s3, None, None, 1.0 / (B * B))
+    v1.backward()
+    s4 = s.double().clone().requires_grad_(True)
+    one = torch.ones(B, B, device=DEV, dtype=torch.float64)
+    r1 = torch.trace(s4.t() @ (torch.diag(one.sum(1)) - one) @ s4) / (B * B)
+    r1.backward()
+    H.assert_close(v1, r1, what="quadratic form, ones")
+    H.assert_close(s3.grad, s4.grad, what="quadratic form gradient, ones")
 
 
 def test_laplacian_quadratic_two_halves():
@@ -113,13 +124,13 @@ def test_laplacian_quadratic_two_halves():
     B, D = 48, 320
     s = torch.rand(2 * B, D, generator=g).to(DEV)
     t = torch.rand(B, 30, generator=g).to(DEV)
-    W = torch.exp(-0.01 * torch.cdist(t, t) ** 2)
-    lap = torch.diag(W.sum(1)) - 0.5 * (W + W.t())
+    W, d = ops.rbf_similarity(t, 0.01)
     s1 = s.clone().requires_grad_(True)
-    v = ops.laplacian_quadratic(s1, lap, 1.0 / (B * B), halves=2)
+    v = ops.laplacian_quadratic(s1, W, d, 1.0 / (B * B), halves=2)
     v.backward()
     s2 = s.double().clone().requires_grad_(True)
-    L = lap.double()
+    Wd = torch.exp(-0.01 * torch.cdist(t.double(), t.double()) ** 2)
+    L = torch.diag(Wd.sum(1)) - Wd
     ref = (torch.trace(s2[:B].t() @ L @ s2[:B]) + torch.trace(s2[B:].t() @ L @ s2[B:])) / (B * B)
     ref.backward()
     H.assert_close(v, ref, what="paired quadratic form")

@@ -433,3 +433,41 @@ def test_reference_training_loop_calling_convention():
         assert data.batch.shape == (n * 90,) and int(data.batch[-1]) == n - 1
     assert seen == len(loader.dataset) == 10 and np.isfinite(total)
     assert model.prob.grad is not None and model.edge_prob.grad is None      # edge_prob is unused, as in the reference
+
+
+@pytest.mark.parametrize("case", ["imgsnp_small", "imgsnp_adni"])
+def test_fused_eval_loop_golden(case):
+    """train.evaluate = eval_loss + eval_acc of the reference (kernel/train_eval_sgcn_img_snps.py:551-600) in one inference sweep:
+    eval-mode BatchNorm on the fused affine kernel, both passes stacked, loss accumulated on the device.  Checked against the
+    oracle's eval-mode step loss (fp64) and the golden eval-mode predictions of the reference model."""
+    from igcn_b200.data import DataLoader, SubjectSet
+    from igcn_b200 import train as T
+    g = H.load(case)
+    m, (L, Hd, R, B, S) = _build(g)
+    lam = list(g["lambda_loss"])
+    loader = DataLoader(SubjectSet(H.subjects(g)), batch_size=B, shuffle=False, device=torch.device(DEV))
+    loss, acc = T.evaluate(m, loader, lam, True)
+    assert not m.training
+    prep = O.go_index_prep(g["adj"].T, g["go_snps"], list(g["pool"]))
+    P64 = H.params(g, dtype=torch.float64)
+    c = O.collate(H.subjects(g), np.arange(B))
+    b64 = {k: torch.from_numpy(v) for k, v in c.items()}
+    for k in ("x", "edge_attr", "snps_feat", "clini_score", "tsne_fdim"):
+        b64[k] = b64[k].double()
+    ref, o, _ = O.train_step_loss(P64, prep, b64, L, R, lam, 0.01, training=False, with_orth=False)
+    H.assert_close(torch.tensor(loss), ref.detach(), what="eval loss")
+    want = float((torch.from_numpy(g["eval/plain/logp"]).argmax(1) == torch.from_numpy(c["y"])).float().mean())
+    assert abs(acc - want) < 1e-9, (acc, want)
+    # two batches: the per-batch losses are weighted by their graph counts, as eval_loss does (:598)
+    if B >= 4:
+        loader2 = DataLoader(SubjectSet(H.subjects(g)), batch_size=B // 2, shuffle=False, device=torch.device(DEV))
+        l2, a2 = T.evaluate(m, loader2, lam, True)
+        refs = []
+        for lo in range(0, B, B // 2):
+            cc = O.collate(H.subjects(g), np.arange(lo, min(B, lo + B // 2)))
+            bb = {k: torch.from_numpy(v) for k, v in cc.items()}
+            for k in ("x", "edge_attr", "snps_feat", "clini_score", "tsne_fdim"):
+                bb[k] = bb[k].double()
+            r_, _, _ = O.train_step_loss(P64, prep, bb, L, R, lam, 0.01, training=False, with_orth=False)
+            refs.append(float(r_) * bb["snps_feat"].shape[0])
+        H.assert_close(torch.tensor(l2), torch.tensor(sum(refs) / B), what="eval loss, two batches")

@@ -52,7 +52,7 @@ def test_no_cpu_fallback():
         lambda: ops.tc_matmul_nt(torch.zeros(2, 8), torch.zeros(4, 8)),
         lambda: ops.bn_act(torch.zeros(6, 4), bn),
         lambda: ops.mask_loss(torch.zeros(5, 3), torch.zeros(7), torch.zeros(1, 4), hp),
-        lambda: ops.laplacian_quadratic(torch.zeros(4, 8), torch.zeros(4, 4)),
+        lambda: ops.laplacian_quadratic(torch.zeros(4, 8), torch.zeros(4, 4), torch.zeros(4)),
         lambda: ops.skinny_linear(torch.zeros(6, 5), torch.zeros(3, 5)),
         lambda: ops.snp_mask_pair(torch.zeros(3, 4), torch.zeros(1, 4)),
         lambda: ops.output_heads(torch.zeros(2, 8), None, torch.zeros(2, 8), None, lin, lin),
