@@ -137,6 +137,9 @@ def call(name, *args, tag=None, nbytes=None):
     fn = getattr(lib(), name)
     if _profile is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # run-ahead pad: a ~15 us spin kernel in front of the bracket lets the CPU enqueue e0 / the call / e1 while the GPU is
+        # still busy, so the interval holds the kernels of this call and not the host's launch latency
+        torch.cuda._sleep(30000)
         e0.record()
         rc = fn(*args)
         e1.record()

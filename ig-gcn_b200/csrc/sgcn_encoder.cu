@@ -491,7 +491,20 @@ static bool use_mma_bwd(int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max
 }
 
 extern "C" int64_t igcn_sgcn_bwd_ctas(int64_t B, int64_t R, int64_t F0, int64_t H, int64_t L, int64_t max_eg) {
-    if (use_fast_bwd(R, F0, H, L, max_eg) || use_mma_bwd(R, F0, H, L, max_eg, true)) {
+    if (use_mma_bwd(R, F0, H, L, max_eg, true)) {
+        // as many CTAs per SM as shared memory, threads and the 96-register budget allow (3 at 90 ROIs, 1 at 264): a small batch
+        // then runs one graph per CTA instead of queueing graphs behind each other
+        const int nthr = mma::mma_bwd_threads((int)R);
+        const size_t smem = mma::bwd_mma_smem((int)R, (int)max_eg, nthr, true);
+        int per_sm = (int)((227 * 1024) / (smem + 1024));
+        if (per_sm > 2048 / nthr) per_sm = 2048 / nthr;
+        if (per_sm > 65536 / (96 * nthr)) per_sm = 65536 / (96 * nthr);
+        if (per_sm < 1) per_sm = 1;
+        int64_t n = (int64_t)sm_count() * per_sm;
+        if (n > B) n = B;
+        return n < 1 ? 1 : n;
+    }
+    if (use_fast_bwd(R, F0, H, L, max_eg)) {
         int64_t n = sm_count();
         if (n > B) n = B;
         return n < 1 ? 1 : n;

@@ -34,9 +34,11 @@ def pytest_sessionfinish(session, exitstatus):
         if H.PARITY_LOG:
             d = os.path.join(ROOT, "gpurun_out")
             os.makedirs(d, exist_ok=True)
+            notes = [r for r in H.PARITY_LOG if "ReLU sign flips" in r["what"]]
+            H.PARITY_LOG[:] = [r for r in H.PARITY_LOG if "ReLU sign flips" not in r["what"]]
             nb = sum(1 for r in H.PARITY_LOG if r["rule"] == "B")
             with open(os.path.join(d, "parity_report.json"), "w") as f:
-                json.dump(dict(rtol=H.RTOL, tensors=len(H.PARITY_LOG), rule_B=nb,
+                json.dump(dict(rtol=H.RTOL, tensors=len(H.PARITY_LOG), rule_B=nb, relu_sign_flips=[r["what"] for r in notes],
                                worst_rule_A=max([r["err32"] for r in H.PARITY_LOG if r["rule"] == "A"] or [0.0]),
                                rule_B_tensors=[r for r in H.PARITY_LOG if r["rule"] == "B"],
                                worst_rule_A_tensors=sorted([r for r in H.PARITY_LOG if r["rule"] == "A"],
