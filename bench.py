@@ -111,10 +111,18 @@ def cupti_kernel_table(replay, n_rep, ms_per_step):
     microseconds, share of the step.  Shares can add up to more than 1: the step runs on three streams."""
     import collections
     from torch.profiler import ProfilerActivity, profile
-    replay()
-    torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for _ in range(n_rep):
+    done = 0
+    try:                                     # exactly n_rep + 1 replays on every rank, whatever the profiler does
+        replay()
+        done += 1
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(n_rep):
+                replay()
+                done += 1
+            torch.cuda.synchronize()
+    finally:
+        for _ in range(n_rep + 1 - done):
             replay()
         torch.cuda.synchronize()
     agg = collections.defaultdict(lambda: [0, 0.0])
@@ -284,7 +292,8 @@ def run_igcn(args, w):
     #      (b) CUDA-event brackets around every C-ABI call of the same step run eagerly (a run-ahead pad in front of each bracket
     #      keeps the host's launch latency out of the interval; see _lib.call), which carry the algorithmic bytes -------------------
     cupti = None
-    if not args.eager and rank == 0:
+    if not args.eager:
+        # EVERY rank replays (the step holds the fused all-reduce, which waits for its peers: ranks must stay in lock-step)
         try:
             cupti = cupti_kernel_table(lambda: graphed(), 5, ms)
         except Exception as e:                                       # noqa: BLE001 -- evidence only; never break the bench line
@@ -619,6 +628,81 @@ def run_eval(args):
                                       "on the device, one host read per sweep", loss=loss, accuracy=acc))), flush=True)
 
 
+def run_config5(args):
+    """BASELINE configs[4]: data-parallel training of the full step (264 ROIs, 4096 graphs per GPU) over synthetic subjects that are
+    GENERATED AND PREPROCESSED ON THE DEVICE of every rank (igcn_b200.device_data: connectivity -> graph diffusion convolution ->
+    COO; nothing is staged on the host) and collated from device-resident arrays every step.  --subjects is the data-set size over
+    all ranks (default 1 000 000).  Prints its own JSON line: graphs/s of the step incl. the device collation, the generation time,
+    and the time of one epoch over the data set at that rate."""
+    import torch.distributed as dist
+    from igcn_b200 import train as T
+    from igcn_b200.device_data import DeviceSubjectSet, collate_device
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOADS["config4"]
+    B = w["B"]
+    n_rank = max(B, args.subjects // world)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ds = DeviceSubjectSet.generate(n_rank, rois=w["R"], n_snps=w["S"], seed=1234, device=dev, first_id=rank * n_rank,
+                                   num_classes=w["num_classes"], num_regr=w["num_regr"], chunk=2048)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    model, _, _ = build_problem(dict(w, B=8), rank, dev)                       # the model only (identical replicas)
+    model = model.to(dev).train()
+    opt = T.FlatAdam(model.parameters(), lr=1e-3)
+    g = torch.Generator(device=dev)
+    g.manual_seed(rank)
+    batch = collate_device(ds, torch.randperm(n_rank, generator=g, device=dev)[:B])
+    graphed = T.GraphedTrainStep(model, opt, batch, LAMBDA, None, True)
+
+    def step():
+        collate_device(ds, torch.randint(0, n_rank, (B,), generator=g, device=dev), out=batch)      # device gather + collate kernel
+        return graphed()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    evs = []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = step()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / args.steps, gen_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        opt.check_dp_error()
+    ms, gen_max = float(t[0]), float(t[1])
+    if rank == 0:
+        rate = B * world / (ms * 1e-3)
+        out = dict(metric=METRIC, value=rate, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms,
+                   higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic (generated on the device)",
+                   config=dict(workload="config5", description="full IG-GCN img+SNP+GO step, 264-ROI graphs, 4096 graphs per GPU, data parallel; "
+                               "subjects generated + GDC-preprocessed on the device, collated from device arrays inside the timed step",
+                               subjects_total=n_rank * world, subjects_per_gpu=n_rank, dataset_bytes_per_gpu=int(ds.nbytes()),
+                               generation_s=gen_max, generation_subjects_per_s=n_rank * world / gen_max,
+                               epoch_s_at_this_rate=n_rank * world / rate, loss_last=float(loss), l2="inputs (%.1f GB per GPU) exceed L2" % (ds.nbytes() / 1e9),
+                               parallelism="dp%d" % world))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(out), flush=True)
+    finish(world)
+
+
 def finish(world):
     """Leave without tearing NCCL down: destroy_process_group() after a captured graph that contains the all-reduce was
     observed to hang at exit on this stack; the timed work is complete and synchronised at this point."""
@@ -705,16 +789,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS) + ["config3", "eval"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS) + ["config3", "config5", "eval"])
+    ap.add_argument("--subjects", type=int, default=1000000, help="config5: data-set size over all ranks")
     ap.add_argument("--impl", default="igcn", choices=["igcn", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config4-kernels", action="store_true", help="skip the side measurement of the SGCN kernels at config-4 size")
     ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying the CUDA graph")
     args = ap.parse_args()
-    if args.workload in ("config3", "eval"):
+    if args.workload in ("config3", "eval", "config5"):
         import __graft_entry__ as ge
-        ge.build()
-        (run_config3 if args.workload == "config3" else run_eval)(args)
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            ge.build()
+        dict(config3=run_config3, eval=run_eval, config5=run_config5)[args.workload](args)
         return
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -73,6 +73,7 @@ SIGNATURES = {
     "igcn_gcn_conv_bwd_ctas": (_I, [_I]),
     "igcn_gcn_conv_bwd_work_floats": (_I, [_I, _I, _I]),
     "igcn_gcn_conv_bwd": (ctypes.c_int, [_P] * 9 + [_I] * 4 + [_P] * 4 + [_I, _P, _P]),
+    "igcn_gdc_topk_emit": (ctypes.c_int, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "igcn_go_spmm_fwd": (ctypes.c_int, [_P] * 4 + [_I] * 5 + [_P, _P]),
     "igcn_go_spmm_bwd": (ctypes.c_int, [_P] * 8 + [_I] * 5 + [_P, _P, _P, _P]),
     "igcn_go_layer_param_count": (_I, [_I, _I, _I]),
@@ -107,6 +108,7 @@ KERNELS_PER_CALL = {
     "igcn_gcn_conv_bwd_ctas": (_I, [_I]),
     "igcn_gcn_conv_bwd_work_floats": (_I, [_I, _I, _I]),
     "igcn_gcn_conv_bwd": (ctypes.c_int, [_P] * 9 + [_I] * 4 + [_P] * 4 + [_I, _P, _P]),
+    "igcn_gdc_topk_emit": (ctypes.c_int, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "igcn_go_spmm_fwd": 1, "igcn_go_spmm_bwd": 2, "igcn_go_layer_fwd": 1, "igcn_go_layer_bwd": 2, "igcn_adam_step": 1, "igcn_dropout_masks": 2, "igcn_cross_attn_fwd": 1, "igcn_cross_attn_bwd": 2, "igcn_cat_linear_fwd": 2, "igcn_cat_linear_bwd": 2, "igcn_gat_layer_fwd": 1, "igcn_gat_layer_bwd": 2,
     "igcn_bn_act_fwd": 1, "igcn_bn_act_bwd": 1, "igcn_mask_loss_fwd": 2, "igcn_mask_loss_bwd": 1, "igcn_dot": 2, "igcn_scale_by_scalar": 1, "igcn_tc_split": 1, "igcn_tc_gemm": 2, "igcn_skinny_linear_fwd": 1, "igcn_skinny_linear_bwd": 2,
     "igcn_snp_mask_pair_fwd": 1, "igcn_snp_mask_pair_bwd": 1, "igcn_heads_fwd": 1, "igcn_heads_bwd": 2, "igcn_step_loss_fwd": 1, "igcn_step_loss_bwd": 1,

@@ -189,7 +189,7 @@ class FlatAdam(object):
             gp = (ctypes.c_int64 * world)(*[int(a) for a in hdl.buffer_ptrs])
             sp = (ctypes.c_int64 * world)(*[int(a) for a in hdl.signal_pad_ptrs])
             self._peer = dict(handle=hdl, grad_ptrs=gp, signal_ptrs=sp, world=world, rank=rank, pad=pad,
-                              timeout_ms=int(float(os.environ.get("IGCN_DP_TIMEOUT_S", "300")) * 1000),
+                              timeout_ms=int(float(os.environ.get("IGCN_DP_TIMEOUT_S", "120")) * 1000),
                               error=torch.zeros(1, dtype=torch.int32, device=dev))
             torch.cuda.synchronize(dev)
         except Exception as e:                                     # noqa: BLE001 -- any failure means "use NCCL"

@@ -389,6 +389,15 @@ int igcn_gcn_conv_bwd(const float* x, const int32_t* rowptr_t, const int32_t* cs
                       int64_t N, int64_t E, int64_t C, int64_t O, float* work, float* dx, float* d_edge_weight, float* partials,
                       int64_t n_cta, float* grads, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * On-device preprocessing: the sparsification step of graph diffusion convolution (util_gdc.py:25-31 get_top_k_matrix + :84-101
+ * dense -> COO; applied per subject as a pre_transform, sgcn_data.py:332-338).  ppr (B,R,R) f64 = the dense PPR matrices
+ * alpha (I - (1-alpha) D^-1/2 A D^-1/2)^-1 (util_gdc.py:7-14).  Per subject and column: keep the k largest entries, divide by their
+ * sum, cast to f32, emit the non-zeros in row-major order: edge_src / edge_dst (B*R*k) i32 LOCAL ids, edge_attr (B*R*k) f32.
+ * Bit-identical edge lists to the numpy restatement for the same input. */
+int igcn_gdc_topk_emit(const double* ppr, int64_t B, int64_t R, int64_t k, int32_t* edge_src, int32_t* edge_dst, float* edge_attr,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif
