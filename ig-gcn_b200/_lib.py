@@ -101,19 +101,11 @@ def lib():
 # ---- launch accounting (bench.py: gpu_launches, per-kernel CUDA-event timing) -------------------------------
 KERNELS_PER_CALL = {
     "igcn_collate_csr": 1, "igcn_csr_from_edge_index": 2, "igcn_sgcn_encoder_fwd": 1, "igcn_sgcn_encoder_bwd": 2,
-    "igcn_graph_csr_work_ints": (_I, [_I, _I]),
-    "igcn_graph_csr": (ctypes.c_int, [_P, _I, _I] + [_P] * 7),
-    "igcn_gcn_conv_saved_floats": (_I, [_I, _I, _I]),
-    "igcn_gcn_conv_fwd": (ctypes.c_int, [_P] * 7 + [_I] * 4 + [_P] * 3),
-    "igcn_gcn_conv_bwd_ctas": (_I, [_I]),
-    "igcn_gcn_conv_bwd_work_floats": (_I, [_I, _I, _I]),
-    "igcn_gcn_conv_bwd": (ctypes.c_int, [_P] * 9 + [_I] * 4 + [_P] * 4 + [_I, _P, _P]),
-    "igcn_gdc_topk_emit": (ctypes.c_int, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "igcn_go_spmm_fwd": 1, "igcn_go_spmm_bwd": 2, "igcn_go_layer_fwd": 1, "igcn_go_layer_bwd": 2, "igcn_adam_step": 1, "igcn_dropout_masks": 2, "igcn_cross_attn_fwd": 1, "igcn_cross_attn_bwd": 2, "igcn_cat_linear_fwd": 2, "igcn_cat_linear_bwd": 2, "igcn_gat_layer_fwd": 1, "igcn_gat_layer_bwd": 2,
     "igcn_bn_act_fwd": 1, "igcn_bn_act_bwd": 1, "igcn_mask_loss_fwd": 2, "igcn_mask_loss_bwd": 1, "igcn_dot": 2, "igcn_scale_by_scalar": 1, "igcn_tc_split": 1, "igcn_tc_gemm": 2, "igcn_skinny_linear_fwd": 1, "igcn_skinny_linear_bwd": 2,
     "igcn_snp_mask_pair_fwd": 1, "igcn_snp_mask_pair_bwd": 1, "igcn_heads_fwd": 1, "igcn_heads_bwd": 2, "igcn_step_loss_fwd": 1, "igcn_step_loss_bwd": 1,
     "igcn_rbf_similarity": 2, "igcn_col_mean": 1, "igcn_laplacian_finish": 2,
-    "igcn_graph_csr": 5, "igcn_gcn_conv_fwd": 4, "igcn_gcn_conv_bwd": 7,
+    "igcn_graph_csr": 5, "igcn_gcn_conv_fwd": 4, "igcn_gcn_conv_bwd": 7, "igcn_gdc_topk_emit": 1, "igcn_bn_eval_act": 1,
 }
 launch_count = 0          # number of igcn kernels launched by this process
 _profile = None           # None, or dict name -> list[(start_event, end_event)]
