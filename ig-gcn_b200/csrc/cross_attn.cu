@@ -29,6 +29,12 @@ struct AttnArgs {
     int B, R, M, E, heads, relu, P;
     int mix;            // 1: y = (x + relu(attn(x))) / 2 in one pass (kernel/sgcn_img_snp.py:239-242 + the fusion average); tensor-core kernels only
     int Rc;             // query rows staged per chunk
+    // table-driven tensor-core path (cross_attn_mma2.cuh): per-graph K'/V'/c/K/V records written by the forward, per-(graph, row
+    // chunk) gradient records written by the backward row kernel and consumed by the chain kernel
+    const float* tab;   // (B, tab_sz)  read side
+    float* tab_out;     // (B, tab_sz)  attn_tables_kernel output
+    float* dtab;        // (B * nchunk, dtab_sz)
+    int tab_sz, dtab_sz, nchunk;
 };
 
 // Register tiling: every thread produces 4 consecutive output features, so one broadcast LDS.32 + one LDS.128 feed 4 FMAs
@@ -392,6 +398,8 @@ static int attn_fill(AttnArgs& a, const char* who, const float* x, const float* 
 
 #include "cross_attn_rows.cuh"
 #include "cross_attn_mma.cuh"
+#include "cross_attn_mma2.cuh"
+#include "cross_attn_mma3.cuh"
 
 namespace igcn {
 
@@ -409,6 +417,22 @@ static bool use_mma_fwd(int64_t R, int64_t M, int64_t E, int64_t heads) {
 static bool use_mma_bwd(int64_t R, int64_t M, int64_t E, int64_t heads) {
     if (getenv("IGCN_ATTN_ROWS")) return false;
     return use_rows(R, M, E, heads) && amma::bwd_geo((int)R, (int)M, (int)heads).smem <= 227 * 1024;
+}
+// table-driven path (cross_attn_mma2.cuh); IGCN_ATTN_V1=1 keeps the single-kernel version (A/B hook)
+static bool use_v2(int64_t R, int64_t M, int64_t E, int64_t heads) {
+    static const bool off = getenv("IGCN_ATTN_V1") != nullptr;
+    if (off || !use_mma_fwd(R, M, E, heads) || !use_mma_bwd(R, M, E, heads)) return false;
+    return amma2::bwd2_geo((int)R, (int)M, (int)heads, 1 << 20).smem <= 110 * 1024 && amma2::chain_smem((int)M, ((int)M + 7) & ~7, (int)heads) <= 100 * 1024;
+}
+// token-side kernels on tensor cores (cross_attn_mma3.cuh) for 2 heads of 16; IGCN_ATTN_SCALAR_TOKENS=1 keeps the scalar versions
+static bool use_mma_tokens(int64_t E, int64_t heads) {
+    static const bool off = getenv("IGCN_ATTN_SCALAR_TOKENS") != nullptr;
+    return !off && E == 32 && heads == 2;
+}
+template <int NT>
+static void launch_bwd2(const AttnArgs& a, const amma2::GeoB2& g, int items, cudaStream_t st) {
+    cudaFuncSetAttribute(amma2::attn_bwd2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    amma2::attn_bwd2_kernel<NT><<<items, g.nthreads, g.smem, st>>>(a, g);
 }
 template <int NT>
 static void launch_mma_bwd(const AttnArgs& a, const amma::GeoB& g, int ctas, cudaStream_t st) {
@@ -456,6 +480,111 @@ extern "C" int64_t igcn_cross_attn_bwd_ctas(int64_t B, int64_t R, int64_t M, int
         return rows_ctas(g, B, g.smem <= 110 * 1024 ? 2 : 1);
     }
     return attn_ctas(attn_bwd_smem(attn_rows_per_chunk((int)R, (int)M, (int)E, (int)heads), (int)M, (int)E, (int)heads, (int)(4 * E * E + 4 * E)), B, 512);
+}
+
+extern "C" int64_t igcn_cross_attn_v2_supported(int64_t R, int64_t M, int64_t E, int64_t heads) { return use_v2(R, M, E, heads) ? 1 : 0; }
+extern "C" int64_t igcn_cross_attn_v2_tab_floats(int64_t M, int64_t heads) {
+    return amma2::tab_floats((int)M, ((int)M + 7) & ~7, (int)heads);
+}
+extern "C" int64_t igcn_cross_attn_v2_work_floats(int64_t B, int64_t R, int64_t M, int64_t heads) {
+    const amma2::GeoB2 g = amma2::bwd2_geo((int)R, (int)M, (int)heads, B);
+    return B * g.nchunk * (int64_t)amma2::dtab_floats(g.MP, (int)heads);
+}
+extern "C" int64_t igcn_cross_attn_v2_bwd_ctas(int64_t B) {
+    int64_t n = (B + amma2::kChainGraphs - 1) / amma2::kChainGraphs;
+    const int64_t cap = (int64_t)sm_count() * 2;
+    if (n > cap) n = cap;
+    return n < 1 ? 1 : n;
+}
+
+extern "C" int igcn_cross_attn_v2_fwd(const float* q_in, const float* kv_in, const float* in_proj_weight, const float* in_proj_bias,
+                                      const float* out_proj_weight, const float* out_proj_bias, int64_t B, int64_t R, int64_t M, int64_t E,
+                                      int64_t heads, int64_t relu, float* out, float* tab, void* stream) {
+    AttnArgs a{};
+    int rc = attn_fill(a, "cross_attn_v2_fwd", q_in, kv_in, in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias, B, R, M, E, heads, relu);
+    if (rc) return rc;
+    IGCN_REQUIRE(use_v2(R, M, E, heads), IGCN_ERR_UNSUPPORTED, "cross_attn_v2_fwd: shape outside the table-driven kernels (see igcn_cross_attn_v2_supported)");
+    IGCN_REQUIRE(out && tab, IGCN_ERR_BAD_ARG, "cross_attn_v2_fwd: null output");
+    IGCN_REQUIRE(((uintptr_t)q_in | (uintptr_t)out | (uintptr_t)tab) % 16 == 0, IGCN_ERR_BAD_ARG, "cross_attn_v2_fwd: buffers must be 16-byte aligned");
+    if (B == 0) return IGCN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const amma::Geo g = amma::fwd_geo((int)R, (int)M, (int)heads);
+    a.y = out; a.tab_out = tab; a.tab = tab; a.tab_sz = amma2::tab_floats((int)M, g.MP, (int)heads);
+    if (use_mma_tokens(E, heads)) {
+        const size_t smem = amma3::tables_smem();
+        if ((rc = allow_smem(amma3::attn_tables_mma_kernel, smem, "cross_attn_tables_mma"))) return rc;
+        int64_t ctas = (B + amma3::kWarps - 1) / amma3::kWarps;
+        if (ctas > (int64_t)sm_count() * 4) ctas = (int64_t)sm_count() * 4;
+        amma3::attn_tables_mma_kernel<<<(int)ctas, amma3::kThreads, smem, st>>>(a, g.MP);
+        IGCN_CHECK_LAUNCH("cross_attn_tables_mma");
+    } else {
+        // the per-graph table area doubles as the 64 x 33 staging tile of the weight transposes
+        const int per_area = amma2::kTabGraphs * g.per_sz > 2 * amma::kE * 33 ? amma2::kTabGraphs * g.per_sz : 2 * amma::kE * 33;
+        const size_t smem = (size_t)4 * (4 * amma::kE * amma::kE + 4 * amma::kE + per_area) + 16;
+        if ((rc = allow_smem(amma2::attn_tables_kernel, smem, "cross_attn_tables"))) return rc;
+        int64_t ctas = (B + amma2::kTabGraphs - 1) / amma2::kTabGraphs;
+        if (ctas > (int64_t)sm_count() * 4) ctas = (int64_t)sm_count() * 4;
+        amma2::attn_tables_kernel<<<(int)ctas, amma2::kTabThreads, smem, st>>>(a, g.per_sz, g.MP);
+        IGCN_CHECK_LAUNCH("cross_attn_tables");
+    }
+    const int64_t groups = (B + g.gpc - 1) / g.gpc;
+    int64_t ctas = (int64_t)sm_count() * 2;
+    if (ctas > groups) ctas = groups;
+    switch (g.MP / 8) {
+        case 1: launch_mma_fwd<1>(a, g, (int)ctas, st); break;
+        case 2: launch_mma_fwd<2>(a, g, (int)ctas, st); break;
+        case 3: launch_mma_fwd<3>(a, g, (int)ctas, st); break;
+        default: launch_mma_fwd<4>(a, g, (int)ctas, st); break;
+    }
+    IGCN_CHECK_LAUNCH("cross_attn_v2_fwd");
+    return IGCN_OK;
+}
+
+extern "C" int igcn_cross_attn_v2_bwd(const float* q_in, const float* kv_in, const float* in_proj_weight, const float* in_proj_bias,
+                                      const float* out_proj_weight, const float* out_proj_bias, const float* out, const float* g_out,
+                                      const float* tab, int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads, int64_t relu,
+                                      float* d_q_in, float* d_kv_in, float* work, float* partials, int64_t n_cta, float* grads, void* stream) {
+    AttnArgs a{};
+    int rc = attn_fill(a, "cross_attn_v2_bwd", q_in, kv_in, in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias, B, R, M, E, heads, relu);
+    if (rc) return rc;
+    IGCN_REQUIRE(use_v2(R, M, E, heads), IGCN_ERR_UNSUPPORTED, "cross_attn_v2_bwd: shape outside the table-driven kernels (see igcn_cross_attn_v2_supported)");
+    IGCN_REQUIRE(out && g_out && tab && d_q_in && d_kv_in && work && partials && grads, IGCN_ERR_BAD_ARG, "cross_attn_v2_bwd: null pointer");
+    IGCN_REQUIRE(((uintptr_t)q_in | (uintptr_t)out | (uintptr_t)g_out | (uintptr_t)d_q_in | (uintptr_t)d_kv_in | (uintptr_t)tab | (uintptr_t)work |
+                  (uintptr_t)partials) % 16 == 0, IGCN_ERR_BAD_ARG, "cross_attn_v2_bwd: buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0) {
+        cudaMemsetAsync(grads, 0, sizeof(float) * a.P, st);
+        return IGCN_OK;
+    }
+    const int want = (int)igcn_cross_attn_v2_bwd_ctas(B);
+    IGCN_REQUIRE(n_cta == want, IGCN_ERR_BAD_ARG, "cross_attn_v2_bwd: n_cta=%lld, expected %d", (long long)n_cta, want);
+    const amma2::GeoB2 g = amma2::bwd2_geo((int)R, (int)M, (int)heads, B);
+    a.yout = out; a.gy = g_out; a.dx = d_q_in; a.da = d_kv_in; a.partials = partials;
+    a.tab = tab; a.tab_sz = amma2::tab_floats((int)M, g.MP, (int)heads);
+    a.dtab = work; a.dtab_sz = amma2::dtab_floats(g.MP, (int)heads); a.nchunk = g.nchunk;
+    IGCN_REQUIRE(B * g.nchunk < (int64_t)2147483647, IGCN_ERR_UNSUPPORTED, "cross_attn_v2_bwd: too many (graph, chunk) items");
+    const int items = (int)(B * g.nchunk);
+    switch (g.MP / 8) {
+        case 1: launch_bwd2<1>(a, g, items, st); break;
+        case 2: launch_bwd2<2>(a, g, items, st); break;
+        case 3: launch_bwd2<3>(a, g, items, st); break;
+        default: launch_bwd2<4>(a, g, items, st); break;
+    }
+    IGCN_CHECK_LAUNCH("cross_attn_v2_bwd_rows");
+    if (use_mma_tokens(E, heads)) {
+        const size_t csm = amma3::chain_smem();
+        if ((rc = allow_smem(amma3::attn_chain_mma_kernel, csm, "cross_attn_chain_mma"))) return rc;
+        amma3::attn_chain_mma_kernel<<<want, amma3::kThreads, csm, st>>>(a, g.MP);
+        IGCN_CHECK_LAUNCH("cross_attn_chain_mma");
+    } else {
+        const size_t csm = amma2::chain_smem((int)M, g.MP, (int)heads);
+        if ((rc = allow_smem(amma2::attn_chain_kernel, csm, "cross_attn_chain"))) return rc;
+        amma2::attn_chain_kernel<<<want, amma2::kChainThreads, csm, st>>>(a, g.MP);
+        IGCN_CHECK_LAUNCH("cross_attn_chain");
+    }
+    reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(partials, want, a.P, grads);
+    IGCN_CHECK_LAUNCH("cross_attn_reduce_partials");
+    return IGCN_OK;
 }
 
 extern "C" int igcn_cross_attn_fwd(const float* q_in, const float* kv_in, const float* in_proj_weight, const float* in_proj_bias,

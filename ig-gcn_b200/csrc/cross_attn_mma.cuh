@@ -198,10 +198,15 @@ __global__ void __launch_bounds__(kThreads, 2) attn_mma_fwd_kernel(AttnArgs a, G
     float* bo = bin + 3 * kE;
     float* per = bo + kE;
     float* Xs = per + geo.gpc * geo.per_sz;
-    rows::load_weights(a, WkvT, Wq, WoT, bin, bo);
+    if (a.tab) {                                            // tables come from attn_tables_kernel: no weights needed here
+        for (int i = tid; i < kE; i += nt) bo[i] = a.bo[i];
+    } else {
+        rows::load_weights(a, WkvT, Wq, WoT, bin, bo);
+    }
     __syncthreads();
     const int T = (R + 15) >> 4;                            // 16-row tiles per graph (tiles never straddle graphs: the tables differ)
     const int oKp = 3 * M * kE, oVp = oKp + H * MP * TS, oC = oVp + H * MP * TS;
+    const int nhead4 = (2 * H * MP * TS + H * MP) >> 2;     // K' | V' | c of a graph, contiguous, in float4 units
     for (int b0 = blockIdx.x * geo.gpc; b0 < a.B; b0 += gridDim.x * geo.gpc) {
         const int ng = min(geo.gpc, a.B - b0), rows = ng * R;
         const float* xg = a.x + (int64_t)b0 * R * kE;
@@ -209,7 +214,15 @@ __global__ void __launch_bounds__(kThreads, 2) attn_mma_fwd_kernel(AttnArgs a, G
             const int row = idx >> 3, ch = idx & 7;
             st4s(Xs + row * TS + 4 * ch, ld4s(xg + (int64_t)idx * 4));
         }
-        graph_tables(a, b0, ng, per, geo.per_sz, MP, WkvT, Wq, WoT, bin);       // ends with a barrier (covers Xs too)
+        if (a.tab) {
+            for (int idx = tid; idx < ng * nhead4; idx += nt) {
+                const int gl = idx / nhead4, i = idx - gl * nhead4;
+                st4s(per + gl * geo.per_sz + oKp + 4 * i, ld4s(a.tab + (int64_t)(b0 + gl) * a.tab_sz + 4 * i));
+            }
+            __syncthreads();
+        } else {
+            graph_tables(a, b0, ng, per, geo.per_sz, MP, WkvT, Wq, WoT, bin);   // ends with a barrier (covers Xs too)
+        }
         for (int item = warp; item < ng * T; item += nwarp) {
             const int gl = item / T, t = item - gl * T;
             const float* tb = per + gl * geo.per_sz;

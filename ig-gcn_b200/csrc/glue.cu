@@ -136,6 +136,125 @@ __global__ void __launch_bounds__(1024) bn_act_bwd_kernel(const float* __restric
     }
 }
 
+// Register-resident variants for the reference's batch sizes (<= BN_EPT values per thread and group): z (and gy, mask) are read from
+// global memory ONCE and the three passes of the kernels above run out of registers -- at a few thousand values per channel the
+// kernels are nothing but dependent trips to L2 (CUPTI: 8.2 us each, ten launches per step).  Same element-to-thread mapping and the
+// same reduction order as the streaming kernels, so the results are bit identical.
+constexpr int BN_EPT = 8;
+
+__global__ void __launch_bounds__(1024) bn_act_fwd_reg_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const float* __restrict__ mask,
+                                                             int N, int C, int L, int groups, float eps, float momentum, int relu,
+                                                             float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                             long long* __restrict__ num_batches_tracked,
+                                                             float* __restrict__ y, float* __restrict__ stats) {
+    __shared__ float sm[33];
+    const int nthr = blockDim.x, c = blockIdx.x, tid = threadIdx.x;
+    const int ng = N / groups, cnt = ng * L;
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 1.f;
+    for (int g = 0; g < groups; ++g) {
+        const int64_t base = ((int64_t)g * ng * C + c) * L;
+        float zv[BN_EPT], mv[BN_EPT];
+        float s = 0.f;
+#pragma unroll
+        for (int u = 0; u < BN_EPT; ++u) {
+            const int e = tid + u * nthr;
+            zv[u] = 0.f; mv[u] = 1.f;
+            if (e < cnt) {
+                const int n = e / L, l = e - n * L;
+                const int64_t i = base + (int64_t)n * C * L + l;
+                zv[u] = z[i];
+                if (mask) mv[u] = mask[i];
+                s += zv[u];
+            }
+        }
+        const float mean = block_sum_any(s, sm) / (float)cnt;
+        float q = 0.f;
+#pragma unroll
+        for (int u = 0; u < BN_EPT; ++u)
+            if (tid + u * nthr < cnt) {
+                const float d = zv[u] - mean;
+                q += d * d;
+            }
+        const float var = block_sum_any(q, sm) / (float)cnt;
+        const float rstd = rsqrtf(var + eps);
+#pragma unroll
+        for (int u = 0; u < BN_EPT; ++u) {
+            const int e = tid + u * nthr;
+            if (e < cnt) {
+                const int n = e / L, l = e - n * L;
+                float v = (zv[u] - mean) * rstd * ga + be;
+                if (relu) v = fmaxf(v, 0.f);
+                if (mask) v *= mv[u];
+                y[base + (int64_t)n * C * L + l] = v;
+            }
+        }
+        if (tid == 0) {
+            stats[((int64_t)g * C + c) * 2 + 0] = mean;
+            stats[((int64_t)g * C + c) * 2 + 1] = rstd;
+        }
+        rm = (1.f - momentum) * rm + momentum * mean;
+        rv = (1.f - momentum) * rv + momentum * var * ((float)cnt / (float)max(cnt - 1, 1));
+    }
+    if (tid == 0) {
+        if (running_mean) running_mean[c] = rm;
+        if (running_var) running_var[c] = rv;
+        if (num_batches_tracked && c == 0) *num_batches_tracked += groups;
+    }
+}
+
+__global__ void __launch_bounds__(1024) bn_act_bwd_reg_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const float* __restrict__ mask,
+                                                             const float* __restrict__ stats, const float* __restrict__ gy,
+                                                             int N, int C, int L, int groups, int relu,
+                                                             float* __restrict__ dz, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float sm[33];
+    const int nthr = blockDim.x, c = blockIdx.x, tid = threadIdx.x;
+    const int ng = N / groups, cnt = ng * L;
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    float dga = 0.f, dbe = 0.f;
+    for (int g = 0; g < groups; ++g) {
+        const int64_t base = ((int64_t)g * ng * C + c) * L;
+        const float mean = stats[((int64_t)g * C + c) * 2 + 0], rstd = stats[((int64_t)g * C + c) * 2 + 1];
+        float xh[BN_EPT], dv[BN_EPT];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int u = 0; u < BN_EPT; ++u) {
+            const int e = tid + u * nthr;
+            xh[u] = 0.f; dv[u] = 0.f;
+            if (e < cnt) {
+                const int n = e / L, l = e - n * L;
+                const int64_t i = base + (int64_t)n * C * L + l;
+                xh[u] = (z[i] - mean) * rstd;
+                float d = gy[i];
+                if (mask) d *= mask[i];
+                if (relu && !(xh[u] * ga + be > 0.f)) d = 0.f;
+                dv[u] = d;
+                s1 += d;
+                s2 += d * xh[u];
+            }
+        }
+        s1 = block_sum_any(s1, sm);
+        s2 = block_sum_any(s2, sm);
+        const float m1 = s1 / (float)cnt, m2 = s2 / (float)cnt;
+#pragma unroll
+        for (int u = 0; u < BN_EPT; ++u) {
+            const int e = tid + u * nthr;
+            if (e < cnt) {
+                const int n = e / L, l = e - n * L;
+                dz[base + (int64_t)n * C * L + l] = ga * rstd * (dv[u] - m1 - xh[u] * m2);
+            }
+        }
+        dga += s2;
+        dbe += s1;
+    }
+    if (tid == 0) {
+        if (dgamma) dgamma[c] = dga;
+        if (dbeta) dbeta[c] = dbe;
+    }
+}
+
 // ---- loss_probability -----------------------------------------------------------------------------------------------------
 // segments: 0 = sigmoid(prob) (n0), 1 = p_e (n1, already a probability), 2 = sigmoid(snps_prob) (n2)
 // loss = sum_seg  [ c_l1[seg] * sum|p| + c_en[seg] * sum -(p log(p+eps) + (1-p) log(1-p+eps)) ] / n_seg
@@ -341,9 +460,14 @@ extern "C" int igcn_bn_act_fwd(const float* z, const float* gamma, const float* 
     IGCN_REQUIRE((N / groups) * L > 1, IGCN_ERR_UNSUPPORTED, "bn_act_fwd: training-mode BatchNorm needs more than one value per channel");
     const int64_t cnt = (N / groups) * L;
     const int nthr = cnt >= 4096 ? 1024 : (cnt >= 1024 ? 512 : 256);
-    bn_act_fwd_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, (int)N, (int)C, (int)L, (int)groups, (float)eps,
-                                                                     (float)momentum, (int)relu, running_mean, running_var,
-                                                                     num_batches_tracked, y, stats);
+    if (cnt <= (int64_t)BN_EPT * nthr)
+        bn_act_fwd_reg_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, (int)N, (int)C, (int)L, (int)groups, (float)eps,
+                                                                             (float)momentum, (int)relu, running_mean, running_var,
+                                                                             num_batches_tracked, y, stats);
+    else
+        bn_act_fwd_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, (int)N, (int)C, (int)L, (int)groups, (float)eps,
+                                                                         (float)momentum, (int)relu, running_mean, running_var,
+                                                                         num_batches_tracked, y, stats);
     IGCN_CHECK_LAUNCH("bn_act_fwd");
     return IGCN_OK;
 }
@@ -355,8 +479,12 @@ extern "C" int igcn_bn_act_bwd(const float* z, const float* gamma, const float* 
     IGCN_REQUIRE(N > 0 && C > 0 && L > 0 && groups > 0 && N % groups == 0, IGCN_ERR_BAD_ARG, "bn_act_bwd: bad sizes");
     const int64_t cnt = (N / groups) * L;
     const int nthr = cnt >= 4096 ? 1024 : (cnt >= 1024 ? 512 : 256);
-    bn_act_bwd_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L, (int)groups,
-                                                                     (int)relu, dz, dgamma, dbeta);
+    if (cnt <= (int64_t)BN_EPT * nthr)
+        bn_act_bwd_reg_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L,
+                                                                             (int)groups, (int)relu, dz, dgamma, dbeta);
+    else
+        bn_act_bwd_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L, (int)groups,
+                                                                         (int)relu, dz, dgamma, dbeta);
     IGCN_CHECK_LAUNCH("bn_act_bwd");
     return IGCN_OK;
 }

@@ -630,6 +630,12 @@ __global__ void __launch_bounds__(256) go_layer_bwd_kernel(GoLayerArgs a) {
     }
 }
 
+}  // namespace igcn
+
+#include "go_small.cuh"
+
+namespace igcn {
+
 static size_t go_fwd_smem(int din, int dout, int Min, int Mrow) {
     return 4 * ((size_t)2 * dout * din + 3 * dout + 8 * dout + 2 * (size_t)Min * dout + (size_t)Mrow * dout);
 }
@@ -662,6 +668,15 @@ static int go_ctas(size_t smem, int64_t B, int nthreads = 256) {
 
 template <int DIN, int DOUT, bool ATTN>
 static int launch_go_fwd(const GoLayerArgs& a, cudaStream_t st) {
+    const gosm::Plan sp = gosm::plan(DIN, DOUT, a.gr.Min, a.gr.Mrow, a.gr.nnz, a.keep_from, ATTN, false, a.B);
+    if (sp.ok) {                              // small hierarchy: several subjects per CTA (go_small.cuh)
+        auto ks = gosm::go_small_fwd_kernel<DIN, DOUT, ATTN>;
+        int rc = allow_smem(ks, sp.smem, "go_small_fwd");
+        if (rc) return rc;
+        ks<<<sp.n_cta, gosm::kThreads, sp.smem, st>>>(a, sp.SUB, sp.Mp);
+        IGCN_CHECK_LAUNCH("go_small_fwd");
+        return IGCN_OK;
+    }
     size_t smem = go_fwd_smem(DIN, DOUT, a.gr.Min, a.gr.Mrow);
     auto k = go_layer_fwd_kernel<DIN, DOUT, ATTN>;
     int rc = allow_smem(k, smem, "go_layer_fwd");
@@ -674,6 +689,17 @@ static int launch_go_fwd(const GoLayerArgs& a, cudaStream_t st) {
 
 template <int DIN, int DOUT, bool ATTN>
 static int launch_go_bwd(const GoLayerArgs& a, int n_cta, float* grads, cudaStream_t st) {
+    const gosm::Plan sp = gosm::plan(DIN, DOUT, a.gr.Min, a.gr.Mrow, a.gr.nnz, a.keep_from, ATTN, true, a.B);
+    if (sp.ok) {
+        auto ks = gosm::go_small_bwd_kernel<DIN, DOUT, ATTN>;
+        int rc = allow_smem(ks, sp.smem, "go_small_bwd");
+        if (rc) return rc;
+        ks<<<n_cta, gosm::kThreads, sp.smem, st>>>(a, sp.SUB, sp.Mp);
+        IGCN_CHECK_LAUNCH("go_small_bwd");
+        reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(a.partials, n_cta, a.P, grads);
+        IGCN_CHECK_LAUNCH("go_reduce_partials");
+        return IGCN_OK;
+    }
     size_t smem = go_bwd_smem(DIN, DOUT, a.gr.Min, a.gr.Mrow, a.gr.nnz, ATTN);
     auto k = go_layer_bwd_kernel<DIN, DOUT, ATTN>;
     int rc = allow_smem(k, smem, "go_layer_bwd");
@@ -779,6 +805,9 @@ extern "C" int64_t igcn_go_layer_param_count(int64_t din, int64_t dout, int64_t 
 }
 
 extern "C" int64_t igcn_go_layer_bwd_ctas(int64_t B, int64_t din, int64_t dout, int64_t m_in, int64_t m_row, int64_t nnz, int64_t attn) {
+    // keep_from only moves the gy staging buffer (smaller when > 0): planning with 0 gives the same SUB and CTA count
+    const gosm::Plan sp = gosm::plan((int)din, (int)dout, (int)m_in, (int)m_row, (int)nnz, 0, attn != 0, true, B);
+    if (sp.ok) return sp.n_cta;
     return go_ctas(go_bwd_smem((int)din, (int)dout, (int)m_in, (int)m_row, (int)nnz, attn != 0), B, go_threads((int)m_in, (int)m_row));
 }
 

@@ -1,0 +1,491 @@
+// GO hierarchy layer for SMALL hierarchies (the ADNI one: 54 / 34 terms, <= 3 parents per term): several subjects per CTA.
+//
+// ncu on the one-subject-per-CTA kernels of go_layers.cu at the benchmarked size (profiles/r2_ncu_go_kernels_c2.json): 512 CTAs of
+// 64 threads, 10 % of the warp slots, 11-18 % issue activity, 14 cycles per warp instruction -- every subject pays the whole
+// prologue (weights), ~10 dependent trips to L2 for the DAG structure and its inputs, and a 65-value block reduction of the
+// parameter gradients (a quarter of all instructions).  Here
+//   * a thread is a (subject slot, node) pair; a 256-thread CTA carries 256 / max(Min, Mrow) subjects per pass;
+//   * weights, LayerNorm affine and the DAG (CSR + CSC) are staged in shared memory ONCE per CTA, and the per-subject inputs of a
+//     pass (x, gy, mask, saved statistics) arrive as four coalesced copies before the first barrier: one trip to L2 per pass;
+//   * the LayerNorm reductions over a subject's nodes are done by (slot, channel) threads straight from shared memory;
+//   * parameter gradients stay in registers over all passes and are reduced once per CTA with a transposing butterfly
+//     (NP - NP/32 shuffles for NP values instead of 5 NP), warp order fixed -> deterministic, no atomics.
+// Same arithmetic per node as go_layer_pre / go_layer_bwd_kernel (go_model.py:226-251, 262-275).
+#pragma once
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace igcn {
+namespace gosm {
+
+constexpr int kThreads = 256;
+
+__host__ __device__ inline int round32(int n) { return (n + 31) & ~31; }
+
+// v[NP] on every lane -> lane l holds the warp totals of values (NP/32) l + r, r < NP/32, in v[0 .. NP/32)
+template <int NP>
+__device__ __forceinline__ void warp_transpose_sum(float (&v)[NP], int lane) {
+    static_assert(NP % 32 == 0, "NP must be a multiple of 32");
+    int h = NP / 2;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < NP / 2; ++i) {
+            if (i < h) {
+                const float send = up ? v[i] : v[i + h];
+                const float keep = up ? v[i + h] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+        }
+        h >>= 1;
+    }
+}
+
+struct Lay {      // shared-memory carve-up (float offsets; int arrays are stored in the same 4-byte slots)
+    int Wa, Ws, u, v, gam, bet, rowptr, col, colptr, crow, cpos, x, Xin, Xs, O, P1, gy, msk, st, r12, ea, edq, rowsum, wred, total;
+};
+__host__ __device__ inline Lay layout(int din, int dout, int Min, int Mrow, int nnz, int keep_from, int SUB, bool attn, bool bwd) {
+    Lay L;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += n; return r; };
+    L.Wa = take(dout * din); L.Ws = take(dout * din); L.u = take(2 * dout); L.v = take(dout);
+    L.gam = take(Mrow); L.bet = take(Mrow);
+    L.rowptr = take(Mrow + 1); L.col = take(nnz);
+    L.colptr = take(bwd ? Min + 1 : 0); L.crow = take(bwd ? nnz : 0); L.cpos = take(bwd ? nnz : 0);
+    L.x = take(SUB * Min * din); L.Xin = take(SUB * Min * dout); L.Xs = take(SUB * Min * dout); L.O = take(SUB * Mrow * dout);
+    L.P1 = take(bwd ? SUB * Mrow * dout : 0);
+    L.gy = take(bwd ? SUB * (Mrow - keep_from) * dout : 0);
+    L.msk = take(SUB * Mrow);
+    L.st = take(SUB * 2 * dout);
+    L.r12 = take(bwd ? SUB * 2 * dout : 0);
+    L.ea = take(bwd && attn ? SUB * nnz : 0); L.edq = take(bwd && attn ? SUB * nnz : 0); L.rowsum = take(bwd && attn ? SUB * Min : 0);
+    L.wred = take(bwd ? (kThreads / 32) * round32(2 * dout * din + 3 * dout) : 0);
+    L.total = o;
+    return L;
+}
+
+// pre-norm output row i of one subject (phase B of go_layer_pre); e_alpha / e_th (ATTN, kKeep): per-slot coefficients for the backward
+template <int DOUT, bool ATTN, bool kKeep>
+__device__ __forceinline__ void row_output(int i, const int* rowptr_s, const int* col_s, const float* Xin, const float* Xs, const float* u_s,
+                                           const float* v_s, int self_off, float* e_alpha, float* e_th, float (&acc)[DOUT]) {
+#pragma unroll
+    for (int f = 0; f < DOUT; ++f) acc[f] = 0.f;
+    const int k0 = rowptr_s[i], k1 = rowptr_s[i + 1];
+    if (ATTN) {
+        float qi = 0.f;
+#pragma unroll
+        for (int f = 0; f < DOUT; ++f) qi = fmaf(u_s[f], Xin[i * DOUT + f], qi);
+        float S = 0.f;
+        for (int k = k0; k < k1; ++k) {
+            const int j = col_s[k];
+            float q = qi;
+#pragma unroll
+            for (int f = 0; f < DOUT; ++f) q = fmaf(u_s[DOUT + f], Xin[j * DOUT + f], q);
+            const float th = tanhf(q);
+            const float ae = __expf(th);
+            S += ae;
+            if (kKeep) {
+                e_alpha[k] = ae;
+                e_th[k] = th;
+            }
+#pragma unroll
+            for (int f = 0; f < DOUT; ++f) acc[f] = fmaf(ae, Xin[j * DOUT + f], acc[f]);
+        }
+        const float inv = (k1 > k0) ? 1.f / S : 0.f;
+#pragma unroll
+        for (int f = 0; f < DOUT; ++f) acc[f] *= inv;
+        if (kKeep)
+            for (int k = k0; k < k1; ++k) e_alpha[k] *= inv;
+        float gz = 0.f;
+#pragma unroll
+        for (int f = 0; f < DOUT; ++f) gz = fmaf(v_s[f], Xs[i * DOUT + f], gz);
+        const float gate = sigmoidf_(gz);
+#pragma unroll
+        for (int f = 0; f < DOUT; ++f) acc[f] = fmaf(Xs[i * DOUT + f], gate, acc[f]);
+    } else {
+        for (int k = k0; k < k1; ++k) {
+            const int j = col_s[k];
+#pragma unroll
+            for (int f = 0; f < DOUT; ++f) acc[f] += Xin[j * DOUT + f];
+        }
+        const float inv = (k1 > k0) ? 1.f / (float)(k1 - k0) : 0.f;
+#pragma unroll
+        for (int f = 0; f < DOUT; ++f) acc[f] *= inv;
+        if (i >= self_off) {
+#pragma unroll
+            for (int f = 0; f < DOUT; ++f) acc[f] += Xs[(i - self_off) * DOUT + f];
+        }
+    }
+}
+
+template <int DIN, int DOUT>
+__device__ __forceinline__ void project_node(const float* xrow, const float* Wa_s, const float* Ws_s, float* xin_row, float* xs_row) {
+    float xv[DIN];
+#pragma unroll
+    for (int k = 0; k < DIN; ++k) xv[k] = xrow[k];
+#pragma unroll
+    for (int f = 0; f < DOUT; ++f) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < DIN; ++k) {
+            s1 = fmaf(xv[k], Wa_s[f * DIN + k], s1);
+            s2 = fmaf(xv[k], Ws_s[f * DIN + k], s2);
+        }
+        xin_row[f] = s1;
+        xs_row[f] = s2;
+    }
+}
+
+template <int DIN, int DOUT, bool ATTN, bool BWD>
+__device__ __forceinline__ void stage_constants(const GoLayerArgs& a, const Lay& L, float* smf) {
+    const int tid = threadIdx.x, Min = a.gr.Min, Mrow = a.gr.Mrow, nnz = a.gr.nnz;
+    int* smi = reinterpret_cast<int*>(smf);
+    for (int i = tid; i < DOUT * DIN; i += kThreads) {
+        smf[L.Wa + i] = a.Wa[i];
+        smf[L.Ws + i] = a.Ws[i];
+    }
+    if (ATTN) {
+        for (int i = tid; i < 2 * DOUT; i += kThreads) smf[L.u + i] = a.u[i];
+        for (int i = tid; i < DOUT; i += kThreads) smf[L.v + i] = a.v[i];
+    }
+    for (int i = tid; i < Mrow; i += kThreads) {
+        smf[L.gam + i] = a.gamma[i];
+        smf[L.bet + i] = a.beta[i];
+    }
+    for (int i = tid; i <= Mrow; i += kThreads) smi[L.rowptr + i] = a.gr.rowptr[i];
+    for (int i = tid; i < nnz; i += kThreads) smi[L.col + i] = a.gr.col[i];
+    if (BWD) {
+        for (int i = tid; i <= Min; i += kThreads) smi[L.colptr + i] = a.gr.colptr[i];
+        for (int i = tid; i < nnz; i += kThreads) {
+            smi[L.crow + i] = a.gr.crow[i];
+            smi[L.cpos + i] = a.gr.cpos[i];
+        }
+    }
+}
+
+template <int DIN, int DOUT, bool ATTN>
+__global__ void __launch_bounds__(kThreads) go_small_fwd_kernel(GoLayerArgs a, int SUB, int Mp) {
+    extern __shared__ float smf[];
+    const int Min = a.gr.Min, Mrow = a.gr.Mrow, nnz = a.gr.nnz, tid = threadIdx.x;
+    const Lay L = layout(DIN, DOUT, Min, Mrow, nnz, a.keep_from, SUB, ATTN, false);
+    const int* smi = reinterpret_cast<const int*>(smf);
+    stage_constants<DIN, DOUT, ATTN, false>(a, L, smf);
+    const int s = tid / Mp, i = tid - s * Mp;
+    const int Mkeep = Mrow - a.keep_from;
+    float* Xin = smf + L.Xin + s * Min * DOUT;
+    float* Xs = smf + L.Xs + s * Min * DOUT;
+    float* O = smf + L.O + s * Mrow * DOUT;
+    for (int b0 = blockIdx.x * SUB; b0 < a.B; b0 += gridDim.x * SUB) {
+        const int ns = min(SUB, a.B - b0);
+        const bool valid = s < ns;
+        {
+            const float* src = a.x + (int64_t)b0 * Min * DIN;
+            for (int k = tid; k < ns * Min * DIN; k += kThreads) smf[L.x + k] = src[k];
+            if (a.mask) {
+                const float* ms = a.mask + (int64_t)b0 * Mrow;
+                for (int k = tid; k < ns * Mrow; k += kThreads) smf[L.msk + k] = ms[k];
+            }
+        }
+        __syncthreads();       // also covers stage_constants on the first pass
+        if (valid && i < Min) project_node<DIN, DOUT>(smf + L.x + (s * Min + i) * DIN, smf + L.Wa, smf + L.Ws, Xin + i * DOUT, Xs + i * DOUT);
+        __syncthreads();
+        float acc[DOUT];
+        if (valid && i < Mrow) {
+            row_output<DOUT, ATTN, false>(i, smi + L.rowptr, smi + L.col, Xin, Xs, smf + L.u, smf + L.v, a.self_off, nullptr, nullptr, acc);
+#pragma unroll
+            for (int f = 0; f < DOUT; ++f) O[i * DOUT + f] = acc[f];
+        }
+        __syncthreads();
+        // LayerNorm statistics over the nodes of a subject: one thread per (slot, channel), two passes over shared memory
+        if (tid < ns * DOUT) {
+            const int sl = tid / DOUT, f = tid - sl * DOUT;
+            const float* Os = smf + L.O + sl * Mrow * DOUT + f;
+            float m = 0.f;
+            for (int r = 0; r < Mrow; ++r) m += Os[r * DOUT];
+            m /= (float)Mrow;
+            float q = 0.f;
+            for (int r = 0; r < Mrow; ++r) {
+                const float d = Os[r * DOUT] - m;
+                q = fmaf(d, d, q);
+            }
+            const float rstd = rsqrtf(q / (float)Mrow + 1e-5f);
+            smf[L.st + sl * 2 * DOUT + f] = m;
+            smf[L.st + sl * 2 * DOUT + DOUT + f] = rstd;
+            a.stats[(int64_t)(b0 + sl) * 2 * DOUT + f] = m;
+            a.stats[(int64_t)(b0 + sl) * 2 * DOUT + DOUT + f] = rstd;
+        }
+        __syncthreads();
+        if (valid && i >= a.keep_from && i < Mrow) {
+            const float ga = smf[L.gam + i], be = smf[L.bet + i];
+            const float ms = a.mask ? smf[L.msk + s * Mrow + i] : 1.f;
+            float* yb = a.y + ((int64_t)(b0 + s) * Mkeep + (i - a.keep_from)) * DOUT;
+#pragma unroll
+            for (int f = 0; f < DOUT; ++f) {
+                const float mean = smf[L.st + s * 2 * DOUT + f], rstd = smf[L.st + s * 2 * DOUT + DOUT + f];
+                const float yh = fmaf((acc[f] - mean) * rstd, ga, be);
+                yb[f] = fmaxf(yh, 0.f) * ms;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// parameter-gradient layout of one layer (go_layers.cu): [dWa | dWs | du | dv | dgamma (Mrow) | dbeta (Mrow)]
+template <int DIN, int DOUT, bool ATTN>
+__global__ void __launch_bounds__(kThreads) go_small_bwd_kernel(GoLayerArgs a, int SUB, int Mp) {
+    extern __shared__ float smf[];
+    const int Min = a.gr.Min, Mrow = a.gr.Mrow, nnz = a.gr.nnz, tid = threadIdx.x;
+    constexpr int NW = 2 * DOUT * DIN + 3 * DOUT;
+    constexpr int NP = (NW + 31) / 32 * 32;
+    const Lay L = layout(DIN, DOUT, Min, Mrow, nnz, a.keep_from, SUB, ATTN, true);
+    const int* smi = reinterpret_cast<const int*>(smf);
+    stage_constants<DIN, DOUT, ATTN, true>(a, L, smf);
+    const int s = tid / Mp, i = tid - s * Mp;
+    const int Mkeep = Mrow - a.keep_from;
+    float* Xin = smf + L.Xin + s * Min * DOUT;
+    float* Xs = smf + L.Xs + s * Min * DOUT;
+    float* O = smf + L.O + s * Mrow * DOUT;
+    float* P1 = smf + L.P1 + s * Mrow * DOUT;
+    float* e_alpha = smf + L.ea + s * nnz;
+    float* e_dq = smf + L.edq + s * nnz;
+    float* rowsum = smf + L.rowsum + s * Min;
+    const float* u_s = smf + L.u;
+    const float* v_s = smf + L.v;
+    float gW[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) gW[k] = 0.f;
+    float dg_acc = 0.f, db_acc = 0.f;
+    const float invM = 1.f / (float)Mrow;
+    for (int b0 = blockIdx.x * SUB; b0 < a.B; b0 += gridDim.x * SUB) {
+        const int ns = min(SUB, a.B - b0);
+        const bool valid = s < ns;
+        {
+            const float* src = a.x + (int64_t)b0 * Min * DIN;
+            for (int k = tid; k < ns * Min * DIN; k += kThreads) smf[L.x + k] = src[k];
+            const float* gs = a.gy + (int64_t)b0 * Mkeep * DOUT;
+            for (int k = tid; k < ns * Mkeep * DOUT; k += kThreads) smf[L.gy + k] = gs[k];
+            if (a.mask) {
+                const float* ms = a.mask + (int64_t)b0 * Mrow;
+                for (int k = tid; k < ns * Mrow; k += kThreads) smf[L.msk + k] = ms[k];
+            }
+            const float* ss = a.stats + (int64_t)b0 * 2 * DOUT;
+            for (int k = tid; k < ns * 2 * DOUT; k += kThreads) smf[L.st + k] = ss[k];
+        }
+        __syncthreads();
+        if (valid && i < Min) project_node<DIN, DOUT>(smf + L.x + (s * Min + i) * DIN, smf + L.Wa, smf + L.Ws, Xin + i * DOUT, Xs + i * DOUT);
+        __syncthreads();
+        // recomputed pre-norm output -> normalised value xh, dY through the dropout scale and the ReLU, LayerNorm reductions
+        float xh[DOUT], dyg[DOUT];
+        float ga = 0.f;
+        if (valid && i < Mrow) {
+            float acc[DOUT];
+            row_output<DOUT, ATTN, true>(i, smi + L.rowptr, smi + L.col, Xin, Xs, u_s, v_s, a.self_off, e_alpha, e_dq, acc);
+            ga = smf[L.gam + i];
+            const float be = smf[L.bet + i];
+            const float ms = a.mask ? smf[L.msk + s * Mrow + i] : 1.f;
+            const float* gyr = smf + L.gy + (s * Mkeep + (i - a.keep_from)) * DOUT;
+            float dg = 0.f, db = 0.f;
+#pragma unroll
+            for (int f = 0; f < DOUT; ++f) {
+                const float mean = smf[L.st + s * 2 * DOUT + f], rstd = smf[L.st + s * 2 * DOUT + DOUT + f];
+                xh[f] = (acc[f] - mean) * rstd;
+                float dy = 0.f;
+                if (i >= a.keep_from) {
+                    const float yh = fmaf(xh[f], ga, be);
+                    dy = (yh > 0.f) ? gyr[f] * ms : 0.f;
+                }
+                dg = fmaf(dy, xh[f], dg);
+                db += dy;
+                dyg[f] = dy * ga;
+                P1[i * DOUT + f] = dyg[f];
+                O[i * DOUT + f] = xh[f];
+            }
+            dg_acc += dg;
+            db_acc += db;
+        }
+        __syncthreads();
+        if (tid < ns * 2 * DOUT) {
+            const int sl = tid / (2 * DOUT), r = tid - sl * 2 * DOUT, f = r % DOUT;
+            const float* Ps = smf + L.P1 + sl * Mrow * DOUT + f;
+            const float* Os = smf + L.O + sl * Mrow * DOUT + f;
+            float t = 0.f;
+            if (r < DOUT)
+                for (int q = 0; q < Mrow; ++q) t += Ps[q * DOUT];
+            else
+                for (int q = 0; q < Mrow; ++q) t = fmaf(Ps[q * DOUT], Os[q * DOUT], t);
+            smf[L.r12 + tid] = t;
+        }
+        __syncthreads();
+        // dO (in place over O), then the attention-row backward of this node's row
+        if (valid && i < Mrow) {
+            float dO[DOUT];
+#pragma unroll
+            for (int f = 0; f < DOUT; ++f) {
+                const float rstd = smf[L.st + s * 2 * DOUT + DOUT + f];
+                const float r1 = smf[L.r12 + s * 2 * DOUT + f], r2 = smf[L.r12 + s * 2 * DOUT + DOUT + f];
+                dO[f] = rstd * (dyg[f] - r1 * invM - xh[f] * r2 * invM);
+                O[i * DOUT + f] = dO[f];
+            }
+            if (ATTN) {
+                float xs[DOUT];
+#pragma unroll
+                for (int f = 0; f < DOUT; ++f) xs[f] = Xs[i * DOUT + f];
+                float gz = 0.f, dot = 0.f;
+#pragma unroll
+                for (int f = 0; f < DOUT; ++f) {
+                    gz = fmaf(v_s[f], xs[f], gz);
+                    dot = fmaf(dO[f], xs[f], dot);
+                }
+                const float gate = sigmoidf_(gz);
+                const float dgz = dot * gate * (1.f - gate);
+#pragma unroll
+                for (int f = 0; f < DOUT; ++f) {
+                    Xs[i * DOUT + f] = fmaf(dgz, v_s[f], dO[f] * gate);           // dXs_i (read back by this thread only: square layer)
+                    gW[2 * DOUT * DIN + 2 * DOUT + f] = fmaf(dgz, xs[f], gW[2 * DOUT * DIN + 2 * DOUT + f]);  // dv
+                }
+                const int k0 = smi[L.rowptr + i], k1 = smi[L.rowptr + i + 1];
+                float t = 0.f;
+                for (int k = k0; k < k1; ++k) {
+                    const int j = smi[L.col + k];
+                    float da = 0.f;
+#pragma unroll
+                    for (int f = 0; f < DOUT; ++f) da = fmaf(dO[f], Xin[j * DOUT + f], da);
+                    t = fmaf(e_alpha[k], da, t);
+                }
+                float xi[DOUT];
+#pragma unroll
+                for (int f = 0; f < DOUT; ++f) xi[f] = Xin[i * DOUT + f];
+                float sdq = 0.f;
+                for (int k = k0; k < k1; ++k) {
+                    const int j = smi[L.col + k];
+                    float xj[DOUT], da = 0.f;
+#pragma unroll
+                    for (int f = 0; f < DOUT; ++f) {
+                        xj[f] = Xin[j * DOUT + f];
+                        da = fmaf(dO[f], xj[f], da);
+                    }
+                    const float th = e_dq[k];
+                    const float dq = e_alpha[k] * (da - t) * (1.f - th * th);
+                    e_dq[k] = dq;
+                    sdq += dq;
+#pragma unroll
+                    for (int f = 0; f < DOUT; ++f) {
+                        gW[2 * DOUT * DIN + f] = fmaf(dq, xi[f], gW[2 * DOUT * DIN + f]);                  // du_row
+                        gW[2 * DOUT * DIN + DOUT + f] = fmaf(dq, xj[f], gW[2 * DOUT * DIN + DOUT + f]);    // du_col
+                    }
+                }
+                rowsum[i] = sdq;
+            }
+        }
+        __syncthreads();
+        // column pass: dXin_j (gather over the CSC), then input / weight gradients
+        if (valid && i < Min) {
+            const int j = i;
+            float dxin[DOUT];
+#pragma unroll
+            for (int f = 0; f < DOUT; ++f) dxin[f] = 0.f;
+            for (int q = smi[L.colptr + j]; q < smi[L.colptr + j + 1]; ++q) {
+                const int r = smi[L.crow + q], k = smi[L.cpos + q];
+                if (ATTN) {
+                    const float al = e_alpha[k], dq = e_dq[k];
+#pragma unroll
+                    for (int f = 0; f < DOUT; ++f) dxin[f] += al * O[r * DOUT + f] + dq * u_s[DOUT + f];
+                } else {
+                    const float al = 1.f / (float)(smi[L.rowptr + r + 1] - smi[L.rowptr + r]);
+#pragma unroll
+                    for (int f = 0; f < DOUT; ++f) dxin[f] = fmaf(al, O[r * DOUT + f], dxin[f]);
+                }
+            }
+            float dxs[DOUT];
+            if (ATTN) {
+                const float sdq = rowsum[j];
+#pragma unroll
+                for (int f = 0; f < DOUT; ++f) {
+                    dxin[f] = fmaf(sdq, u_s[f], dxin[f]);
+                    dxs[f] = Xs[j * DOUT + f];
+                }
+            } else {
+                const int r = j + a.self_off;          // uniform decoder: dXs_j = dO_{j + self_off}
+#pragma unroll
+                for (int f = 0; f < DOUT; ++f) dxs[f] = (r < Mrow) ? O[r * DOUT + f] : 0.f;
+            }
+            float xv[DIN], dxv[DIN];
+#pragma unroll
+            for (int k = 0; k < DIN; ++k) {
+                xv[k] = smf[L.x + (s * Min + j) * DIN + k];
+                dxv[k] = 0.f;
+            }
+#pragma unroll
+            for (int f = 0; f < DOUT; ++f) {
+#pragma unroll
+                for (int k = 0; k < DIN; ++k) {
+                    gW[f * DIN + k] = fmaf(dxin[f], xv[k], gW[f * DIN + k]);
+                    gW[DOUT * DIN + f * DIN + k] = fmaf(dxs[f], xv[k], gW[DOUT * DIN + f * DIN + k]);
+                    dxv[k] += dxin[f] * smf[L.Wa + f * DIN + k] + dxs[f] * smf[L.Ws + f * DIN + k];
+                }
+            }
+            float* dxb = a.dx + ((int64_t)(b0 + s) * Min + j) * DIN;
+#pragma unroll
+            for (int k = 0; k < DIN; ++k) dxb[k] = dxv[k];
+        }
+        __syncthreads();
+    }
+    // ---- per-CTA partial row ---------------------------------------------------------------------------------------------------
+    const int lane = tid & 31, warp = tid >> 5;
+    warp_transpose_sum<NP>(gW, lane);
+    float* wred = smf + L.wred;
+#pragma unroll
+    for (int r = 0; r < NP / 32; ++r) wred[warp * NP + (NP / 32) * lane + r] = gW[r];
+    float* dgs = smf + L.P1;                        // (SUB, Mrow, 2): the last pass ended with a barrier, P1 is free
+    if (s < SUB && i < Mrow) {
+        dgs[(s * Mrow + i) * 2] = dg_acc;
+        dgs[(s * Mrow + i) * 2 + 1] = db_acc;
+    }
+    __syncthreads();
+    float* prow = a.partials + (int64_t)blockIdx.x * a.P;
+    for (int k = tid; k < NW; k += kThreads) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) t += wred[w * NP + k];
+        prow[k] = t;
+    }
+    for (int k = tid; k < Mrow; k += kThreads) {
+        float tg = 0.f, tb = 0.f;
+        for (int q = 0; q < SUB; ++q) {
+            tg += dgs[(q * Mrow + k) * 2];
+            tb += dgs[(q * Mrow + k) * 2 + 1];
+        }
+        prow[NW + k] = tg;
+        prow[NW + Mrow + k] = tb;
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------------------
+struct Plan {
+    bool ok;
+    int SUB, Mp, n_cta;
+    size_t smem;
+};
+static Plan plan(int din, int dout, int Min, int Mrow, int nnz, int keep_from, bool attn, bool bwd, int64_t B) {
+    Plan p{};
+    static const bool off = [] { const char* e = getenv("IGCN_GO_SMALL"); return e && e[0] == '0'; }();
+    p.Mp = Min > Mrow ? Min : Mrow;
+    if (off || p.Mp > 128 || nnz > 4096) return p;
+    p.SUB = kThreads / p.Mp;
+    (void)keep_from;                          // sized for keep_from = 0 (the largest gy buffer): one decision per layer shape
+    const Lay L = layout(din, dout, Min, Mrow, nnz, 0, p.SUB, attn, bwd);
+    p.smem = (size_t)4 * L.total;
+    if (p.smem > 100 * 1024) return p;
+    int64_t n = (B + p.SUB - 1) / p.SUB;
+    const int64_t cap = (int64_t)sm_count() * 2;
+    if (n > cap) n = cap;
+    if (n < 1) n = 1;
+    p.n_cta = (int)n;
+    p.ok = true;
+    return p;
+}
+
+}  // namespace gosm
+}  // namespace igcn

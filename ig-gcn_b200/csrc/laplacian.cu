@@ -78,8 +78,11 @@ __global__ void __launch_bounds__(256) colmean_kernel(const float* __restrict__ 
     const int g = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
     float acc = 0.f;
-    if (c < D)
-        for (int i = w; i < B; i += 8) acc += s[((int64_t)g * B + i) * D + c];
+    if (c < D) {
+        const float* sp = s + (int64_t)g * B * D + c;
+#pragma unroll 8
+        for (int i = w; i < B; i += 8) acc += sp[(int64_t)i * D];          // unrolled: 8 loads in flight per thread
+    }
     sm[w][lane] = acc;
     __syncthreads();
     if (w == 0 && c < D) {
@@ -94,16 +97,18 @@ __global__ void __launch_bounds__(256) finish_kernel(const float* __restrict__ s
                                                      const float* __restrict__ U, int B, int D, int groups, float dconst,
                                                      float* __restrict__ T, float* __restrict__ partials) {
     __shared__ float sm[8];
-    const int64_t n = (int64_t)groups * B * D;
     float acc = 0.f;
-    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * 256) {
-        const int64_t row = idx / D;
-        const int c = (int)(idx - row * D);
-        const int g = (int)(row / B), i = (int)(row - (int64_t)g * B);
-        const float sc = s[idx] - m[(int64_t)g * D + c];
-        const float tv = (d ? d[i] : dconst) * sc - (U ? U[idx] : 0.f);
-        T[idx] = tv;
-        acc = fmaf(sc, tv, acc);
+    for (int row = blockIdx.x; row < groups * B; row += gridDim.x) {        // a CTA walks whole rows: no per-element divisions
+        const int g = row / B, i = row - g * B;
+        const float di = d ? d[i] : dconst;
+        const float* mp = m + (int64_t)g * D;
+        const int64_t base = (int64_t)row * D;
+        for (int c = threadIdx.x; c < D; c += 256) {
+            const float sc = s[base + c] - mp[c];
+            const float tv = di * sc - (U ? U[base + c] : 0.f);
+            T[base + c] = tv;
+            acc = fmaf(sc, tv, acc);
+        }
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;

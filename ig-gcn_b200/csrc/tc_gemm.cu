@@ -176,10 +176,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant_
         // ---- epilogue: warp w owns TMEM lanes [32w, 32w+32) = output rows m0 + 32w + lane -------------------------------
         mbar_wait(bar_tmem, 0u, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int m = m0 + warp * 32 + lane;
-        float* prow = partials ? partials + ((int64_t)split * M + m) * N : nullptr;
+        // The accumulator arrives with lane = output row; stored that way every lane writes its own row (32 sectors per store
+        // instruction, 4 bytes each: the 8x write amplification ncu showed on the Laplacian product).  Each warp turns its 32 x 32
+        // block around through a padded tile in the (now idle) operand ring, so a store instruction covers 128 contiguous bytes
+        // of ONE output row.
+        float* tb = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + warp * (32 * 33);
+        const int mrow0 = m0 + warp * 32;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
+            __syncwarp();                                             // converged for the .aligned TMEM load; previous tile readers done
             uint32_t r[32];
             const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c;
             asm volatile(
@@ -191,39 +196,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant_
                   "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (m >= M) continue;
-            const int nbase = n0 + c;
-            if (prow) {                                               // split-K partial tile, raw
-                if (nbase + 32 <= N && (N & 3) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(prow + nbase + j) =
-                            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (nbase + j < N) prow[nbase + j] = __uint_as_float(r[j]);
-                }
+            for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = __uint_as_float(r[j]);
+            __syncwarp();
+            int n = n0 + c + lane;                                    // this lane's output column for the whole block
+            if (n >= N) continue;
+            if (partials) {                                           // split-K partial tile, raw
+                float* pcol = partials + (int64_t)split * M * N + n;
+#pragma unroll 4
+                for (int rr = 0; rr < 32; ++rr)
+                    if (mrow0 + rr < M) pcol[(int64_t)(mrow0 + rr) * N] = tb[rr * 33 + lane];
                 continue;
             }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                int n = nbase + j;
-                if (n >= N) break;
-                float v = __uint_as_float(r[j]);
-                if (bias) v += bias[n];
-                if (relu) v = fmaxf(v, 0.f);
-                int sidx = 0;
-                if (n >= dst.w[0]) {
-                    n -= dst.w[0];
-                    sidx = 1;
-                    if (n >= dst.w[1]) {
-                        n -= dst.w[1];
-                        sidx = 2;
-                    }
+            const float bv = bias ? bias[n] : 0.f;
+            int sidx = 0;
+            if (n >= dst.w[0]) {
+                n -= dst.w[0];
+                sidx = 1;
+                if (n >= dst.w[1]) {
+                    n -= dst.w[1];
+                    sidx = 2;
                 }
-                float* p = dst.p[sidx];
-                if (p) p[(int64_t)m * dst.ld[sidx] + n] = v;
+            }
+            float* p = dst.p[sidx];
+            if (!p) continue;
+            const int64_t ld = dst.ld[sidx];
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+                if (mrow0 + rr >= M) break;
+                float v = tb[rr * 33 + lane] + bv;
+                if (relu) v = fmaxf(v, 0.f);
+                p[(int64_t)(mrow0 + rr) * ld + n] = v;
             }
         }
     }

@@ -360,6 +360,10 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             side2.wait_stream(main)
             with torch.cuda.stream(side2):
                 h_plain, _ = ops.sgcn_encoder(x, csr, Ws, bs)
+                if consist and stacked and self.isSoftSimilarity and _PREFETCH_CONSIST:
+                    # the similarity matrix of the consistency loss depends on the batch only: built here, off the path that
+                    # later waits for out_z (consist_loss_pair finds it in the cache)
+                    self._similarity(B, data.tsne_fdim, x)
         else:
             h_plain, _ = ops.sgcn_encoder(x, csr, Ws, bs)
         h_expl, p_e = ops.sgcn_encoder(x, csr, Ws, bs, self.prob, self.prob_bias, want_pe=True)

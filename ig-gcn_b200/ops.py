@@ -269,6 +269,21 @@ class _CatLinearFn(torch.autograd.Function):
             raise RuntimeError("cat_linear: source widths %s do not add up to in_features=%d" % (widths, K))
         Wc, bc = W.contiguous().float(), bias.contiguous().float()
         ctx.set_materialize_grads(False)
+        # small batches: warp-level tensor-core kernels that read the sources in place (csrc/catlin_mma.cu), one launch per product
+        ctx.mma = bool(USE_TC and M > 0 and lib.igcn_catlin_mma_supported(M, N, K))
+        if ctx.mma:
+            out = torch.empty((M, N), dtype=torch.float32, device=W.device)
+            rows = [1 if t is None else t.shape[0] for t in cs]
+            hw, hs, hr = (ctypes.c_int64 * 3)(*widths), (ctypes.c_int64 * 3)(*strides), (ctypes.c_int64 * 3)(*rows)
+            with torch.cuda.device(W.device):
+                _lib.call("igcn_catlin_mma_fwd", _lib_ptr_strided(cs[0]), _lib_ptr_strided(cs[1]), _lib_ptr_strided(cs[2]),
+                          ctypes.addressof(hw), ctypes.addressof(hs), ctypes.addressof(hr), _lib.ptr(Wc), _lib.ptr(bc), M, N, K, int(relu),
+                          _lib.ptr(out), _lib.stream(), tag="cat_linear_fwd_mma[M=%d,N=%d,K=%d]" % (M, N, K), nbytes=4 * (M * K + N * K + M * N))
+            ctx.relu, ctx.widths, ctx.strides, ctx.rows, ctx.tc = bool(relu), widths, strides, rows, False
+            ctx.need = [t is not None and t.requires_grad for t in srcs]
+            ctx.save_for_backward(Wc, out, *[t for t in cs if t is not None])
+            ctx.present = [t is not None for t in cs]
+            return out
         ctx.tc = USE_TC and M > 0
         if ctx.tc:
             # tensor cores: one split launch folds the concatenation, then one 3xTF32 product with bias + ReLU in its epilogue
@@ -317,6 +332,46 @@ class _CatLinearFn(torch.autograd.Function):
                for need, w in zip(ctx.need, ctx.widths)]
         dW = torch.empty_like(W)
         db = torch.empty(N, dtype=torch.float32, device=W.device)
+        if ctx.mma:
+            dev = W.device
+            g_out = g_out.contiguous()
+            hw, hs, hr = (ctypes.c_int64 * 3)(*ctx.widths), (ctypes.c_int64 * 3)(*ctx.strides), (ctypes.c_int64 * 3)(*ctx.rows)
+            hd = (ctypes.c_int64 * 3)(*[0 if t is None else t.stride(0) for t in dxs])
+            # the two products are independent: the weight gradient runs on an auxiliary stream beside the input gradient the rest of
+            # the backward waits for
+            cur = torch.cuda.current_stream(dev)
+            aux = _aux_stream(dev) if _AUX_STREAM else None
+
+            def weight_grad():
+                _lib.call("igcn_catlin_mma_bwd_dw", _lib_ptr_strided(cs[0]), _lib_ptr_strided(cs[1]), _lib_ptr_strided(cs[2]),
+                          ctypes.addressof(hw), ctypes.addressof(hs), ctypes.addressof(hr), _lib.ptr(out), _lib.ptr(g_out), M, N, K,
+                          int(ctx.relu), _lib.ptr(dW), _lib.ptr(db), _lib.stream(), tag="cat_linear_bwd_w_mma[M=%d,N=%d,K=%d]" % (M, N, K),
+                          nbytes=4 * (M * K + N * K + 2 * M * N))
+
+            with torch.cuda.device(dev):
+                if aux is not None:
+                    aux.wait_stream(cur)
+                    with torch.cuda.stream(aux):
+                        weight_grad()
+                    for t in [g_out, out, dW, db] + [t for t in cs if t is not None]:
+                        t.record_stream(aux)
+                if any(d is not None for d in dxs):
+                    _lib.call("igcn_catlin_mma_bwd_dx", ctypes.addressof(hw), _lib.ptr(W), _lib.ptr(out), _lib.ptr(g_out), M, N, K,
+                              int(ctx.relu), _lib.ptr(dxs[0]), _lib.ptr(dxs[1]), _lib.ptr(dxs[2]), ctypes.addressof(hd), _lib.stream(),
+                              tag="cat_linear_bwd_x_mma[M=%d,N=%d,K=%d]" % (M, N, K),
+                              nbytes=4 * (N * K + 2 * M * N + sum(M * w for w, d in zip(ctx.widths, dxs) if d is not None)))
+                if aux is not None:
+                    cur.wait_stream(aux)
+                else:
+                    weight_grad()
+            for i, rp in enumerate(ctx.reps):                # a repeated source collects the gradient of every repetition
+                if rp > 1 and dxs[i] is not None:
+                    h = M // rp
+                    acc = dxs[i][:h]
+                    for k in range(1, rp):
+                        acc = acc + dxs[i][k * h:(k + 1) * h]
+                    dxs[i] = acc
+            return dxs[0], dxs[1], dxs[2], dW, db, None
         if ctx.tc:
             dev = W.device
             g_out = g_out.contiguous()
@@ -393,25 +448,50 @@ class _CrossAttnFn(torch.autograd.Function):
         B, R, E = q.shape
         M = kv.shape[1]
         out = torch.empty_like(q)
+        lib = _lib.lib()
+        # table-driven kernels (csrc/cross_attn_mma2.cuh) for the reference's shape: the per-graph key tables are saved for the backward
+        tab = None
+        if lib.igcn_cross_attn_v2_supported(R, M, E, heads):
+            tab = torch.empty((B, lib.igcn_cross_attn_v2_tab_floats(M, heads)), dtype=torch.float32, device=q.device)
         with torch.cuda.device(q.device):
-            _lib.call("igcn_cross_attn_fwd", _lib.ptr(q), _lib.ptr(kv), _lib.ptr(in_w), _lib.ptr(in_b), _lib.ptr(out_w), _lib.ptr(out_b),
-                      B, R, M, E, heads, int(relu), _lib.ptr(out), _lib.stream(), tag="cross_attn_fwd[R=%d,M=%d,E=%d]" % (R, M, E),
-                      nbytes=4 * (2 * B * R * E + B * M * E + 4 * E * E + 4 * E))
-        ctx.heads, ctx.relu = heads, int(relu)
-        ctx.save_for_backward(q, kv, in_w, in_b, out_w, out_b, out)
+            if tab is not None:
+                _lib.call("igcn_cross_attn_v2_fwd", _lib.ptr(q), _lib.ptr(kv), _lib.ptr(in_w), _lib.ptr(in_b), _lib.ptr(out_w), _lib.ptr(out_b),
+                          B, R, M, E, heads, int(relu), _lib.ptr(out), _lib.ptr(tab), _lib.stream(),
+                          tag="cross_attn_fwd[R=%d,M=%d,E=%d]" % (R, M, E), nbytes=4 * (2 * B * R * E + B * M * E + 4 * E * E + 4 * E))
+            else:
+                _lib.call("igcn_cross_attn_fwd", _lib.ptr(q), _lib.ptr(kv), _lib.ptr(in_w), _lib.ptr(in_b), _lib.ptr(out_w), _lib.ptr(out_b),
+                          B, R, M, E, heads, int(relu), _lib.ptr(out), _lib.stream(), tag="cross_attn_fwd[R=%d,M=%d,E=%d]" % (R, M, E),
+                          nbytes=4 * (2 * B * R * E + B * M * E + 4 * E * E + 4 * E))
+        ctx.heads, ctx.relu, ctx.v2 = heads, int(relu), tab is not None
+        if tab is not None:
+            ctx.save_for_backward(q, kv, in_w, in_b, out_w, out_b, out, tab)
+        else:
+            ctx.save_for_backward(q, kv, in_w, in_b, out_w, out_b, out)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        q, kv, in_w, in_b, out_w, out_b, out = ctx.saved_tensors
+        if ctx.v2:
+            q, kv, in_w, in_b, out_w, out_b, out, tab = ctx.saved_tensors
+        else:
+            q, kv, in_w, in_b, out_w, out_b, out = ctx.saved_tensors
         lib = _lib.lib()
         B, R, E = q.shape
         M = kv.shape[1]
         P = lib.igcn_cross_attn_param_count(E)
-        n_cta = lib.igcn_cross_attn_bwd_ctas(B, R, M, E, ctx.heads)
+        n_cta = lib.igcn_cross_attn_v2_bwd_ctas(B) if ctx.v2 else lib.igcn_cross_attn_bwd_ctas(B, R, M, E, ctx.heads)
         dq, dkv = torch.empty_like(q), torch.empty_like(kv)
         partials = torch.empty((max(n_cta, 1), P), dtype=torch.float32, device=q.device)
         grads = torch.empty(P, dtype=torch.float32, device=q.device)
+        if ctx.v2:
+            work = torch.empty(max(lib.igcn_cross_attn_v2_work_floats(B, R, M, ctx.heads), 4), dtype=torch.float32, device=q.device)
+            with torch.cuda.device(q.device):
+                _lib.call("igcn_cross_attn_v2_bwd", _lib.ptr(q), _lib.ptr(kv), _lib.ptr(in_w), _lib.ptr(in_b), _lib.ptr(out_w), _lib.ptr(out_b),
+                          _lib.ptr(out), _lib.ptr(g.contiguous()), _lib.ptr(tab), B, R, M, E, ctx.heads, int(ctx.relu), _lib.ptr(dq),
+                          _lib.ptr(dkv), _lib.ptr(work), _lib.ptr(partials), n_cta, _lib.ptr(grads), _lib.stream(),
+                          tag="cross_attn_bwd[R=%d,M=%d,E=%d]" % (R, M, E), nbytes=4 * (4 * B * R * E + 2 * B * M * E + 2 * (4 * E * E + 4 * E)))
+            o1, o2, o3 = 3 * E * E, 3 * E * E + 3 * E, 4 * E * E + 3 * E
+            return dq, dkv, grads[:o1].view(3 * E, E), grads[o1:o2], grads[o2:o3].view(E, E), grads[o3:], None, None
         with torch.cuda.device(q.device):
             _lib.call("igcn_cross_attn_bwd", _lib.ptr(q), _lib.ptr(kv), _lib.ptr(in_w), _lib.ptr(in_b), _lib.ptr(out_w), _lib.ptr(out_b),
                       _lib.ptr(out), _lib.ptr(g.contiguous()), B, R, M, E, ctx.heads, int(ctx.relu), _lib.ptr(dq), _lib.ptr(dkv),

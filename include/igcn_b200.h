@@ -185,6 +185,25 @@ int igcn_cross_attn_bwd(const float* q_in, const float* kv_in, const float* in_p
                         int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads, int64_t relu,
                         float* d_q_in, float* d_kv_in, float* partials, int64_t n_cta, float* grads, void* stream);
 
+/* Table-driven variant of the same operator (csrc/cross_attn_mma2.cuh), used when igcn_cross_attn_v2_supported(...) = 1 (the
+ * reference's shape: E = 32, 2 heads, M <= 32 tokens, R <= 288): the forward first writes a per-graph record
+ *   tab (B, igcn_cross_attn_v2_tab_floats(M, heads)) = K' | V' | c | K | V        (the query-side projections folded into key tables)
+ * which the forward row kernel and the backward read (the caller keeps it with `out` for the backward).  The backward is a row kernel
+ * over (graph, row chunk) items that writes per-item gradient records into `work` (igcn_cross_attn_v2_work_floats(B,R,M,heads)
+ * floats) and a chain kernel that turns them into d_kv_in and the parameter gradients: partials (n_cta, P) with
+ * n_cta = igcn_cross_attn_v2_bwd_ctas(B).  Same results as igcn_cross_attn_fwd/bwd to rounding; relu = 0, 1, 2 as above. */
+int64_t igcn_cross_attn_v2_supported(int64_t R, int64_t M, int64_t E, int64_t heads);
+int64_t igcn_cross_attn_v2_tab_floats(int64_t M, int64_t heads);
+int64_t igcn_cross_attn_v2_work_floats(int64_t B, int64_t R, int64_t M, int64_t heads);
+int64_t igcn_cross_attn_v2_bwd_ctas(int64_t B);
+int igcn_cross_attn_v2_fwd(const float* q_in, const float* kv_in, const float* in_proj_weight, const float* in_proj_bias,
+                           const float* out_proj_weight, const float* out_proj_bias,
+                           int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads, int64_t relu, float* out, float* tab, void* stream);
+int igcn_cross_attn_v2_bwd(const float* q_in, const float* kv_in, const float* in_proj_weight, const float* in_proj_bias,
+                           const float* out_proj_weight, const float* out_proj_bias, const float* out, const float* g_out,
+                           const float* tab, int64_t B, int64_t R, int64_t M, int64_t E, int64_t heads, int64_t relu,
+                           float* d_q_in, float* d_kv_in, float* work, float* partials, int64_t n_cta, float* grads, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fusion heads: out = act([X0 | X1 | X2] W^T + b) without materialising the concatenation (reference:
  * kernel/sgcn_img_snp.py:287-301 -- cat(out_z, latent) -> lin1 -> relu ; cat(out_lin, img_feat) -> lin1_regr -> relu).
@@ -201,6 +220,22 @@ int igcn_cat_linear_fwd(const float* x0, const float* x1, const float* x2, const
 int igcn_cat_linear_bwd(const float* x0, const float* x1, const float* x2, const int64_t* host_widths, const int64_t* host_strides,
                         const float* W, const float* out, const float* g_out, int64_t M, int64_t N, int64_t K, int64_t relu,
                         float* dx0, float* dx1, float* dx2, const int64_t* host_dstrides, float* dW, float* db, void* stream);
+
+/* The same operator on warp-level tensor cores (csrc/catlin_mma.cu; mma.sync TF32 split in three, fp32 accumulate) for the reference's
+ * batch sizes: igcn_catlin_mma_supported(M,N,K) = 1 for M <= 2048, N <= 64 (a multiple of 16).  One launch per product, operands read
+ * in place.  host_rows[i] = number of rows of source i: a source with fewer rows than M is read cyclically (row m -> m % rows_i; the
+ * stacked plain / explain passes share img_feat).  bwd_dx writes dx_i (M, width_i) for every non-NULL dx_i (a cyclic source gets one
+ * gradient row per product row; the caller adds the repetitions); bwd_dw writes dW (N,K) and db (N, may be NULL).  The two backward
+ * products are independent and may run on different streams.  Deterministic. */
+int64_t igcn_catlin_mma_supported(int64_t M, int64_t N, int64_t K);
+int igcn_catlin_mma_fwd(const float* x0, const float* x1, const float* x2, const int64_t* host_widths, const int64_t* host_strides,
+                        const int64_t* host_rows, const float* W, const float* bias, int64_t M, int64_t N, int64_t K, int64_t relu,
+                        float* out, void* stream);
+int igcn_catlin_mma_bwd_dx(const int64_t* host_widths, const float* W, const float* out, const float* g_out, int64_t M, int64_t N, int64_t K,
+                           int64_t relu, float* dx0, float* dx1, float* dx2, const int64_t* host_dx_strides, void* stream);
+int igcn_catlin_mma_bwd_dw(const float* x0, const float* x1, const float* x2, const int64_t* host_widths, const int64_t* host_strides,
+                           const int64_t* host_rows, const float* out, const float* g_out, int64_t M, int64_t N, int64_t K, int64_t relu,
+                           float* dW, float* db, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * All dropout masks of one forward pass in one launch (the reference draws nine per pass: Dropout2d(0.4) x4 and

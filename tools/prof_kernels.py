@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Runs the igcn kernels in isolation (for `ncu -k regex:igcn`) and prints CUDA-event timings + roofline fractions.
 
-    python tools/prof_kernels.py --B 4096 --R 264 [--iters 5] [--what sgcn|go|all]
+    python tools/prof_kernels.py --B 4096 --R 264 [--iters 5] [--what sgcn|attn|tc|go|gat|all]
 """
 import argparse
 import json
@@ -79,6 +79,28 @@ def main():
             out = ops.cross_attention(q, kv, mha, relu=True)
             flush.zero_()
             out.backward(go)
+        for k, (c, tot, nb) in _lib.profile_end().items():
+            ms = tot / c
+            res[k] = dict(us=ms * 1e3, alg_MB=nb / 1e6, GBs=nb / ms / 1e6, frac_of_measured_peak=nb / ms / 1e6 / peak)
+    if a.what in ("gat", "all"):
+        # BASELINE configs[1] (SGCN_GCN): GATConv(3 -> H, edge_dim=1) + GATConv(H -> H) over a batch of brain graphs
+        from igcn_b200 import pyg
+        nuniq = min(a.B, 256)
+        sub = syn.make_subjects(nuniq, rois=a.R, n_snps=a.S, seed=7)
+        b = Batch.collate(SubjectSet(sub), np.arange(a.B) % nuniq, dev)
+        torch.manual_seed(0)
+        convs = [pyg.GATConv(3, a.H, edge_dim=1).to(dev), pyg.GATConv(a.H, a.H, edge_dim=1).to(dev)]
+        x = b.x.clone().requires_grad_(True)
+        ea = b.edge_attr.clone().requires_grad_(True)
+        go = None
+        for it in range(a.iters + 2):
+            flush.zero_()
+            if it == 2:
+                _lib.profile_begin()
+            h = convs[1](torch.relu(convs[0](x, b.edge_index, ea)), b.edge_index, ea)
+            if go is None:
+                go = torch.randn_like(h)
+            h.backward(go)
         for k, (c, tot, nb) in _lib.profile_end().items():
             ms = tot / c
             res[k] = dict(us=ms * 1e3, alg_MB=nb / 1e6, GBs=nb / ms / 1e6, frac_of_measured_peak=nb / ms / 1e6 / peak)
