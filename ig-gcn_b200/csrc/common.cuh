@@ -65,8 +65,11 @@ static __global__ void __launch_bounds__(256) reduce_partials_kernel(const float
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + lane;
     double s = 0.0;
-    if (j < P)
-        for (int r = warp; r < n_rows; r += 8) s += (double)partials[(int64_t)r * P + j];
+    if (j < P) {
+        const float* pp = partials + j;
+#pragma unroll 8
+        for (int r = warp; r < n_rows; r += 8) s += (double)pp[(int64_t)r * P];   // unrolled: 8 independent loads in flight per thread
+    }
     sm[warp][lane] = s;
     __syncthreads();
     if (warp == 0 && j < P) {

@@ -210,14 +210,36 @@ __global__ void __launch_bounds__(kThreads, 2) attn_mma_fwd_kernel(AttnArgs a, G
     for (int b0 = blockIdx.x * geo.gpc; b0 < a.B; b0 += gridDim.x * geo.gpc) {
         const int ng = min(geo.gpc, a.B - b0), rows = ng * R;
         const float* xg = a.x + (int64_t)b0 * R * kE;
-        for (int idx = tid; idx < rows * 8; idx += nt) {    // coalesced 16-byte loads -> padded rows
-            const int row = idx >> 3, ch = idx & 7;
-            st4s(Xs + row * TS + 4 * ch, ld4s(xg + (int64_t)idx * 4));
+        for (int i0 = 0; i0 < rows * 8; i0 += 4 * nt) {     // coalesced 16-byte loads -> padded rows; four per thread in flight
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + tid + u * nt < rows * 8) v[u] = ld4s(xg + (int64_t)(i0 + tid + u * nt) * 4);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = i0 + tid + u * nt;
+                if (idx < rows * 8) st4s(Xs + (idx >> 3) * TS + 4 * (idx & 7), v[u]);
+            }
         }
         if (a.tab) {
-            for (int idx = tid; idx < ng * nhead4; idx += nt) {
-                const int gl = idx / nhead4, i = idx - gl * nhead4;
-                st4s(per + gl * geo.per_sz + oKp + 4 * i, ld4s(a.tab + (int64_t)(b0 + gl) * a.tab_sz + 4 * i));
+            for (int i0 = 0; i0 < ng * nhead4; i0 += 5 * nt) {
+                float4 v[5];
+#pragma unroll
+                for (int u = 0; u < 5; ++u) {
+                    const int idx = i0 + tid + u * nt;
+                    if (idx < ng * nhead4) {
+                        const int gl = idx / nhead4, i = idx - gl * nhead4;
+                        v[u] = ld4s(a.tab + (int64_t)(b0 + gl) * a.tab_sz + 4 * i);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 5; ++u) {
+                    const int idx = i0 + tid + u * nt;
+                    if (idx < ng * nhead4) {
+                        const int gl = idx / nhead4, i = idx - gl * nhead4;
+                        st4s(per + gl * geo.per_sz + oKp + 4 * i, v[u]);
+                    }
+                }
             }
             __syncthreads();
         } else {

@@ -120,32 +120,54 @@ __global__ void __launch_bounds__(192, 3) attn_bwd2_kernel(AttnArgs a, GeoB2 geo
     {
         const float* tb = a.tab + (int64_t)b * a.tab_sz;
         const int nhead4 = tab_head(MP, H) >> 2;
-        for (int i = tid; i < nhead4; i += nt) st4s(smf + 4 * i, ld4s(tb + 4 * i));
+        for (int i0 = 0; i0 < nhead4; i0 += 5 * nt) {            // five loads per thread in flight (a load -> store loop is one L2 trip per iteration)
+            float4 v[5];
+#pragma unroll
+            for (int u = 0; u < 5; ++u)
+                if (i0 + tid + u * nt < nhead4) v[u] = ld4s(tb + 4 * (i0 + tid + u * nt));
+#pragma unroll
+            for (int u = 0; u < 5; ++u)
+                if (i0 + tid + u * nt < nhead4) st4s(smf + 4 * (i0 + tid + u * nt), v[u]);
+        }
     }
     const int64_t gofs = ((int64_t)b * R + row0) * kE;
     const float* xg = a.x + gofs;
     const float* gg = a.gy + gofs;
     const float* yg = a.yout + gofs;
-    for (int idx = tid; idx < ntile * 16 * 8; idx += nt) {
-        const int row = idx >> 3, c4 = idx & 7;
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), g = xv;              // rows past the graph's last row: zeros (they add nothing)
-        if (row < nrows) {
-            xv = ld4s(xg + (int64_t)idx * 4);
-            g = ld4s(gg + (int64_t)idx * 4);
-            if (a.relu) {
-                float4 yv = ld4s(yg + (int64_t)idx * 4);
-                if (a.mix) {        // saved output is (x + relu(y)) / 2: relu(y) = 2 out - x ; the attention branch sees half the gradient
-                    yv.x = 2.f * yv.x - xv.x; yv.y = 2.f * yv.y - xv.y; yv.z = 2.f * yv.z - xv.z; yv.w = 2.f * yv.w - xv.w;
-                    g.x *= 0.5f; g.y *= 0.5f; g.z *= 0.5f; g.w *= 0.5f;
-                }
-                if (!(yv.x > 0.f)) g.x = 0.f;
-                if (!(yv.y > 0.f)) g.y = 0.f;
-                if (!(yv.z > 0.f)) g.z = 0.f;
-                if (!(yv.w > 0.f)) g.w = 0.f;
+    // 4 float4 groups per thread (16 rows x 8 groups per tile, 32 threads per tile): all of a thread's loads are issued before the
+    // first use -- one L2 round trip per item instead of four
+    {
+        float4 xv[4], gv[4], yv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = tid + u * nt;
+            xv[u] = gv[u] = yv[u] = make_float4(0.f, 0.f, 0.f, 0.f);          // rows past the graph's last row: zeros (they add nothing)
+            if (idx < ntile * 16 * 8 && (idx >> 3) < nrows) {
+                xv[u] = ld4s(xg + (int64_t)idx * 4);
+                gv[u] = ld4s(gg + (int64_t)idx * 4);
+                if (a.relu) yv[u] = ld4s(yg + (int64_t)idx * 4);
             }
         }
-        st4s(Xs + row * TS + 4 * c4, xv);
-        st4s(Ys + row * TS + 4 * c4, g);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = tid + u * nt;
+            if (idx >= ntile * 16 * 8) continue;
+            const int row = idx >> 3, c4 = idx & 7;
+            float4 g = gv[u];
+            if (a.relu && row < nrows) {
+                float4 y = yv[u];
+                if (a.mix) {        // saved output is (x + relu(y)) / 2: relu(y) = 2 out - x ; the attention branch sees half the gradient
+                    y.x = 2.f * y.x - xv[u].x; y.y = 2.f * y.y - xv[u].y; y.z = 2.f * y.z - xv[u].z; y.w = 2.f * y.w - xv[u].w;
+                    g.x *= 0.5f; g.y *= 0.5f; g.z *= 0.5f; g.w *= 0.5f;
+                }
+                if (!(y.x > 0.f)) g.x = 0.f;
+                if (!(y.y > 0.f)) g.y = 0.f;
+                if (!(y.z > 0.f)) g.z = 0.f;
+                if (!(y.w > 0.f)) g.w = 0.f;
+            }
+            st4s(Xs + row * TS + 4 * c4, xv[u]);
+            st4s(Ys + row * TS + 4 * c4, g);
+        }
     }
     __syncthreads();
     float* drec = a.dtab + (int64_t)item * a.dtab_sz;

@@ -79,16 +79,39 @@ __global__ void __launch_bounds__(kThreads) attn_tables_mma_kernel(AttnArgs a, i
     float* Wo_l = Wo_h + 32 * TS;
     float* bin = Wo_l + 32 * TS;             // bq | bk | bv (+ 32 unused)
     float* As = bin + 4 * kE;                // kWarps staged token tiles; first used as the 64 x 33 transpose tile
-    for (int i = tid; i < 2 * kE * kE; i += kThreads) As[(i >> 5) * 33 + (i & 31)] = a.Win[kE * kE + i];
-    for (int i = tid; i < kE * kE; i += kThreads) put_split(a.Win[i], Wq_h, Wq_l, (i >> 5) * TS + (i & 31));
-    for (int i = tid; i < 3 * kE; i += kThreads) bin[i] = a.bin[i];
+    // every weight load of the prologue is issued before the first use (ncu: with load -> store loops the prologue was 70 % of this
+    // kernel's samples, all of them waiting on one L2 round trip per iteration)
+    constexpr int PER = kE * kE / kThreads;            // 8 elements of a 32 x 32 matrix per thread
+    float wkv[2 * PER], wq[PER], wo[PER];
+#pragma unroll
+    for (int u = 0; u < 2 * PER; ++u) wkv[u] = __ldg(a.Win + kE * kE + tid + u * kThreads);
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        wq[u] = __ldg(a.Win + tid + u * kThreads);
+        wo[u] = __ldg(a.Wo + tid + u * kThreads);
+    }
+    if (tid < 3 * kE) bin[tid] = a.bin[tid];
+#pragma unroll
+    for (int u = 0; u < 2 * PER; ++u) {
+        const int i = tid + u * kThreads;
+        As[(i >> 5) * 33 + (i & 31)] = wkv[u];
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int i = tid + u * kThreads;
+        put_split(wq[u], Wq_h, Wq_l, (i >> 5) * TS + (i & 31));
+    }
     __syncthreads();
     for (int o = tid; o < 2 * kE * kE; o += kThreads) {
         const int k = o >> 6, n = o & 63;
         put_split(As[n * 33 + k], Wkv_h, Wkv_l, k * LW + n);
     }
     __syncthreads();
-    for (int i = tid; i < kE * kE; i += kThreads) As[(i >> 5) * 33 + (i & 31)] = a.Wo[i];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int i = tid + u * kThreads;
+        As[(i >> 5) * 33 + (i & 31)] = wo[u];
+    }
     __syncthreads();
     for (int o = tid; o < kE * kE; o += kThreads) {
         const int k = o >> 5, f = o & 31;
@@ -101,7 +124,19 @@ __global__ void __launch_bounds__(kThreads) attn_tables_mma_kernel(AttnArgs a, i
     const int head = amma2::tab_head(MP, H);
     for (int b = blockIdx.x * kWarps + warp; b < a.B; b += gridDim.x * kWarps) {      // warp-private from here on (no block barriers)
         const float* ag = a.a + (int64_t)b * M * kE;
-        for (int i = lane; i < M * 8; i += 32) st4s(as + (i >> 3) * TS + 4 * (i & 7), ld4s(ag + 4 * i));
+        {
+            float4 v[8];                                       // M <= 32 tokens: at most 8 float4 per lane, all in flight together
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = lane + 32 * u;
+                if (i < M * 8) v[u] = ld4s(ag + 4 * i);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = lane + 32 * u;
+                if (i < M * 8) st4s(as + (i >> 3) * TS + 4 * (i & 7), v[u]);
+            }
+        }
         __syncwarp();
         float* tb = a.tab_out + (int64_t)b * a.tab_sz;
 #pragma unroll 1
@@ -230,14 +265,27 @@ __global__ void __launch_bounds__(kThreads) attn_chain_mma_kernel(AttnArgs a, in
     float* dKs = dVp + 2 * TILE;
     float* dVs = dKs + TILE;
     float* dbo_s = dVs + TILE;
-    for (int i = tid; i < kE * kE; i += kThreads) {
-        const int r = i >> 5, c = i & 31;
-        As[r * 33 + c] = a.Win[i];                                          // Wq, transposed below
-        put_split(a.Wo[i], Wo_h, Wo_l, r * LQ + c);
-        put_split(a.Win[kE * kE + i], Wk_h, Wk_l, r * LQ + c);
-        put_split(a.Win[2 * kE * kE + i], Wv_h, Wv_l, r * LQ + c);
+    {
+        constexpr int PER = kE * kE / kThreads;        // all 32 weight loads of a thread in flight before the first use
+        float wq[PER], wo[PER], wk[PER], wv[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int i = tid + u * kThreads;
+            wq[u] = __ldg(a.Win + i);
+            wo[u] = __ldg(a.Wo + i);
+            wk[u] = __ldg(a.Win + kE * kE + i);
+            wv[u] = __ldg(a.Win + 2 * kE * kE + i);
+        }
+        if (tid < kE) bq[tid] = a.bin[tid];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int i = tid + u * kThreads, r = i >> 5, c = i & 31;
+            As[r * 33 + c] = wq[u];                                         // Wq, transposed below
+            put_split(wo[u], Wo_h, Wo_l, r * LQ + c);
+            put_split(wk[u], Wk_h, Wk_l, r * LQ + c);
+            put_split(wv[u], Wv_h, Wv_l, r * LQ + c);
+        }
     }
-    if (tid < kE) bq[tid] = a.bin[tid];
     __syncthreads();
     for (int o = tid; o < kE * kE; o += kThreads) {
         const int e = o >> 5, f = o & 31;
@@ -259,21 +307,56 @@ __global__ void __launch_bounds__(kThreads) attn_chain_mma_kernel(AttnArgs a, in
         {
             const float* ab = a.a + (int64_t)b * M * kE;
             const float* tbk = a.tab + (int64_t)b * a.tab_sz + head;
-            for (int i = tid; i < M * 8; i += kThreads) {
-                const int o = (i >> 3) * TS + 4 * (i & 7);
-                st4s(As + o, ld4s(ab + 4 * i));
-                st4s(Ks + o, ld4s(tbk + 4 * i));
-                st4s(Vs + o, ld4s(tbk + M * kE + 4 * i));
+            {
+                float4 va[2], vk[2], vv[2];                                  // M * 8 <= 256 float4 per table: two per thread, batched
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int i = tid + u * kThreads;
+                    if (i < M * 8) {
+                        va[u] = ld4s(ab + 4 * i);
+                        vk[u] = ld4s(tbk + 4 * i);
+                        vv[u] = ld4s(tbk + M * kE + 4 * i);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int i = tid + u * kThreads;
+                    if (i < M * 8) {
+                        const int o = (i >> 3) * TS + 4 * (i & 7);
+                        st4s(As + o, va[u]);
+                        st4s(Ks + o, vk[u]);
+                        st4s(Vs + o, vv[u]);
+                    }
+                }
             }
             const float* d0 = a.dtab + (int64_t)b * a.nchunk * a.dtab_sz;
-            for (int i = tid; i < 2 * nrec4; i += kThreads) {               // chunk records summed in chunk order
-                float4 v = ld4s(d0 + 4 * i);
-                for (int c = 1; c < a.nchunk; ++c) {
-                    const float4 w = ld4s(d0 + (int64_t)c * a.dtab_sz + 4 * i);
-                    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+            for (int i0 = 0; i0 < 2 * nrec4; i0 += 4 * kThreads) {          // chunk records summed in chunk order, 4 groups per thread in flight
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + tid + u * kThreads;
+                    if (i < 2 * nrec4) v[u] = ld4s(d0 + 4 * i);
                 }
-                const int q = i >= nrec4, r = q ? i - nrec4 : i, hj = r >> 3, c4 = r & 7, h = hj / MP, j = hj - h * MP;
-                st4s((q ? dKp : dVp) + h * TILE + j * TS + 4 * c4, v);      // record order: dV' first, then dK'
+                for (int c = 1; c < a.nchunk; ++c) {
+                    float4 w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + tid + u * kThreads;
+                        if (i < 2 * nrec4) w[u] = ld4s(d0 + (int64_t)c * a.dtab_sz + 4 * i);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        v[u].x += w[u].x; v[u].y += w[u].y; v[u].z += w[u].z; v[u].w += w[u].w;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + tid + u * kThreads;
+                    if (i < 2 * nrec4) {
+                        const int q = i >= nrec4, r = q ? i - nrec4 : i, hj = r >> 3, c4 = r & 7, h = hj / MP, j = hj - h * MP;
+                        st4s((q ? dKp : dVp) + h * TILE + j * TS + 4 * c4, v[u]);      // record order: dV' first, then dK'
+                    }
+                }
             }
             for (int i = tid; i < H * MP + kE; i += kThreads) {
                 float v = d0[2 * H * MP * kE + i];

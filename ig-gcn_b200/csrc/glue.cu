@@ -255,6 +255,141 @@ __global__ void __launch_bounds__(1024) bn_act_bwd_reg_kernel(const float* __res
     }
 }
 
+// Two stacked passes (groups = 2, the benchmarked step): the two groups of a channel are independent until the running-statistics
+// update, so each half of the CTA takes one group and they run side by side -- half the serial length of the kernels above
+// (CUPTI: 8.8 us -> see profiles/).  The halves share the block barriers; sums are per half, warp order fixed.
+constexpr int BN_EPT2 = 16;
+
+__device__ __forceinline__ float half_sum(float v, float* sm /* 32 floats */, int half, int wph /* warps per half */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < wph; ++w) t += sm[half * wph + w];
+    return t;
+}
+
+__global__ void __launch_bounds__(1024) bn_act_fwd_pair_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, const float* __restrict__ mask,
+                                                              int N, int C, int L, float eps, float momentum, int relu,
+                                                              float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                              long long* __restrict__ num_batches_tracked,
+                                                              float* __restrict__ y, float* __restrict__ stats) {
+    __shared__ float sm[33];
+    __shared__ float res[4];                       // mean, var of group 0 ; mean, var of group 1
+    const int nh = blockDim.x >> 1, c = blockIdx.x, g = threadIdx.x >= nh, tid = threadIdx.x - g * nh, wph = nh >> 5;
+    const int ng = N >> 1, cnt = ng * L;
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const int64_t base = ((int64_t)g * ng * C + c) * L;
+    float zv[BN_EPT2], mv[BN_EPT2];
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < BN_EPT2; ++u) {
+        const int e = tid + u * nh;
+        zv[u] = 0.f; mv[u] = 1.f;
+        if (e < cnt) {
+            const int n = e / L, l = e - n * L;
+            const int64_t i = base + (int64_t)n * C * L + l;
+            zv[u] = z[i];
+            if (mask) mv[u] = mask[i];
+            s += zv[u];
+        }
+    }
+    const float mean = half_sum(s, sm, g, wph) / (float)cnt;
+    float q = 0.f;
+#pragma unroll
+    for (int u = 0; u < BN_EPT2; ++u)
+        if (tid + u * nh < cnt) {
+            const float d = zv[u] - mean;
+            q += d * d;
+        }
+    const float var = half_sum(q, sm, g, wph) / (float)cnt;
+    const float rstd = rsqrtf(var + eps);
+#pragma unroll
+    for (int u = 0; u < BN_EPT2; ++u) {
+        const int e = tid + u * nh;
+        if (e < cnt) {
+            const int n = e / L, l = e - n * L;
+            float v = (zv[u] - mean) * rstd * ga + be;
+            if (relu) v = fmaxf(v, 0.f);
+            if (mask) v *= mv[u];
+            y[base + (int64_t)n * C * L + l] = v;
+        }
+    }
+    if (tid == 0) {
+        stats[((int64_t)g * C + c) * 2 + 0] = mean;
+        stats[((int64_t)g * C + c) * 2 + 1] = rstd;
+        res[2 * g] = mean;
+        res[2 * g + 1] = var;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                        // the running buffers receive the two updates in pass order
+        float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 1.f;
+        const float unb = (float)cnt / (float)max(cnt - 1, 1);
+        for (int k = 0; k < 2; ++k) {
+            rm = (1.f - momentum) * rm + momentum * res[2 * k];
+            rv = (1.f - momentum) * rv + momentum * res[2 * k + 1] * unb;
+        }
+        if (running_mean) running_mean[c] = rm;
+        if (running_var) running_var[c] = rv;
+        if (num_batches_tracked && c == 0) *num_batches_tracked += 2;
+    }
+}
+
+__global__ void __launch_bounds__(1024) bn_act_bwd_pair_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, const float* __restrict__ mask,
+                                                              const float* __restrict__ stats, const float* __restrict__ gy,
+                                                              int N, int C, int L, int relu,
+                                                              float* __restrict__ dz, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float sm[33];
+    __shared__ float res[4];
+    const int nh = blockDim.x >> 1, c = blockIdx.x, g = threadIdx.x >= nh, tid = threadIdx.x - g * nh, wph = nh >> 5;
+    const int ng = N >> 1, cnt = ng * L;
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const int64_t base = ((int64_t)g * ng * C + c) * L;
+    const float mean = stats[((int64_t)g * C + c) * 2 + 0], rstd = stats[((int64_t)g * C + c) * 2 + 1];
+    float xh[BN_EPT2], dv[BN_EPT2];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < BN_EPT2; ++u) {
+        const int e = tid + u * nh;
+        xh[u] = 0.f; dv[u] = 0.f;
+        if (e < cnt) {
+            const int n = e / L, l = e - n * L;
+            const int64_t i = base + (int64_t)n * C * L + l;
+            xh[u] = (z[i] - mean) * rstd;
+            float d = gy[i];
+            if (mask) d *= mask[i];
+            if (relu && !(xh[u] * ga + be > 0.f)) d = 0.f;
+            dv[u] = d;
+            s1 += d;
+            s2 += d * xh[u];
+        }
+    }
+    s1 = half_sum(s1, sm, g, wph);
+    s2 = half_sum(s2, sm, g, wph);
+    const float m1 = s1 / (float)cnt, m2 = s2 / (float)cnt;
+#pragma unroll
+    for (int u = 0; u < BN_EPT2; ++u) {
+        const int e = tid + u * nh;
+        if (e < cnt) {
+            const int n = e / L, l = e - n * L;
+            dz[base + (int64_t)n * C * L + l] = ga * rstd * (dv[u] - m1 - xh[u] * m2);
+        }
+    }
+    if (tid == 0) {
+        res[2 * g] = s2;
+        res[2 * g + 1] = s1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (dgamma) dgamma[c] = res[0] + res[2];
+        if (dbeta) dbeta[c] = res[1] + res[3];
+    }
+}
+
 // ---- loss_probability -----------------------------------------------------------------------------------------------------
 // segments: 0 = sigmoid(prob) (n0), 1 = p_e (n1, already a probability), 2 = sigmoid(snps_prob) (n2)
 // loss = sum_seg  [ c_l1[seg] * sum|p| + c_en[seg] * sum -(p log(p+eps) + (1-p) log(1-p+eps)) ] / n_seg
@@ -358,8 +493,17 @@ __global__ void __launch_bounds__(256) skinny_linear_fwd_kernel(const float* __r
         const int64_t r = idx / Lout;
         const int l = (int)(idx - r * Lout);
         const float* xr = x + r * Kin;
+        const float* wr = Ws + l * Kin;
         float v = 0.f;
-        for (int k = 0; k < Kin; ++k) v = fmaf(xr[k], Ws[l * Kin + k], v);
+        // the row's inputs are loaded 8 at a time before the FMAs (a load -> FMA loop over a runtime Kin costs one L2 trip per k)
+        for (int k0 = 0; k0 < Kin; k0 += 8) {
+            float xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xv[u] = (k0 + u < Kin) ? xr[k0 + u] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (k0 + u < Kin) v = fmaf(xv[u], wr[k0 + u], v);
+        }
         z[idx] = v;
     }
 }
@@ -379,8 +523,22 @@ __global__ void __launch_bounds__(256) skinny_linear_bwd_kernel(const float* __r
     for (int64_t r0 = (int64_t)blockIdx.x * SK_ROWS; r0 < rows; r0 += (int64_t)gridDim.x * SK_ROWS) {
         const int nr = (int)min((int64_t)SK_ROWS, rows - r0);
         __syncthreads();
-        for (int i = tid; i < nr * Lout; i += 256) dzs[i] = dz[r0 * Lout + i];
-        for (int i = tid; i < nr * Kin; i += 256) xs[i] = x[r0 * Kin + i];
+        {   // <= 8 values per thread and array (SK_ROWS * 32 / 256): all loads in flight before the first store
+            float a[8], b[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = tid + u * 256;
+                a[u] = i < nr * Lout ? dz[r0 * Lout + i] : 0.f;
+                b[u] = i < nr * Kin ? x[r0 * Kin + i] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = tid + u * 256;
+                if (i < nr * Lout) dzs[i] = a[u];
+                if (i < nr * Kin) xs[i] = b[u];
+            }
+            for (int i = tid + 8 * 256; i < nr * Lout; i += 256) dzs[i] = dz[r0 * Lout + i];      // Lout > 32 only
+        }
         __syncthreads();
         if (dx)
             for (int i = tid; i < nr * Kin; i += 256) {
@@ -460,7 +618,11 @@ extern "C" int igcn_bn_act_fwd(const float* z, const float* gamma, const float* 
     IGCN_REQUIRE((N / groups) * L > 1, IGCN_ERR_UNSUPPORTED, "bn_act_fwd: training-mode BatchNorm needs more than one value per channel");
     const int64_t cnt = (N / groups) * L;
     const int nthr = cnt >= 4096 ? 1024 : (cnt >= 1024 ? 512 : 256);
-    if (cnt <= (int64_t)BN_EPT * nthr)
+    if (groups == 2 && cnt <= (int64_t)BN_EPT2 * (nthr / 2) && nthr >= 128)
+        bn_act_fwd_pair_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, (int)N, (int)C, (int)L, (float)eps,
+                                                                              (float)momentum, (int)relu, running_mean, running_var,
+                                                                              num_batches_tracked, y, stats);
+    else if (cnt <= (int64_t)BN_EPT * nthr)
         bn_act_fwd_reg_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, (int)N, (int)C, (int)L, (int)groups, (float)eps,
                                                                              (float)momentum, (int)relu, running_mean, running_var,
                                                                              num_batches_tracked, y, stats);
@@ -479,7 +641,10 @@ extern "C" int igcn_bn_act_bwd(const float* z, const float* gamma, const float* 
     IGCN_REQUIRE(N > 0 && C > 0 && L > 0 && groups > 0 && N % groups == 0, IGCN_ERR_BAD_ARG, "bn_act_bwd: bad sizes");
     const int64_t cnt = (N / groups) * L;
     const int nthr = cnt >= 4096 ? 1024 : (cnt >= 1024 ? 512 : 256);
-    if (cnt <= (int64_t)BN_EPT * nthr)
+    if (groups == 2 && cnt <= (int64_t)BN_EPT2 * (nthr / 2) && nthr >= 128)
+        bn_act_bwd_pair_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L,
+                                                                              (int)relu, dz, dgamma, dbeta);
+    else if (cnt <= (int64_t)BN_EPT * nthr)
         bn_act_bwd_reg_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L,
                                                                              (int)groups, (int)relu, dz, dgamma, dbeta);
     else
@@ -778,11 +943,13 @@ __global__ void __launch_bounds__(1024) step_loss_fwd_kernel(const float* __rest
     for (int pass = 0; pass < 2; ++pass) {
         const float* r = reg + pass * n_reg;
         const float* x = xhat + pass * n_rec;
+#pragma unroll 4
         for (int64_t i = threadIdx.x; i < n_reg; i += 1024) {
             const float d = r[i] - target[i];
             s1 = fmaf(d, d, s1);
         }
-        for (int64_t i = threadIdx.x; i < n_rec; i += 1024) {
+#pragma unroll 8
+        for (int64_t i = threadIdx.x; i < n_rec; i += 1024) {      // unrolled: the loads of 8 iterations are issued before the first use
             const float d = x[i] - snps[i];
             s2 = fmaf(d, d, s2);
         }

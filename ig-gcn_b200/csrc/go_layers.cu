@@ -352,7 +352,7 @@ __device__ __forceinline__ void go_layer_pre(const GoLayerArgs& a, int b, const 
 }
 
 template <int DIN, int DOUT, bool ATTN>
-__global__ void __launch_bounds__(256) go_layer_fwd_kernel(GoLayerArgs a) {
+__global__ void __launch_bounds__(1024) go_layer_fwd_kernel(GoLayerArgs a) {
     extern __shared__ float smf[];
     const int Min = a.gr.Min, Mrow = a.gr.Mrow;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -360,8 +360,8 @@ __global__ void __launch_bounds__(256) go_layer_fwd_kernel(GoLayerArgs a) {
     float* Ws_s = Wa_s + DOUT * DIN;      // DOUT*DIN
     float* u_s = Ws_s + DOUT * DIN;       // 2*DOUT
     float* v_s = u_s + 2 * DOUT;          // DOUT
-    float* red = v_s + DOUT;              // 8*DOUT
-    float* Xin = red + 8 * DOUT;          // Min*DOUT
+    float* red = v_s + DOUT;              // 32*DOUT (one slot per warp, up to 32 warps)
+    float* Xin = red + 32 * DOUT;         // Min*DOUT
     float* Xs = Xin + Min * DOUT;         // Min*DOUT
     float* O = Xs + Min * DOUT;           // Mrow*DOUT
     for (int i = tid; i < DOUT * DIN; i += nt) {
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(256) go_layer_fwd_kernel(GoLayerArgs a) {
 
 // parameter-gradient layout of one layer: [dWa (DOUT*DIN) | dWs (DOUT*DIN) | du (2*DOUT) | dv (DOUT) | dgamma (Mrow) | dbeta (Mrow)]
 template <int DIN, int DOUT, bool ATTN>
-__global__ void __launch_bounds__(256) go_layer_bwd_kernel(GoLayerArgs a) {
+__global__ void __launch_bounds__(512) go_layer_bwd_kernel(GoLayerArgs a) {
     extern __shared__ float smf[];
     const int Min = a.gr.Min, Mrow = a.gr.Mrow, nnz = a.gr.nnz;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -433,8 +433,8 @@ __global__ void __launch_bounds__(256) go_layer_bwd_kernel(GoLayerArgs a) {
     float* Ws_s = Wa_s + DOUT * DIN;
     float* u_s = Ws_s + DOUT * DIN;
     float* v_s = u_s + 2 * DOUT;
-    float* red = v_s + DOUT;              // 8*NW  (also used for the DOUT-wide reductions)
-    float* Xin = red + 8 * NW;            // Min*DOUT   -> becomes dXin
+    float* red = v_s + DOUT;              // 16*NW  (one slot per warp, up to 16 warps; also used for the DOUT-wide reductions)
+    float* Xin = red + 16 * NW;           // Min*DOUT   -> becomes dXin
     float* Xs = Xin + Min * DOUT;         // Min*DOUT   -> becomes dXs
     float* O = Xs + Min * DOUT;           // Mrow*DOUT  -> becomes dO
     float* dgam = O + Mrow * DOUT;        // Mrow  (accumulates across the CTA's subjects)
@@ -637,20 +637,23 @@ __global__ void __launch_bounds__(256) go_layer_bwd_kernel(GoLayerArgs a) {
 namespace igcn {
 
 static size_t go_fwd_smem(int din, int dout, int Min, int Mrow) {
-    return 4 * ((size_t)2 * dout * din + 3 * dout + 8 * dout + 2 * (size_t)Min * dout + (size_t)Mrow * dout);
+    return 4 * ((size_t)2 * dout * din + 3 * dout + 32 * dout + 2 * (size_t)Min * dout + (size_t)Mrow * dout);
 }
 static size_t go_bwd_smem(int din, int dout, int Min, int Mrow, int nnz, bool attn) {
     const int NW = 2 * dout * din + 3 * dout;
-    return 4 * ((size_t)2 * dout * din + 3 * dout + 8 * NW + 2 * (size_t)Min * dout + (size_t)Mrow * dout + 2 * (size_t)Mrow +
+    return 4 * ((size_t)2 * dout * din + 3 * dout + 16 * NW + 2 * (size_t)Min * dout + (size_t)Mrow * dout + 2 * (size_t)Mrow +
                 (attn ? 2 * (size_t)nnz : 0) + (size_t)Min);
 }
 
 // threads per CTA: the row / column phases give one node to a thread, so a CTA wider than the node count only idles
-static int go_threads(int m_in, int m_row) {
+// (large hierarchies: ncu at config-3 size showed 12 % of the warp slots and 13 cycles per warp instruction with 256 threads and
+// 8 nodes per thread -- profiles/r2_ncu_go_kernels_c3.json -- so the forward takes up to 1024 threads, the backward, which holds
+// the layer's parameter gradients in registers, up to 512)
+static int go_threads(int m_in, int m_row, int cap = 512) {
     const int m = m_in > m_row ? m_in : m_row;
     int nt = (m + 31) / 32 * 32;
     if (nt < 64) nt = 64;
-    if (nt > 256) nt = 256;
+    if (nt > cap) nt = cap;
     return nt;
 }
 
@@ -681,7 +684,7 @@ static int launch_go_fwd(const GoLayerArgs& a, cudaStream_t st) {
     auto k = go_layer_fwd_kernel<DIN, DOUT, ATTN>;
     int rc = allow_smem(k, smem, "go_layer_fwd");
     if (rc) return rc;
-    const int nthr = go_threads(a.gr.Min, a.gr.Mrow);
+    const int nthr = go_threads(a.gr.Min, a.gr.Mrow, 1024);
     k<<<go_ctas(smem, a.B, nthr), nthr, smem, st>>>(a);
     IGCN_CHECK_LAUNCH("go_layer_fwd");
     return IGCN_OK;

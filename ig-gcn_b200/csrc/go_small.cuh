@@ -43,6 +43,25 @@ __device__ __forceinline__ void warp_transpose_sum(float (&v)[NP], int lane) {
     }
 }
 
+// n floats global -> shared with U loads per thread in flight (a load -> store loop costs one L2 round trip per iteration, and these
+// kernels are nothing but latency)
+template <int U>
+__device__ __forceinline__ void copy_in(float* dst, const float* __restrict__ src, int n) {
+    for (int i0 = 0; i0 < n; i0 += U * kThreads) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + threadIdx.x + u * kThreads;
+            v[u] = i < n ? src[i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + threadIdx.x + u * kThreads;
+            if (i < n) dst[i] = v[u];
+        }
+    }
+}
+
 struct Lay {      // shared-memory carve-up (float offsets; int arrays are stored in the same 4-byte slots)
     int Wa, Ws, u, v, gam, bet, rowptr, col, colptr, crow, cpos, x, Xin, Xs, O, P1, gy, msk, st, r12, ea, edq, rowsum, wred, total;
 };
@@ -180,14 +199,8 @@ __global__ void __launch_bounds__(kThreads) go_small_fwd_kernel(GoLayerArgs a, i
     for (int b0 = blockIdx.x * SUB; b0 < a.B; b0 += gridDim.x * SUB) {
         const int ns = min(SUB, a.B - b0);
         const bool valid = s < ns;
-        {
-            const float* src = a.x + (int64_t)b0 * Min * DIN;
-            for (int k = tid; k < ns * Min * DIN; k += kThreads) smf[L.x + k] = src[k];
-            if (a.mask) {
-                const float* ms = a.mask + (int64_t)b0 * Mrow;
-                for (int k = tid; k < ns * Mrow; k += kThreads) smf[L.msk + k] = ms[k];
-            }
-        }
+        copy_in<6>(smf + L.x, a.x + (int64_t)b0 * Min * DIN, ns * Min * DIN);
+        if (a.mask) copy_in<2>(smf + L.msk, a.mask + (int64_t)b0 * Mrow, ns * Mrow);
         __syncthreads();       // also covers stage_constants on the first pass
         if (valid && i < Min) project_node<DIN, DOUT>(smf + L.x + (s * Min + i) * DIN, smf + L.Wa, smf + L.Ws, Xin + i * DOUT, Xs + i * DOUT);
         __syncthreads();
@@ -261,18 +274,10 @@ __global__ void __launch_bounds__(kThreads) go_small_bwd_kernel(GoLayerArgs a, i
     for (int b0 = blockIdx.x * SUB; b0 < a.B; b0 += gridDim.x * SUB) {
         const int ns = min(SUB, a.B - b0);
         const bool valid = s < ns;
-        {
-            const float* src = a.x + (int64_t)b0 * Min * DIN;
-            for (int k = tid; k < ns * Min * DIN; k += kThreads) smf[L.x + k] = src[k];
-            const float* gs = a.gy + (int64_t)b0 * Mkeep * DOUT;
-            for (int k = tid; k < ns * Mkeep * DOUT; k += kThreads) smf[L.gy + k] = gs[k];
-            if (a.mask) {
-                const float* ms = a.mask + (int64_t)b0 * Mrow;
-                for (int k = tid; k < ns * Mrow; k += kThreads) smf[L.msk + k] = ms[k];
-            }
-            const float* ss = a.stats + (int64_t)b0 * 2 * DOUT;
-            for (int k = tid; k < ns * 2 * DOUT; k += kThreads) smf[L.st + k] = ss[k];
-        }
+        copy_in<6>(smf + L.x, a.x + (int64_t)b0 * Min * DIN, ns * Min * DIN);
+        copy_in<6>(smf + L.gy, a.gy + (int64_t)b0 * Mkeep * DOUT, ns * Mkeep * DOUT);
+        if (a.mask) copy_in<2>(smf + L.msk, a.mask + (int64_t)b0 * Mrow, ns * Mrow);
+        copy_in<1>(smf + L.st, a.stats + (int64_t)b0 * 2 * DOUT, ns * 2 * DOUT);
         __syncthreads();
         if (valid && i < Min) project_node<DIN, DOUT>(smf + L.x + (s * Min + i) * DIN, smf + L.Wa, smf + L.Ws, Xin + i * DOUT, Xs + i * DOUT);
         __syncthreads();

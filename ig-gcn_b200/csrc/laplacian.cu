@@ -103,11 +103,25 @@ __global__ void __launch_bounds__(256) finish_kernel(const float* __restrict__ s
         const float di = d ? d[i] : dconst;
         const float* mp = m + (int64_t)g * D;
         const int64_t base = (int64_t)row * D;
-        for (int c = threadIdx.x; c < D; c += 256) {
-            const float sc = s[base + c] - mp[c];
-            const float tv = di * sc - (U ? U[base + c] : 0.f);
-            T[base + c] = tv;
-            acc = fmaf(sc, tv, acc);
+        for (int c0 = 0; c0 < D; c0 += 4 * 256) {               // four columns per thread in flight (12 loads) before the first store
+            float sv[4], mv[4], uv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + threadIdx.x + u * 256;
+                sv[u] = c < D ? s[base + c] : 0.f;
+                mv[u] = c < D ? mp[c] : 0.f;
+                uv[u] = (U && c < D) ? U[base + c] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + threadIdx.x + u * 256;
+                if (c < D) {
+                    const float sc = sv[u] - mv[u];
+                    const float tv = di * sc - uv[u];
+                    T[base + c] = tv;
+                    acc = fmaf(sc, tv, acc);
+                }
+            }
         }
     }
     acc = warp_sum(acc);

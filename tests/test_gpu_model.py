@@ -362,7 +362,19 @@ def test_cross_attention_vs_torch_mha(B, R, M, E):
     g = torch.randn(B, R, E, device=DEV)
     out = ops.cross_attention(q, kv, mha, relu=True)
     (out * g).sum().backward()
-    o64 = torch.relu(ref(q64, kv64, kv64, need_weights=False)[0])
+    # The ReLU that follows the attention is not continuous in its gradient: a pre-activation within rounding of zero may be active
+    # in one implementation and inactive in another, and then a whole row of dq differs although both outputs are right to 1e-6.
+    # The checkers therefore use the ACTIVE SET of the run under test (as the benched-step tests do), and the test bounds how many
+    # elements flipped and how close to zero they were.
+    active = (out > 0).detach()
+    p64 = ref(q64, kv64, kv64, need_weights=False)[0]
+    flips = (p64 > 0) != active
+    assert int(flips.sum()) <= max(2, int(2e-5 * out.numel())), "ReLU sign flips: %d of %d" % (int(flips.sum()), out.numel())
+    assert float(p64[flips].abs().max()) < 1e-5 if bool(flips.any()) else True
+    if bool(flips.any()):
+        H.PARITY_LOG.append(dict(what="attn B%d R%d M%d E%d ReLU sign flips vs fp64: %d" % (B, R, M, E, int(flips.sum())), rule="A",
+                                 err32=float(flips.sum())))
+    o64 = p64 * active
     (o64 * g.double()).sum().backward()
     # fp32 reference of rule B: torch's own nn.MultiheadAttention in fp32 on the same inputs (the checker, not the product)
     r32 = torch.nn.MultiheadAttention(E, 2, batch_first=True).to(DEV)
@@ -370,7 +382,7 @@ def test_cross_attention_vs_torch_mha(B, R, M, E):
     q32, kv32 = q.detach().clone().requires_grad_(True), kv.detach().clone().requires_grad_(True)
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
-    o32 = torch.relu(r32(q32, kv32, kv32, need_weights=False)[0])
+    o32 = r32(q32, kv32, kv32, need_weights=False)[0] * active
     (o32 * g).sum().backward()
     torch.backends.cuda.matmul.allow_tf32 = prev
     tag = "attn B%d R%d M%d E%d " % (B, R, M, E)

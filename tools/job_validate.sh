@@ -25,3 +25,15 @@ if [ "$2" = "gat" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:gat_ --launch-skip 4 -c 4 -f -o gpurun_out/r2_gat_c1 python tools/prof_kernels.py --compact --iters 1 --what gat --B 32 --R 90 > gpurun_out/r2_gat_c1_ncu.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:gat_ --launch-skip 4 -c 4 -f -o gpurun_out/r2_gat_big python tools/prof_kernels.py --compact --iters 1 --what gat --B 4096 --R 264 > gpurun_out/r2_gat_big_ncu.log 2>&1
 fi
+if [ "$3" = "more" ]; then
+  timeout 600 python bench.py --workload config3 > gpurun_out/r2_bench_c3_$T.json 2> gpurun_out/r2_bench_c3_$T.err
+  timeout 900 python bench.py --workload config4 > gpurun_out/r2_bench_c4_$T.json 2> gpurun_out/r2_bench_c4_$T.err
+  python - <<PY
+import json
+for f in ('c3','c4'):
+    try:
+        d=json.loads(open('gpurun_out/r2_bench_%s_$T.json'%f).read().strip().splitlines()[-1])
+        print(f, d['value'], d['ms_per_step'], d.get('config',{}).get('description','')[-60:])
+    except Exception as e: print(f, 'parse', e)
+PY
+fi
