@@ -98,7 +98,7 @@ def build_problem(w, rank, dev):
 
 # CUPTI kernel name (torch.profiler on the graph replay) -> the C-ABI call tag that carries its algorithmic bytes
 KERNEL_TAGS = [
-    ("attn_mma_bwd_kernel", "cross_attn_bwd"), ("attn_mma_fwd_kernel", "cross_attn_fwd"),
+    ("attn_bwd2_kernel", "cross_attn_bwd"), ("attn_mma_bwd_kernel", "cross_attn_bwd"), ("attn_mma_fwd_kernel", "cross_attn_fwd"),
     ("attn_rows_bwd_kernel", "cross_attn_bwd"), ("attn_rows_fwd_kernel", "cross_attn_fwd"),
     ("sgcn_bwd_mma_kernel<(bool)1>", "sgcn_encoder_bwd[explain"), ("sgcn_bwd_mma_kernel<(bool)0>", "sgcn_encoder_bwd[plain"),
     ("sgcn_fwd_mma_kernel<(bool)1", "sgcn_encoder_fwd[explain"), ("sgcn_fwd_mma_kernel<(bool)0", "sgcn_encoder_fwd[plain"),

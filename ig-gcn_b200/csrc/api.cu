@@ -1,5 +1,6 @@
 // Error channel + small queries of the C ABI (include/igcn_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -37,6 +38,12 @@ long long sm_clock_khz() {
         cached[dev] = khz;
     }
     return cached[dev];
+}
+
+// programmatic dependent launch for the library's kernels (common.cuh): IGCN_PDL=1 / 0, default off
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("IGCN_PDL"); return e && e[0] == '1'; }();
+    return on;
 }
 }  // namespace igcn
 

@@ -172,6 +172,7 @@ __device__ __forceinline__ void attn_forward_chunk(const AttnArgs& a, const Attn
 }
 
 __global__ void __launch_bounds__(256) cross_attn_fwd_kernel(AttnArgs a) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) float smf[];
     const int tid = threadIdx.x, nt = blockDim.x, R = a.R, E = a.E, Rc = a.Rc, E4 = E >> 2;
     AttnSmem s = attn_carve(smf, Rc, a.M, E, a.heads);
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(256) cross_attn_fwd_kernel(AttnArgs a) {
 }
 
 __global__ void __launch_bounds__(512) cross_attn_bwd_kernel(AttnArgs a) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) float smf[];
     const int tid = threadIdx.x, nt = blockDim.x, R = a.R, M = a.M, E = a.E, H = a.heads, hd = E / H, Rc = a.Rc;
     const int EP = E + 4, E4 = E >> 2;
@@ -432,17 +434,17 @@ static bool use_mma_tokens(int64_t E, int64_t heads) {
 template <int NT>
 static void launch_bwd2(const AttnArgs& a, const amma2::GeoB2& g, int items, cudaStream_t st) {
     cudaFuncSetAttribute(amma2::attn_bwd2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-    amma2::attn_bwd2_kernel<NT><<<items, g.nthreads, g.smem, st>>>(a, g);
+    igcn::launch_k(amma2::attn_bwd2_kernel<NT>, dim3(items), dim3(g.nthreads), g.smem, st, a, g);
 }
 template <int NT>
 static void launch_mma_bwd(const AttnArgs& a, const amma::GeoB& g, int ctas, cudaStream_t st) {
     cudaFuncSetAttribute(amma::attn_mma_bwd_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-    amma::attn_mma_bwd_kernel<NT><<<ctas, g.nthreads, g.smem, st>>>(a, g);
+    igcn::launch_k(amma::attn_mma_bwd_kernel<NT>, dim3(ctas), dim3(g.nthreads), g.smem, st, a, g);
 }
 template <int NT>
 static void launch_mma_fwd(const AttnArgs& a, const amma::Geo& g, int ctas, cudaStream_t st) {
     cudaFuncSetAttribute(amma::attn_mma_fwd_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-    amma::attn_mma_fwd_kernel<NT><<<ctas, amma::kThreads, g.smem, st>>>(a, g);
+    igcn::launch_k(amma::attn_mma_fwd_kernel<NT>, dim3(ctas), dim3(amma::kThreads), g.smem, st, a, g);
 }
 static int rows_ctas(const rows::Geo& g, int64_t B, int per_sm) {
     const int64_t groups = (B + g.gpc - 1) / g.gpc;
@@ -453,12 +455,12 @@ static int rows_ctas(const rows::Geo& g, int64_t B, int per_sm) {
 template <int MC>
 static void launch_rows_fwd(const AttnArgs& a, const rows::Geo& g, int ctas, cudaStream_t st) {
     cudaFuncSetAttribute(rows::attn_rows_fwd_kernel<MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-    rows::attn_rows_fwd_kernel<MC><<<ctas, g.nthreads, g.smem, st>>>(a, g);
+    igcn::launch_k(rows::attn_rows_fwd_kernel<MC>, dim3(ctas), dim3(g.nthreads), g.smem, st, a, g);
 }
 template <int MC>
 static void launch_rows_bwd(const AttnArgs& a, const rows::Geo& g, int ctas, cudaStream_t st) {
     cudaFuncSetAttribute(rows::attn_rows_bwd_kernel<MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-    rows::attn_rows_bwd_kernel<MC><<<ctas, g.nthreads, g.smem, st>>>(a, g);
+    igcn::launch_k(rows::attn_rows_bwd_kernel<MC>, dim3(ctas), dim3(g.nthreads), g.smem, st, a, g);
 }
 
 }  // namespace igcn
@@ -515,7 +517,7 @@ extern "C" int igcn_cross_attn_v2_fwd(const float* q_in, const float* kv_in, con
         if ((rc = allow_smem(amma3::attn_tables_mma_kernel, smem, "cross_attn_tables_mma"))) return rc;
         int64_t ctas = (B + amma3::kWarps - 1) / amma3::kWarps;
         if (ctas > (int64_t)sm_count() * 4) ctas = (int64_t)sm_count() * 4;
-        amma3::attn_tables_mma_kernel<<<(int)ctas, amma3::kThreads, smem, st>>>(a, g.MP);
+        igcn::launch_k(amma3::attn_tables_mma_kernel, dim3((int)ctas), dim3(amma3::kThreads), smem, st, a, g.MP);
         IGCN_CHECK_LAUNCH("cross_attn_tables_mma");
     } else {
         // the per-graph table area doubles as the 64 x 33 staging tile of the weight transposes
@@ -524,7 +526,7 @@ extern "C" int igcn_cross_attn_v2_fwd(const float* q_in, const float* kv_in, con
         if ((rc = allow_smem(amma2::attn_tables_kernel, smem, "cross_attn_tables"))) return rc;
         int64_t ctas = (B + amma2::kTabGraphs - 1) / amma2::kTabGraphs;
         if (ctas > (int64_t)sm_count() * 4) ctas = (int64_t)sm_count() * 4;
-        amma2::attn_tables_kernel<<<(int)ctas, amma2::kTabThreads, smem, st>>>(a, g.per_sz, g.MP);
+        igcn::launch_k(amma2::attn_tables_kernel, dim3((int)ctas), dim3(amma2::kTabThreads), smem, st, a, g.per_sz, g.MP);
         IGCN_CHECK_LAUNCH("cross_attn_tables");
     }
     const int64_t groups = (B + g.gpc - 1) / g.gpc;
@@ -574,15 +576,15 @@ extern "C" int igcn_cross_attn_v2_bwd(const float* q_in, const float* kv_in, con
     if (use_mma_tokens(E, heads)) {
         const size_t csm = amma3::chain_smem();
         if ((rc = allow_smem(amma3::attn_chain_mma_kernel, csm, "cross_attn_chain_mma"))) return rc;
-        amma3::attn_chain_mma_kernel<<<want, amma3::kThreads, csm, st>>>(a, g.MP);
+        igcn::launch_k(amma3::attn_chain_mma_kernel, dim3(want), dim3(amma3::kThreads), csm, st, a, g.MP);
         IGCN_CHECK_LAUNCH("cross_attn_chain_mma");
     } else {
         const size_t csm = amma2::chain_smem((int)M, g.MP, (int)heads);
         if ((rc = allow_smem(amma2::attn_chain_kernel, csm, "cross_attn_chain"))) return rc;
-        amma2::attn_chain_kernel<<<want, amma2::kChainThreads, csm, st>>>(a, g.MP);
+        igcn::launch_k(amma2::attn_chain_kernel, dim3(want), dim3(amma2::kChainThreads), csm, st, a, g.MP);
         IGCN_CHECK_LAUNCH("cross_attn_chain");
     }
-    reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(partials, want, a.P, grads);
+    igcn::launch_k(reduce_partials_kernel, dim3((a.P + 31) / 32), dim3(reduce_threads(want)), 0, st, partials, want, a.P, grads);
     IGCN_CHECK_LAUNCH("cross_attn_reduce_partials");
     return IGCN_OK;
 }
@@ -626,7 +628,7 @@ extern "C" int igcn_cross_attn_fwd(const float* q_in, const float* kv_in, const 
     }
     size_t smem = attn_fwd_smem(a.Rc, a.M, a.E, a.heads);
     if ((rc = allow_smem(cross_attn_fwd_kernel, smem, "cross_attn_fwd"))) return rc;
-    cross_attn_fwd_kernel<<<attn_ctas(smem, B), 256, smem, (cudaStream_t)stream>>>(a);
+    igcn::launch_k(cross_attn_fwd_kernel, dim3(attn_ctas(smem, B)), dim3(256), smem, (cudaStream_t)stream, a);
     IGCN_CHECK_LAUNCH("cross_attn_fwd");
     return IGCN_OK;
 }
@@ -659,7 +661,7 @@ extern "C" int igcn_cross_attn_bwd(const float* q_in, const float* kv_in, const 
             default: launch_mma_bwd<4>(a, g, want, st); break;
         }
         IGCN_CHECK_LAUNCH("cross_attn_mma_bwd");
-        reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(partials, want, a.P, grads);
+        igcn::launch_k(reduce_partials_kernel, dim3((a.P + 31) / 32), dim3(reduce_threads(want)), 0, st, partials, want, a.P, grads);
         IGCN_CHECK_LAUNCH("cross_attn_reduce_partials");
         return IGCN_OK;
     }
@@ -671,15 +673,15 @@ extern "C" int igcn_cross_attn_bwd(const float* q_in, const float* kv_in, const 
         else if (M <= 24) launch_rows_bwd<24>(a, g, want, st);
         else launch_rows_bwd<32>(a, g, want, st);
         IGCN_CHECK_LAUNCH("cross_attn_rows_bwd");
-        reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(partials, want, a.P, grads);
+        igcn::launch_k(reduce_partials_kernel, dim3((a.P + 31) / 32), dim3(reduce_threads(want)), 0, st, partials, want, a.P, grads);
         IGCN_CHECK_LAUNCH("cross_attn_reduce_partials");
         return IGCN_OK;
     }
     size_t smem = attn_bwd_smem(a.Rc, a.M, a.E, a.heads, a.P);
     if ((rc = allow_smem(cross_attn_bwd_kernel, smem, "cross_attn_bwd"))) return rc;
-    cross_attn_bwd_kernel<<<want, 512, smem, st>>>(a);   // one graph per CTA, 16 warps: the per-graph chain is latency bound
+    igcn::launch_k(cross_attn_bwd_kernel, dim3(want), dim3(512), smem, st, a);   // one graph per CTA, 16 warps: the per-graph chain is latency bound
     IGCN_CHECK_LAUNCH("cross_attn_bwd");
-    reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(partials, want, a.P, grads);
+    igcn::launch_k(reduce_partials_kernel, dim3((a.P + 31) / 32), dim3(reduce_threads(want)), 0, st, partials, want, a.P, grads);
     IGCN_CHECK_LAUNCH("cross_attn_reduce_partials");
     return IGCN_OK;
 }

@@ -187,6 +187,7 @@ __device__ __forceinline__ void load_rows_a(const float* tile_rows, int lane, ui
 
 template <int NT>
 __global__ void __launch_bounds__(kThreads, 2) attn_mma_fwd_kernel(AttnArgs a, Geo geo) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) float smf[];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     const int gq = lane >> 2, tq = lane & 3;
@@ -359,6 +360,7 @@ __device__ __forceinline__ void rows_t_times_frag(const float* tile_rows, const 
 
 template <int NT>
 __global__ void __launch_bounds__(kThreads, 1) attn_mma_bwd_kernel(AttnArgs a, GeoB geo) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) float smf[];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     const int gq = lane >> 2, tq = lane & 3;

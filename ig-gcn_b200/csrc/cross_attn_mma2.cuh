@@ -51,6 +51,7 @@ __device__ __forceinline__ void stage_transposed(const float* __restrict__ src, 
 }
 
 __global__ void __launch_bounds__(kTabThreads, 4) attn_tables_kernel(AttnArgs a, int per_sz, int MP) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) float smf[];
     const int tid = threadIdx.x, nt = blockDim.x, M = a.M, H = a.heads;
     float* WkvT = smf;
@@ -102,6 +103,7 @@ static GeoB2 bwd2_geo(int R, int M, int H, int64_t B) {
 
 template <int NT>
 __global__ void __launch_bounds__(192, 3) attn_bwd2_kernel(AttnArgs a, GeoB2 geo) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) float smf[];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     const int gq = lane >> 2, tq = lane & 3;
@@ -337,6 +339,7 @@ __host__ __device__ inline int chain_per_sz(int M, int MP, int H) { return 5 * M
 static size_t chain_smem(int M, int MP, int H) { return (size_t)4 * (4 * kE * kE + kE + kChainGraphs * chain_per_sz(M, MP, H)) + 16; }
 
 __global__ void __launch_bounds__(kChainThreads, 4) attn_chain_kernel(AttnArgs a, int MP) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) float smf[];
     const int tid = threadIdx.x, M = a.M, H = a.heads, hd = kE / H;
     const float scale = rsqrtf((float)hd);

@@ -67,6 +67,7 @@ __device__ __forceinline__ void acc_as_a(const float (&acc)[4], uint32_t (&ah)[4
 static size_t tables_smem() { return (size_t)4 * (2 * 32 * LW + 4 * 32 * TS + 4 * kE + kWarps * TILE) + 16; }
 
 __global__ void __launch_bounds__(kThreads) attn_tables_mma_kernel(AttnArgs a, int MP) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) float smf[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int M = a.M, H = a.heads, hd = kE / H;
@@ -244,6 +245,7 @@ __device__ __forceinline__ void outer_acc(const float* L, int lcol0, const float
 }
 
 __global__ void __launch_bounds__(kThreads) attn_chain_mma_kernel(AttnArgs a, int MP) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) float smf[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int M = a.M, H = a.heads, hd = kE / H;

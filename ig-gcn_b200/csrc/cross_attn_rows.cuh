@@ -182,6 +182,7 @@ __device__ __forceinline__ void row_softmax(const float4 (&x)[8], const float* K
 
 template <int MC>
 __global__ void __launch_bounds__(288, 2) attn_rows_fwd_kernel(AttnArgs a, Geo geo) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) float smf[];
     const int tid = threadIdx.x, nt = blockDim.x, R = a.R, M = a.M, H = a.heads, HM = H * M;
     float* WkvT = smf;
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(288, 2) attn_rows_fwd_kernel(AttnArgs a, Geo g
 // acc layout (= AttnArgs::partials row, shared with the staged kernel): [dWin (3E,E) | dbin (3E) | dWo (E,E) | dbo (E)]
 template <int MC>
 __global__ void __launch_bounds__(288) attn_rows_bwd_kernel(AttnArgs a, Geo geo) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) float smf[];
     const int tid = threadIdx.x, nt = blockDim.x, R = a.R, M = a.M, H = a.heads, hd = kE / H, HM = H * M, MCP = geo.mcp, JQ = MCP / 4;
     const int HMP = (HM + 3) & ~3;

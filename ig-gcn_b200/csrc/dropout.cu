@@ -19,6 +19,7 @@ struct MaskPlan {
 
 __global__ void __launch_bounds__(256) dropout_masks_kernel(float* __restrict__ out, MaskPlan plan, int64_t total, uint64_t seed,
                                                             const unsigned long long* __restrict__ counter) {
+    IGCN_PDL_SYNC();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t i0 = t * 4;
     if (i0 >= total) return;
@@ -37,7 +38,8 @@ __global__ void __launch_bounds__(256) dropout_masks_kernel(float* __restrict__ 
     }
 }
 
-__global__ void counter_inc_kernel(unsigned long long* counter) { counter[0] += 1ull; }
+__global__ void counter_inc_kernel(unsigned long long* counter) {
+    IGCN_PDL_SYNC(); counter[0] += 1ull; }
 
 }  // namespace igcn
 
@@ -59,10 +61,10 @@ extern "C" int igcn_dropout_masks(float* out, const int64_t* host_seg_end, const
     cudaStream_t st = (cudaStream_t)stream;
     if (total > 0) {
         const int64_t threads = (total + 3) / 4;
-        dropout_masks_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(out, plan, total, seed, counter);
+        igcn::launch_k(dropout_masks_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, out, plan, total, seed, counter);
         IGCN_CHECK_LAUNCH("dropout_masks");
     }
-    counter_inc_kernel<<<1, 1, 0, st>>>(counter);
+    igcn::launch_k(counter_inc_kernel, dim3(1), dim3(1), 0, st, counter);
     IGCN_CHECK_LAUNCH("dropout_counter_inc");
     return IGCN_OK;
 }

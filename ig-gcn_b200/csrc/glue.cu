@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(1024) bn_act_fwd_kernel(const float* __restric
                                                          float* __restrict__ running_mean, float* __restrict__ running_var,
                                                          long long* __restrict__ num_batches_tracked,
                                                          float* __restrict__ y, float* __restrict__ stats /* (groups, C, 2) */) {
+    IGCN_PDL_SYNC();
     __shared__ float sm[33];
     const int nthr = blockDim.x;
     const int c = blockIdx.x, tid = threadIdx.x;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(1024) bn_act_bwd_kernel(const float* __restric
                                                          const float* __restrict__ stats, const float* __restrict__ gy,
                                                          int N, int C, int L, int groups, int relu,
                                                          float* __restrict__ dz, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    IGCN_PDL_SYNC();
     __shared__ float sm[33];
     const int nthr = blockDim.x;
     const int c = blockIdx.x, tid = threadIdx.x;
@@ -141,6 +143,17 @@ __global__ void __launch_bounds__(1024) bn_act_bwd_kernel(const float* __restric
 // kernels are nothing but dependent trips to L2 (CUPTI: 8.2 us each, ten launches per step).  Same element-to-thread mapping and the
 // same reduction order as the streaming kernels, so the results are bit identical.
 constexpr int BN_EPT = 8;
+// offset of element e = n * L + l of a channel inside a (N, C, L) tensor, relative to the channel's first element, without an integer
+// division in the common cases (L = 1, L a power of two): three divisions per element were ~half of these kernels' instructions
+__device__ __forceinline__ int bn_off(int e, int L, int CL) {
+    if (L == 1) return e * CL;
+    if ((L & (L - 1)) == 0) {
+        const int sh = __ffs(L) - 1;
+        return (e >> sh) * CL + (e & (L - 1));
+    }
+    const int n = e / L;
+    return n * CL + (e - n * L);
+}
 
 __global__ void __launch_bounds__(1024) bn_act_fwd_reg_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const float* __restrict__ mask,
@@ -148,6 +161,7 @@ __global__ void __launch_bounds__(1024) bn_act_fwd_reg_kernel(const float* __res
                                                              float* __restrict__ running_mean, float* __restrict__ running_var,
                                                              long long* __restrict__ num_batches_tracked,
                                                              float* __restrict__ y, float* __restrict__ stats) {
+    IGCN_PDL_SYNC();
     __shared__ float sm[33];
     const int nthr = blockDim.x, c = blockIdx.x, tid = threadIdx.x;
     const int ng = N / groups, cnt = ng * L;
@@ -209,6 +223,7 @@ __global__ void __launch_bounds__(1024) bn_act_bwd_reg_kernel(const float* __res
                                                              const float* __restrict__ stats, const float* __restrict__ gy,
                                                              int N, int C, int L, int groups, int relu,
                                                              float* __restrict__ dz, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    IGCN_PDL_SYNC();
     __shared__ float sm[33];
     const int nthr = blockDim.x, c = blockIdx.x, tid = threadIdx.x;
     const int ng = N / groups, cnt = ng * L;
@@ -277,6 +292,7 @@ __global__ void __launch_bounds__(1024) bn_act_fwd_pair_kernel(const float* __re
                                                               float* __restrict__ running_mean, float* __restrict__ running_var,
                                                               long long* __restrict__ num_batches_tracked,
                                                               float* __restrict__ y, float* __restrict__ stats) {
+    IGCN_PDL_SYNC();
     __shared__ float sm[33];
     __shared__ float res[4];                       // mean, var of group 0 ; mean, var of group 1
     const int nh = blockDim.x >> 1, c = blockIdx.x, g = threadIdx.x >= nh, tid = threadIdx.x - g * nh, wph = nh >> 5;
@@ -284,14 +300,15 @@ __global__ void __launch_bounds__(1024) bn_act_fwd_pair_kernel(const float* __re
     const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
     const int64_t base = ((int64_t)g * ng * C + c) * L;
     float zv[BN_EPT2], mv[BN_EPT2];
+    int off[BN_EPT2];
     float s = 0.f;
 #pragma unroll
     for (int u = 0; u < BN_EPT2; ++u) {
         const int e = tid + u * nh;
-        zv[u] = 0.f; mv[u] = 1.f;
+        zv[u] = 0.f; mv[u] = 1.f; off[u] = 0;
         if (e < cnt) {
-            const int n = e / L, l = e - n * L;
-            const int64_t i = base + (int64_t)n * C * L + l;
+            off[u] = bn_off(e, L, C * L);
+            const int64_t i = base + off[u];
             zv[u] = z[i];
             if (mask) mv[u] = mask[i];
             s += zv[u];
@@ -311,11 +328,10 @@ __global__ void __launch_bounds__(1024) bn_act_fwd_pair_kernel(const float* __re
     for (int u = 0; u < BN_EPT2; ++u) {
         const int e = tid + u * nh;
         if (e < cnt) {
-            const int n = e / L, l = e - n * L;
             float v = (zv[u] - mean) * rstd * ga + be;
             if (relu) v = fmaxf(v, 0.f);
             if (mask) v *= mv[u];
-            y[base + (int64_t)n * C * L + l] = v;
+            y[base + off[u]] = v;
         }
     }
     if (tid == 0) {
@@ -343,6 +359,7 @@ __global__ void __launch_bounds__(1024) bn_act_bwd_pair_kernel(const float* __re
                                                               const float* __restrict__ stats, const float* __restrict__ gy,
                                                               int N, int C, int L, int relu,
                                                               float* __restrict__ dz, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    IGCN_PDL_SYNC();
     __shared__ float sm[33];
     __shared__ float res[4];
     const int nh = blockDim.x >> 1, c = blockIdx.x, g = threadIdx.x >= nh, tid = threadIdx.x - g * nh, wph = nh >> 5;
@@ -351,14 +368,15 @@ __global__ void __launch_bounds__(1024) bn_act_bwd_pair_kernel(const float* __re
     const int64_t base = ((int64_t)g * ng * C + c) * L;
     const float mean = stats[((int64_t)g * C + c) * 2 + 0], rstd = stats[((int64_t)g * C + c) * 2 + 1];
     float xh[BN_EPT2], dv[BN_EPT2];
+    int off[BN_EPT2];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int u = 0; u < BN_EPT2; ++u) {
         const int e = tid + u * nh;
-        xh[u] = 0.f; dv[u] = 0.f;
+        xh[u] = 0.f; dv[u] = 0.f; off[u] = 0;
         if (e < cnt) {
-            const int n = e / L, l = e - n * L;
-            const int64_t i = base + (int64_t)n * C * L + l;
+            off[u] = bn_off(e, L, C * L);
+            const int64_t i = base + off[u];
             xh[u] = (z[i] - mean) * rstd;
             float d = gy[i];
             if (mask) d *= mask[i];
@@ -374,10 +392,7 @@ __global__ void __launch_bounds__(1024) bn_act_bwd_pair_kernel(const float* __re
 #pragma unroll
     for (int u = 0; u < BN_EPT2; ++u) {
         const int e = tid + u * nh;
-        if (e < cnt) {
-            const int n = e / L, l = e - n * L;
-            dz[base + (int64_t)n * C * L + l] = ga * rstd * (dv[u] - m1 - xh[u] * m2);
-        }
+        if (e < cnt) dz[base + off[u]] = ga * rstd * (dv[u] - m1 - xh[u] * m2);
     }
     if (tid == 0) {
         res[2 * g] = s2;
@@ -409,6 +424,7 @@ __device__ __forceinline__ float mask_loss_term(const MaskLossArgs& a, int seg, 
 }
 
 __global__ void __launch_bounds__(256) mask_loss_partial_kernel(MaskLossArgs a, float* __restrict__ partials) {
+    IGCN_PDL_SYNC();
     __shared__ float sm[9];
     float s = 0.f;
     const int64_t stride = (int64_t)gridDim.x * 256;
@@ -420,6 +436,7 @@ __global__ void __launch_bounds__(256) mask_loss_partial_kernel(MaskLossArgs a, 
 
 // out[0] = sum of partials[0..n) in index order; one block
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ partials, int n, float scale, float* __restrict__ out) {
+    IGCN_PDL_SYNC();
     __shared__ float sm[9];
     float s = 0.f;
     for (int i = threadIdx.x; i < n; i += 256) s += partials[i];
@@ -430,6 +447,7 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restri
 // d p_raw[i] = g * dloss/dp * (dp/draw)
 __global__ void __launch_bounds__(256) mask_loss_bwd_kernel(MaskLossArgs a, const float* __restrict__ g_out, float* __restrict__ d0,
                                                             float* __restrict__ d1, float* __restrict__ d2) {
+    IGCN_PDL_SYNC();
     const float g = g_out[0];
     float* d[3] = {d0, d1, d2};
     const int64_t stride = (int64_t)gridDim.x * 256;
@@ -450,6 +468,7 @@ __global__ void __launch_bounds__(256) mask_loss_bwd_kernel(MaskLossArgs a, cons
 // ---- dot product with a fixed summation order -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dot_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
                                                           float* __restrict__ partials) {
+    IGCN_PDL_SYNC();
     __shared__ float sm[9];
     float s = 0.f;
     const int64_t stride = (int64_t)gridDim.x * 256 * 4;
@@ -466,6 +485,7 @@ __global__ void __launch_bounds__(256) dot_partial_kernel(const float* __restric
 // out[i] = a[i] * (s[0] * scale)
 __global__ void __launch_bounds__(256) scale_by_scalar_kernel(const float* __restrict__ a, const float* __restrict__ s, float scale,
                                                               int64_t n, float* __restrict__ out) {
+    IGCN_PDL_SYNC();
     const float f = s[0] * scale;
     const int64_t stride = (int64_t)gridDim.x * 256 * 4;
     const int64_t n4 = n & ~(int64_t)3;
@@ -485,14 +505,15 @@ constexpr int SK_MAXK = 32, SK_MAXL = 64, SK_ROWS = 64, SK_ACC = (SK_MAXK * SK_M
 
 __global__ void __launch_bounds__(256) skinny_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, int64_t rows, int Kin,
                                                                 int Lout, float* __restrict__ z) {
+    IGCN_PDL_SYNC();
     __shared__ float Ws[SK_MAXL * SK_MAXK];
     for (int i = threadIdx.x; i < Lout * Kin; i += 256) Ws[i] = W[i];
     __syncthreads();
-    const int64_t total = rows * Lout;
-    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
-        const int64_t r = idx / Lout;
-        const int l = (int)(idx - r * Lout);
-        const float* xr = x + r * Kin;
+    const uint32_t total = (uint32_t)(rows * Lout);              // < 2^31 (checked by the host wrapper)
+    for (uint32_t idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
+        const uint32_t r = idx / (uint32_t)Lout;                 // 32-bit: the 64-bit division was most of this kernel
+        const int l = (int)(idx - r * (uint32_t)Lout);
+        const float* xr = x + (int64_t)r * Kin;
         const float* wr = Ws + l * Kin;
         float v = 0.f;
         // the row's inputs are loaded 8 at a time before the FMAs (a load -> FMA loop over a runtime Kin costs one L2 trip per k)
@@ -512,6 +533,7 @@ __global__ void __launch_bounds__(256) skinny_linear_fwd_kernel(const float* __r
 __global__ void __launch_bounds__(256) skinny_linear_bwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                                 const float* __restrict__ dz, int64_t rows, int Kin, int Lout,
                                                                 float* __restrict__ dx, float* __restrict__ partials) {
+    IGCN_PDL_SYNC();
     __shared__ float Ws[SK_MAXL * SK_MAXK];
     __shared__ float dzs[SK_ROWS * SK_MAXL];
     __shared__ float xs[SK_ROWS * SK_MAXK];
@@ -582,6 +604,7 @@ __global__ void __launch_bounds__(256) bn_eval_act_kernel(const float* __restric
                                                          const float* __restrict__ beta, const float* __restrict__ rm,
                                                          const float* __restrict__ rv, int64_t total, int C, int L, float eps, int relu,
                                                          const float* __restrict__ gy, float* __restrict__ y) {
+    IGCN_PDL_SYNC();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
         const int c = (int)((i / L) % C);
         const float sc = (gamma ? gamma[c] : 1.f) * rsqrtf(rv[c] + eps);
@@ -603,7 +626,7 @@ extern "C" int igcn_bn_eval_act(const float* z, const float* gamma, const float*
     if (N == 0) return IGCN_OK;
     IGCN_REQUIRE(z && running_mean && running_var && y, IGCN_ERR_BAD_ARG, "bn_eval_act: null pointer");
     const int64_t total = N * C * L;
-    bn_eval_act_kernel<<<(unsigned)blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(z, gamma, beta, running_mean, running_var, total,
+    igcn::launch_k(bn_eval_act_kernel, dim3((unsigned)blocks_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, z, gamma, beta, running_mean, running_var, total,
                                                                                           (int)C, (int)L, (float)eps, (int)relu, g_y, y);
     IGCN_CHECK_LAUNCH("bn_eval_act");
     return IGCN_OK;
@@ -619,15 +642,15 @@ extern "C" int igcn_bn_act_fwd(const float* z, const float* gamma, const float* 
     const int64_t cnt = (N / groups) * L;
     const int nthr = cnt >= 4096 ? 1024 : (cnt >= 1024 ? 512 : 256);
     if (groups == 2 && cnt <= (int64_t)BN_EPT2 * (nthr / 2) && nthr >= 128)
-        bn_act_fwd_pair_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, (int)N, (int)C, (int)L, (float)eps,
+        igcn::launch_k(bn_act_fwd_pair_kernel, dim3((unsigned)C), dim3(nthr), 0, (cudaStream_t)stream, z, gamma, beta, mask, (int)N, (int)C, (int)L, (float)eps,
                                                                               (float)momentum, (int)relu, running_mean, running_var,
                                                                               num_batches_tracked, y, stats);
     else if (cnt <= (int64_t)BN_EPT * nthr)
-        bn_act_fwd_reg_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, (int)N, (int)C, (int)L, (int)groups, (float)eps,
+        igcn::launch_k(bn_act_fwd_reg_kernel, dim3((unsigned)C), dim3(nthr), 0, (cudaStream_t)stream, z, gamma, beta, mask, (int)N, (int)C, (int)L, (int)groups, (float)eps,
                                                                              (float)momentum, (int)relu, running_mean, running_var,
                                                                              num_batches_tracked, y, stats);
     else
-        bn_act_fwd_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, (int)N, (int)C, (int)L, (int)groups, (float)eps,
+        igcn::launch_k(bn_act_fwd_kernel, dim3((unsigned)C), dim3(nthr), 0, (cudaStream_t)stream, z, gamma, beta, mask, (int)N, (int)C, (int)L, (int)groups, (float)eps,
                                                                          (float)momentum, (int)relu, running_mean, running_var,
                                                                          num_batches_tracked, y, stats);
     IGCN_CHECK_LAUNCH("bn_act_fwd");
@@ -642,13 +665,13 @@ extern "C" int igcn_bn_act_bwd(const float* z, const float* gamma, const float* 
     const int64_t cnt = (N / groups) * L;
     const int nthr = cnt >= 4096 ? 1024 : (cnt >= 1024 ? 512 : 256);
     if (groups == 2 && cnt <= (int64_t)BN_EPT2 * (nthr / 2) && nthr >= 128)
-        bn_act_bwd_pair_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L,
+        igcn::launch_k(bn_act_bwd_pair_kernel, dim3((unsigned)C), dim3(nthr), 0, (cudaStream_t)stream, z, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L,
                                                                               (int)relu, dz, dgamma, dbeta);
     else if (cnt <= (int64_t)BN_EPT * nthr)
-        bn_act_bwd_reg_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L,
+        igcn::launch_k(bn_act_bwd_reg_kernel, dim3((unsigned)C), dim3(nthr), 0, (cudaStream_t)stream, z, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L,
                                                                              (int)groups, (int)relu, dz, dgamma, dbeta);
     else
-        bn_act_bwd_kernel<<<(unsigned)C, nthr, 0, (cudaStream_t)stream>>>(z, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L, (int)groups,
+        igcn::launch_k(bn_act_bwd_kernel, dim3((unsigned)C), dim3(nthr), 0, (cudaStream_t)stream, z, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L, (int)groups,
                                                                          (int)relu, dz, dgamma, dbeta);
     IGCN_CHECK_LAUNCH("bn_act_bwd");
     return IGCN_OK;
@@ -678,9 +701,9 @@ extern "C" int igcn_mask_loss_fwd(const float* prob, int64_t n_prob, const float
     if (rc) return rc;
     IGCN_REQUIRE(partials && loss && n_partials >= 1, IGCN_ERR_BAD_ARG, "mask_loss_fwd: null workspace");
     cudaStream_t st = (cudaStream_t)stream;
-    mask_loss_partial_kernel<<<(unsigned)n_partials, 256, 0, st>>>(a, partials);
+    igcn::launch_k(mask_loss_partial_kernel, dim3((unsigned)n_partials), dim3(256), 0, st, a, partials);
     IGCN_CHECK_LAUNCH("mask_loss_partial");
-    sum_partials_kernel<<<1, 256, 0, st>>>(partials, (int)n_partials, 1.f, loss);
+    igcn::launch_k(sum_partials_kernel, dim3(1), dim3(256), 0, st, partials, (int)n_partials, 1.f, loss);
     IGCN_CHECK_LAUNCH("sum_partials");
     return IGCN_OK;
 }
@@ -693,7 +716,7 @@ extern "C" int igcn_mask_loss_bwd(const float* prob, int64_t n_prob, const float
     if (rc) return rc;
     IGCN_REQUIRE(g_loss, IGCN_ERR_BAD_ARG, "mask_loss_bwd: null g_loss");
     const int64_t nmax = n_prob > n_e ? (n_prob > n_snps ? n_prob : n_snps) : (n_e > n_snps ? n_e : n_snps);
-    mask_loss_bwd_kernel<<<blocks_for(nmax, 256), 256, 0, (cudaStream_t)stream>>>(a, g_loss, d_prob, d_pe, d_snps_prob);
+    igcn::launch_k(mask_loss_bwd_kernel, dim3(blocks_for(nmax, 256)), dim3(256), 0, (cudaStream_t)stream, a, g_loss, d_prob, d_pe, d_snps_prob);
     IGCN_CHECK_LAUNCH("mask_loss_bwd");
     return IGCN_OK;
 }
@@ -702,9 +725,9 @@ extern "C" int igcn_dot(const float* a, const float* b, int64_t n, double scale,
     IGCN_REQUIRE(a && b && partials && out && n >= 0 && n_partials >= 1, IGCN_ERR_BAD_ARG, "dot: bad argument");
     IGCN_REQUIRE((((uintptr_t)a | (uintptr_t)b) & 15) == 0, IGCN_ERR_BAD_ARG, "dot: operands must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    dot_partial_kernel<<<(unsigned)n_partials, 256, 0, st>>>(a, b, n, partials);
+    igcn::launch_k(dot_partial_kernel, dim3((unsigned)n_partials), dim3(256), 0, st, a, b, n, partials);
     IGCN_CHECK_LAUNCH("dot_partial");
-    sum_partials_kernel<<<1, 256, 0, st>>>(partials, (int)n_partials, (float)scale, out);
+    igcn::launch_k(sum_partials_kernel, dim3(1), dim3(256), 0, st, partials, (int)n_partials, (float)scale, out);
     IGCN_CHECK_LAUNCH("sum_partials");
     return IGCN_OK;
 }
@@ -712,7 +735,7 @@ extern "C" int igcn_dot(const float* a, const float* b, int64_t n, double scale,
 extern "C" int igcn_scale_by_scalar(const float* a, const float* s, double scale, int64_t n, float* out, void* stream) {
     IGCN_REQUIRE(a && s && out && n >= 0, IGCN_ERR_BAD_ARG, "scale_by_scalar: bad argument");
     IGCN_REQUIRE((((uintptr_t)a | (uintptr_t)out) & 15) == 0, IGCN_ERR_BAD_ARG, "scale_by_scalar: operands must be 16-byte aligned");
-    scale_by_scalar_kernel<<<blocks_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(a, s, (float)scale, n, out);
+    igcn::launch_k(scale_by_scalar_kernel, dim3(blocks_for(n, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, a, s, (float)scale, n, out);
     IGCN_CHECK_LAUNCH("scale_by_scalar");
     return IGCN_OK;
 }
@@ -721,6 +744,7 @@ static int skinny_check(const char* who, int64_t rows, int64_t Kin, int64_t Lout
     IGCN_REQUIRE(rows >= 0 && Kin >= 1 && Lout >= 1, IGCN_ERR_BAD_ARG, "%s: bad size", who);
     IGCN_REQUIRE(Kin <= SK_MAXK && Lout <= SK_MAXL, IGCN_ERR_UNSUPPORTED, "%s: in_features <= %d and out_features <= %d only (got %lld, %lld)", who,
                  SK_MAXK, SK_MAXL, (long long)Kin, (long long)Lout);
+    IGCN_REQUIRE(rows * Lout < (int64_t)1 << 31 && rows * Kin < (int64_t)1 << 31, IGCN_ERR_UNSUPPORTED, "%s: more than 2^31 elements", who);
     return IGCN_OK;
 }
 
@@ -736,7 +760,7 @@ extern "C" int igcn_skinny_linear_fwd(const float* x, const float* W, int64_t ro
     if (rc) return rc;
     IGCN_REQUIRE(x && W && z, IGCN_ERR_BAD_ARG, "skinny_linear_fwd: null pointer");
     if (rows == 0) return IGCN_OK;
-    skinny_linear_fwd_kernel<<<blocks_for(rows * Lout, 256 * 4), 256, 0, (cudaStream_t)stream>>>(x, W, rows, (int)Kin, (int)Lout, z);
+    igcn::launch_k(skinny_linear_fwd_kernel, dim3(blocks_for(rows * Lout, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, x, W, rows, (int)Kin, (int)Lout, z);
     IGCN_CHECK_LAUNCH("skinny_linear_fwd");
     return IGCN_OK;
 }
@@ -753,9 +777,9 @@ extern "C" int igcn_skinny_linear_bwd(const float* x, const float* W, const floa
         cudaMemsetAsync(dW, 0, sizeof(float) * LK, st);
         return IGCN_OK;
     }
-    skinny_linear_bwd_kernel<<<(unsigned)n_cta, 256, 0, st>>>(x, W, dz, rows, (int)Kin, (int)Lout, dx, partials);
+    igcn::launch_k(skinny_linear_bwd_kernel, dim3((unsigned)n_cta), dim3(256), 0, st, x, W, dz, rows, (int)Kin, (int)Lout, dx, partials);
     IGCN_CHECK_LAUNCH("skinny_linear_bwd");
-    reduce_partials_kernel<<<(LK + 31) / 32, 256, 0, st>>>(partials, (int)n_cta, LK, dW);
+    igcn::launch_k(reduce_partials_kernel, dim3((LK + 31) / 32), dim3(reduce_threads((int)n_cta)), 0, st, partials, (int)n_cta, LK, dW);
     IGCN_CHECK_LAUNCH("skinny_linear_reduce");
     return IGCN_OK;
 }
@@ -768,6 +792,7 @@ namespace igcn {
 // ---- SNP mask of the stacked passes: rows [0,B) = snps, rows [B,2B) = snps * sigmoid(snps_prob)  (sgcn_img_snp.py:147-148) ----
 __global__ void __launch_bounds__(256) snp_mask_pair_fwd_kernel(const float* __restrict__ snps, const float* __restrict__ p, int B, int S,
                                                                 float* __restrict__ out) {
+    IGCN_PDL_SYNC();
     // grid.y strides the rows, threads walk the columns: no integer division per element
     const int64_t n = (int64_t)B * S;
     for (int s = blockIdx.x * 256 + threadIdx.x; s < S; s += gridDim.x * 256) {
@@ -782,6 +807,7 @@ __global__ void __launch_bounds__(256) snp_mask_pair_fwd_kernel(const float* __r
 // d p[s] = sig'(p[s]) * sum_b g[B + b][s] * snps[b][s]: 32 columns per CTA, 8 warps take every 8th row, warp partials added in order
 __global__ void __launch_bounds__(256) snp_mask_pair_bwd_kernel(const float* __restrict__ snps, const float* __restrict__ p,
                                                                 const float* __restrict__ g, int B, int S, float* __restrict__ dp) {
+    IGCN_PDL_SYNC();
     __shared__ float part[8][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = blockIdx.x * 32 + lane;
@@ -810,6 +836,7 @@ struct HeadArgs {
 
 // warp per row: lane l owns features l and l + 32 (K <= 64), the C <= 8 outputs are warp sums
 __global__ void __launch_bounds__(256) heads_fwd_kernel(HeadArgs a, float* __restrict__ logp, float* __restrict__ reg) {
+    IGCN_PDL_SYNC();
     const int K = a.K, C1 = a.C1, C2 = a.C2, lane = threadIdx.x & 31;
     const int warp_g = blockIdx.x * 8 + (threadIdx.x >> 5), nwarp = gridDim.x * 8;
     float w1[HEAD_MAXC][2], w2[HEAD_MAXC][2];
@@ -858,6 +885,7 @@ __global__ void __launch_bounds__(256) heads_fwd_kernel(HeadArgs a, float* __res
 __global__ void __launch_bounds__(256) heads_bwd_kernel(HeadArgs a, const float* __restrict__ logp, const float* __restrict__ g_logp,
                                                         const float* __restrict__ g_reg, float* __restrict__ dh1, float* __restrict__ dh2,
                                                         float* __restrict__ partials) {
+    IGCN_PDL_SYNC();
     __shared__ float red[8][2 * HEAD_MAXC * 64 + 2 * HEAD_MAXC];
     const int K = a.K, C1 = a.C1, C2 = a.C2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int warp_g = blockIdx.x * 8 + warp, nwarp = gridDim.x * 8;
@@ -938,6 +966,7 @@ __global__ void __launch_bounds__(1024) step_loss_fwd_kernel(const float* __rest
                                                              const float* __restrict__ xhat, const float* __restrict__ snps, int64_t n_rec,
                                                              const float* __restrict__ loss_prob, const float* __restrict__ quad, float c_reg,
                                                              float c_rec, float c_prob, float c_clu, float* __restrict__ out) {
+    IGCN_PDL_SYNC();
     __shared__ float sm[33];
     float s1 = 0.f, s2 = 0.f;
     for (int pass = 0; pass < 2; ++pass) {
@@ -964,6 +993,7 @@ __global__ void __launch_bounds__(256) step_loss_bwd_kernel(const float* __restr
                                                             const float* __restrict__ g, float c_reg, float c_rec, float c_prob, float c_clu,
                                                             float* __restrict__ d_reg, float* __restrict__ d_xhat, float* __restrict__ d_prob,
                                                             float* __restrict__ d_quad) {
+    IGCN_PDL_SYNC();
     const float gv = g[0];
     const int64_t stride = (int64_t)gridDim.x * 256, t0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const float k1 = gv * c_reg * 2.f / (float)(2 * n_reg), k2 = gv * c_rec * 2.f;
@@ -986,14 +1016,14 @@ extern "C" int igcn_snp_mask_pair_fwd(const float* snps, const float* snps_prob,
     unsigned gy = (unsigned)(sm_count() * 2 / gx);
     if (gy < 1) gy = 1;
     if (gy > (unsigned)B) gy = (unsigned)B;
-    snp_mask_pair_fwd_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(snps, snps_prob, (int)B, (int)S, out);
+    igcn::launch_k(snp_mask_pair_fwd_kernel, dim3(dim3(gx, gy)), dim3(256), 0, (cudaStream_t)stream, snps, snps_prob, (int)B, (int)S, out);
     IGCN_CHECK_LAUNCH("snp_mask_pair_fwd");
     return IGCN_OK;
 }
 extern "C" int igcn_snp_mask_pair_bwd(const float* snps, const float* snps_prob, const float* g_out, int64_t B, int64_t S, float* d_snps_prob,
                                       void* stream) {
     IGCN_REQUIRE(snps && snps_prob && g_out && d_snps_prob && B >= 0 && S > 0, IGCN_ERR_BAD_ARG, "snp_mask_pair_bwd: bad argument");
-    snp_mask_pair_bwd_kernel<<<(unsigned)((S + 31) / 32), 256, 0, (cudaStream_t)stream>>>(snps, snps_prob, g_out, (int)B, (int)S, d_snps_prob);
+    igcn::launch_k(snp_mask_pair_bwd_kernel, dim3((unsigned)((S + 31) / 32)), dim3(256), 0, (cudaStream_t)stream, snps, snps_prob, g_out, (int)B, (int)S, d_snps_prob);
     IGCN_CHECK_LAUNCH("snp_mask_pair_bwd");
     return IGCN_OK;
 }
@@ -1021,7 +1051,7 @@ extern "C" int igcn_heads_fwd(const float* h1, const float* m1, const float* h2,
     if (rc) return rc;
     IGCN_REQUIRE(logp && reg, IGCN_ERR_BAD_ARG, "heads_fwd: null output");
     if (rows == 0) return IGCN_OK;
-    heads_fwd_kernel<<<(unsigned)igcn_heads_bwd_ctas(rows), 256, 0, (cudaStream_t)stream>>>(a, logp, reg);
+    igcn::launch_k(heads_fwd_kernel, dim3((unsigned)igcn_heads_bwd_ctas(rows)), dim3(256), 0, (cudaStream_t)stream, a, logp, reg);
     IGCN_CHECK_LAUNCH("heads_fwd");
     return IGCN_OK;
 }
@@ -1040,9 +1070,9 @@ extern "C" int igcn_heads_bwd(const float* h1, const float* m1, const float* h2,
         cudaMemsetAsync(grads, 0, sizeof(float) * P, st);
         return IGCN_OK;
     }
-    heads_bwd_kernel<<<(unsigned)n_cta, 256, 0, st>>>(a, logp, g_logp, g_reg, dh1, dh2, partials);
+    igcn::launch_k(heads_bwd_kernel, dim3((unsigned)n_cta), dim3(256), 0, st, a, logp, g_logp, g_reg, dh1, dh2, partials);
     IGCN_CHECK_LAUNCH("heads_bwd");
-    reduce_partials_kernel<<<(P + 31) / 32, 256, 0, st>>>(partials, (int)n_cta, P, grads);
+    igcn::launch_k(reduce_partials_kernel, dim3((P + 31) / 32), dim3(reduce_threads((int)n_cta)), 0, st, partials, (int)n_cta, P, grads);
     IGCN_CHECK_LAUNCH("heads_reduce");
     return IGCN_OK;
 }
@@ -1051,7 +1081,7 @@ extern "C" int igcn_step_loss_fwd(const float* reg, const float* target, int64_t
                                   const float* loss_prob, const float* quad, double c_reg, double c_rec, double c_prob, double c_clu,
                                   float* out, void* stream) {
     IGCN_REQUIRE(reg && target && xhat && snps && out && n_reg > 0 && n_rec > 0, IGCN_ERR_BAD_ARG, "step_loss_fwd: bad argument");
-    step_loss_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(reg, target, n_reg, xhat, snps, n_rec, loss_prob, quad, (float)c_reg, (float)c_rec,
+    igcn::launch_k(step_loss_fwd_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, reg, target, n_reg, xhat, snps, n_rec, loss_prob, quad, (float)c_reg, (float)c_rec,
                                                               (float)c_prob, (float)c_clu, out);
     IGCN_CHECK_LAUNCH("step_loss_fwd");
     return IGCN_OK;
@@ -1060,7 +1090,7 @@ extern "C" int igcn_step_loss_bwd(const float* reg, const float* target, int64_t
                                   const float* g_loss, double c_reg, double c_rec, double c_prob, double c_clu, float* d_reg, float* d_xhat,
                                   float* d_loss_prob, float* d_quad, void* stream) {
     IGCN_REQUIRE(reg && target && xhat && snps && g_loss && d_reg && d_xhat && n_reg > 0 && n_rec > 0, IGCN_ERR_BAD_ARG, "step_loss_bwd: bad argument");
-    step_loss_bwd_kernel<<<blocks_for(2 * (n_reg > n_rec ? n_reg : n_rec), 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+    igcn::launch_k(step_loss_bwd_kernel, dim3(blocks_for(2 * (n_reg > n_rec ? n_reg : n_rec), 256 * 4)), dim3(256), 0, (cudaStream_t)stream, 
         reg, target, n_reg, xhat, snps, n_rec, g_loss, (float)c_reg, (float)c_rec, (float)c_prob, (float)c_clu, d_reg, d_xhat, d_loss_prob, d_quad);
     IGCN_CHECK_LAUNCH("step_loss_bwd");
     return IGCN_OK;

@@ -38,6 +38,7 @@ template <int C>
 __global__ void __launch_bounds__(256) go_spmm_fwd_kernel(const float* __restrict__ in, const int32_t* __restrict__ rowptr,
                                                           const int32_t* __restrict__ col, const float* __restrict__ vals,
                                                           int B, int Nin, int Nrow, int nnz, float* __restrict__ out) {
+    IGCN_PDL_SYNC();
     extern __shared__ float smf[];
     float* xin = smf;  // Nin
     __shared__ int heavy[kMaxHeavy];
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256) go_spmm_bwd_in_kernel(const float* __rest
                                                              const int32_t* __restrict__ crow, const int32_t* __restrict__ cpos,
                                                              const float* __restrict__ vals, int B, int Nin, int Nrow, int nnz,
                                                              float* __restrict__ d_in) {
+    IGCN_PDL_SYNC();
     extern __shared__ float smf[];
     float* gs = smf;  // Nrow*C
     __shared__ int heavy[kMaxHeavy];
@@ -154,6 +156,7 @@ template <int C>
 __global__ void __launch_bounds__(256) go_spmm_bwd_vals_kernel(const float* __restrict__ g, const float* __restrict__ in,
                                                                const int32_t* __restrict__ row_of, const int32_t* __restrict__ col,
                                                                int B, int Nin, int Nrow, int nnz, float* __restrict__ d_vals) {
+    IGCN_PDL_SYNC();
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (k >= nnz) return;
@@ -180,6 +183,7 @@ __global__ void __launch_bounds__(256) go_spmm_bwd_vals_kernel(const float* __re
 //      the results are bit identical.
 __global__ void __launch_bounds__(256) transpose2_kernel(const float* __restrict__ a, int ra, int ca, float* __restrict__ at,
                                                          const float* __restrict__ b, int rb, int cb, float* __restrict__ bt) {
+    IGCN_PDL_SYNC();
     __shared__ float tile[32][33];
     const float* src = blockIdx.y ? b : a;
     float* dst = blockIdx.y ? bt : at;
@@ -208,6 +212,7 @@ __global__ void __launch_bounds__(256) go_spmm_bwd_vals_t_kernel(const float* __
                                                                  const float* __restrict__ inT /* (Nin, B) */,
                                                                  const int32_t* __restrict__ row_of, const int32_t* __restrict__ col, int B,
                                                                  int nnz, float* __restrict__ d_vals) {
+    IGCN_PDL_SYNC();
     const int lane = threadIdx.x & 31;
     for (int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < nnz; k += gridDim.x * (blockDim.x >> 5)) {
         const int r = row_of[k], s = col[k];
@@ -353,6 +358,7 @@ __device__ __forceinline__ void go_layer_pre(const GoLayerArgs& a, int b, const 
 
 template <int DIN, int DOUT, bool ATTN>
 __global__ void __launch_bounds__(1024) go_layer_fwd_kernel(GoLayerArgs a) {
+    IGCN_PDL_SYNC();
     extern __shared__ float smf[];
     const int Min = a.gr.Min, Mrow = a.gr.Mrow;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -425,6 +431,7 @@ __global__ void __launch_bounds__(1024) go_layer_fwd_kernel(GoLayerArgs a) {
 // parameter-gradient layout of one layer: [dWa (DOUT*DIN) | dWs (DOUT*DIN) | du (2*DOUT) | dv (DOUT) | dgamma (Mrow) | dbeta (Mrow)]
 template <int DIN, int DOUT, bool ATTN>
 __global__ void __launch_bounds__(512) go_layer_bwd_kernel(GoLayerArgs a) {
+    IGCN_PDL_SYNC();
     extern __shared__ float smf[];
     const int Min = a.gr.Min, Mrow = a.gr.Mrow, nnz = a.gr.nnz;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -676,7 +683,7 @@ static int launch_go_fwd(const GoLayerArgs& a, cudaStream_t st) {
         auto ks = gosm::go_small_fwd_kernel<DIN, DOUT, ATTN>;
         int rc = allow_smem(ks, sp.smem, "go_small_fwd");
         if (rc) return rc;
-        ks<<<sp.n_cta, gosm::kThreads, sp.smem, st>>>(a, sp.SUB, sp.Mp);
+        igcn::launch_k(ks, dim3(sp.n_cta), dim3(gosm::kThreads), sp.smem, st, a, sp.SUB, sp.Mp);
         IGCN_CHECK_LAUNCH("go_small_fwd");
         return IGCN_OK;
     }
@@ -685,7 +692,7 @@ static int launch_go_fwd(const GoLayerArgs& a, cudaStream_t st) {
     int rc = allow_smem(k, smem, "go_layer_fwd");
     if (rc) return rc;
     const int nthr = go_threads(a.gr.Min, a.gr.Mrow, 1024);
-    k<<<go_ctas(smem, a.B, nthr), nthr, smem, st>>>(a);
+    igcn::launch_k(k, dim3(go_ctas(smem, a.B, nthr)), dim3(nthr), smem, st, a);
     IGCN_CHECK_LAUNCH("go_layer_fwd");
     return IGCN_OK;
 }
@@ -697,9 +704,9 @@ static int launch_go_bwd(const GoLayerArgs& a, int n_cta, float* grads, cudaStre
         auto ks = gosm::go_small_bwd_kernel<DIN, DOUT, ATTN>;
         int rc = allow_smem(ks, sp.smem, "go_small_bwd");
         if (rc) return rc;
-        ks<<<n_cta, gosm::kThreads, sp.smem, st>>>(a, sp.SUB, sp.Mp);
+        igcn::launch_k(ks, dim3(n_cta), dim3(gosm::kThreads), sp.smem, st, a, sp.SUB, sp.Mp);
         IGCN_CHECK_LAUNCH("go_small_bwd");
-        reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(a.partials, n_cta, a.P, grads);
+        igcn::launch_k(reduce_partials_kernel, dim3((a.P + 31) / 32), dim3(reduce_threads(n_cta)), 0, st, a.partials, n_cta, a.P, grads);
         IGCN_CHECK_LAUNCH("go_reduce_partials");
         return IGCN_OK;
     }
@@ -707,9 +714,9 @@ static int launch_go_bwd(const GoLayerArgs& a, int n_cta, float* grads, cudaStre
     auto k = go_layer_bwd_kernel<DIN, DOUT, ATTN>;
     int rc = allow_smem(k, smem, "go_layer_bwd");
     if (rc) return rc;
-    k<<<n_cta, go_threads(a.gr.Min, a.gr.Mrow), smem, st>>>(a);
+    igcn::launch_k(k, dim3(n_cta), dim3(go_threads(a.gr.Min, a.gr.Mrow)), smem, st, a);
     IGCN_CHECK_LAUNCH("go_layer_bwd");
-    reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(a.partials, n_cta, a.P, grads);
+    igcn::launch_k(reduce_partials_kernel, dim3((a.P + 31) / 32), dim3(reduce_threads(n_cta)), 0, st, a.partials, n_cta, a.P, grads);
     IGCN_CHECK_LAUNCH("go_reduce_partials");
     return IGCN_OK;
 }
@@ -730,10 +737,10 @@ extern "C" int igcn_go_spmm_fwd(const float* in, const int32_t* rowptr, const in
     int rc;
     if (channels == 1) {
         if ((rc = allow_smem(go_spmm_fwd_kernel<1>, smem, "go_spmm_fwd"))) return rc;
-        go_spmm_fwd_kernel<1><<<grid, 256, smem, st>>>(in, rowptr, col, vals, (int)B, (int)n_in, (int)n_row, (int)nnz, out);
+        igcn::launch_k(go_spmm_fwd_kernel<1>, dim3(grid), dim3(256), smem, st, in, rowptr, col, vals, (int)B, (int)n_in, (int)n_row, (int)nnz, out);
     } else {
         if ((rc = allow_smem(go_spmm_fwd_kernel<2>, smem, "go_spmm_fwd"))) return rc;
-        go_spmm_fwd_kernel<2><<<grid, 256, smem, st>>>(in, rowptr, col, vals, (int)B, (int)n_in, (int)n_row, (int)nnz, out);
+        igcn::launch_k(go_spmm_fwd_kernel<2>, dim3(grid), dim3(256), smem, st, in, rowptr, col, vals, (int)B, (int)n_in, (int)n_row, (int)nnz, out);
     }
     IGCN_CHECK_LAUNCH("go_spmm_fwd");
     return IGCN_OK;
@@ -757,27 +764,27 @@ extern "C" int igcn_go_spmm_bwd(const float* g_out, const float* in, const int32
     if (channels == 1) {
         if (d_in) {
             if ((rc = allow_smem(go_spmm_bwd_in_kernel<1>, smem, "go_spmm_bwd"))) return rc;
-            go_spmm_bwd_in_kernel<1><<<grid, 256, smem, st>>>(g_out, colptr, crow, cpos, vals, (int)B, (int)n_in, (int)n_row, (int)nnz, d_in);
+            igcn::launch_k(go_spmm_bwd_in_kernel<1>, dim3(grid), dim3(256), smem, st, g_out, colptr, crow, cpos, vals, (int)B, (int)n_in, (int)n_row, (int)nnz, d_in);
         }
         if (nnz && workspace) {
             float* gT = workspace;
             float* inT = workspace + (size_t)n_row * B;
-            transpose2_kernel<<<dim3(sm_count() * 4, 2), 256, 0, st>>>(g_out, (int)B, (int)n_row, gT, in, (int)B, (int)n_in, inT);
-            go_spmm_bwd_vals_t_kernel<1><<<sm_count() * 8, 256, 0, st>>>(gT, inT, row_of, col, (int)B, (int)nnz, d_vals);
+            igcn::launch_k(transpose2_kernel, dim3(dim3(sm_count() * 4, 2)), dim3(256), 0, st, g_out, (int)B, (int)n_row, gT, in, (int)B, (int)n_in, inT);
+            igcn::launch_k(go_spmm_bwd_vals_t_kernel<1>, dim3(sm_count() * 8), dim3(256), 0, st, gT, inT, row_of, col, (int)B, (int)nnz, d_vals);
         } else if (nnz)
-            go_spmm_bwd_vals_kernel<1><<<(int)((nnz + 7) / 8), 256, 0, st>>>(g_out, in, row_of, col, (int)B, (int)n_in, (int)n_row, (int)nnz, d_vals);
+            igcn::launch_k(go_spmm_bwd_vals_kernel<1>, dim3((int)((nnz + 7) / 8)), dim3(256), 0, st, g_out, in, row_of, col, (int)B, (int)n_in, (int)n_row, (int)nnz, d_vals);
     } else {
         if (d_in) {
             if ((rc = allow_smem(go_spmm_bwd_in_kernel<2>, smem, "go_spmm_bwd"))) return rc;
-            go_spmm_bwd_in_kernel<2><<<grid, 256, smem, st>>>(g_out, colptr, crow, cpos, vals, (int)B, (int)n_in, (int)n_row, (int)nnz, d_in);
+            igcn::launch_k(go_spmm_bwd_in_kernel<2>, dim3(grid), dim3(256), smem, st, g_out, colptr, crow, cpos, vals, (int)B, (int)n_in, (int)n_row, (int)nnz, d_in);
         }
         if (nnz && workspace) {
             float* gT = workspace;
             float* inT = workspace + (size_t)n_row * 2 * B;
-            transpose2_kernel<<<dim3(sm_count() * 4, 2), 256, 0, st>>>(g_out, (int)B, (int)n_row * 2, gT, in, (int)B, (int)n_in, inT);
-            go_spmm_bwd_vals_t_kernel<2><<<sm_count() * 8, 256, 0, st>>>(gT, inT, row_of, col, (int)B, (int)nnz, d_vals);
+            igcn::launch_k(transpose2_kernel, dim3(dim3(sm_count() * 4, 2)), dim3(256), 0, st, g_out, (int)B, (int)n_row * 2, gT, in, (int)B, (int)n_in, inT);
+            igcn::launch_k(go_spmm_bwd_vals_t_kernel<2>, dim3(sm_count() * 8), dim3(256), 0, st, gT, inT, row_of, col, (int)B, (int)nnz, d_vals);
         } else if (nnz)
-            go_spmm_bwd_vals_kernel<2><<<(int)((nnz + 7) / 8), 256, 0, st>>>(g_out, in, row_of, col, (int)B, (int)n_in, (int)n_row, (int)nnz, d_vals);
+            igcn::launch_k(go_spmm_bwd_vals_kernel<2>, dim3((int)((nnz + 7) / 8)), dim3(256), 0, st, g_out, in, row_of, col, (int)B, (int)n_in, (int)n_row, (int)nnz, d_vals);
     }
     IGCN_CHECK_LAUNCH("go_spmm_bwd");
     return IGCN_OK;

@@ -186,6 +186,7 @@ __device__ __forceinline__ void stage_constants(const GoLayerArgs& a, const Lay&
 
 template <int DIN, int DOUT, bool ATTN>
 __global__ void __launch_bounds__(kThreads) go_small_fwd_kernel(GoLayerArgs a, int SUB, int Mp) {
+    IGCN_PDL_SYNC();
     extern __shared__ float smf[];
     const int Min = a.gr.Min, Mrow = a.gr.Mrow, nnz = a.gr.nnz, tid = threadIdx.x;
     const Lay L = layout(DIN, DOUT, Min, Mrow, nnz, a.keep_from, SUB, ATTN, false);
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(kThreads) go_small_fwd_kernel(GoLayerArgs a, i
 // parameter-gradient layout of one layer (go_layers.cu): [dWa | dWs | du | dv | dgamma (Mrow) | dbeta (Mrow)]
 template <int DIN, int DOUT, bool ATTN>
 __global__ void __launch_bounds__(kThreads) go_small_bwd_kernel(GoLayerArgs a, int SUB, int Mp) {
+    IGCN_PDL_SYNC();
     extern __shared__ float smf[];
     const int Min = a.gr.Min, Mrow = a.gr.Mrow, nnz = a.gr.nnz, tid = threadIdx.x;
     constexpr int NW = 2 * DOUT * DIN + 3 * DOUT;

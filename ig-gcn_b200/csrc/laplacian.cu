@@ -18,6 +18,7 @@ namespace lap {
 constexpr int TB = 64;      // similarity tile
 // W[i][j] = exp(-gamma * ||t_i - t_j||^2), 64 x 64 tiles, 256 threads (4 x 4 per thread), k-chunks of 32 staged in shared memory
 __global__ void __launch_bounds__(256) rbf_kernel(const float* __restrict__ t, int B, int R, float gamma, float* __restrict__ W) {
+    IGCN_PDL_SYNC();
     __shared__ float ta[32][TB + 1], tb[32][TB + 1];
     const int i0 = blockIdx.y * TB, j0 = blockIdx.x * TB;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256) rbf_kernel(const float* __restrict__ t, i
 }
 // d[i] = sum_j W[i][j] : warp per row, fixed order
 __global__ void __launch_bounds__(256) rowsum_kernel(const float* __restrict__ W, int B, float* __restrict__ d) {
+    IGCN_PDL_SYNC();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= B) return;
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const float* __restrict__ W
 }
 // m[g][c] = mean over the B rows of group g of s[(g*B + i)][c] : block = 32 columns x 8 row-lanes, fixed order
 __global__ void __launch_bounds__(256) colmean_kernel(const float* __restrict__ s, int B, int D, float* __restrict__ m) {
+    IGCN_PDL_SYNC();
     __shared__ float sm[8][33];
     const int g = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
@@ -96,6 +99,7 @@ __global__ void __launch_bounds__(256) colmean_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) finish_kernel(const float* __restrict__ s, const float* __restrict__ m, const float* __restrict__ d,
                                                      const float* __restrict__ U, int B, int D, int groups, float dconst,
                                                      float* __restrict__ T, float* __restrict__ partials) {
+    IGCN_PDL_SYNC();
     __shared__ float sm[8];
     float acc = 0.f;
     for (int row = blockIdx.x; row < groups * B; row += gridDim.x) {        // a CTA walks whole rows: no per-element divisions
@@ -135,6 +139,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const float* __restrict__ s
     }
 }
 __global__ void __launch_bounds__(256) sum_scale_kernel(const float* __restrict__ partials, int n, float scale, float* __restrict__ out) {
+    IGCN_PDL_SYNC();
     __shared__ double sm[8];
     double acc = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) acc += (double)partials[i];
@@ -160,9 +165,9 @@ extern "C" int igcn_rbf_similarity(const float* t, int64_t B, int64_t R, double 
     IGCN_REQUIRE(t && W && d, IGCN_ERR_BAD_ARG, "rbf_similarity: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int tiles = (int)((B + lap::TB - 1) / lap::TB);
-    lap::rbf_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(t, (int)B, (int)R, (float)gamma, W);
+    igcn::launch_k(lap::rbf_kernel, dim3(dim3(tiles, tiles)), dim3(256), 0, st, t, (int)B, (int)R, (float)gamma, W);
     IGCN_CHECK_LAUNCH("rbf_similarity");
-    lap::rowsum_kernel<<<(int)((B + 7) / 8), 256, 0, st>>>(W, (int)B, d);
+    igcn::launch_k(lap::rowsum_kernel, dim3((int)((B + 7) / 8)), dim3(256), 0, st, W, (int)B, d);
     IGCN_CHECK_LAUNCH("rbf_rowsum");
     return IGCN_OK;
 }
@@ -171,7 +176,7 @@ extern "C" int igcn_rbf_similarity(const float* t, int64_t B, int64_t R, double 
 extern "C" int igcn_col_mean(const float* s, int64_t B, int64_t D, int64_t groups, float* m, void* stream) {
     IGCN_REQUIRE(B > 0 && D > 0 && groups > 0, IGCN_ERR_BAD_ARG, "col_mean: bad size");
     IGCN_REQUIRE(s && m, IGCN_ERR_BAD_ARG, "col_mean: null pointer");
-    lap::colmean_kernel<<<dim3((unsigned)((D + 31) / 32), (unsigned)groups), 256, 0, (cudaStream_t)stream>>>(s, (int)B, (int)D, m);
+    igcn::launch_k(lap::colmean_kernel, dim3(dim3((unsigned)((D + 31) / 32), (unsigned)groups)), dim3(256), 0, (cudaStream_t)stream, s, (int)B, (int)D, m);
     IGCN_CHECK_LAUNCH("col_mean");
     return IGCN_OK;
 }
@@ -182,9 +187,9 @@ extern "C" int igcn_laplacian_finish(const float* s, const float* m, const float
     IGCN_REQUIRE(B > 0 && D > 0 && groups > 0 && n_partials > 0, IGCN_ERR_BAD_ARG, "laplacian_finish: bad size");
     IGCN_REQUIRE(s && m && T && partials && out, IGCN_ERR_BAD_ARG, "laplacian_finish: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    lap::finish_kernel<<<(unsigned)n_partials, 256, 0, st>>>(s, m, d, U, (int)B, (int)D, (int)groups, (float)d_const, T, partials);
+    igcn::launch_k(lap::finish_kernel, dim3((unsigned)n_partials), dim3(256), 0, st, s, m, d, U, (int)B, (int)D, (int)groups, (float)d_const, T, partials);
     IGCN_CHECK_LAUNCH("laplacian_finish");
-    lap::sum_scale_kernel<<<1, 256, 0, st>>>(partials, (int)n_partials, (float)scale, out);
+    igcn::launch_k(lap::sum_scale_kernel, dim3(1), dim3(256), 0, st, partials, (int)n_partials, (float)scale, out);
     IGCN_CHECK_LAUNCH("laplacian_sum");
     return IGCN_OK;
 }

@@ -131,6 +131,7 @@ __device__ __forceinline__ void dense_xw(const float* Hprev, int ldh, int Fin, c
 // forward
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sgcn_encoder_fwd_kernel(EncArgs a) {
+    IGCN_PDL_SYNC();
     extern __shared__ float smf[];
     const int R = a.R, F0 = a.F0, H = a.H, L = a.L, LH = L * H, maxEg = a.maxEg;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(256) sgcn_encoder_fwd_kernel(EncArgs a) {
 // backward
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sgcn_encoder_bwd_kernel(EncArgs a) {
+    IGCN_PDL_SYNC();
     extern __shared__ float smf[];
     const int R = a.R, F0 = a.F0, H = a.H, L = a.L, LH = L * H, maxEg = a.maxEg;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -545,7 +547,7 @@ extern "C" int igcn_sgcn_encoder_fwd(const float* x, const int32_t* rowptr_t, co
             if (per_sm < 1) per_sm = 1;
             int64_t grid = (int64_t)sm_count() * per_sm;
             if (grid > B) grid = B;
-            kern<<<(int)grid, nthr, smem, (cudaStream_t)stream>>>(a);
+            igcn::launch_k(kern, dim3((int)grid), dim3(nthr), smem, (cudaStream_t)stream, a);
             IGCN_CHECK_LAUNCH("sgcn_fwd_mma");
             return IGCN_OK;
         }
@@ -563,7 +565,7 @@ extern "C" int igcn_sgcn_encoder_fwd(const float* x, const int32_t* rowptr_t, co
             if (per_sm < 1) per_sm = 1;
             int64_t grid = (int64_t)sm_count() * per_sm;
             if (grid > B) grid = B;
-            kern<<<(int)grid, nthr, smem, (cudaStream_t)stream>>>(a);
+            igcn::launch_k(kern, dim3((int)grid), dim3(nthr), smem, (cudaStream_t)stream, a);
             IGCN_CHECK_LAUNCH("sgcn_fwd_h16");
             return IGCN_OK;
         }
@@ -571,7 +573,7 @@ extern "C" int igcn_sgcn_encoder_fwd(const float* x, const int32_t* rowptr_t, co
     size_t smem = fwd_smem(a.R, a.F0, a.H, a.L, a.maxEg);
     rc = allow_smem(sgcn_encoder_fwd_kernel, smem, "sgcn_encoder_fwd");
     if (rc) return rc;
-    sgcn_encoder_fwd_kernel<<<ctas_for(smem, B), 256, smem, (cudaStream_t)stream>>>(a);
+    igcn::launch_k(sgcn_encoder_fwd_kernel, dim3(ctas_for(smem, B)), dim3(256), smem, (cudaStream_t)stream, a);
     IGCN_CHECK_LAUNCH("sgcn_encoder_fwd");
     return IGCN_OK;
 }
@@ -610,23 +612,23 @@ extern "C" int igcn_sgcn_encoder_bwd(const float* x, const int32_t* rowptr_t, co
         auto kern = prob ? mma::sgcn_bwd_mma_kernel<true> : mma::sgcn_bwd_mma_kernel<false>;
         rc = allow_smem(kern, smem, "sgcn_bwd_mma");
         if (rc) return rc;
-        kern<<<want, nthr, smem, st>>>(a);
+        igcn::launch_k(kern, dim3(want), dim3(nthr), smem, st, a);
         IGCN_CHECK_LAUNCH("sgcn_bwd_mma");
     } else if (use_fast_bwd(R, F0, H, L, max_eg)) {
         size_t smem = bwd_fast_smem(a.R, a.maxEg);
         auto kern = prob ? sgcn_bwd_h16_kernel<true> : sgcn_bwd_h16_kernel<false>;
         rc = allow_smem(kern, smem, "sgcn_bwd_h16");
         if (rc) return rc;
-        kern<<<want, fast_threads_bwd(a.R), smem, st>>>(a);
+        igcn::launch_k(kern, dim3(want), dim3(fast_threads_bwd(a.R)), smem, st, a);
         IGCN_CHECK_LAUNCH("sgcn_bwd_h16");
     } else {
         size_t smem = bwd_smem(a.R, a.F0, a.H, a.L, a.maxEg, a.P);
         rc = allow_smem(sgcn_encoder_bwd_kernel, smem, "sgcn_encoder_bwd");
         if (rc) return rc;
-        sgcn_encoder_bwd_kernel<<<want, 256, smem, st>>>(a);
+        igcn::launch_k(sgcn_encoder_bwd_kernel, dim3(want), dim3(256), smem, st, a);
         IGCN_CHECK_LAUNCH("sgcn_encoder_bwd");
     }
-    reduce_partials_kernel<<<(a.P + 31) / 32, 256, 0, st>>>(partials, want, a.P, grads);
+    igcn::launch_k(reduce_partials_kernel, dim3((a.P + 31) / 32), dim3(reduce_threads(want)), 0, st, partials, want, a.P, grads);
     IGCN_CHECK_LAUNCH("sgcn_reduce_partials");
     return IGCN_OK;
 }

@@ -164,6 +164,7 @@ constexpr int kHP = 20;   // padded row stride (floats) of the staged hidden act
 // kHoist: L == 2, both layers' weights stay in registers across all graphs of the CTA.
 template <bool kHoist>
 __global__ void __launch_bounds__(256, 2) sgcn_fwd_h16_kernel(EncArgs a) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) float smf[];
     const int R = a.R, L = a.L, LH = L * kH, maxEg = a.maxEg;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -356,6 +357,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 
 template <bool kExplain>
 __global__ void __launch_bounds__(384, 1) sgcn_bwd_h16_kernel(EncArgs a) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) float smf[];
     const int R = a.R, maxEg = a.maxEg;
     constexpr int LH = 2 * kH;

@@ -138,6 +138,7 @@ __host__ __device__ inline int win_words(int n) { return ((n + 3) & ~3) + 8; }  
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool kExplain, int kMinBlocks>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) sgcn_fwd_mma_kernel(EncArgs a) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) uint32_t smw[];
     const int R = a.R, maxEg = a.maxEg;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -426,6 +427,7 @@ struct StageBwd {
 
 template <bool kExplain>
 __global__ void __launch_bounds__(kBwdMaxThreads, 1) sgcn_bwd_mma_kernel(EncArgs a) {
+    IGCN_PDL_SYNC();
     extern __shared__ __align__(16) uint32_t smw[];
     const int R = a.R, maxEg = a.maxEg;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;

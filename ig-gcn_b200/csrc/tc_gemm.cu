@@ -6,7 +6,7 @@
 // config-4 step -- the "genuine dense contraction" the north star asks to see before using tensor cores.
 //
 // Precision: one TF32 product (10-bit mantissa) cannot hold the 1e-4 parity bar through the cancellation in the Laplacian
-// form, so every operand is split as x = hi + lo (hi = rn_tf32(x), lo = rn_tf32(x - hi)) and C = Ah*Bh + Ah*Bl + Al*Bh is
+// form, so every operand is split as x = hi + lo (hi = the top 19 bits of x, lo = x - hi: exact) and C = Ah*Bh + Ah*Bl + Al*Bh is
 // accumulated in fp32 in TMEM ("3xTF32"); the dropped Al*Bl term is 2^-22 relative.  Measured against fp64: ~3e-7.
 //
 // Shape of the kernel (one CTA per 128 x BN output tile and K split; 192 threads):
@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ CUtensorMap tm_al,
                const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bl, int M, int N, int kblocks,
                int kb_per_split, const float* __restrict__ bias, int relu, SegDst dst, float* __restrict__ partials) {
+    IGCN_PDL_SYNC();
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // SWIZZLE_128B tiles need 1024-byte alignment
@@ -241,6 +242,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant_
 // out segment[m][n] = act(sum_s partials[s][m][n] + bias[n]) in split order (deterministic)
 __global__ void __launch_bounds__(256) tc_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ bias, int M, int N,
                                                         int S, int relu, SegDst dst) {
+    IGCN_PDL_SYNC();
     const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (idx >= (int64_t)M * N) return;
     const int m = (int)(idx / N);
@@ -275,16 +277,17 @@ struct SplitJobs {
     SplitJob j[MAX_JOBS];
 };
 
+// x = hi + lo exactly: hi keeps the 19 bits kind::tf32 reads (1 + 8 + 10), lo = x - hi is exact in fp32 and the tensor core reads
+// its top 10 mantissa bits, so what is dropped is < 2^-21 |x| (cvt.rna.tf32 is emulated on sm_100a by a 4-instruction sequence per
+// conversion; this is a LOP3 and an FADD -- the split of mma_util.cuh)
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    uint32_t h, l;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
-    lo = __uint_as_float(l);
+    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    lo = x - hi;
 }
 
 // grid: (tiles of 32 x 32 over the largest job, njobs); block 32 x 8
 __global__ void __launch_bounds__(256) tc_split_kernel(SplitJobs jobs) {
+    IGCN_PDL_SYNC();
     __shared__ float tile[32][33];
     const SplitJob& J = jobs.j[blockIdx.y];
     const int tiles_c = (J.cols + 31) / 32, tiles_r = (J.rows + 31) / 32;
@@ -379,11 +382,11 @@ static int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const 
     const int kblocks = (int)((K + BK - 1) / BK);
     const int kb_per = (int)((kblocks + S - 1) / S);
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)S);
-    tc_gemm_kernel<BN><<<grid, THREADS, C::SMEM_BYTES, st>>>(ta, tal, tb, tbl, (int)M, (int)N, kblocks, kb_per, S > 1 ? nullptr : bias,
+    igcn::launch_k(tc_gemm_kernel<BN>, dim3(grid), dim3(THREADS), C::SMEM_BYTES, st, ta, tal, tb, tbl, (int)M, (int)N, kblocks, kb_per, S > 1 ? nullptr : bias,
                                                             S > 1 ? 0 : relu, dst, S > 1 ? partials : nullptr);
     IGCN_CHECK_LAUNCH("tc_gemm");
     if (S > 1) {
-        tc_reduce_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(partials, bias, (int)M, (int)N, (int)S, relu, dst);
+        igcn::launch_k(tc_reduce_kernel, dim3((unsigned)((M * N + 255) / 256)), dim3(256), 0, st, partials, bias, (int)M, (int)N, (int)S, relu, dst);
         IGCN_CHECK_LAUNCH("tc_reduce");
     }
     return IGCN_OK;
@@ -457,7 +460,7 @@ extern "C" int igcn_tc_split(const int64_t* host_jobs, int64_t njobs, void* stre
     }
     const int64_t cap = (int64_t)sm_count() * 16;
     dim3 grid((unsigned)(max_tiles < cap ? max_tiles : cap), (unsigned)njobs);
-    tc::tc_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(jobs);
+    igcn::launch_k(tc::tc_split_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, jobs);
     IGCN_CHECK_LAUNCH("tc_split");
     return IGCN_OK;
 }

@@ -13,7 +13,10 @@ import json
 import re
 
 # kernel function -> C-ABI operation (the tag prefix bench.py uses)
-OPS = [("sgcn_fwd_h16", "sgcn_encoder_fwd"), ("sgcn_encoder_fwd", "sgcn_encoder_fwd"), ("sgcn_bwd_h16", "sgcn_encoder_bwd"),
+OPS = [("sgcn_fwd_mma", "sgcn_encoder_fwd"), ("sgcn_bwd_mma", "sgcn_encoder_bwd"), ("attn_mma_fwd", "cross_attn_fwd"),
+       ("attn_bwd2", "cross_attn_bwd"), ("attn_tables", "cross_attn_tables"), ("attn_chain", "cross_attn_chain"),
+       ("go_small_fwd", "go_layer_fwd"), ("go_small_bwd", "go_layer_bwd"),
+       ("sgcn_fwd_h16", "sgcn_encoder_fwd"), ("sgcn_encoder_fwd", "sgcn_encoder_fwd"), ("sgcn_bwd_h16", "sgcn_encoder_bwd"),
        ("sgcn_encoder_bwd", "sgcn_encoder_bwd"), ("attn_rows_fwd", "cross_attn_fwd"), ("cross_attn_fwd", "cross_attn_fwd"),
        ("attn_rows_bwd", "cross_attn_bwd"), ("cross_attn_bwd", "cross_attn_bwd"), ("go_layer_fwd", "go_layer_fwd"),
        ("go_layer_bwd", "go_layer_bwd"), ("go_spmm_fwd", "go_spmm_fwd"), ("go_spmm_bwd", "go_spmm_bwd"), ("tc_gemm_kernel", "tc_gemm"),
