@@ -804,23 +804,37 @@ __global__ void __launch_bounds__(256) snp_mask_pair_fwd_kernel(const float* __r
         }
     }
 }
-// d p[s] = sig'(p[s]) * sum_b g[B + b][s] * snps[b][s]: 32 columns per CTA, 8 warps take every 8th row, warp partials added in order
-__global__ void __launch_bounds__(256) snp_mask_pair_bwd_kernel(const float* __restrict__ snps, const float* __restrict__ p,
-                                                                const float* __restrict__ g, int B, int S, float* __restrict__ dp) {
+// d p[s] = sig'(p[s]) * sum_b g[B + b][s] * snps[b][s]: 32 columns per CTA, 32 warps take every 32nd row, warp partials added in order
+__global__ void __launch_bounds__(1024) snp_mask_pair_bwd_kernel(const float* __restrict__ snps, const float* __restrict__ p,
+                                                                 const float* __restrict__ g, int B, int S, float* __restrict__ dp) {
     IGCN_PDL_SYNC();
-    __shared__ float part[8][33];
+    __shared__ float part[32][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = blockIdx.x * 32 + lane;
     const float* g2 = g + (int64_t)B * S;
     float acc = 0.f;
-    if (s < S)
-        for (int b = warp; b < B; b += 8) acc = fmaf(g2[(int64_t)b * S + s], snps[(int64_t)b * S + s], acc);
+    if (s < S) {
+        // 32 warps take every 32nd row, four rows (eight loads) in flight per thread: with 8 warps and a load -> FMA loop this
+        // kernel was 32 dependent L2 trips long (8 us for 54 columns x 256 rows)
+        int b = warp;
+        for (; b + 96 < B; b += 128) {
+            float gv[4], xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                gv[u] = g2[(int64_t)(b + 32 * u) * S + s];
+                xv[u] = snps[(int64_t)(b + 32 * u) * S + s];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc = fmaf(gv[u], xv[u], acc);
+        }
+        for (; b < B; b += 32) acc = fmaf(g2[(int64_t)b * S + s], snps[(int64_t)b * S + s], acc);
+    }
     part[warp][lane] = acc;
     __syncthreads();
     if (warp == 0 && s < S) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += part[w][lane];
+        for (int w = 0; w < 32; ++w) t += part[w][lane];
         const float sg = sigmoidf_(p[s]);
         dp[s] = t * sg * (1.f - sg);
     }
@@ -1023,7 +1037,7 @@ extern "C" int igcn_snp_mask_pair_fwd(const float* snps, const float* snps_prob,
 extern "C" int igcn_snp_mask_pair_bwd(const float* snps, const float* snps_prob, const float* g_out, int64_t B, int64_t S, float* d_snps_prob,
                                       void* stream) {
     IGCN_REQUIRE(snps && snps_prob && g_out && d_snps_prob && B >= 0 && S > 0, IGCN_ERR_BAD_ARG, "snp_mask_pair_bwd: bad argument");
-    igcn::launch_k(snp_mask_pair_bwd_kernel, dim3((unsigned)((S + 31) / 32)), dim3(256), 0, (cudaStream_t)stream, snps, snps_prob, g_out, (int)B, (int)S, d_snps_prob);
+    igcn::launch_k(snp_mask_pair_bwd_kernel, dim3((unsigned)((S + 31) / 32)), dim3(1024), 0, (cudaStream_t)stream, snps, snps_prob, g_out, (int)B, (int)S, d_snps_prob);
     IGCN_CHECK_LAUNCH("snp_mask_pair_bwd");
     return IGCN_OK;
 }
