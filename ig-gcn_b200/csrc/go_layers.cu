@@ -59,7 +59,24 @@ __global__ void __launch_bounds__(256) go_spmm_fwd_kernel(const float* __restric
             float acc[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) acc[c] = 0.f;
-            for (int k = k0; k < k1; ++k) {
+            int k = k0;
+            for (; k + 3 < k1; k += 4) {        // four entries per trip: indices and values are loaded before the first use
+                int cj[4];
+                float vv[4][C];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    cj[u] = col[k + u];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) vv[u][c] = vals[(int64_t)c * nnz + k + u];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float xv = xin[cj[u]];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[c] = fmaf(vv[u][c], xv, acc[c]);
+                }
+            }
+            for (; k < k1; ++k) {
                 const float xv = xin[col[k]];
 #pragma unroll
                 for (int c = 0; c < C; ++c) acc[c] = fmaf(vals[(int64_t)c * nnz + k], xv, acc[c]);
@@ -74,6 +91,7 @@ __global__ void __launch_bounds__(256) go_spmm_fwd_kernel(const float* __restric
             float acc[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll 4
             for (int k = rowptr[r] + tid; k < rowptr[r + 1]; k += nt) {
                 const float xv = xin[col[k]];
 #pragma unroll
@@ -120,7 +138,25 @@ __global__ void __launch_bounds__(256) go_spmm_bwd_in_kernel(const float* __rest
                 if (slot < kMaxHeavy) continue;
             }
             float acc = 0.f;
-            for (int q = q0; q < q1; ++q) {
+            int q = q0;
+            for (; q + 3 < q1; q += 4) {        // four entries per trip (was two dependent trips per entry: cpos -> vals)
+                int rr[4], kk[4];
+                float vv[4][C];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    rr[u] = crow[q + u];
+                    kk[u] = cpos[q + u];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) vv[u][c] = vals[(int64_t)c * nnz + kk[u]];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc = fmaf(vv[u][c], gs[rr[u] * C + c], acc);
+            }
+            for (; q < q1; ++q) {
                 const int r = crow[q], k = cpos[q];
 #pragma unroll
                 for (int c = 0; c < C; ++c) acc = fmaf(vals[(int64_t)c * nnz + k], gs[r * C + c], acc);
@@ -132,6 +168,7 @@ __global__ void __launch_bounds__(256) go_spmm_bwd_in_kernel(const float* __rest
         for (int hidx = 0; hidx < nh; ++hidx) {
             const int s = heavy[hidx];
             float acc = 0.f;
+#pragma unroll 4
             for (int q = colptr[s] + tid; q < colptr[s + 1]; q += nt) {
                 const int r = crow[q], k = cpos[q];
 #pragma unroll
@@ -221,6 +258,7 @@ __global__ void __launch_bounds__(256) go_spmm_bwd_vals_t_kernel(const float* __
         float acc[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll 4
         for (int b = lane; b < B; b += 32) {
             const float xv = xi[b];
 #pragma unroll
@@ -310,8 +348,7 @@ __device__ __forceinline__ void go_layer_pre(const GoLayerArgs& a, int b, const 
 #pragma unroll
             for (int f = 0; f < DOUT; ++f) qi = fmaf(u_s[f], Xin[i * DOUT + f], qi);
             float S = 0.f;
-            for (int k = k0; k < k1; ++k) {
-                const int j = a.gr.col[k];
+            auto edge = [&](int k, int j) {
                 float q = qi;
 #pragma unroll
                 for (int f = 0; f < DOUT; ++f) q = fmaf(u_s[DOUT + f], Xin[j * DOUT + f], q);
@@ -324,7 +361,15 @@ __device__ __forceinline__ void go_layer_pre(const GoLayerArgs& a, int b, const 
                 }
 #pragma unroll
                 for (int f = 0; f < DOUT; ++f) acc[f] = fmaf(ae, Xin[j * DOUT + f], acc[f]);
-            }
+            };
+            // a GO term has <= 3 parents: the first four column indices of the row are loaded together (one trip to L2, not one per edge)
+            int cj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cj[u] = (k0 + u < k1) ? a.gr.col[k0 + u] : 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k0 + u < k1) edge(k0 + u, cj[u]);
+            for (int k = k0 + 4; k < k1; ++k) edge(k, a.gr.col[k]);
             const float inv = (k1 > k0) ? 1.f / S : 0.f;
 #pragma unroll
             for (int f = 0; f < DOUT; ++f) acc[f] *= inv;
@@ -338,7 +383,16 @@ __device__ __forceinline__ void go_layer_pre(const GoLayerArgs& a, int b, const 
 #pragma unroll
             for (int f = 0; f < DOUT; ++f) acc[f] = fmaf(Xs[i * DOUT + f], gate, acc[f]);
         } else {
-            for (int k = k0; k < k1; ++k) {
+            int cj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cj[u] = (k0 + u < k1) ? a.gr.col[k0 + u] : 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k0 + u < k1) {
+#pragma unroll
+                    for (int f = 0; f < DOUT; ++f) acc[f] += Xin[cj[u] * DOUT + f];
+                }
+            for (int k = k0 + 4; k < k1; ++k) {
                 const int j = a.gr.col[k];
 #pragma unroll
                 for (int f = 0; f < DOUT; ++f) acc[f] += Xin[j * DOUT + f];

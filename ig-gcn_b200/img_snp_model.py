@@ -401,12 +401,26 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         # out_lin is a RETURNED tensor only (eval_scores collects it, train() never reads it): the stacked fast path of
         # train.step_loss does not materialise the concatenation
         out_lin = None if stacked else torch.cat(parts, -1).detach()
-        linear_outf = ops.cat_linear(parts, self.lin1.weight, self.lin1.bias, relu=True)
         rparts = parts
         if self.isuseProb4Regr:
             img_feat = (x.view(B, self.rois, -1) * self.prob).reshape(B, -1)
             rparts = parts + [img_feat]                      # B rows: cat_linear reads it for both stacked passes
-        r = ops.cat_linear(rparts, self.lin1_regr.weight, self.lin1_regr.bias, relu=True)
+        # lin1 reads a column prefix of what lin1_regr reads: one operand-split launch serves both products, and the two products
+        # (GEMM + split-K reduce each) run side by side on two streams
+        ops.presplit_heads(rparts, [self.lin1.weight, self.lin1_regr.weight])
+        aux = ops._aux_stream(x.device) if (_TWO_STREAMS and ops._AUX_STREAM) else None
+        if aux is not None:
+            aux.wait_stream(main)
+            with torch.cuda.stream(aux):
+                r = ops.cat_linear(rparts, self.lin1_regr.weight, self.lin1_regr.bias, relu=True)
+            for t in rparts + ([ops._PRESPLIT["A"]] + list(ops._PRESPLIT["weights"].values()) if ops._PRESPLIT else []):
+                t.record_stream(aux)
+        linear_outf = ops.cat_linear(parts, self.lin1.weight, self.lin1.bias, relu=True)
+        if aux is not None:
+            main.wait_stream(aux)
+            r.record_stream(main)
+        else:
+            r = ops.cat_linear(rparts, self.lin1_regr.weight, self.lin1_regr.bias, relu=True)
         # dropout, lin2 + log_softmax and lin2_regr of both heads in one launch (glue.cu)
         logp, our_reg = ops.output_heads(linear_outf, self._mask_of("lin1", linear_outf, 0.5), r, self._mask_of("lin1_regr", r, 0.3),
                                          self.lin2, self.lin2_regr)

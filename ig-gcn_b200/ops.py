@@ -190,11 +190,11 @@ _AUX_STREAM = os.environ.get("IGCN_NO_AUX_STREAM", "") == ""
 _aux_streams = {}
 
 
-def _aux_stream(dev):
-    st = _aux_streams.get(str(dev))
+def _aux_stream(dev, which=0):
+    st = _aux_streams.get((str(dev), which))
     if st is None:
         st = torch.cuda.Stream(device=dev)
-        _aux_streams[str(dev)] = st
+        _aux_streams[(str(dev), which)] = st
     return st
 
 
@@ -243,6 +243,68 @@ def tc_matmul_nt(a, b, bias=None, relu=False):
     return out
 
 
+# ---- operands shared by several heads: ONE split launch ------------------------------------------------------------------------------
+_PRESPLIT = {}
+
+
+def _src_key(t):
+    return None if t is None else (t.data_ptr(), tuple(t.shape), t.stride(0))
+
+
+def presplit_heads(xs, weights):
+    """The fusion heads lin1 / lin1_regr read the same concatenation (lin1 a column prefix of it): their tcgen05 operands are prepared
+    by ONE igcn_tc_split launch here -- the (hi, lo) image of [x0 | x1 | x2] and of every weight -- and the cat_linear calls that follow
+    in the same forward pick them up (one shot: every entry is consumed by the call that uses it, so nothing stale survives a
+    parameter update).  No-op when the tensor-core path is off or a weight does not fit."""
+    _PRESPLIT.clear()
+    xs = list(xs) + [None] * (3 - len(xs))
+    if not USE_TC or any(t is not None and not t.is_cuda for t in xs):
+        return
+    M = max(t.shape[0] for t in xs if t is not None)
+    reps = [1 if t is None else M // t.shape[0] for t in xs]
+    if any(t is not None and t.shape[0] * r != M for t, r in zip(xs, reps)) or M == 0:
+        return
+    cs = [None if t is None else (t.detach().float() if t.stride(-1) == 1 else t.detach().contiguous().float()) for t in xs]
+    widths = [0 if t is None else t.shape[1] for t in cs]
+    K = sum(widths)
+    dev = next(t for t in cs if t is not None).device
+    A = torch.empty((2, M, _pad4(K)), dtype=torch.float32, device=dev)
+    jobs, off = [], 0
+    for t, w, rp in zip(cs, widths, reps):
+        if t is not None and w:
+            for k in range(rp):
+                jobs.append(_job(t, A, M // rp, w, t.stride(0), row_off=k * (M // rp), col_off=off))
+        off += w
+    wsplit = {}
+    for W in weights:
+        Wc = W.detach().contiguous().float()
+        if Wc.shape[1] > K:
+            _PRESPLIT.clear()
+            return
+        Bw = torch.empty((2, Wc.shape[0], _pad4(Wc.shape[1])), dtype=torch.float32, device=dev)
+        jobs.append(_job(Wc, Bw, Wc.shape[0], Wc.shape[1], Wc.shape[1]))
+        wsplit[Wc.data_ptr()] = Bw
+    if len(jobs) > 8:
+        return
+    _tc_split(jobs, dev)
+    _PRESPLIT.update(A=A, M=M, srcs=[_src_key(t) for t in cs], reps=reps, widths=widths, weights=wsplit)
+
+
+def _presplit_take(cs, widths, reps, Wc, M):
+    """(A, Bw) prepared by presplit_heads for exactly these sources (a prefix of the prepared concatenation) and this weight."""
+    c = _PRESPLIT
+    if not c or c["M"] != M or Wc.data_ptr() not in c["weights"]:
+        return None
+    n = max(i + 1 for i, t in enumerate(cs) if t is not None)
+    for i in range(3):
+        if i < n:
+            if _src_key(cs[i]) != c["srcs"][i] or reps[i] != c["reps"][i] or widths[i] != c["widths"][i]:
+                return None
+        elif cs[i] is not None:
+            return None
+    return c["A"], c["weights"].pop(Wc.data_ptr())
+
+
 class _CatLinearFn(torch.autograd.Function):
     """act([x0 | x1 | x2] W^T + b) via igcn_cat_linear_* (sources may be None)."""
 
@@ -287,16 +349,20 @@ class _CatLinearFn(torch.autograd.Function):
         ctx.tc = USE_TC and M > 0
         if ctx.tc:
             # tensor cores: one split launch folds the concatenation, then one 3xTF32 product with bias + ReLU in its epilogue
-            A = torch.empty((2, M, _pad4(K)), dtype=torch.float32, device=W.device)
-            Bw = torch.empty((2, N, _pad4(K)), dtype=torch.float32, device=W.device)
-            jobs, off = [], 0
-            for t, w, ld, rp in zip(cs, widths, strides, reps):
-                if t is not None and w:
-                    for k in range(rp):
-                        jobs.append(_job(t, A, M // rp, w, ld, row_off=k * (M // rp), col_off=off))
-                off += w
-            jobs.append(_job(Wc, Bw, N, K, K))
-            _tc_split(jobs, W.device)
+            pre = _presplit_take(cs, widths, reps, Wc, M)
+            if pre is not None:                  # operands already prepared by presplit_heads (shared with the other head)
+                A, Bw = pre
+            else:
+                A = torch.empty((2, M, _pad4(K)), dtype=torch.float32, device=W.device)
+                Bw = torch.empty((2, N, _pad4(K)), dtype=torch.float32, device=W.device)
+                jobs, off = [], 0
+                for t, w, ld, rp in zip(cs, widths, strides, reps):
+                    if t is not None and w:
+                        for k in range(rp):
+                            jobs.append(_job(t, A, M // rp, w, ld, row_off=k * (M // rp), col_off=off))
+                    off += w
+                jobs.append(_job(Wc, Bw, N, K, K))
+                _tc_split(jobs, W.device)
             out = torch.empty((M, N), dtype=torch.float32, device=W.device)
             _tc_gemm(A, Bw, M, N, K, [out], [N], [N], bc, relu, tag="cat_linear_fwd_tc")
             ctx.relu, ctx.widths, ctx.strides = bool(relu), widths, strides
@@ -380,33 +446,41 @@ class _CatLinearFn(torch.autograd.Function):
             gzt = torch.empty((2, N, _pad4(M)), dtype=torch.float32, device=dev)         # gZ^T        (N, M): A of dW
             wt = torch.empty((2, K, _pad4(N)), dtype=torch.float32, device=dev)          # W^T         (K, N): B of dX
             xt = torch.empty((2, K + 1, _pad4(M)), dtype=torch.float32, device=dev)      # [X | 1]^T (K+1, M): B of dW (ones row -> d bias)
-            jobs = [_job(g_out, gz, M, N, N, mask=mask), _job(g_out, gzt, M, N, N, transpose=True, mask=mask),
-                    _job(W, wt, N, K, K, transpose=True)]
+            # operands of the input gradient (small: gZ and W^T) and of the weight gradient (large: gZ^T and the transposed sources)
+            jobs_x = [_job(g_out, gz, M, N, N, mask=mask), _job(W, wt, N, K, K, transpose=True)]
+            jobs_w = [_job(g_out, gzt, M, N, N, transpose=True, mask=mask)]
             off = 0
             for t, w, ld, rp in zip(cs, ctx.widths, ctx.strides, ctx.reps):
                 if t is not None and w:
                     for k in range(rp):
-                        jobs.append(_job(t, xt, M // rp, w, ld, row_off=off, col_off=k * (M // rp), transpose=True))
+                        jobs_w.append(_job(t, xt, M // rp, w, ld, row_off=off, col_off=k * (M // rp), transpose=True))
                 off += w
-            jobs.append(_job(None, xt, M, 1, 1, row_off=K, transpose=True))
-            for i in range(0, len(jobs), 8):                 # igcn_tc_split takes up to 8 jobs per launch
-                _tc_split(jobs[i:i + 8], dev)
-            # the two products are independent: the weight gradient runs on an auxiliary stream, so the input gradient -- which the
-            # rest of the backward waits for -- is not queued behind it
+            jobs_w.append(_job(None, xt, M, 1, 1, row_off=K, transpose=True))
+
+            def weight_grad():
+                for i in range(0, len(jobs_w), 8):           # igcn_tc_split takes up to 8 jobs per launch
+                    _tc_split(jobs_w[i:i + 8], dev)
+                _tc_gemm(gzt, xt, N, K + 1, M, [dW, db], [K, 1], [K, 1], tag="cat_linear_bwd_w_tc")
+
+            # the two products are independent: the weight gradient -- with its (much larger) operand preparation -- runs on an
+            # auxiliary stream, so the input gradient the rest of the backward waits for is queued behind two small split jobs only
             cur = torch.cuda.current_stream(dev)
             aux = _aux_stream(dev) if _AUX_STREAM else None
+            if aux is not None and aux == cur:       # this head's forward already ran on the auxiliary stream (forward_pair)
+                aux = _aux_stream(dev, 1)
             if aux is not None:
                 aux.wait_stream(cur)
                 with torch.cuda.stream(aux):
-                    _tc_gemm(gzt, xt, N, K + 1, M, [dW, db], [K, 1], [K, 1], tag="cat_linear_bwd_w_tc")
-                for t in (gzt, xt, dW, db):
+                    weight_grad()
+                for t in [g_out, gzt, xt, dW, db] + ([mask] if mask is not None else []) + [t for t in cs if t is not None]:
                     t.record_stream(aux)
             if any(d is not None for d in dxs):
+                _tc_split(jobs_x, dev)
                 _tc_gemm(gz, wt, M, K, N, dxs, ctx.widths, [0 if d is None else d.stride(0) for d in dxs], tag="cat_linear_bwd_x_tc")
             if aux is not None:
                 cur.wait_stream(aux)
             else:
-                _tc_gemm(gzt, xt, N, K + 1, M, [dW, db], [K, 1], [K, 1], tag="cat_linear_bwd_w_tc")
+                weight_grad()
             for i, rp in enumerate(ctx.reps):                # a repeated source collects the gradient of every repetition
                 if rp > 1 and dxs[i] is not None:
                     h = M // rp
