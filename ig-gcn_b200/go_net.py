@@ -212,6 +212,9 @@ class Gene_ontology_network(nn.Module):
         self.dropout_masks = None     # test hook: dict name -> multiplicative scale tensor (oracle.GO_MASK_NAMES)
         self.mask_bank = MaskBank()   # all masks of a pass from one kernel launch (shared with the enclosing model)
         self.atten_ready = None       # optional torch.cuda.Event recorded as soon as atten_out is enqueued
+        self.branch_stream = None     # optional torch.cuda.Stream for the decoder branch (runs beside the latent read-outs)
+        self.latent_stream = None     # optional torch.cuda.Stream for the latent read-outs (run beside the attention tokens' read-out)
+        self.decoder_joined = True    # False after a forward that left x_D on branch_stream: the caller joins that stream
 
     # graph index tensors follow the module's device lazily (they are not parameters / state_dict entries)
     def _g(self, name, dev):
@@ -265,20 +268,48 @@ class Gene_ontology_network(nn.Module):
             mask = self._mask("go_enc%d" % j, (x.shape[0], g["n_rows"]), 0.4, dev)
             x = _GoLayerFn.apply(x, self.w_inc[j].weight, self.w_s_loop[j].weight, self.w_att_in[j].weight, self.w_att_s[j].weight,
                                  self.G_B[j].weight, self.G_B[j].bias, mask, g, True, 0, pool[j])
+        ls = self.latent_stream if (self.branch_stream is not None and x.is_cuda) else None
+        if ls is not None:                        # the fusion heads wait for `latent`: its six kernels start right here, on their own stream
+            ls.wait_stream(torch.cuda.current_stream(dev))
         atten_out = self._bn_act(self.conc_for_attention[1], self._lin(self.conc_for_attention[0], x))
         if self.atten_ready is not None:          # lets a caller on another stream start the cross attention before the decoder is done
             self.atten_ready.record(torch.cuda.current_stream(dev))
-        inp = self._lin(self.conc, x).squeeze(-1)
-        inp_out = self._bn_act(self.B[0], inp, "go_B", 0.5)
-        for j in range(n_l):
-            g = self._g("dec%d" % j, dev)
-            mask = self._mask("go_dec%d" % j, (x.shape[0], g["n_rows"]), 0.4, dev)
-            x = _GoLayerFn.apply(x, self.w_out[j].weight, self.w_s_loop_out[j].weight, None, None, self.G_B_D[j].weight,
-                                 self.G_B_D[j].bias, mask, g, False, pool[n_l - j - 1], 0)
-        out_D = self._bn_act(self.B_D[0], self._lin(self.conc_D, x).squeeze(-1), "go_BD", 0.5)
-        x_D = _GoSpmmFn.apply(out_D, self.t_D[0].unsqueeze(0), self._g("ag_t", dev)).squeeze(-1)
-        h = self._bn_act(self.latent[1], self._lin(self.latent[0], inp_out), "go_latent", 0.5)
-        latent = self._bn_act(self.latent[5], self._lin(self.latent[4], h))
+        def decoder(x):
+            for j in range(n_l):
+                g = self._g("dec%d" % j, dev)
+                mask = self._mask("go_dec%d" % j, (x.shape[0], g["n_rows"]), 0.4, dev)
+                x = _GoLayerFn.apply(x, self.w_out[j].weight, self.w_s_loop_out[j].weight, None, None, self.G_B_D[j].weight,
+                                     self.G_B_D[j].bias, mask, g, False, pool[n_l - j - 1], 0)
+            out_D = self._bn_act(self.B_D[0], self._lin(self.conc_D, x).squeeze(-1), "go_BD", 0.5)
+            return _GoSpmmFn.apply(out_D, self.t_D[0].unsqueeze(0), self._g("ag_t", dev)).squeeze(-1)
+
+        def latent_head(x):
+            inp = self._lin(self.conc, x).squeeze(-1)
+            inp_out = self._bn_act(self.B[0], inp, "go_B", 0.5)
+            h = self._bn_act(self.latent[1], self._lin(self.latent[0], inp_out), "go_latent", 0.5)
+            return self._bn_act(self.latent[5], self._lin(self.latent[4], h))
+
+        # The decoder (-> x_D, needed by the reconstruction loss only) and the latent read-outs (-> the fusion heads) both hang off
+        # the encoder output and are ~6 kernels each: on one stream the heads waited for the decoder.  With a branch stream they
+        # run side by side (and, because autograd replays a node on the stream of its forward, so do their backward chains).
+        br = self.branch_stream
+        if br is not None and x.is_cuda:
+            cur = torch.cuda.current_stream(dev)
+            br.wait_stream(cur)
+            with torch.cuda.stream(br):
+                x_D = decoder(x)
+            x.record_stream(br)
+            if ls is not None:
+                with torch.cuda.stream(ls):
+                    latent = latent_head(x)
+                x.record_stream(ls)
+            else:
+                latent = latent_head(x)
+            self.decoder_joined = False
+        else:
+            x_D = decoder(x)
+            latent = latent_head(x)
+            self.decoder_joined = True
         if own_pass:
             self.mask_bank.end_pass()
         return latent, x_D, [torch.zeros(3, device=dev)], atten_out

@@ -351,10 +351,15 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         if side is not None:
             side.wait_stream(main)
             go.atten_ready = torch.cuda.Event() if early else None
+            branch = self._go_stream(x.device, 2) if (early and os.environ.get("IGCN_GO_BRANCH", "1") == "1") else None
+            go.branch_stream = branch                    # decoder branch beside the latent read-outs (go_net.forward)
+            lat_st = self._go_stream(x.device, 3) if (branch is not None and os.environ.get("IGCN_GO_LATENT_STREAM", "1") == "1") else None
+            go.latent_stream = lat_st
             with torch.cuda.stream(side):
                 latent, x_hat, _, atten_out = go(snps2, temperature, device, groups=2)
             snps2.record_stream(side)
             atten_ev, go.atten_ready = go.atten_ready, None
+            go.branch_stream = go.latent_stream = None
         side2 = self._go_stream(x.device, 1) if _TWO_STREAMS and os.environ.get("IGCN_ENC_STREAM", "1") == "1" else None
         if side2 is not None:                                                       # the plain pass on a third stream
             side2.wait_stream(main)
@@ -394,9 +399,12 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             out_z.record_stream(side2)
             self._quad_cache = (out_z, tsne, quad, side2)
         if side is not None and early:
-            main.wait_stream(side)               # latent (fusion heads) and x_hat (reconstruction loss) are needed from here on
-            for t in (latent, x_hat):
-                t.record_stream(main)
+            main.wait_stream(side)               # latent (fusion heads) is needed from here on
+            if lat_st is not None:
+                main.wait_stream(lat_st)
+            latent.record_stream(main)
+            if go.decoder_joined:
+                x_hat.record_stream(main)
         parts = [out_z, latent]
         # out_lin is a RETURNED tensor only (eval_scores collects it, train() never reads it): the stacked fast path of
         # train.step_loss does not materialise the concatenation
@@ -424,6 +432,10 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         # dropout, lin2 + log_softmax and lin2_regr of both heads in one launch (glue.cu)
         logp, our_reg = ops.output_heads(linear_outf, self._mask_of("lin1", linear_outf, 0.5), r, self._mask_of("lin1_regr", r, 0.3),
                                          self.lin2, self.lin2_regr)
+        if side is not None and not go.decoder_joined:
+            main.wait_stream(branch)             # x_hat (reconstruction loss) is needed by the caller, after the heads are queued
+            x_hat.record_stream(main)
+            go.decoder_joined = True
         if use_bank:
             bank.end_pass()
         outs = (logp, x_hat, out_z, out_lin, linear_outf, our_reg)
@@ -434,7 +446,7 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
     def _go_stream(self, device, which=0):
         sts = getattr(self, "_side_streams", None)
         if sts is None or sts[0].device != device:
-            sts = [torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)]
+            sts = [torch.cuda.Stream(device=device) for _ in range(4)]
             self._side_streams = sts
         return sts[which]
 
