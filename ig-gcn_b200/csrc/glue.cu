@@ -405,6 +405,221 @@ __global__ void __launch_bounds__(1024) bn_act_bwd_pair_kernel(const float* __re
     }
 }
 
+// ---- per-node read-out Linear fused with its BatchNorm (kernel/go_model.py:117-131: conc_for_attention, conc -> B, conc_D -> B_D) ----
+// z[n][c][l] = sum_k x[n][c][k] W[l][k] feeds BatchNorm1d over the channel (GO term) axis c directly, so the CTA of a channel computes
+// its z values from the channel's (N x K) slice of x, staged once in shared memory -- z is never written or read, and the backward
+// recomputes it the same way.  One launch each way instead of two / three (the read-out of the attention tokens is on the step's
+// critical path twice).  Two stacked passes (one per half of the CTA, as bn_act_*_pair_kernel), L = 1 or 32, K <= 8.
+constexpr int LB_MAXK = 8, LB_EPT = 16;
+
+template <bool BWD>
+__device__ __forceinline__ void lb_stage(const float* __restrict__ x, const float* __restrict__ W, int N, int C, int L, int K, int c,
+                                         float* Ws, float* xs) {
+    for (int i = threadIdx.x; i < L * K; i += blockDim.x) Ws[i] = W[i];
+    const int tot = N * K;                                   // the channel's slice of x: rows of K floats, row stride C * K
+    for (int i0 = 0; i0 < tot; i0 += 8 * blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + threadIdx.x + u * blockDim.x;
+            if (i < tot) {
+                const int n = i / K, k = i - n * K;
+                v[u] = x[((int64_t)n * C + c) * K + k];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + threadIdx.x + u * blockDim.x;
+            if (i < tot) xs[i] = v[u];
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) lin_bn_act_fwd_pair_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ mask, int N, int C, int L, int K, float eps,
+                                                                  float momentum, int relu, float* __restrict__ running_mean,
+                                                                  float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
+                                                                  float* __restrict__ y, float* __restrict__ stats) {
+    IGCN_PDL_SYNC();
+    extern __shared__ float lbs[];
+    __shared__ float sm[33];
+    __shared__ float res[4];
+    float* Ws = lbs;
+    float* xs = lbs + L * K;
+    const int nh = blockDim.x >> 1, c = blockIdx.x, g = threadIdx.x >= nh, tid = threadIdx.x - g * nh, wph = nh >> 5;
+    const int ng = N >> 1, cnt = ng * L, lsh = __ffs(L) - 1;
+    lb_stage<false>(x, W, N, C, L, K, c, Ws, xs);
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const int64_t base = ((int64_t)g * ng * C + c) * L;
+    float zv[LB_EPT], mv[LB_EPT];
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < LB_EPT; ++u) {
+        const int e = tid + u * nh;
+        zv[u] = 0.f; mv[u] = 1.f;
+        if (e < cnt) {
+            const int n = e >> lsh, l = e & (L - 1);
+            const float* xr = xs + (g * ng + n) * K;
+            const float* wr = Ws + l * K;
+            float z = 0.f;
+            for (int k = 0; k < K; ++k) z = fmaf(xr[k], wr[k], z);
+            zv[u] = z;
+            if (mask) mv[u] = mask[base + (int64_t)n * C * L + l];
+            s += z;
+        }
+    }
+    const float mean = half_sum(s, sm, g, wph) / (float)cnt;
+    float q = 0.f;
+#pragma unroll
+    for (int u = 0; u < LB_EPT; ++u)
+        if (tid + u * nh < cnt) {
+            const float d = zv[u] - mean;
+            q += d * d;
+        }
+    const float var = half_sum(q, sm, g, wph) / (float)cnt;
+    const float rstd = rsqrtf(var + eps);
+#pragma unroll
+    for (int u = 0; u < LB_EPT; ++u) {
+        const int e = tid + u * nh;
+        if (e < cnt) {
+            const int n = e >> lsh, l = e & (L - 1);
+            float v = (zv[u] - mean) * rstd * ga + be;
+            if (relu) v = fmaxf(v, 0.f);
+            if (mask) v *= mv[u];
+            y[base + (int64_t)n * C * L + l] = v;
+        }
+    }
+    if (tid == 0) {
+        stats[((int64_t)g * C + c) * 2 + 0] = mean;
+        stats[((int64_t)g * C + c) * 2 + 1] = rstd;
+        res[2 * g] = mean;
+        res[2 * g + 1] = var;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                        // the running buffers receive the two updates in pass order
+        float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 1.f;
+        const float unb = (float)cnt / (float)max(cnt - 1, 1);
+        for (int k = 0; k < 2; ++k) {
+            rm = (1.f - momentum) * rm + momentum * res[2 * k];
+            rv = (1.f - momentum) * rv + momentum * res[2 * k + 1] * unb;
+        }
+        if (running_mean) running_mean[c] = rm;
+        if (running_var) running_var[c] = rv;
+        if (num_batches_tracked && c == 0) *num_batches_tracked += 2;
+    }
+}
+
+// dx[n][c][k] = sum_l dz[n][c][l] W[l][k] (complete inside the channel's CTA); partial dW[l][k] of channel c = sum_n dz[n][c][l] x[n][c][k]
+__global__ void __launch_bounds__(1024) lin_bn_act_bwd_pair_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ mask, const float* __restrict__ stats,
+                                                                  const float* __restrict__ gy, int N, int C, int L, int K, int relu,
+                                                                  float* __restrict__ dx, float* __restrict__ partials /* (C, L*K) */,
+                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    IGCN_PDL_SYNC();
+    extern __shared__ float lbs[];
+    __shared__ float sm[33];
+    __shared__ float res[4];
+    float* Ws = lbs;
+    float* xs = lbs + L * K;
+    float* red = xs + N * K;                       // (K, blockDim.x): the threads' dW partials
+    float* dzs = red + K * blockDim.x;             // L = 32 only: (N, 33) dz, padded rows (conflict-free row walks)
+    const int nt = blockDim.x, nh = nt >> 1, c = blockIdx.x, g = threadIdx.x >= nh, tid = threadIdx.x - g * nh, wph = nh >> 5;
+    const int lane = threadIdx.x & 31;
+    const int ng = N >> 1, cnt = ng * L, lsh = __ffs(L) - 1;
+    lb_stage<true>(x, W, N, C, L, K, c, Ws, xs);
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const int64_t base = ((int64_t)g * ng * C + c) * L;
+    const float mean = stats[((int64_t)g * C + c) * 2 + 0], rstd = stats[((int64_t)g * C + c) * 2 + 1];
+    float xh[LB_EPT], dv[LB_EPT];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < LB_EPT; ++u) {
+        const int e = tid + u * nh;
+        xh[u] = 0.f; dv[u] = 0.f;
+        if (e < cnt) {
+            const int n = e >> lsh, l = e & (L - 1);
+            const float* xr = xs + (g * ng + n) * K;
+            const float* wr = Ws + l * K;
+            float z = 0.f;
+            for (int k = 0; k < K; ++k) z = fmaf(xr[k], wr[k], z);
+            xh[u] = (z - mean) * rstd;
+            const int64_t i = base + (int64_t)n * C * L + l;
+            float d = gy[i];
+            if (mask) d *= mask[i];
+            if (relu && !(xh[u] * ga + be > 0.f)) d = 0.f;
+            dv[u] = d;
+            s1 += d;
+            s2 += d * xh[u];
+        }
+    }
+    s1 = half_sum(s1, sm, g, wph);
+    s2 = half_sum(s2, sm, g, wph);
+    const float m1 = s1 / (float)cnt, m2 = s2 / (float)cnt;
+    float accw[LB_MAXK];
+#pragma unroll
+    for (int k = 0; k < LB_MAXK; ++k) accw[k] = 0.f;
+    const int l = tid & (L - 1);                   // nh is a multiple of L: a thread's elements share l
+#pragma unroll
+    for (int u = 0; u < LB_EPT; ++u) {
+        const int e = tid + u * nh;
+        const bool on = e < cnt;                   // uniform per warp when L = 32 (cnt is a multiple of 32); the shuffles below need all lanes
+        const int n = on ? (e >> lsh) : 0;
+        const float dz = on ? ga * rstd * (dv[u] - m1 - xh[u] * m2) : 0.f;
+        const float* xr = xs + (g * ng + n) * K;
+#pragma unroll
+        for (int k = 0; k < LB_MAXK; ++k)
+            if (k < K) {
+                accw[k] = fmaf(dz, xr[k], accw[k]);
+                if (L == 1 && on) dx[((int64_t)(g * ng + n) * C + c) * K + k] = dz * Ws[k];
+            }
+        if (L == 32 && on) dzs[(g * ng + n) * 33 + l] = dz;
+    }
+    if (L == 32) {
+        // dx[n][k] = sum_l dz[n][l] W[l][k]: a thread per (n, k) walks the 32 outputs of its row in shared memory (a warp-shuffle sum per
+        // element and k was 800 instructions per thread: the first version of this kernel took 40 us)
+        __syncthreads();
+        for (int o = threadIdx.x; o < N * K; o += nt) {
+            const int n = o / K, k = o - n * K;
+            const float* dr = dzs + n * 33;
+            float t = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) t = fmaf(dr[j], Ws[j * K + k], t);
+            dx[((int64_t)n * C + c) * K + k] = t;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < LB_MAXK; ++k)
+        if (k < K) {
+            if (L == 1) {                          // every thread holds a partial of the same dW[0][k]: warp sums first
+                const float v = warp_sum(accw[k]);
+                if (lane == 0) red[k * nt + (threadIdx.x >> 5)] = v;
+            } else {
+                red[k * nt + threadIdx.x] = accw[k];
+            }
+        }
+    if (tid == 0) {
+        res[2 * g] = s2;
+        res[2 * g + 1] = s1;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < L * K; o += nt) {   // dW[l][k] of this channel: the partials with this l, in thread (warp) order
+        const int lo = o / K, k = o - lo * K;
+        float t = 0.f;
+        if (L == 1)
+            for (int w = 0; w < (nt >> 5); ++w) t += red[k * nt + w];
+        else
+            for (int j = lo; j < nt; j += L) t += red[k * nt + j];
+        partials[(int64_t)c * L * K + o] = t;
+    }
+    if (threadIdx.x == 0) {
+        if (dgamma) dgamma[c] = res[0] + res[2];
+        if (dbeta) dbeta[c] = res[1] + res[3];
+    }
+}
+
 // ---- loss_probability -----------------------------------------------------------------------------------------------------
 // segments: 0 = sigmoid(prob) (n0), 1 = p_e (n1, already a probability), 2 = sigmoid(snps_prob) (n2)
 // loss = sum_seg  [ c_l1[seg] * sum|p| + c_en[seg] * sum -(p log(p+eps) + (1-p) log(1-p+eps)) ] / n_seg
@@ -674,6 +889,52 @@ extern "C" int igcn_bn_act_bwd(const float* z, const float* gamma, const float* 
         igcn::launch_k(bn_act_bwd_kernel, dim3((unsigned)C), dim3(nthr), 0, (cudaStream_t)stream, z, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L, (int)groups,
                                                                          (int)relu, dz, dgamma, dbeta);
     IGCN_CHECK_LAUNCH("bn_act_bwd");
+    return IGCN_OK;
+}
+
+static int lb_threads(int64_t cnt) { return cnt >= 4096 ? 1024 : (cnt >= 1024 ? 512 : 256); }
+
+extern "C" int64_t igcn_lin_bn_act_supported(int64_t N, int64_t C, int64_t L, int64_t K, int64_t groups) {
+    if (groups != 2 || N < 2 || (N & 1) || C < 1 || K < 1 || K > LB_MAXK || !(L == 1 || L == 32)) return 0;
+    const int64_t cnt = (N / 2) * L;
+    const int nthr = lb_threads(cnt);
+    if (cnt <= 1 || cnt > (int64_t)LB_EPT * (nthr / 2) || (L == 32 && (cnt % 32) != 0)) return 0;
+    return (L * K + N * K + K * nthr + (L == 32 ? N * 33 : 0)) * 4 <= 160 * 1024 ? 1 : 0;
+}
+
+extern "C" int igcn_lin_bn_act_fwd(const float* x, const float* W, const float* gamma, const float* beta, const float* mask, int64_t N,
+                                   int64_t C, int64_t L, int64_t K, int64_t groups, double eps, double momentum, int64_t relu,
+                                   float* running_mean, float* running_var, long long* num_batches_tracked, float* y, float* stats,
+                                   void* stream) {
+    IGCN_REQUIRE(x && W && y && stats, IGCN_ERR_BAD_ARG, "lin_bn_act_fwd: null pointer");
+    IGCN_REQUIRE(igcn_lin_bn_act_supported(N, C, L, K, groups), IGCN_ERR_UNSUPPORTED,
+                 "lin_bn_act_fwd: shape (N=%lld C=%lld L=%lld K=%lld groups=%lld) not supported (see igcn_lin_bn_act_supported)", (long long)N,
+                 (long long)C, (long long)L, (long long)K, (long long)groups);
+    const int nthr = lb_threads((N / 2) * L);
+    const size_t smem = sizeof(float) * (size_t)(L * K + N * K);
+    int rc = allow_smem(lin_bn_act_fwd_pair_kernel, smem, "lin_bn_act_fwd");
+    if (rc) return rc;
+    igcn::launch_k(lin_bn_act_fwd_pair_kernel, dim3((unsigned)C), dim3(nthr), smem, (cudaStream_t)stream, x, W, gamma, beta, mask, (int)N, (int)C,
+                   (int)L, (int)K, (float)eps, (float)momentum, (int)relu, running_mean, running_var, num_batches_tracked, y, stats);
+    IGCN_CHECK_LAUNCH("lin_bn_act_fwd");
+    return IGCN_OK;
+}
+
+extern "C" int igcn_lin_bn_act_bwd(const float* x, const float* W, const float* gamma, const float* beta, const float* mask, const float* stats,
+                                   const float* g_y, int64_t N, int64_t C, int64_t L, int64_t K, int64_t groups, int64_t relu, float* dx,
+                                   float* partials, float* dW, float* dgamma, float* dbeta, void* stream) {
+    IGCN_REQUIRE(x && W && stats && g_y && dx && partials && dW, IGCN_ERR_BAD_ARG, "lin_bn_act_bwd: null pointer");
+    IGCN_REQUIRE(igcn_lin_bn_act_supported(N, C, L, K, groups), IGCN_ERR_UNSUPPORTED, "lin_bn_act_bwd: shape not supported");
+    const int nthr = lb_threads((N / 2) * L);
+    const size_t smem = sizeof(float) * (size_t)(L * K + N * K + K * nthr + (L == 32 ? N * 33 : 0));
+    int rc = allow_smem(lin_bn_act_bwd_pair_kernel, smem, "lin_bn_act_bwd");
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    igcn::launch_k(lin_bn_act_bwd_pair_kernel, dim3((unsigned)C), dim3(nthr), smem, st, x, W, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L,
+                   (int)K, (int)relu, dx, partials, dgamma, dbeta);
+    IGCN_CHECK_LAUNCH("lin_bn_act_bwd");
+    igcn::launch_k(reduce_partials_kernel, dim3((unsigned)((L * K + 31) / 32)), dim3(reduce_threads(C)), 0, st, partials, (int)C, (int)(L * K), dW);
+    IGCN_CHECK_LAUNCH("lin_bn_act_reduce");
     return IGCN_OK;
 }
 

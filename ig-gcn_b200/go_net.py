@@ -244,6 +244,14 @@ class Gene_ontology_network(nn.Module):
         mask = self._mask(name, z.shape, p, z.device) if (name and self.training) else None
         return ops.bn_act(z, bn, mask, self._groups, relu=True)
 
+    def _lin_bn(self, lin, bn, x, name=None, p=0.0):
+        """dropout(relu(bn(lin(x)))) of a per-node read-out (x (N, C, K) -> (N, C, L)) as ONE fused launch each way (ops.lin_bn_act)."""
+        N, C = x.shape[0], x.shape[1]
+        L = lin.weight.shape[0]
+        mshape = (N, C) if L == 1 else (N, C, L)
+        mask = self._mask(name, mshape, p, x.device) if (name and self.training) else None
+        return ops.lin_bn_act(x, lin.weight, bn, mask, self._groups, relu=True)
+
     @staticmethod
     def _lin(mod, x):
         """Bias-free read-out projection; the skinny shapes (in <= 32, out <= 64) run on their own kernels (glue.cu); anything larger
@@ -271,7 +279,7 @@ class Gene_ontology_network(nn.Module):
         ls = self.latent_stream if (self.branch_stream is not None and x.is_cuda) else None
         if ls is not None:                        # the fusion heads wait for `latent`: its six kernels start right here, on their own stream
             ls.wait_stream(torch.cuda.current_stream(dev))
-        atten_out = self._bn_act(self.conc_for_attention[1], self._lin(self.conc_for_attention[0], x))
+        atten_out = self._lin_bn(self.conc_for_attention[0], self.conc_for_attention[1], x)
         if self.atten_ready is not None:          # lets a caller on another stream start the cross attention before the decoder is done
             self.atten_ready.record(torch.cuda.current_stream(dev))
         def decoder(x):
@@ -280,12 +288,11 @@ class Gene_ontology_network(nn.Module):
                 mask = self._mask("go_dec%d" % j, (x.shape[0], g["n_rows"]), 0.4, dev)
                 x = _GoLayerFn.apply(x, self.w_out[j].weight, self.w_s_loop_out[j].weight, None, None, self.G_B_D[j].weight,
                                      self.G_B_D[j].bias, mask, g, False, pool[n_l - j - 1], 0)
-            out_D = self._bn_act(self.B_D[0], self._lin(self.conc_D, x).squeeze(-1), "go_BD", 0.5)
+            out_D = self._lin_bn(self.conc_D, self.B_D[0], x, "go_BD", 0.5).squeeze(-1)
             return _GoSpmmFn.apply(out_D, self.t_D[0].unsqueeze(0), self._g("ag_t", dev)).squeeze(-1)
 
         def latent_head(x):
-            inp = self._lin(self.conc, x).squeeze(-1)
-            inp_out = self._bn_act(self.B[0], inp, "go_B", 0.5)
+            inp_out = self._lin_bn(self.conc, self.B[0], x, "go_B", 0.5).squeeze(-1)
             h = self._bn_act(self.latent[1], self._lin(self.latent[0], inp_out), "go_latent", 0.5)
             return self._bn_act(self.latent[5], self._lin(self.latent[4], h))
 

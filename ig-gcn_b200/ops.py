@@ -759,6 +759,63 @@ class _BnActFn(torch.autograd.Function):
         return dz, dg, db, None, None, None, None
 
 
+class _LinBnActFn(torch.autograd.Function):
+    """mask * relu(BatchNorm1d_c(x W^T)) for x (N, C, K), bias-free W (L, K): the read-out Linear fused with the BatchNorm head that
+    follows it (igcn_lin_bn_act_*; training mode, two stacked passes).  z = x W^T is never materialised."""
+
+    @staticmethod
+    def forward(ctx, x, W, gamma, beta, mask, bn, relu: bool):
+        _lib.require_cuda(x, W, gamma, beta, mask)
+        xc, Wc = x.contiguous().float(), W.contiguous().float()
+        N, C, K = xc.shape
+        L = Wc.shape[0]
+        mc = None if mask is None else mask.reshape(N, C, -1).expand(N, C, L).contiguous().float()
+        y = torch.empty((N, C, L), dtype=torch.float32, device=xc.device)
+        stats = torch.empty((2, C, 2), dtype=torch.float32, device=xc.device)
+        mom = 0.1 if bn.momentum is None else float(bn.momentum)
+        with torch.cuda.device(xc.device):
+            _lib.call("igcn_lin_bn_act_fwd", _lib.ptr(xc), _lib.ptr(Wc), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(mc), N, C, L, K, 2,
+                      float(bn.eps), mom, int(relu), _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var), _lib.ptr(bn.num_batches_tracked),
+                      _lib.ptr(y), _lib.ptr(stats), _lib.stream(), tag="lin_bn_act_fwd[C=%d,K=%d,L=%d]" % (C, K, L),
+                      nbytes=4 * (N * C * (K + L * (1 + (mc is not None)))))
+        ctx.relu = bool(relu)
+        ctx.save_for_backward(xc, Wc, gamma, beta, mc, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, Wc, gamma, beta, mc, stats = ctx.saved_tensors
+        N, C, K = xc.shape
+        L = Wc.shape[0]
+        dx = torch.empty_like(xc)
+        dW = torch.empty_like(Wc)
+        part = torch.empty((C, L * K), dtype=torch.float32, device=xc.device)
+        dg = torch.empty(C, dtype=torch.float32, device=xc.device) if gamma is not None else None
+        db = torch.empty(C, dtype=torch.float32, device=xc.device) if beta is not None else None
+        with torch.cuda.device(xc.device):
+            _lib.call("igcn_lin_bn_act_bwd", _lib.ptr(xc), _lib.ptr(Wc), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(mc), _lib.ptr(stats),
+                      _lib.ptr(gy.contiguous().float()), N, C, L, K, 2, int(ctx.relu), _lib.ptr(dx), _lib.ptr(part), _lib.ptr(dW), _lib.ptr(dg),
+                      _lib.ptr(db), _lib.stream(), tag="lin_bn_act_bwd[C=%d,K=%d,L=%d]" % (C, K, L),
+                      nbytes=4 * (N * C * (2 * K + L * (1 + (mc is not None)))))
+        return dx, dW, dg, db, None, None, None
+
+
+def lin_bn_act(x, weight, bn: torch.nn.BatchNorm1d, mask=None, groups=1, relu=True):
+    """mask * relu(bn(x @ weight.T)) for x (N, C, K) and a bias-free Linear weight (L, K), BatchNorm over the C axis: one fused launch
+    each way when the shape fits (training mode, two stacked passes, K <= 8, L in {1, 32}); otherwise skinny_linear + bn_act.
+    Returns (N, C, L)."""
+    N, C, K = x.shape
+    L = weight.shape[0]
+    if (os.environ.get("IGCN_NO_LIN_BN", "") == "" and bn.training and bn.track_running_stats and x.is_cuda
+            and _lib.lib().igcn_lin_bn_act_supported(N, C, L, K, groups)):
+        return _LinBnActFn.apply(x, weight, bn.weight, bn.bias, mask, bn, relu)
+    z = skinny_linear(x, weight) if (K <= 32 and L <= 64) else torch.nn.functional.linear(x, weight)
+    if L == 1:                                            # BatchNorm1d over (N, C): the reference squeezes the last axis
+        m2 = None if mask is None else mask.reshape(N, C)
+        return bn_act(z.squeeze(-1), bn, m2, groups, relu).unsqueeze(-1)
+    return bn_act(z, bn, None if mask is None else mask.reshape(N, C, -1).expand(N, C, L), groups, relu)
+
+
 class _BnEvalActFn(torch.autograd.Function):
     """relu(BatchNorm1d(z)) with the running statistics (model.eval()): one elementwise launch each way (igcn_bn_eval_act)."""
 

@@ -280,6 +280,20 @@ int igcn_bn_act_bwd(const float* z, const float* gamma, const float* beta, const
 int igcn_bn_eval_act(const float* z, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                      int64_t N, int64_t C, int64_t L, double eps, int64_t relu, const float* g_y, float* y, void* stream);
 
+/* The per-node read-out Linear (bias-free, K <= 8 inputs, L = 1 or 32 outputs) fused with the training-mode BatchNorm1d + ReLU +
+ * dropout scale that follows it (kernel/go_model.py:117-131: conc_for_attention, conc -> B, conc_D -> B_D):
+ *   y = mask * relu(BatchNorm_c(x W^T)),  x (N, C, K), W (L, K), y / mask (N, C, L), statistics per channel c over (n, l) and per
+ *   stacked pass (groups = 2 only).  z = x W^T is never materialised; the backward recomputes it.  igcn_lin_bn_act_supported(...) = 1
+ *   when the shape fits (otherwise use igcn_skinny_linear_* + igcn_bn_act_*).  bwd: dx (N, C, K), dW (L, K) via partials (C, L*K),
+ *   dgamma / dbeta (C).  Deterministic. */
+int64_t igcn_lin_bn_act_supported(int64_t N, int64_t C, int64_t L, int64_t K, int64_t groups);
+int igcn_lin_bn_act_fwd(const float* x, const float* W, const float* gamma, const float* beta, const float* mask, int64_t N, int64_t C,
+                        int64_t L, int64_t K, int64_t groups, double eps, double momentum, int64_t relu, float* running_mean,
+                        float* running_var, long long* num_batches_tracked, float* y, float* stats, void* stream);
+int igcn_lin_bn_act_bwd(const float* x, const float* W, const float* gamma, const float* beta, const float* mask, const float* stats,
+                        const float* g_y, int64_t N, int64_t C, int64_t L, int64_t K, int64_t groups, int64_t relu, float* dx,
+                        float* partials, float* dW, float* dgamma, float* dbeta, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * loss_probability (kernel/sgcn_img_snp.py:153-181): for p in {sigmoid(prob) (n_prob), p_e (n_e), sigmoid(snps_prob)
  * (n_snps)}:  c_l1 * mean|p| + c_ent * mean(-(p log(p+eps) + (1-p) log(1-p+eps))), summed.

@@ -59,6 +59,61 @@ def test_bn_act_vs_torch(shape, groups, with_mask):
     assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked) == groups
 
 
+@pytest.mark.parametrize("N,C,K,L,with_mask", [(512, 19, 5, 32, False), (512, 19, 5, 1, True), (512, 54, 2, 1, True), (64, 7, 8, 32, True),
+                                               (30, 5, 3, 4, False)])
+def test_lin_bn_act_vs_torch(N, C, K, L, with_mask):
+    """The read-out Linear fused with its BatchNorm head (igcn_lin_bn_act_*; kernel/go_model.py:117-131) against fp64 torch:
+    nn.Linear(bias=False) -> BatchNorm1d (training, one call per stacked pass) -> relu -> mask.  The last shape (L = 4) is outside the fused
+    kernel's range and goes through the unfused ops (same checks)."""
+    from igcn_b200 import _lib, ops
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(N, C, K, generator=g) + 0.3).to(DEV)
+    W = (torch.randn(L, K, generator=g) * 0.7).to(DEV)
+    bn = torch.nn.BatchNorm1d(C).to(DEV).train()
+    ref = torch.nn.BatchNorm1d(C).to(DEV).double().train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        bn.bias.copy_(torch.rand(C, generator=g) - 0.5)
+        ref.weight.copy_(bn.weight.double())
+        ref.bias.copy_(bn.bias.double())
+    mshape = (N, C) if L == 1 else (N, C, L)
+    mask = ((torch.rand(mshape, generator=g) > 0.4).float() / 0.6).to(DEV) if with_mask else None
+    assert bool(_lib.lib().igcn_lin_bn_act_supported(N, C, L, K, 2)) == (L in (1, 32))
+    x1, W1 = x.clone().requires_grad_(True), W.clone().requires_grad_(True)
+    y = ops.lin_bn_act(x1, W1, bn, mask, groups=2)
+    w = torch.randn(N, C, L, generator=g).to(DEV)
+    (y * w).sum().backward()
+    x2, W2 = x.double().clone().requires_grad_(True), W.double().clone().requires_grad_(True)
+    z = x2 @ W2.t()
+    h = N // 2
+    zz = z.squeeze(-1) if L == 1 else z
+    yr = torch.cat([F.relu(ref(zz[i * h:(i + 1) * h])) for i in range(2)], 0)
+    if mask is not None:
+        yr = yr * mask.double()
+    yr = yr.reshape(N, C, L)
+    (yr * w.double()).sum().backward()
+    H.assert_close(y, yr, what="lin_bn_act y")
+    # fp32 reference for rule B: the same torch ops in fp32
+    x3, W3 = x.clone().requires_grad_(True), W.clone().requires_grad_(True)
+    bn32 = torch.nn.BatchNorm1d(C).to(DEV).train()
+    with torch.no_grad():
+        bn32.weight.copy_(ref.weight.float())
+        bn32.bias.copy_(ref.bias.float())
+    z3 = x3 @ W3.t()
+    z3 = z3.squeeze(-1) if L == 1 else z3
+    y3 = torch.cat([F.relu(bn32(z3[i * h:(i + 1) * h])) for i in range(2)], 0)
+    if mask is not None:
+        y3 = y3 * mask
+    (y3.reshape(N, C, L) * w).sum().backward()
+    H.assert_parity(x1.grad, x3.grad, x2.grad, what="lin_bn_act dx %s" % ((N, C, K, L),))
+    H.assert_parity(W1.grad, W3.grad, W2.grad, what="lin_bn_act dW %s" % ((N, C, K, L),))
+    H.assert_parity(bn.weight.grad, bn32.weight.grad, ref.weight.grad, what="lin_bn_act dgamma")
+    H.assert_parity(bn.bias.grad, bn32.bias.grad, ref.bias.grad, what="lin_bn_act dbeta")
+    H.assert_close(bn.running_mean, ref.running_mean, what="lin_bn_act running_mean")
+    H.assert_close(bn.running_var, ref.running_var, what="lin_bn_act running_var")
+    assert int(bn.num_batches_tracked) == 2
+
+
 @pytest.mark.parametrize("R,S,E", [(90, 54, 7000), (264, 10000, 300001), (5, 3, 0)])
 def test_mask_loss_vs_torch(R, S, E):
     from igcn_b200 import ops
