@@ -361,23 +361,27 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             atten_ev, go.atten_ready = go.atten_ready, None
             go.branch_stream = go.latent_stream = None
         side2 = self._go_stream(x.device, 1) if _TWO_STREAMS and os.environ.get("IGCN_ENC_STREAM", "1") == "1" else None
+        # both passes write straight into the halves of ONE (2B, R, L*H) buffer: no torch.cat afterwards (277 MB each way at config 4)
+        LH = sum(w.shape[0] for w in Ws)
+        stacked_buf = torch.empty((2 * B, self.rois, LH), dtype=torch.float32, device=x.device)
         if side2 is not None:                                                       # the plain pass on a third stream
             side2.wait_stream(main)
+            stacked_buf.record_stream(side2)
             with torch.cuda.stream(side2):
-                h_plain, _ = ops.sgcn_encoder(x, csr, Ws, bs)
+                h_plain, _ = ops.sgcn_encoder(x, csr, Ws, bs, out=stacked_buf[:B])
                 if consist and stacked and self.isSoftSimilarity and _PREFETCH_CONSIST:
                     # the similarity matrix of the consistency loss depends on the batch only: built here, off the path that
                     # later waits for out_z (consist_loss_pair finds it in the cache)
                     self._similarity(B, data.tsne_fdim, x)
         else:
-            h_plain, _ = ops.sgcn_encoder(x, csr, Ws, bs)
-        h_expl, p_e = ops.sgcn_encoder(x, csr, Ws, bs, self.prob, self.prob_bias, want_pe=True)
+            h_plain, _ = ops.sgcn_encoder(x, csr, Ws, bs, out=stacked_buf[:B])
+        h_expl, p_e = ops.sgcn_encoder(x, csr, Ws, bs, self.prob, self.prob_bias, want_pe=True, out=stacked_buf[B:])
         self._pe_cache = ((x.data_ptr(), edge_index.data_ptr(), self.prob._version, self.prob_bias._version), p_e,
                           torch.is_grad_enabled())
         if side2 is not None:
             main.wait_stream(side2)
             h_plain.record_stream(main)
-        batch_x = torch.cat([h_plain, h_expl], 0)                                   # (2B, R, LH)
+        batch_x = ops.join_halves(h_plain, h_expl, stacked_buf)                     # (2B, R, LH), no copy
         if side is not None:
             if early:
                 main.wait_event(atten_ev)        # the attention needs only atten_out; decoder and latent MLP keep running on `side`

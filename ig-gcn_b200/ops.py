@@ -18,6 +18,11 @@ def pack_layer_params(weights, biases):
     return torch.cat(parts) if parts else None
 
 
+def _alias(t):
+    """A new tensor over the storage of the contiguous tensor t that autograd does not track as a view of it."""
+    return torch.empty(0, dtype=t.dtype, device=t.device).set_(t.untyped_storage(), t.storage_offset(), t.shape, t.stride())
+
+
 def _adjacent_view(tensors):
     """If the tensors sit back to back in one storage (train.FlatAdam lays the parameters out in registration order, which for
     the SGCN layers IS the wb order), return a zero-copy 1-D view over all of them; else None."""
@@ -63,7 +68,7 @@ class _SplitGradFn(torch.autograd.Function):
 
 class _SGCNEncoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, prob, prob_bias, wb, csr: GraphCSR, L: int, H: int, want_pe: bool, relu: bool = True):
+    def forward(ctx, x, prob, prob_bias, wb, csr: GraphCSR, L: int, H: int, want_pe: bool, relu: bool = True, out_buf=None):
         _lib.require_cuda(x, prob, prob_bias, wb)
         lib = _lib.lib()
         x = x.contiguous().float()
@@ -74,7 +79,12 @@ class _SGCNEncoderFn(torch.autograd.Function):
         probc = prob.contiguous().float() if explain else None
         pbc = prob_bias.contiguous().float().view(-1) if explain else None
         wbc = wb.contiguous().float() if wb is not None else None
-        out = torch.empty((B, R, L * H), dtype=torch.float32, device=x.device)
+        if out_buf is not None:                  # caller-provided destination (a slice of the stacked two-pass buffer): no copy later
+            if tuple(out_buf.shape) != (B, R, L * H) or not out_buf.is_contiguous() or out_buf.dtype != torch.float32:
+                raise RuntimeError("sgcn_encoder: out buffer must be a contiguous float32 (%d, %d, %d) tensor" % (B, R, L * H))
+            out = _alias(out_buf)                # same storage, no view relationship (the buffer has no autograd history)
+        else:
+            out = torch.empty((B, R, L * H), dtype=torch.float32, device=x.device)
         p_e = torch.empty(csr.E, dtype=torch.float32, device=x.device) if (explain and want_pe) else None
         with torch.cuda.device(x.device):
             _lib.call("igcn_sgcn_encoder_fwd", _lib.ptr(x), _lib.ptr(csr.rowptr_t), _lib.ptr(csr.csr_src), _lib.ptr(csr.csr_w),
@@ -113,15 +123,40 @@ class _SGCNEncoderFn(torch.autograd.Function):
         d_wb = grads[:nwb] if wb is not None else None
         d_prob = grads[nwb:nwb + R * F0].view(R, F0) if ctx.explain else None
         d_pb = grads[nwb + R * F0:].view(2 * F0, 1) if ctx.explain else None
-        return dx, d_prob, d_pb, d_wb, None, None, None, None, None
+        return dx, d_prob, d_pb, d_wb, None, None, None, None, None, None
 
 
-def sgcn_encoder(x, csr: GraphCSR, weights, biases, prob=None, prob_bias=None, want_pe=False, relu=True):
-    """Fused SGCN encoder. Returns (out (B,R,L*H), p_e (E,) in CSR-slot order or empty)."""
+class _JoinHalvesFn(torch.autograd.Function):
+    """The stacked (2B, ...) tensor whose halves ARE `a` and `b` (two adjacent slices of one buffer, each written in place by its
+    producer): no copy forward, two views backward.  Replaces torch.cat([a, b], 0) of kernel-produced halves."""
+
+    @staticmethod
+    def forward(ctx, a, b, whole):
+        if a.data_ptr() != whole.data_ptr() or b.data_ptr() != whole.data_ptr() + a.numel() * a.element_size() \
+                or a.numel() + b.numel() != whole.numel():
+            raise RuntimeError("join_halves: the halves are not the two halves of the buffer")
+        ctx.n = a.shape[0]
+        return _alias(whole)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        return g[:ctx.n], g[ctx.n:], None
+
+
+def sgcn_encoder(x, csr: GraphCSR, weights, biases, prob=None, prob_bias=None, want_pe=False, relu=True, out=None):
+    """Fused SGCN encoder. Returns (out (B,R,L*H), p_e (E,) in CSR-slot order or empty).  `out`: optional destination buffer (a
+    contiguous (B,R,L*H) float32 tensor without autograd history, e.g. one half of a stacked two-pass buffer; see join_halves)."""
     L = len(weights)
     H = weights[0].shape[0] if L else 0
     wb = _SplitGradFn.apply(*[t for w, b in zip(weights, biases) for t in (w, b)]) if L else None
-    return _SGCNEncoderFn.apply(x, prob, prob_bias, wb, csr, L, H, want_pe, relu)
+    return _SGCNEncoderFn.apply(x, prob, prob_bias, wb, csr, L, H, want_pe, relu, out)
+
+
+def join_halves(a, b, whole):
+    """`whole` (2B, ...) as an autograd tensor whose halves are a and b -- the tensors two producers wrote into whole[:B] / whole[B:]
+    through their `out=` argument -- without the copy of torch.cat([a, b], 0)."""
+    return _JoinHalvesFn.apply(a, b, whole)
 
 
 def edge_mask(x, csr: GraphCSR, prob, prob_bias):
