@@ -50,6 +50,8 @@ SIGNATURES = {
     "igcn_catlin_mma_bwd_dw": (ctypes.c_int, [_P] * 8 + [_I] * 4 + [_P] * 3),
     "igcn_dropout_masks": (ctypes.c_int, [_P, _P, _P, _I, ctypes.c_uint64, _P, _P]),
     "igcn_adam_step": (ctypes.c_int, [_P] * 6 + [ctypes.c_double] * 4 + [_I, _P]),
+    "igcn_gather_flat": (ctypes.c_int, [_P, _P, _P, _I, _P, _I, _P]),
+    "igcn_gather_flat_launches": (_I, [_I]),
     "igcn_bn_act_fwd": (ctypes.c_int, [_P] * 4 + [_I] * 4 + [ctypes.c_double] * 2 + [_I] + [_P] * 6),
     "igcn_bn_act_bwd": (ctypes.c_int, [_P] * 6 + [_I] * 5 + [_P] * 4),
     "igcn_bn_eval_act": (ctypes.c_int, [_P] * 5 + [_I] * 3 + [ctypes.c_double, _I, _P, _P, _P]),
@@ -114,7 +116,7 @@ def lib():
 # ---- launch accounting (bench.py: gpu_launches, per-kernel CUDA-event timing) -------------------------------
 KERNELS_PER_CALL = {
     "igcn_collate_csr": 1, "igcn_csr_from_edge_index": 2, "igcn_sgcn_encoder_fwd": 1, "igcn_sgcn_encoder_bwd": 2,
-    "igcn_go_spmm_fwd": 1, "igcn_go_spmm_bwd": 2, "igcn_go_layer_fwd": 1, "igcn_go_layer_bwd": 2, "igcn_adam_step": 1, "igcn_dropout_masks": 2, "igcn_cross_attn_fwd": 1, "igcn_cross_attn_bwd": 2, "igcn_cross_attn_v2_fwd": 2, "igcn_cross_attn_v2_bwd": 3, "igcn_cat_linear_fwd": 2, "igcn_cat_linear_bwd": 2, "igcn_lin_bn_act_fwd": 1, "igcn_lin_bn_act_bwd": 2, "igcn_catlin_mma_fwd": 1, "igcn_catlin_mma_bwd_dx": 1, "igcn_catlin_mma_bwd_dw": 1, "igcn_gat_layer_fwd": 1, "igcn_gat_layer_bwd": 2,
+    "igcn_go_spmm_fwd": 1, "igcn_go_spmm_bwd": 2, "igcn_go_layer_fwd": 1, "igcn_go_layer_bwd": 2, "igcn_adam_step": 1, "igcn_gather_flat": 1, "igcn_dropout_masks": 2, "igcn_cross_attn_fwd": 1, "igcn_cross_attn_bwd": 2, "igcn_cross_attn_v2_fwd": 2, "igcn_cross_attn_v2_bwd": 3, "igcn_cat_linear_fwd": 2, "igcn_cat_linear_bwd": 2, "igcn_lin_bn_act_fwd": 1, "igcn_lin_bn_act_bwd": 2, "igcn_catlin_mma_fwd": 1, "igcn_catlin_mma_bwd_dx": 1, "igcn_catlin_mma_bwd_dw": 1, "igcn_gat_layer_fwd": 1, "igcn_gat_layer_bwd": 2,
     "igcn_bn_act_fwd": 1, "igcn_bn_act_bwd": 1, "igcn_mask_loss_fwd": 2, "igcn_mask_loss_bwd": 1, "igcn_dot": 2, "igcn_scale_by_scalar": 1, "igcn_tc_split": 1, "igcn_tc_gemm": 2, "igcn_skinny_linear_fwd": 1, "igcn_skinny_linear_bwd": 2,
     "igcn_snp_mask_pair_fwd": 1, "igcn_snp_mask_pair_bwd": 1, "igcn_heads_fwd": 1, "igcn_heads_bwd": 2, "igcn_step_loss_fwd": 1, "igcn_step_loss_bwd": 1,
     "igcn_rbf_similarity": 2, "igcn_col_mean": 1, "igcn_laplacian_finish": 2,

@@ -81,6 +81,17 @@ inline void launch_k(void (*kernel)(Params...), dim3 grid, dim3 block, size_t sm
     cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
 }
 
+// CTAs for a persistent kernel that walks `units` work items with at most `slots` CTAs resident: the same number of rounds as
+// min(slots, units) CTAs would need, but no more CTAs than that many rounds require -- 512 graphs on 444 slots are two rounds either
+// way, and 256 CTAs leave 40 % of the SM slots to the kernels of the other streams (the device timeline of the config-2 step showed
+// the GO backward chain waiting for an SGCN backward that had filled every SM: profiles/r2_timeline_config2_*.json).
+static inline int64_t balanced_ctas(int64_t slots, int64_t units) {
+    if (slots < 1) slots = 1;
+    if (units <= slots) return units < 1 ? 1 : units;
+    const int64_t rounds = (units + slots - 1) / slots;
+    return (units + rounds - 1) / rounds;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

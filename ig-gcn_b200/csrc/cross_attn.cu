@@ -493,10 +493,7 @@ extern "C" int64_t igcn_cross_attn_v2_work_floats(int64_t B, int64_t R, int64_t 
     return B * g.nchunk * (int64_t)amma2::dtab_floats(g.MP, (int)heads);
 }
 extern "C" int64_t igcn_cross_attn_v2_bwd_ctas(int64_t B) {
-    int64_t n = (B + amma2::kChainGraphs - 1) / amma2::kChainGraphs;
-    const int64_t cap = (int64_t)sm_count() * 2;
-    if (n > cap) n = cap;
-    return n < 1 ? 1 : n;
+    return balanced_ctas((int64_t)sm_count() * 2, (B + amma2::kChainGraphs - 1) / amma2::kChainGraphs);
 }
 
 extern "C" int igcn_cross_attn_v2_fwd(const float* q_in, const float* kv_in, const float* in_proj_weight, const float* in_proj_bias,

@@ -1252,10 +1252,19 @@ __global__ void __launch_bounds__(1024) step_loss_fwd_kernel(const float* __rest
             const float d = r[i] - target[i];
             s1 = fmaf(d, d, s1);
         }
-#pragma unroll 8
-        for (int64_t i = threadIdx.x; i < n_rec; i += 1024) {      // unrolled: the loads of 8 iterations are issued before the first use
-            const float d = x[i] - snps[i];
-            s2 = fmaf(d, d, s2);
+        for (int64_t i0 = 0; i0 < n_rec; i0 += 8 * 1024) {         // 16 loads per thread in flight, then the arithmetic: this kernel is
+            float xa[8], sa[8];                                     // one CTA on the step's critical path (12 us as a load -> FMA loop)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t i = i0 + threadIdx.x + u * 1024;
+                xa[u] = i < n_rec ? x[i] : 0.f;
+                sa[u] = i < n_rec ? snps[i] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float d = xa[u] - sa[u];
+                s2 = fmaf(d, d, s2);
+            }
         }
     }
     s1 = block_sum_any(s1, sm);

@@ -45,7 +45,76 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
 #undef IGCN_ADAM1
 }
 
+// Gradient gather: copies up to GATHER_MAX separate gradient tensors into their slots of the flat buffer in ONE launch
+// (a null source zero-fills the slot).  The table travels by value, so the launch can sit in a captured graph.
+constexpr int GATHER_MAX = 96;
+struct GatherTable {
+    const float* src[GATHER_MAX];
+    int64_t off[GATHER_MAX];
+    int n[GATHER_MAX];
+};
+
+__global__ void __launch_bounds__(256) gather_flat_kernel(const __grid_constant__ GatherTable t, float* __restrict__ dst) {
+    const int e = blockIdx.y;
+    const float* __restrict__ s = t.src[e];
+    float* __restrict__ d = dst + t.off[e];
+    const int n = t.n[e];
+    const int stride = gridDim.x * 256;
+    const int i0 = blockIdx.x * 256 + threadIdx.x;
+    if (s != nullptr && (reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+        const int n4 = n >> 2;
+        for (int i = i0; i < n4; i += 4 * stride) {                 // 4 x 16-byte loads in flight per thread
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + u * stride < n4) v[u] = reinterpret_cast<const float4*>(s)[i + u * stride];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + u * stride < n4) reinterpret_cast<float4*>(d)[i + u * stride] = v[u];
+        }
+        for (int i = (n4 << 2) + i0; i < n; i += stride) d[i] = s[i];
+    } else {
+        for (int i = i0; i < n; i += stride) d[i] = s ? s[i] : 0.f;
+    }
+}
+
 }  // namespace igcn
+
+extern "C" int igcn_gather_flat(const int64_t* host_src_ptrs, const int64_t* host_offsets, const int64_t* host_sizes, int64_t count,
+                                float* flat, int64_t flat_n, void* stream) {
+    using namespace igcn;
+    IGCN_REQUIRE(count >= 0, IGCN_ERR_BAD_ARG, "gather_flat: negative count");
+    if (count == 0) return IGCN_OK;
+    IGCN_REQUIRE(host_src_ptrs && host_offsets && host_sizes && flat, IGCN_ERR_BAD_ARG, "gather_flat: null pointer");
+    IGCN_REQUIRE((uintptr_t)flat % 16 == 0, IGCN_ERR_BAD_ARG, "gather_flat: flat buffer must be 16-byte aligned");
+    for (int64_t i = 0; i < count; ++i) {
+        IGCN_REQUIRE(host_sizes[i] >= 0 && host_sizes[i] < (int64_t(1) << 31) && host_offsets[i] >= 0 && (host_offsets[i] & 3) == 0 &&
+                         host_offsets[i] + host_sizes[i] <= flat_n,
+                     IGCN_ERR_BAD_ARG, "gather_flat: slot %lld (offset %lld, size %lld) outside the flat buffer of %lld or not 16-byte aligned",
+                     (long long)i, (long long)host_offsets[i], (long long)host_sizes[i], (long long)flat_n);
+        IGCN_REQUIRE(host_src_ptrs[i] % 4 == 0, IGCN_ERR_BAD_ARG, "gather_flat: source %lld is not 4-byte aligned", (long long)i);
+    }
+    for (int64_t base = 0; base < count; base += GATHER_MAX) {
+        GatherTable t;
+        const int m = (int)((count - base) < GATHER_MAX ? (count - base) : GATHER_MAX);
+        int64_t biggest = 1;
+        for (int e = 0; e < m; ++e) {
+            t.src[e] = reinterpret_cast<const float*>(host_src_ptrs[base + e]);
+            t.off[e] = host_offsets[base + e];
+            t.n[e] = (int)host_sizes[base + e];
+            if (host_sizes[base + e] > biggest) biggest = host_sizes[base + e];
+        }
+        for (int e = m; e < GATHER_MAX; ++e) { t.src[e] = nullptr; t.off[e] = 0; t.n[e] = 0; }
+        int64_t gx = (biggest / 4 + 256 * 4 - 1) / (256 * 4);       // one round of 4 float4 per thread covers the largest tensor ...
+        if (gx > 16) gx = 16;                                       // ... up to 16 CTAs per tensor
+        if (gx < 1) gx = 1;
+        gather_flat_kernel<<<dim3((unsigned)gx, (unsigned)m), 256, 0, (cudaStream_t)stream>>>(t, flat);
+        IGCN_CHECK_LAUNCH("gather_flat");
+    }
+    return IGCN_OK;
+}
+
+extern "C" int64_t igcn_gather_flat_launches(int64_t count) { return count <= 0 ? 0 : (count + igcn::GATHER_MAX - 1) / igcn::GATHER_MAX; }
 
 extern "C" int igcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* step,
                               const float* lr, double beta1, double beta2, double eps, double grad_scale, int64_t n, void* stream) {

@@ -502,9 +502,7 @@ extern "C" int64_t igcn_sgcn_bwd_ctas(int64_t B, int64_t R, int64_t F0, int64_t 
         if (per_sm > 2048 / nthr) per_sm = 2048 / nthr;
         if (per_sm > 65536 / (96 * nthr)) per_sm = 65536 / (96 * nthr);
         if (per_sm < 1) per_sm = 1;
-        int64_t n = (int64_t)sm_count() * per_sm;
-        if (n > B) n = B;
-        return n < 1 ? 1 : n;
+        return balanced_ctas((int64_t)sm_count() * per_sm, B);
     }
     if (use_fast_bwd(R, F0, H, L, max_eg)) {
         int64_t n = sm_count();
@@ -545,8 +543,7 @@ extern "C" int igcn_sgcn_encoder_fwd(const float* x, const int32_t* rowptr_t, co
             if (per_sm > by_threads) per_sm = by_threads;
             if (per_sm > 8) per_sm = 8;
             if (per_sm < 1) per_sm = 1;
-            int64_t grid = (int64_t)sm_count() * per_sm;
-            if (grid > B) grid = B;
+            const int64_t grid = balanced_ctas((int64_t)sm_count() * per_sm, B);
             igcn::launch_k(kern, dim3((int)grid), dim3(nthr), smem, (cudaStream_t)stream, a);
             IGCN_CHECK_LAUNCH("sgcn_fwd_mma");
             return IGCN_OK;
@@ -563,8 +560,7 @@ extern "C" int igcn_sgcn_encoder_fwd(const float* x, const int32_t* rowptr_t, co
             const int by_regs = 65536 / (128 * nthr);
             if (per_sm > by_regs) per_sm = by_regs;
             if (per_sm < 1) per_sm = 1;
-            int64_t grid = (int64_t)sm_count() * per_sm;
-            if (grid > B) grid = B;
+            const int64_t grid = balanced_ctas((int64_t)sm_count() * per_sm, B);
             igcn::launch_k(kern, dim3((int)grid), dim3(nthr), smem, (cudaStream_t)stream, a);
             IGCN_CHECK_LAUNCH("sgcn_fwd_h16");
             return IGCN_OK;

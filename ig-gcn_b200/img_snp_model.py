@@ -317,7 +317,7 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
             bank.end_pass()
         return logp, x_hat, out_z, out_lin, linear_outf, our_reg
 
-    def forward_pair(self, data, temperature=None, device=None, stacked=False, consist=False):
+    def forward_pair(self, data, temperature=None, device=None, stacked=False, consist=False, mask_loss_hp=None):
         """Plain pass and explain pass of ONE batch in a single sweep: everything downstream of the two encoder
         launches (GO network, cross attention, fusion heads) runs once on the 2B stacked samples, with BatchNorm
         applied per pass, so the results equal `forward(data)` followed by `forward(data, isExplain=True)` while every
@@ -364,11 +364,16 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         # both passes write straight into the halves of ONE (2B, R, L*H) buffer: no torch.cat afterwards (277 MB each way at config 4)
         LH = sum(w.shape[0] for w in Ws)
         stacked_buf = torch.empty((2 * B, self.rois, LH), dtype=torch.float32, device=x.device)
+        img_feat = None
         if side2 is not None:                                                       # the plain pass on a third stream
             side2.wait_stream(main)
             stacked_buf.record_stream(side2)
             with torch.cuda.stream(side2):
                 h_plain, _ = ops.sgcn_encoder(x, csr, Ws, bs, out=stacked_buf[:B])
+                if self.isuseProb4Regr:
+                    # the regression head's masked image features depend on x and the node mask only: made here so that their
+                    # backward (an elementwise product and a reduction over the batch) also runs beside the main stream
+                    img_feat = (x.view(B, self.rois, -1) * self.prob).reshape(B, -1)
                 if consist and stacked and self.isSoftSimilarity and _PREFETCH_CONSIST:
                     # the similarity matrix of the consistency loss depends on the batch only: built here, off the path that
                     # later waits for out_z (consist_loss_pair finds it in the cache)
@@ -381,6 +386,18 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         if side2 is not None:
             main.wait_stream(side2)
             h_plain.record_stream(main)
+            if img_feat is not None:
+                img_feat.record_stream(main)
+        if side2 is not None and mask_loss_hp is not None and stacked:
+            # the mask loss needs only the explain encoder's edge probabilities: it (and its backward) runs on the third stream while
+            # the attention occupies the main one; train.step_loss finds it in the cache
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side2.wait_event(ev)
+            with torch.cuda.stream(side2):
+                lp = self.loss_probability(x, edge_index, data.edge_attr, mask_loss_hp)
+            p_e.record_stream(side2)
+            self._lp_cache = (mask_loss_hp, lp, side2)
         batch_x = ops.join_halves(h_plain, h_expl, stacked_buf)                     # (2B, R, LH), no copy
         if side is not None:
             if early:
@@ -415,7 +432,8 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         out_lin = None if stacked else torch.cat(parts, -1).detach()
         rparts = parts
         if self.isuseProb4Regr:
-            img_feat = (x.view(B, self.rois, -1) * self.prob).reshape(B, -1)
+            if img_feat is None:
+                img_feat = (x.view(B, self.rois, -1) * self.prob).reshape(B, -1)
             rparts = parts + [img_feat]                      # B rows: cat_linear reads it for both stacked passes
         # lin1 reads a column prefix of what lin1_regr reads: one operand-split launch serves both products, and the two products
         # (GEMM + split-K reduce each) run side by side on two streams
@@ -450,7 +468,10 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
     def _go_stream(self, device, which=0):
         sts = getattr(self, "_side_streams", None)
         if sts is None or sts[0].device != device:
-            sts = [torch.cuda.Stream(device=device) for _ in range(4)]
+            # the GO encoder chain (0) and the latent read-outs (3) are the long poles of the step: their CTAs are scheduled ahead of
+            # the wide SGCN / Laplacian kernels they share the SMs with (stream priority is captured into the graph's kernel nodes)
+            hi = os.environ.get("IGCN_GO_PRIORITY", "1") == "1"
+            sts = [torch.cuda.Stream(device=device, priority=-1 if (hi and i in (0, 3)) else 0) for i in range(4)]
             self._side_streams = sts
         return sts[which]
 

@@ -340,6 +340,42 @@ def _presplit_take(cs, widths, reps, Wc, M):
     return c["A"], c["weights"].pop(Wc.data_ptr())
 
 
+# Weight gradients computed on an auxiliary stream are read only by the optimizer: inside train.train_step (which opens the scope,
+# and joins before it gathers the gradients) the consumer stream does not wait for them where they are produced.
+_DEFERRED = None            # None, or {"events": [(device, event)], "seen": set(id(weight))}
+
+
+def defer_weight_grad_joins():
+    global _DEFERRED
+    _DEFERRED = dict(events=[], seen=set())
+
+
+def join_weight_grads():
+    """Makes the CURRENT stream (the one the optimizer runs on) wait for the deferred weight-gradient products; closes the scope."""
+    global _DEFERRED
+    d, _DEFERRED = _DEFERRED, None
+    if d:
+        for dev, ev in d["events"]:
+            torch.cuda.current_stream(dev).wait_event(ev)
+
+
+def _join_or_defer(cur, aux, W):
+    d = _DEFERRED
+    if d is None or os.environ.get("IGCN_NO_DEFER_DW") == "1":
+        cur.wait_stream(aux)
+        return
+    if id(W) in d["seen"]:
+        # a second use of the same weight: autograd will ADD this gradient to the earlier one on `cur`, so both must have landed
+        for _, ev in d["events"]:
+            cur.wait_event(ev)
+        cur.wait_stream(aux)
+        return
+    d["seen"].add(id(W))
+    ev = torch.cuda.Event()
+    ev.record(aux)
+    d["events"].append((cur.device, ev))
+
+
 class _CatLinearFn(torch.autograd.Function):
     """act([x0 | x1 | x2] W^T + b) via igcn_cat_linear_* (sources may be None)."""
 
@@ -504,16 +540,18 @@ class _CatLinearFn(torch.autograd.Function):
             if aux is not None and aux == cur:       # this head's forward already ran on the auxiliary stream (forward_pair)
                 aux = _aux_stream(dev, 1)
             if aux is not None:
-                aux.wait_stream(cur)
+                entry = torch.cuda.Event()
+                entry.record(cur)
+            if any(d is not None for d in dxs):          # queued first: the rest of the backward waits for it
+                _tc_split(jobs_x, dev)
+                _tc_gemm(gz, wt, M, K, N, dxs, ctx.widths, [0 if d is None else d.stride(0) for d in dxs], tag="cat_linear_bwd_x_tc")
+            if aux is not None:
+                aux.wait_event(entry)
                 with torch.cuda.stream(aux):
                     weight_grad()
                 for t in [g_out, gzt, xt, dW, db] + ([mask] if mask is not None else []) + [t for t in cs if t is not None]:
                     t.record_stream(aux)
-            if any(d is not None for d in dxs):
-                _tc_split(jobs_x, dev)
-                _tc_gemm(gz, wt, M, K, N, dxs, ctx.widths, [0 if d is None else d.stride(0) for d in dxs], tag="cat_linear_bwd_x_tc")
-            if aux is not None:
-                cur.wait_stream(aux)
+                _join_or_defer(cur, aux, W)
             else:
                 weight_grad()
             for i, rp in enumerate(ctx.reps):                # a repeated source collects the gradient of every repetition

@@ -29,10 +29,18 @@ def step_loss(model, data, lambda_loss=None, isSoftSimilarity=True, temperature=
         # both passes in one sweep on 2B stacked samples (identical results, half the launches; SGCN_GCN_IMGSNP.forward_pair);
         # every loss term of train() is the mean of its plain and explain values, so it is evaluated on the stacked tensors
         # directly and no slicing enters the autograd graph
-        out2, snps_hat2, out_feat2, _, _, our_reg2 = model.forward_pair(data, temperature, dev, stacked=True, consist=True)
+        out2, snps_hat2, out_feat2, _, _, our_reg2 = model.forward_pair(data, temperature, dev, stacked=True, consist=True,
+                                                                        mask_loss_hp=hyper)
         B = data.snps_feat.shape[0]
         from . import ops
-        lp = model.loss_probability(data.x, data.edge_index, data.edge_attr, hyper)
+        c, model._lp_cache = getattr(model, "_lp_cache", None), None
+        if c is not None and c[0] is hyper:              # already queued beside the attention by forward_pair
+            lp = c[1]
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_stream(c[2])
+            lp.record_stream(cur)
+        else:
+            lp = model.loss_probability(data.x, data.edge_index, data.edge_attr, hyper)
         quad = model.consist_loss_pair(out_feat2, data.tsne_fdim)
         # lam1 * (mse + mse_p)/2 + lam2 * loss_prob + lam3 * (recon + recon_p)/2 + lam4 * (cluster + cluster_p)/2 as one launch
         loss_reg = ops.step_loss_pair(our_reg2, cs, snps_hat2, snps, lp, quad, lam[1], lam[3] / 2, lam[2], lam[4] / 2)
@@ -232,10 +240,30 @@ class FlatAdam(object):
             self._lr_seen = lr
 
     def gather_grads(self):
-        have = [(v, p.grad) for v, p in zip(self.grad_views, self.params) if p.grad is not None]
-        self.flat_grad.zero_()
-        if have:
-            torch._foreach_copy_([a for a, _ in have], [b for _, b in have])
+        """p.grad of every parameter -> its slot of flat_grad, one launch (igcn_gather_flat); a parameter without a gradient gets
+        zeros.  Gradients that are not plain contiguous f32 tensors (none in this package's models) take a torch copy."""
+        from . import _lib
+        import ctypes
+        n = len(self.params)
+        src, odd = (ctypes.c_int64 * n)(), []
+        for i, p in enumerate(self.params):
+            g = p.grad
+            if g is None:
+                src[i] = 0
+            elif g.dtype == torch.float32 and g.is_contiguous() and g.device == self.flat_grad.device and not g.is_sparse:
+                src[i] = g.data_ptr()
+            else:
+                src[i] = 0
+                odd.append((self.grad_views[i], g))
+        if getattr(self, "_gather_tab", None) is None:
+            self._gather_tab = ((ctypes.c_int64 * n)(*self.offsets), (ctypes.c_int64 * n)(*[p.numel() for p in self.params]))
+        off, sizes = self._gather_tab
+        with torch.cuda.device(self.flat_grad.device):
+            _lib.call("igcn_gather_flat", ctypes.addressof(src), ctypes.addressof(off), ctypes.addressof(sizes), n,
+                      _lib.ptr(self.flat_grad), self.n, _lib.stream(), tag="gather_flat", nbytes=8 * self.n)
+            _lib.launch_count += int(_lib.lib().igcn_gather_flat_launches(n)) - 1
+        for v, g in odd:
+            v.copy_(g)
 
     def step(self):
         from . import _lib
@@ -276,7 +304,12 @@ def train_step(model, data, optimizer=None, lambda_loss=None, flat: FlatGradAllR
     if data.x.grad is not None:
         data.x.grad = None
     loss = step_loss(model, data, lambda_loss, isSoftSimilarity)
-    loss.backward()
+    from . import ops
+    ops.defer_weight_grad_joins()         # weight-gradient products on auxiliary streams are joined once, here, before the optimizer
+    try:
+        loss.backward()
+    finally:
+        ops.join_weight_grads()
     if getattr(model, "_pe_cache", None) is not None:
         model._pe_cache = None            # drop the last reference to this step's autograd graph
     if getattr(model, "_w_cache", None) is not None:

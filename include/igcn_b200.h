@@ -257,6 +257,17 @@ int igcn_dropout_masks(float* out, const int64_t* host_seg_end, const float* hos
 int igcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* step, const float* lr,
                    double beta1, double beta2, double eps, double grad_scale, int64_t n, void* stream);
 
+/* Gathers `count` separately allocated gradient tensors into their slots of the flat gradient buffer igcn_adam_step /
+ * igcn_dp_allreduce_adam read (the reference's optimizer walks p.grad of every parameter, torch.optim.Adam.step called at
+ * kernel/train_eval_sgcn_img_snps.py:547; here the per-parameter walk is one copy launch per 96 tensors).
+ *   host_src_ptrs / host_offsets / host_sizes: HOST arrays of `count` entries -- device address of a contiguous f32 gradient
+ *   (0: the slot is zero-filled, a parameter that received no gradient), element offset of its slot in `flat` (multiple of 4)
+ *   and element count.  The table is passed to the kernel by value: the host arrays may be freed on return and the launch can be
+ *   captured in a CUDA graph (the captured addresses are the graph's own).  igcn_gather_flat_launches = kernels launched. */
+int igcn_gather_flat(const int64_t* host_src_ptrs, const int64_t* host_offsets, const int64_t* host_sizes, int64_t count,
+                     float* flat, int64_t flat_n, void* stream);
+int64_t igcn_gather_flat_launches(int64_t count);
+
 /* ------------------------------------------------------------------------------------------
  * Read-out heads of the GO network: mask * relu(BatchNorm1d(z)) in TRAINING mode as one launch (forward) and one
  * launch (backward).  Replaces nn.BatchNorm1d + nn.ReLU + nn.Dropout as chained in kernel/go_model.py:117-146

@@ -304,3 +304,34 @@ def test_dp_allreduce_adam_single_rank_equals_adam_step():
     torch.cuda.synchronize()
     assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)
     assert int(pad.abs().sum()) == 0 and int(err) == 0
+
+
+def test_gather_flat_bit_exact():
+    """FlatAdam.gather_grads (igcn_gather_flat): every p.grad lands in its slot bit for bit, parameters without a gradient read
+    zero, slot padding stays zero -- more tensors than one launch's table holds, 16-byte-unaligned sources, sizes 1 .. 70 001."""
+    from igcn_b200.train import FlatAdam
+    g = torch.Generator().manual_seed(3)
+    sizes = [1, 3, 4, 5, 31, 1024, 70001, 4099] + [int(v) for v in torch.randint(1, 3000, (120,), generator=g)]
+    params = [torch.nn.Parameter(torch.randn(n, generator=g).to(DEV)) for n in sizes]
+    opt = FlatAdam(params, lr=1e-3)
+    pool = torch.randn(sum(sizes) + len(sizes), generator=g).to(DEV)
+    off = 1                                           # +1: sources that are views at odd element offsets (not 16-byte aligned)
+    for i, (p, n) in enumerate(zip(params, sizes)):
+        if i % 7 == 3:
+            p.grad = None
+        elif i % 2:
+            p.grad = pool[off:off + n]
+        else:
+            p.grad = torch.randn(n, generator=g).to(DEV)
+        off += n
+    opt.flat_grad.fill_(7.0)                          # stale contents must not survive in any slot
+    pad = torch.ones(opt.n, dtype=torch.bool, device=DEV)
+    for o, n in zip(opt.offsets, sizes):
+        pad[o:o + n] = False
+    opt.flat_grad[pad] = 0.0
+    opt.gather_grads()
+    torch.cuda.synchronize()
+    for p, v in zip(params, opt.grad_views):
+        want = torch.zeros_like(p) if p.grad is None else p.grad
+        assert torch.equal(v, want)
+    assert float(opt.flat_grad[pad].abs().sum()) == 0.0
