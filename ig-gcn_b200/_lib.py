@@ -56,11 +56,13 @@ SIGNATURES = {
     "igcn_bn_act_bwd": (ctypes.c_int, [_P] * 6 + [_I] * 5 + [_P] * 4),
     "igcn_bn_eval_act": (ctypes.c_int, [_P] * 5 + [_I] * 3 + [ctypes.c_double, _I, _P, _P, _P]),
     "igcn_lin_bn_act_supported": (_I, [_I] * 5),
+    "igcn_lin_bn_act_partial_rows": (_I, [_I] * 4),
     "igcn_lin_bn_act_fwd": (ctypes.c_int, [_P] * 5 + [_I] * 5 + [ctypes.c_double, ctypes.c_double, _I] + [_P] * 6),
     "igcn_lin_bn_act_bwd": (ctypes.c_int, [_P] * 7 + [_I] * 6 + [_P] * 6),
     "igcn_reduce_blocks": (_I, [_I]),
     "igcn_mask_loss_fwd": (ctypes.c_int, [_P, _I, _P, _I, _P, _I, _P, ctypes.c_double, _P, _I, _P, _P]),
     "igcn_mask_loss_bwd": (ctypes.c_int, [_P, _I, _P, _I, _P, _I, _P, ctypes.c_double, _P, _P, _P, _P, _P]),
+    "igcn_sum3": (ctypes.c_int, [_P, _P, _P, _I, _P, _P]),
     "igcn_dot": (ctypes.c_int, [_P, _P, _I, ctypes.c_double, _P, _I, _P, _P]),
     "igcn_rbf_similarity": (ctypes.c_int, [_P, _I, _I, ctypes.c_double, _P, _P, _P]),
     "igcn_col_mean": (ctypes.c_int, [_P, _I, _I, _I, _P, _P]),

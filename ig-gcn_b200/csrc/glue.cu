@@ -8,6 +8,8 @@
 //   igcn_mask_loss_fwd/bwd: loss_probability of kernel/sgcn_img_snp.py:153-181 (L1 + binary entropy of sigmoid(prob),
 //                           p_e and sigmoid(snps_prob)) as one reduction.
 //   igcn_dot              : <a, b> with a fixed summation order (the Laplacian quadratic form of consist_loss).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace igcn {
@@ -410,21 +412,38 @@ __global__ void __launch_bounds__(1024) bn_act_bwd_pair_kernel(const float* __re
 // its z values from the channel's (N x K) slice of x, staged once in shared memory -- z is never written or read, and the backward
 // recomputes it the same way.  One launch each way instead of two / three (the read-out of the attention tokens is on the step's
 // critical path twice).  Two stacked passes (one per half of the CTA, as bn_act_*_pair_kernel), L = 1 or 32, K <= 8.
-constexpr int LB_MAXK = 8, LB_EPT = 16;
+constexpr int LB_MAXK = 8, LB_EPT = 16, LB_MAXCL = 8;
+// A channel's rows are split over the `CL` CTAs of a thread-block cluster (CL = 1, 2, 4 or 8: 19 channels alone would use 19 of 148
+// SMs); the CTAs exchange their partial statistics through distributed shared memory and combine them in rank order, so every CTA of
+// the cluster holds bit-identical (mean, rstd).  Rank r owns rows [r * rpr, (r + 1) * rpr) of EACH pass, rpr = ceil(N/2 / CL).
+struct LbGeo {
+    int c, rank, ng, rpr, r0, nl;
+};
 
-template <bool BWD>
-__device__ __forceinline__ void lb_stage(const float* __restrict__ x, const float* __restrict__ W, int N, int C, int L, int K, int c,
+__device__ __forceinline__ LbGeo lb_geo(int N, int CL) {
+    LbGeo q;
+    q.c = blockIdx.x / CL;
+    q.rank = blockIdx.x - q.c * CL;
+    q.ng = N >> 1;
+    q.rpr = (q.ng + CL - 1) / CL;
+    q.r0 = min(q.ng, q.rank * q.rpr);
+    q.nl = min(q.ng, q.r0 + q.rpr) - q.r0;
+    return q;
+}
+
+__device__ __forceinline__ void lb_stage(const float* __restrict__ x, const float* __restrict__ W, int C, int L, int K, const LbGeo& q,
                                          float* Ws, float* xs) {
     for (int i = threadIdx.x; i < L * K; i += blockDim.x) Ws[i] = W[i];
-    const int tot = N * K;                                   // the channel's slice of x: rows of K floats, row stride C * K
+    const int per = q.rpr * K, tot = 2 * per;                // this CTA's slice of x: pass-major, rows of K floats (row stride C * K)
     for (int i0 = 0; i0 < tot; i0 += 8 * blockDim.x) {
         float v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + threadIdx.x + u * blockDim.x;
+            v[u] = 0.f;
             if (i < tot) {
-                const int n = i / K, k = i - n * K;
-                v[u] = x[((int64_t)n * C + c) * K + k];
+                const int g = i >= per, j = i - g * per, n = j / K, k = j - n * K;
+                if (n < q.nl) v[u] = x[((int64_t)(g * q.ng + q.r0 + n) * C + q.c) * K + k];
             }
         }
 #pragma unroll
@@ -436,9 +455,23 @@ __device__ __forceinline__ void lb_stage(const float* __restrict__ x, const floa
     __syncthreads();
 }
 
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// value `idx` of the exchange block `xch` (this CTA's shared memory) as CTA `r` of the cluster holds it
+__device__ __forceinline__ float cluster_peek(const float* xch, int idx, int r) {
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(xch + idx);
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    return v;
+}
+
 __global__ void __launch_bounds__(1024) lin_bn_act_fwd_pair_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                  const float* __restrict__ mask, int N, int C, int L, int K, float eps,
+                                                                  const float* __restrict__ mask, int N, int C, int L, int K, int CL, float eps,
                                                                   float momentum, int relu, float* __restrict__ running_mean,
                                                                   float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
                                                                   float* __restrict__ y, float* __restrict__ stats) {
@@ -446,22 +479,24 @@ __global__ void __launch_bounds__(1024) lin_bn_act_fwd_pair_kernel(const float* 
     extern __shared__ float lbs[];
     __shared__ float sm[33];
     __shared__ float res[4];
+    __shared__ float xch[4];                       // (sum, M2 about the CTA's own mean) of pass 0 ; of pass 1
     float* Ws = lbs;
     float* xs = lbs + L * K;
-    const int nh = blockDim.x >> 1, c = blockIdx.x, g = threadIdx.x >= nh, tid = threadIdx.x - g * nh, wph = nh >> 5;
-    const int ng = N >> 1, cnt = ng * L, lsh = __ffs(L) - 1;
-    lb_stage<false>(x, W, N, C, L, K, c, Ws, xs);
+    const LbGeo q = lb_geo(N, CL);
+    const int nh = blockDim.x >> 1, c = q.c, g = threadIdx.x >= nh, tid = threadIdx.x - g * nh, wph = nh >> 5;
+    const int cnt = q.ng * L, cl = q.nl * L, lsh = __ffs(L) - 1;
+    lb_stage(x, W, C, L, K, q, Ws, xs);
     const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-    const int64_t base = ((int64_t)g * ng * C + c) * L;
+    const int64_t base = ((int64_t)(g * q.ng + q.r0) * C + c) * L;
     float zv[LB_EPT], mv[LB_EPT];
     float s = 0.f;
 #pragma unroll
     for (int u = 0; u < LB_EPT; ++u) {
         const int e = tid + u * nh;
         zv[u] = 0.f; mv[u] = 1.f;
-        if (e < cnt) {
+        if (e < cl) {
             const int n = e >> lsh, l = e & (L - 1);
-            const float* xr = xs + (g * ng + n) * K;
+            const float* xr = xs + (g * q.rpr + n) * K;
             const float* wr = Ws + l * K;
             float z = 0.f;
             for (int k = 0; k < K; ++k) z = fmaf(xr[k], wr[k], z);
@@ -470,20 +505,45 @@ __global__ void __launch_bounds__(1024) lin_bn_act_fwd_pair_kernel(const float* 
             s += z;
         }
     }
-    const float mean = half_sum(s, sm, g, wph) / (float)cnt;
-    float q = 0.f;
+    const float s_own = half_sum(s, sm, g, wph);
+    const float m_own = cl > 0 ? s_own / (float)cl : 0.f;
+    float qq = 0.f;
 #pragma unroll
     for (int u = 0; u < LB_EPT; ++u)
-        if (tid + u * nh < cnt) {
-            const float d = zv[u] - mean;
-            q += d * d;
+        if (tid + u * nh < cl) {
+            const float d = zv[u] - m_own;
+            qq += d * d;
         }
-    const float var = half_sum(q, sm, g, wph) / (float)cnt;
+    const float q_own = half_sum(qq, sm, g, wph);
+    float mean = m_own, var = q_own / (float)cnt;
+    if (CL > 1) {
+        // Chan's combination of the CTAs' (count, mean, M2): one exchange, no cancellation
+        if (tid == 0) { xch[2 * g] = s_own; xch[2 * g + 1] = q_own; }
+        cluster_sync_all();
+        float sr[LB_MAXCL], qr[LB_MAXCL];
+#pragma unroll
+        for (int r = 0; r < LB_MAXCL; ++r)
+            if (r < CL) { sr[r] = cluster_peek(xch, 2 * g, r); qr[r] = cluster_peek(xch, 2 * g + 1, r); }
+        float tot = 0.f;
+#pragma unroll
+        for (int r = 0; r < LB_MAXCL; ++r)
+            if (r < CL) tot += sr[r];
+        mean = tot / (float)cnt;
+        float m2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < LB_MAXCL; ++r)
+            if (r < CL) {
+                const int nr = (min(q.ng, (r + 1) * q.rpr) - min(q.ng, r * q.rpr)) * L;
+                const float d = nr > 0 ? sr[r] / (float)nr - mean : 0.f;
+                m2 += qr[r] + (float)nr * d * d;
+            }
+        var = m2 / (float)cnt;
+    }
     const float rstd = rsqrtf(var + eps);
 #pragma unroll
     for (int u = 0; u < LB_EPT; ++u) {
         const int e = tid + u * nh;
-        if (e < cnt) {
+        if (e < cl) {
             const int n = e >> lsh, l = e & (L - 1);
             float v = (zv[u] - mean) * rstd * ga + be;
             if (relu) v = fmaxf(v, 0.f);
@@ -492,13 +552,15 @@ __global__ void __launch_bounds__(1024) lin_bn_act_fwd_pair_kernel(const float* 
         }
     }
     if (tid == 0) {
-        stats[((int64_t)g * C + c) * 2 + 0] = mean;
-        stats[((int64_t)g * C + c) * 2 + 1] = rstd;
         res[2 * g] = mean;
         res[2 * g + 1] = var;
+        if (q.rank == 0) {
+            stats[((int64_t)g * C + c) * 2 + 0] = mean;
+            stats[((int64_t)g * C + c) * 2 + 1] = rstd;
+        }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {                        // the running buffers receive the two updates in pass order
+    if (threadIdx.x == 0 && q.rank == 0) {         // the running buffers receive the two updates in pass order
         float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 1.f;
         const float unb = (float)cnt / (float)max(cnt - 1, 1);
         for (int k = 0; k < 2; ++k) {
@@ -509,29 +571,33 @@ __global__ void __launch_bounds__(1024) lin_bn_act_fwd_pair_kernel(const float* 
         if (running_var) running_var[c] = rv;
         if (num_batches_tracked && c == 0) *num_batches_tracked += 2;
     }
+    if (CL > 1) cluster_sync_all();                // no CTA leaves while a peer may still read its exchange block
 }
 
-// dx[n][c][k] = sum_l dz[n][c][l] W[l][k] (complete inside the channel's CTA); partial dW[l][k] of channel c = sum_n dz[n][c][l] x[n][c][k]
+// dx[n][c][k] = sum_l dz[n][c][l] W[l][k] (complete inside the row's CTA); partial dW[l][k] of CTA (c, rank) = sum over its rows of
+// dz[n][c][l] x[n][c][k]
 __global__ void __launch_bounds__(1024) lin_bn_act_bwd_pair_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ mask, const float* __restrict__ stats,
-                                                                  const float* __restrict__ gy, int N, int C, int L, int K, int relu,
-                                                                  float* __restrict__ dx, float* __restrict__ partials /* (C, L*K) */,
+                                                                  const float* __restrict__ gy, int N, int C, int L, int K, int CL, int relu,
+                                                                  float* __restrict__ dx, float* __restrict__ partials /* (C * CL, L*K) */,
                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
     IGCN_PDL_SYNC();
     extern __shared__ float lbs[];
     __shared__ float sm[33];
     __shared__ float res[4];
+    __shared__ float xch[4];                       // (sum dy, sum dy * xhat) of pass 0 ; of pass 1
+    const LbGeo q = lb_geo(N, CL);
     float* Ws = lbs;
     float* xs = lbs + L * K;
-    float* red = xs + N * K;                       // (K, blockDim.x): the threads' dW partials
-    float* dzs = red + K * blockDim.x;             // L = 32 only: (N, 33) dz, padded rows (conflict-free row walks)
-    const int nt = blockDim.x, nh = nt >> 1, c = blockIdx.x, g = threadIdx.x >= nh, tid = threadIdx.x - g * nh, wph = nh >> 5;
+    float* red = xs + 2 * q.rpr * K;               // (K, blockDim.x): the threads' dW partials
+    float* dzs = red + K * blockDim.x;             // L = 32 only: (2 * rpr, 33) dz, padded rows (conflict-free row walks)
+    const int nt = blockDim.x, nh = nt >> 1, c = q.c, g = threadIdx.x >= nh, tid = threadIdx.x - g * nh, wph = nh >> 5;
     const int lane = threadIdx.x & 31;
-    const int ng = N >> 1, cnt = ng * L, lsh = __ffs(L) - 1;
-    lb_stage<true>(x, W, N, C, L, K, c, Ws, xs);
+    const int cnt = q.ng * L, cl = q.nl * L, lsh = __ffs(L) - 1;
+    lb_stage(x, W, C, L, K, q, Ws, xs);
     const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-    const int64_t base = ((int64_t)g * ng * C + c) * L;
+    const int64_t base = ((int64_t)(g * q.ng + q.r0) * C + c) * L;
     const float mean = stats[((int64_t)g * C + c) * 2 + 0], rstd = stats[((int64_t)g * C + c) * 2 + 1];
     float xh[LB_EPT], dv[LB_EPT];
     float s1 = 0.f, s2 = 0.f;
@@ -539,9 +605,9 @@ __global__ void __launch_bounds__(1024) lin_bn_act_bwd_pair_kernel(const float* 
     for (int u = 0; u < LB_EPT; ++u) {
         const int e = tid + u * nh;
         xh[u] = 0.f; dv[u] = 0.f;
-        if (e < cnt) {
+        if (e < cl) {
             const int n = e >> lsh, l = e & (L - 1);
-            const float* xr = xs + (g * ng + n) * K;
+            const float* xr = xs + (g * q.rpr + n) * K;
             const float* wr = Ws + l * K;
             float z = 0.f;
             for (int k = 0; k < K; ++k) z = fmaf(xr[k], wr[k], z);
@@ -557,6 +623,18 @@ __global__ void __launch_bounds__(1024) lin_bn_act_bwd_pair_kernel(const float* 
     }
     s1 = half_sum(s1, sm, g, wph);
     s2 = half_sum(s2, sm, g, wph);
+    if (CL > 1) {
+        if (tid == 0) { xch[2 * g] = s1; xch[2 * g + 1] = s2; }
+        cluster_sync_all();
+        float a1[LB_MAXCL], a2[LB_MAXCL];
+#pragma unroll
+        for (int r = 0; r < LB_MAXCL; ++r)
+            if (r < CL) { a1[r] = cluster_peek(xch, 2 * g, r); a2[r] = cluster_peek(xch, 2 * g + 1, r); }
+        s1 = 0.f; s2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < LB_MAXCL; ++r)
+            if (r < CL) { s1 += a1[r]; s2 += a2[r]; }
+    }
     const float m1 = s1 / (float)cnt, m2 = s2 / (float)cnt;
     float accw[LB_MAXK];
 #pragma unroll
@@ -565,29 +643,32 @@ __global__ void __launch_bounds__(1024) lin_bn_act_bwd_pair_kernel(const float* 
 #pragma unroll
     for (int u = 0; u < LB_EPT; ++u) {
         const int e = tid + u * nh;
-        const bool on = e < cnt;                   // uniform per warp when L = 32 (cnt is a multiple of 32); the shuffles below need all lanes
+        const bool on = e < cl;                    // uniform per warp when L = 32 (cl is a multiple of 32)
         const int n = on ? (e >> lsh) : 0;
         const float dz = on ? ga * rstd * (dv[u] - m1 - xh[u] * m2) : 0.f;
-        const float* xr = xs + (g * ng + n) * K;
+        const float* xr = xs + (g * q.rpr + n) * K;
 #pragma unroll
         for (int k = 0; k < LB_MAXK; ++k)
             if (k < K) {
                 accw[k] = fmaf(dz, xr[k], accw[k]);
-                if (L == 1 && on) dx[((int64_t)(g * ng + n) * C + c) * K + k] = dz * Ws[k];
+                if (L == 1 && on) dx[((int64_t)(g * q.ng + q.r0 + n) * C + c) * K + k] = dz * Ws[k];
             }
-        if (L == 32 && on) dzs[(g * ng + n) * 33 + l] = dz;
+        if (L == 32 && on) dzs[(g * q.rpr + n) * 33 + l] = dz;
     }
     if (L == 32) {
         // dx[n][k] = sum_l dz[n][l] W[l][k]: a thread per (n, k) walks the 32 outputs of its row in shared memory (a warp-shuffle sum per
         // element and k was 800 instructions per thread: the first version of this kernel took 40 us)
         __syncthreads();
-        for (int o = threadIdx.x; o < N * K; o += nt) {
-            const int n = o / K, k = o - n * K;
-            const float* dr = dzs + n * 33;
-            float t = 0.f;
+        const int per = q.rpr * K;
+        for (int o = threadIdx.x; o < 2 * per; o += nt) {
+            const int gg = o >= per, j = o - gg * per, n = j / K, k = j - n * K;
+            if (n < q.nl) {
+                const float* dr = dzs + (gg * q.rpr + n) * 33;
+                float t = 0.f;
 #pragma unroll 8
-            for (int j = 0; j < 32; ++j) t = fmaf(dr[j], Ws[j * K + k], t);
-            dx[((int64_t)n * C + c) * K + k] = t;
+                for (int jj = 0; jj < 32; ++jj) t = fmaf(dr[jj], Ws[jj * K + k], t);
+                dx[((int64_t)(gg * q.ng + q.r0 + n) * C + c) * K + k] = t;
+            }
         }
     }
 #pragma unroll
@@ -605,19 +686,20 @@ __global__ void __launch_bounds__(1024) lin_bn_act_bwd_pair_kernel(const float* 
         res[2 * g + 1] = s1;
     }
     __syncthreads();
-    for (int o = threadIdx.x; o < L * K; o += nt) {   // dW[l][k] of this channel: the partials with this l, in thread (warp) order
+    for (int o = threadIdx.x; o < L * K; o += nt) {   // dW[l][k] of this CTA's rows: the partials with this l, in thread (warp) order
         const int lo = o / K, k = o - lo * K;
         float t = 0.f;
         if (L == 1)
             for (int w = 0; w < (nt >> 5); ++w) t += red[k * nt + w];
         else
             for (int j = lo; j < nt; j += L) t += red[k * nt + j];
-        partials[(int64_t)c * L * K + o] = t;
+        partials[(int64_t)blockIdx.x * L * K + o] = t;
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && q.rank == 0) {
         if (dgamma) dgamma[c] = res[0] + res[2];
         if (dbeta) dbeta[c] = res[1] + res[3];
     }
+    if (CL > 1) cluster_sync_all();
 }
 
 // ---- loss_probability -----------------------------------------------------------------------------------------------------
@@ -695,6 +777,27 @@ __global__ void __launch_bounds__(256) dot_partial_kernel(const float* __restric
     if (blockIdx.x == 0 && threadIdx.x < (int)(n - n4)) s += a[n4 + threadIdx.x] * b[n4 + threadIdx.x];
     s = block_sum_256(s, sm);
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+// out[i] = (a[i] + b[i]) + c[i]  (c may be null): the gradient of a tensor with several consumers, in one launch
+__global__ void __launch_bounds__(256) sum3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                                   int64_t n, float* __restrict__ out) {
+    IGCN_PDL_SYNC();
+    const int64_t stride = (int64_t)gridDim.x * 256 * 4;
+    const int64_t n4 = n & ~(int64_t)3;
+    for (int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; i < n4; i += stride) {
+        const float4 x = *reinterpret_cast<const float4*>(a + i);
+        const float4 y = *reinterpret_cast<const float4*>(b + i);
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c) z = *reinterpret_cast<const float4*>(c + i);
+        float4 r;
+        r.x = (x.x + y.x) + z.x; r.y = (x.y + y.y) + z.y; r.z = (x.z + y.z) + z.z; r.w = (x.w + y.w) + z.w;
+        *reinterpret_cast<float4*>(out + i) = r;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n - n4)) {
+        const int64_t i = n4 + threadIdx.x;
+        out[i] = (a[i] + b[i]) + (c ? c[i] : 0.f);
+    }
 }
 
 // out[i] = a[i] * (s[0] * scale)
@@ -894,12 +997,58 @@ extern "C" int igcn_bn_act_bwd(const float* z, const float* gamma, const float* 
 
 static int lb_threads(int64_t cnt) { return cnt >= 4096 ? 1024 : (cnt >= 1024 ? 512 : 256); }
 
+// CTAs per channel (cluster size): halve the rows per CTA while a CTA keeps >= 32 rows of each pass and the grid stays within ~2 CTAs per SM
+static int lb_cluster(int64_t N, int64_t C, int64_t L) {
+    static int off = -1;
+    if (off < 0) {
+        const char* e = getenv("IGCN_LIN_BN_CLUSTER");
+        off = (e && e[0] == '0') ? 1 : 0;
+    }
+    if (off || L != 32) return 1;
+    int cl = 1;
+    while (cl < LB_MAXCL && (N / 2) / (cl * 2) >= 32 && C * cl * 2 <= (int64_t)sm_count() * 2) cl *= 2;
+    return cl;
+}
+
+static int64_t lb_rows(int64_t N, int cl) { return (N / 2 + cl - 1) / cl; }
+
+template <typename... Params, typename... Args>
+static void launch_cluster(void (*kernel)(Params...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, int cl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cl;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+    if (igcn::pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
 extern "C" int64_t igcn_lin_bn_act_supported(int64_t N, int64_t C, int64_t L, int64_t K, int64_t groups) {
     if (groups != 2 || N < 2 || (N & 1) || C < 1 || K < 1 || K > LB_MAXK || !(L == 1 || L == 32)) return 0;
-    const int64_t cnt = (N / 2) * L;
+    const int cl = lb_cluster(N, C, L);
+    const int64_t rpr = lb_rows(N, cl), cnt = rpr * L;
     const int nthr = lb_threads(cnt);
-    if (cnt <= 1 || cnt > (int64_t)LB_EPT * (nthr / 2) || (L == 32 && (cnt % 32) != 0)) return 0;
-    return (L * K + N * K + K * nthr + (L == 32 ? N * 33 : 0)) * 4 <= 160 * 1024 ? 1 : 0;
+    if ((N / 2) * L <= 1 || cnt > (int64_t)LB_EPT * (nthr / 2)) return 0;
+    return (L * K + 2 * rpr * K + K * nthr + (L == 32 ? 2 * rpr * 33 : 0)) * 4 <= 160 * 1024 ? 1 : 0;
+}
+
+/* rows of the `partials` workspace of igcn_lin_bn_act_bwd (one per CTA) */
+extern "C" int64_t igcn_lin_bn_act_partial_rows(int64_t N, int64_t C, int64_t L, int64_t K) {
+    (void)K;
+    return C * lb_cluster(N, C, L);
 }
 
 extern "C" int igcn_lin_bn_act_fwd(const float* x, const float* W, const float* gamma, const float* beta, const float* mask, int64_t N,
@@ -910,12 +1059,14 @@ extern "C" int igcn_lin_bn_act_fwd(const float* x, const float* W, const float* 
     IGCN_REQUIRE(igcn_lin_bn_act_supported(N, C, L, K, groups), IGCN_ERR_UNSUPPORTED,
                  "lin_bn_act_fwd: shape (N=%lld C=%lld L=%lld K=%lld groups=%lld) not supported (see igcn_lin_bn_act_supported)", (long long)N,
                  (long long)C, (long long)L, (long long)K, (long long)groups);
-    const int nthr = lb_threads((N / 2) * L);
-    const size_t smem = sizeof(float) * (size_t)(L * K + N * K);
+    const int cl = lb_cluster(N, C, L);
+    const int64_t rpr = lb_rows(N, cl);
+    const int nthr = lb_threads(rpr * L);
+    const size_t smem = sizeof(float) * (size_t)(L * K + 2 * rpr * K);
     int rc = allow_smem(lin_bn_act_fwd_pair_kernel, smem, "lin_bn_act_fwd");
     if (rc) return rc;
-    igcn::launch_k(lin_bn_act_fwd_pair_kernel, dim3((unsigned)C), dim3(nthr), smem, (cudaStream_t)stream, x, W, gamma, beta, mask, (int)N, (int)C,
-                   (int)L, (int)K, (float)eps, (float)momentum, (int)relu, running_mean, running_var, num_batches_tracked, y, stats);
+    launch_cluster(lin_bn_act_fwd_pair_kernel, (unsigned)(C * cl), (unsigned)nthr, smem, (cudaStream_t)stream, cl, x, W, gamma, beta, mask, (int)N,
+                   (int)C, (int)L, (int)K, cl, (float)eps, (float)momentum, (int)relu, running_mean, running_var, num_batches_tracked, y, stats);
     IGCN_CHECK_LAUNCH("lin_bn_act_fwd");
     return IGCN_OK;
 }
@@ -925,15 +1076,18 @@ extern "C" int igcn_lin_bn_act_bwd(const float* x, const float* W, const float* 
                                    float* partials, float* dW, float* dgamma, float* dbeta, void* stream) {
     IGCN_REQUIRE(x && W && stats && g_y && dx && partials && dW, IGCN_ERR_BAD_ARG, "lin_bn_act_bwd: null pointer");
     IGCN_REQUIRE(igcn_lin_bn_act_supported(N, C, L, K, groups), IGCN_ERR_UNSUPPORTED, "lin_bn_act_bwd: shape not supported");
-    const int nthr = lb_threads((N / 2) * L);
-    const size_t smem = sizeof(float) * (size_t)(L * K + N * K + K * nthr + (L == 32 ? N * 33 : 0));
+    const int cl = lb_cluster(N, C, L);
+    const int64_t rpr = lb_rows(N, cl);
+    const int nthr = lb_threads(rpr * L);
+    const size_t smem = sizeof(float) * (size_t)(L * K + 2 * rpr * K + K * nthr + (L == 32 ? 2 * rpr * 33 : 0));
     int rc = allow_smem(lin_bn_act_bwd_pair_kernel, smem, "lin_bn_act_bwd");
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    igcn::launch_k(lin_bn_act_bwd_pair_kernel, dim3((unsigned)C), dim3(nthr), smem, st, x, W, gamma, beta, mask, stats, g_y, (int)N, (int)C, (int)L,
-                   (int)K, (int)relu, dx, partials, dgamma, dbeta);
+    launch_cluster(lin_bn_act_bwd_pair_kernel, (unsigned)(C * cl), (unsigned)nthr, smem, st, cl, x, W, gamma, beta, mask, stats, g_y, (int)N, (int)C,
+                   (int)L, (int)K, cl, (int)relu, dx, partials, dgamma, dbeta);
     IGCN_CHECK_LAUNCH("lin_bn_act_bwd");
-    igcn::launch_k(reduce_partials_kernel, dim3((unsigned)((L * K + 31) / 32)), dim3(reduce_threads(C)), 0, st, partials, (int)C, (int)(L * K), dW);
+    igcn::launch_k(reduce_partials_kernel, dim3((unsigned)((L * K + 31) / 32)), dim3(reduce_threads(C * cl)), 0, st, partials, (int)(C * cl),
+                   (int)(L * K), dW);
     IGCN_CHECK_LAUNCH("lin_bn_act_reduce");
     return IGCN_OK;
 }
@@ -990,6 +1144,15 @@ extern "C" int igcn_dot(const float* a, const float* b, int64_t n, double scale,
     IGCN_CHECK_LAUNCH("dot_partial");
     igcn::launch_k(sum_partials_kernel, dim3(1), dim3(256), 0, st, partials, (int)n_partials, (float)scale, out);
     IGCN_CHECK_LAUNCH("sum_partials");
+    return IGCN_OK;
+}
+
+extern "C" int igcn_sum3(const float* a, const float* b, const float* c, int64_t n, float* out, void* stream) {
+    IGCN_REQUIRE(a && b && out && n >= 0, IGCN_ERR_BAD_ARG, "sum3: bad argument");
+    IGCN_REQUIRE((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)out) & 15) == 0, IGCN_ERR_BAD_ARG, "sum3: operands must be 16-byte aligned");
+    if (n == 0) return IGCN_OK;
+    igcn::launch_k(sum3_kernel, dim3(blocks_for(n, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, a, b, c, n, out);
+    IGCN_CHECK_LAUNCH("sum3");
     return IGCN_OK;
 }
 

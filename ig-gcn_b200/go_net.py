@@ -279,7 +279,9 @@ class Gene_ontology_network(nn.Module):
         ls = self.latent_stream if (self.branch_stream is not None and x.is_cuda) else None
         if ls is not None:                        # the fusion heads wait for `latent`: its six kernels start right here, on their own stream
             ls.wait_stream(torch.cuda.current_stream(dev))
-        atten_out = self._lin_bn(self.conc_for_attention[0], self.conc_for_attention[1], x)
+        # three consumers of the encoder output (attention tokens, decoder, latent read-outs): their gradients are summed once
+        x_att, x_dec, x_lat = ops.fan_out(x, 3)
+        atten_out = self._lin_bn(self.conc_for_attention[0], self.conc_for_attention[1], x_att)
         if self.atten_ready is not None:          # lets a caller on another stream start the cross attention before the decoder is done
             self.atten_ready.record(torch.cuda.current_stream(dev))
         def decoder(x):
@@ -304,18 +306,18 @@ class Gene_ontology_network(nn.Module):
             cur = torch.cuda.current_stream(dev)
             br.wait_stream(cur)
             with torch.cuda.stream(br):
-                x_D = decoder(x)
+                x_D = decoder(x_dec)
             x.record_stream(br)
             if ls is not None:
                 with torch.cuda.stream(ls):
-                    latent = latent_head(x)
+                    latent = latent_head(x_lat)
                 x.record_stream(ls)
             else:
-                latent = latent_head(x)
+                latent = latent_head(x_lat)
             self.decoder_joined = False
         else:
-            x_D = decoder(x)
-            latent = latent_head(x)
+            x_D = decoder(x_dec)
+            latent = latent_head(x_lat)
             self.decoder_joined = True
         if own_pass:
             self.mask_bank.end_pass()

@@ -374,6 +374,8 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
                     # the regression head's masked image features depend on x and the node mask only: made here so that their
                     # backward (an elementwise product and a reduction over the batch) also runs beside the main stream
                     img_feat = (x.view(B, self.rois, -1) * self.prob).reshape(B, -1)
+                plain_done = torch.cuda.Event()
+                plain_done.record(side2)          # main joins HERE: the similarity matrix below is not needed before the consistency loss
                 if consist and stacked and self.isSoftSimilarity and _PREFETCH_CONSIST:
                     # the similarity matrix of the consistency loss depends on the batch only: built here, off the path that
                     # later waits for out_z (consist_loss_pair finds it in the cache)
@@ -384,7 +386,7 @@ class SGCN_GCN_IMGSNP(nn.Module, MaskedEncoderMixin):
         self._pe_cache = ((x.data_ptr(), edge_index.data_ptr(), self.prob._version, self.prob_bias._version), p_e,
                           torch.is_grad_enabled())
         if side2 is not None:
-            main.wait_stream(side2)
+            main.wait_event(plain_done)
             h_plain.record_stream(main)
             if img_feat is not None:
                 img_feat.record_stream(main)

@@ -153,6 +153,43 @@ def sgcn_encoder(x, csr: GraphCSR, weights, biases, prob=None, prob_bias=None, w
     return _SGCNEncoderFn.apply(x, prob, prob_bias, wb, csr, L, H, want_pe, relu, out)
 
 
+class _FanOutFn(torch.autograd.Function):
+    """k aliases of one tensor for k consumers.  Backward: ONE sum of the consumers' gradients, taken when the last has arrived.
+    autograd's own accumulation adds the gradients pairwise as they arrive, each add on the producer's stream -- which puts the
+    fast consumers' backward chains in front of the slow consumer's on that stream (device timeline)."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        x = x.contiguous()
+        return tuple(_alias(x) for _ in range(k))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        gs = [g.contiguous() for g in gs if g is not None]
+        if not gs:
+            return None, None
+        if len(gs) == 1:
+            return gs[0], None
+        acc = gs[0]
+        rest = gs[1:]
+        while rest:
+            b, c = rest[0], (rest[1] if len(rest) > 1 else None)
+            rest = rest[2:]
+            out = torch.empty_like(acc)
+            with torch.cuda.device(acc.device):
+                _lib.call("igcn_sum3", _lib.ptr(acc), _lib.ptr(b), _lib.ptr(c), acc.numel(), _lib.ptr(out), _lib.stream(), tag="fan_out_sum",
+                          nbytes=4 * acc.numel() * (3 + (c is not None)))
+            acc = out
+        return acc, None
+
+
+def fan_out(x, k):
+    """x for k consumers whose gradients are summed in one launch (CUDA tensors that need a gradient; otherwise x itself k times)."""
+    if k < 2 or not x.is_cuda or not (torch.is_grad_enabled() and x.requires_grad) or os.environ.get("IGCN_NO_FAN_OUT") == "1":
+        return (x,) * k
+    return _FanOutFn.apply(x, k)
+
+
 def join_halves(a, b, whole):
     """`whole` (2B, ...) as an autograd tensor whose halves are a and b -- the tensors two producers wrote into whole[:B] / whole[B:]
     through their `out=` argument -- without the copy of torch.cat([a, b], 0)."""
@@ -539,13 +576,15 @@ class _CatLinearFn(torch.autograd.Function):
             aux = _aux_stream(dev) if _AUX_STREAM else None
             if aux is not None and aux == cur:       # this head's forward already ran on the auxiliary stream (forward_pair)
                 aux = _aux_stream(dev, 1)
-            if aux is not None:
-                entry = torch.cuda.Event()
-                entry.record(cur)
             if any(d is not None for d in dxs):          # queued first: the rest of the backward waits for it
                 _tc_split(jobs_x, dev)
                 _tc_gemm(gz, wt, M, K, N, dxs, ctx.widths, [0 if d is None else d.stride(0) for d in dxs], tag="cat_linear_bwd_x_tc")
             if aux is not None:
+                # the weight-gradient side starts when the input-gradient GEMM has been issued, not beside it: its operand split fills
+                # every SM with small CTAs, and the GEMM (one CTA per SM, all of its shared memory) then waits for the split to drain
+                # -- measured on the device timeline as 8 us added to the path the attention backward waits for
+                entry = torch.cuda.Event()
+                entry.record(cur)
                 aux.wait_event(entry)
                 with torch.cuda.stream(aux):
                     weight_grad()
@@ -862,7 +901,7 @@ class _LinBnActFn(torch.autograd.Function):
         L = Wc.shape[0]
         dx = torch.empty_like(xc)
         dW = torch.empty_like(Wc)
-        part = torch.empty((C, L * K), dtype=torch.float32, device=xc.device)
+        part = torch.empty((int(_lib.lib().igcn_lin_bn_act_partial_rows(N, C, L, K)), L * K), dtype=torch.float32, device=xc.device)
         dg = torch.empty(C, dtype=torch.float32, device=xc.device) if gamma is not None else None
         db = torch.empty(C, dtype=torch.float32, device=xc.device) if beta is not None else None
         with torch.cuda.device(xc.device):

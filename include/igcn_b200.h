@@ -295,9 +295,11 @@ int igcn_bn_eval_act(const float* z, const float* gamma, const float* beta, cons
  * dropout scale that follows it (kernel/go_model.py:117-131: conc_for_attention, conc -> B, conc_D -> B_D):
  *   y = mask * relu(BatchNorm_c(x W^T)),  x (N, C, K), W (L, K), y / mask (N, C, L), statistics per channel c over (n, l) and per
  *   stacked pass (groups = 2 only).  z = x W^T is never materialised; the backward recomputes it.  igcn_lin_bn_act_supported(...) = 1
- *   when the shape fits (otherwise use igcn_skinny_linear_* + igcn_bn_act_*).  bwd: dx (N, C, K), dW (L, K) via partials (C, L*K),
- *   dgamma / dbeta (C).  Deterministic. */
+ *   when the shape fits (otherwise use igcn_skinny_linear_* + igcn_bn_act_*).  bwd: dx (N, C, K), dW (L, K) via partials
+ *   (igcn_lin_bn_act_partial_rows(N, C, L, K), L*K), dgamma / dbeta (C).  Deterministic.  For L = 32 a channel's rows are split over
+ *   a thread-block cluster of up to 8 CTAs that combine their statistics through distributed shared memory. */
 int64_t igcn_lin_bn_act_supported(int64_t N, int64_t C, int64_t L, int64_t K, int64_t groups);
+int64_t igcn_lin_bn_act_partial_rows(int64_t N, int64_t C, int64_t L, int64_t K);
 int igcn_lin_bn_act_fwd(const float* x, const float* W, const float* gamma, const float* beta, const float* mask, int64_t N, int64_t C,
                         int64_t L, int64_t K, int64_t groups, double eps, double momentum, int64_t relu, float* running_mean,
                         float* running_var, long long* num_batches_tracked, float* y, float* stats, void* stream);
@@ -325,6 +327,11 @@ int igcn_mask_loss_bwd(const float* prob, int64_t n_prob, const float* p_e, int6
  * loss tr(s^T (D - W) s) / B^2 of kernel/sgcn_img_snp.py:183-196 and its gradient 2 T g / B^2. */
 int igcn_dot(const float* a, const float* b, int64_t n, double scale, float* partials, int64_t n_partials, float* out, void* stream);
 int igcn_scale_by_scalar(const float* a, const float* s, double scale, int64_t n, float* out, void* stream);
+
+/* out[i] = (a[i] + b[i]) + c[i] over n f32 values (c may be NULL; all 16-byte aligned): the gradient of a tensor read by up to three
+ * consumers, summed when the last one has arrived.  The reference leaves this to autograd (one add per extra consumer, e.g. the
+ * GO encoder output read by conc_for_attention, conc and the decoder, kernel/go_model.py:232-262); see ops.fan_out. */
+int igcn_sum3(const float* a, const float* b, const float* c, int64_t n, float* out, void* stream);
 
 /* The consistency loss without its cancellation (csrc/laplacian.cu): with L = D - W and L 1 = 0,
  *   <s, L s> = <s', T>,  T = L s = d .* s' - W s',  s' = s - column means,  d = row sums of W.
