@@ -421,7 +421,7 @@ def dp_allreduce_check(opt, world, dev):
         p.grad = None
     opt.flat_grad.copy_(grad)
     gg = opt.gather_grads
-    opt.gather_grads = lambda: None
+    opt.gather_grads = lambda count_step=False: (opt.step_t.add_(1.0) if count_step else None)
     torch.cuda.synchronize()
     dist.barrier()
     opt.step()

@@ -50,7 +50,7 @@ SIGNATURES = {
     "igcn_catlin_mma_bwd_dw": (ctypes.c_int, [_P] * 8 + [_I] * 4 + [_P] * 3),
     "igcn_dropout_masks": (ctypes.c_int, [_P, _P, _P, _I, ctypes.c_uint64, _P, _P]),
     "igcn_adam_step": (ctypes.c_int, [_P] * 6 + [ctypes.c_double] * 4 + [_I, _P]),
-    "igcn_gather_flat": (ctypes.c_int, [_P, _P, _P, _I, _P, _I, _P]),
+    "igcn_gather_flat": (ctypes.c_int, [_P, _P, _P, _I, _P, _I, _P, _P]),
     "igcn_gather_flat_launches": (_I, [_I]),
     "igcn_bn_act_fwd": (ctypes.c_int, [_P] * 4 + [_I] * 4 + [ctypes.c_double] * 2 + [_I] + [_P] * 6),
     "igcn_bn_act_bwd": (ctypes.c_int, [_P] * 6 + [_I] * 5 + [_P] * 4),

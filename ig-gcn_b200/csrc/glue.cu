@@ -999,12 +999,10 @@ static int lb_threads(int64_t cnt) { return cnt >= 4096 ? 1024 : (cnt >= 1024 ? 
 
 // CTAs per channel (cluster size): halve the rows per CTA while a CTA keeps >= 32 rows of each pass and the grid stays within ~2 CTAs per SM
 static int lb_cluster(int64_t N, int64_t C, int64_t L) {
-    static int off = -1;
-    if (off < 0) {
-        const char* e = getenv("IGCN_LIN_BN_CLUSTER");
-        off = (e && e[0] == '0') ? 1 : 0;
-    }
-    if (off || L != 32) return 1;
+    // opt-in (IGCN_LIN_BN_CLUSTER=1): measured SLOWER inside the step (0.447 vs 0.401 ms on the same box) although the kernels alone are
+    // not -- a cluster needs its 8 CTAs co-scheduled in one GPC, which the concurrent SGCN / attention kernels rarely leave free
+    const char* e = getenv("IGCN_LIN_BN_CLUSTER");
+    if (!(e && e[0] == '1') || L != 32) return 1;
     int cl = 1;
     while (cl < LB_MAXCL && (N / 2) / (cl * 2) >= 32 && C * cl * 2 <= (int64_t)sm_count() * 2) cl *= 2;
     return cl;

@@ -54,7 +54,9 @@ struct GatherTable {
     int n[GATHER_MAX];
 };
 
-__global__ void __launch_bounds__(256) gather_flat_kernel(const __grid_constant__ GatherTable t, float* __restrict__ dst) {
+__global__ void __launch_bounds__(256) gather_flat_kernel(const __grid_constant__ GatherTable t, float* __restrict__ dst,
+                                                          float* __restrict__ step_counter) {
+    if (step_counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) step_counter[0] += 1.f;
     const int e = blockIdx.y;
     const float* __restrict__ s = t.src[e];
     float* __restrict__ d = dst + t.off[e];
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(256) gather_flat_kernel(const __grid_constant_
 }  // namespace igcn
 
 extern "C" int igcn_gather_flat(const int64_t* host_src_ptrs, const int64_t* host_offsets, const int64_t* host_sizes, int64_t count,
-                                float* flat, int64_t flat_n, void* stream) {
+                                float* flat, int64_t flat_n, float* step_counter, void* stream) {
     using namespace igcn;
     IGCN_REQUIRE(count >= 0, IGCN_ERR_BAD_ARG, "gather_flat: negative count");
     if (count == 0) return IGCN_OK;
@@ -108,7 +110,7 @@ extern "C" int igcn_gather_flat(const int64_t* host_src_ptrs, const int64_t* hos
         int64_t gx = (biggest / 4 + 256 * 4 - 1) / (256 * 4);       // one round of 4 float4 per thread covers the largest tensor ...
         if (gx > 16) gx = 16;                                       // ... up to 16 CTAs per tensor
         if (gx < 1) gx = 1;
-        gather_flat_kernel<<<dim3((unsigned)gx, (unsigned)m), 256, 0, (cudaStream_t)stream>>>(t, flat);
+        gather_flat_kernel<<<dim3((unsigned)gx, (unsigned)m), 256, 0, (cudaStream_t)stream>>>(t, flat, base == 0 ? step_counter : nullptr);
         IGCN_CHECK_LAUNCH("gather_flat");
     }
     return IGCN_OK;

@@ -239,9 +239,10 @@ class FlatAdam(object):
             self.lr_t.fill_(lr)
             self._lr_seen = lr
 
-    def gather_grads(self):
+    def gather_grads(self, count_step=False):
         """p.grad of every parameter -> its slot of flat_grad, one launch (igcn_gather_flat); a parameter without a gradient gets
-        zeros.  Gradients that are not plain contiguous f32 tensors (none in this package's models) take a torch copy."""
+        zeros.  Gradients that are not plain contiguous f32 tensors (none in this package's models) take a torch copy.
+        count_step: the same launch increments the device step counter the update reads."""
         from . import _lib
         import ctypes
         n = len(self.params)
@@ -260,7 +261,8 @@ class FlatAdam(object):
         off, sizes = self._gather_tab
         with torch.cuda.device(self.flat_grad.device):
             _lib.call("igcn_gather_flat", ctypes.addressof(src), ctypes.addressof(off), ctypes.addressof(sizes), n,
-                      _lib.ptr(self.flat_grad), self.n, _lib.stream(), tag="gather_flat", nbytes=8 * self.n)
+                      _lib.ptr(self.flat_grad), self.n, _lib.ptr(self.step_t) if count_step else None, _lib.stream(),
+                      tag="gather_flat", nbytes=8 * self.n)
             _lib.launch_count += int(_lib.lib().igcn_gather_flat_launches(n)) - 1
         for v, g in odd:
             v.copy_(g)
@@ -270,10 +272,9 @@ class FlatAdam(object):
         import ctypes
         if not torch.cuda.is_current_stream_capturing():
             self.sync_lr()
-        self.gather_grads()
+        self.gather_grads(count_step=True)
         if self._peer is not None:
             # gradient all-reduce (sum in rank order, / world) + Adam in one kernel over peer memory
-            self.step_t += 1.0
             g, pr = self.param_groups[0], self._peer
             with torch.cuda.device(self.flat_param.device):
                 _lib.call("igcn_dp_allreduce_adam", ctypes.addressof(pr["grad_ptrs"]), ctypes.addressof(pr["signal_ptrs"]), pr["rank"], pr["world"],
@@ -287,12 +288,25 @@ class FlatAdam(object):
                 and not os.environ.get("IGCN_DIAG_NO_ALLREDUCE"):       # diagnostic switch: isolates the collective's cost
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
             scale = 1.0 / dist.get_world_size(self.group)
-        self.step_t += 1.0
         g = self.param_groups[0]
         with torch.cuda.device(self.flat_param.device):
             _lib.call("igcn_adam_step", _lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
                       _lib.ptr(self.exp_avg_sq), _lib.ptr(self.step_t), _lib.ptr(self.lr_t), float(g["betas"][0]),
                       float(g["betas"][1]), float(g["eps"]), scale, self.n, _lib.stream())
+
+
+_SEEDS = {}
+
+
+def _grad_seed(loss):
+    key = (loss.device, loss.dtype, tuple(loss.shape))
+    t = _SEEDS.get(key)
+    if t is None:
+        if loss.is_cuda and torch.cuda.is_current_stream_capturing():
+            return None                   # never allocate the persistent seed inside a capture; the warm-up steps create it
+        t = torch.ones_like(loss)
+        _SEEDS[key] = t
+    return t
 
 
 def train_step(model, data, optimizer=None, lambda_loss=None, flat: FlatGradAllReduce = None, isSoftSimilarity=True):
@@ -307,7 +321,7 @@ def train_step(model, data, optimizer=None, lambda_loss=None, flat: FlatGradAllR
     from . import ops
     ops.defer_weight_grad_joins()         # weight-gradient products on auxiliary streams are joined once, here, before the optimizer
     try:
-        loss.backward()
+        loss.backward(_grad_seed(loss))   # a cached ones tensor: torch would launch a fill for the seed, on the step's critical path
     finally:
         ops.join_weight_grads()
     if getattr(model, "_pe_cache", None) is not None:

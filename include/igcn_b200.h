@@ -263,9 +263,11 @@ int igcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp
  *   host_src_ptrs / host_offsets / host_sizes: HOST arrays of `count` entries -- device address of a contiguous f32 gradient
  *   (0: the slot is zero-filled, a parameter that received no gradient), element offset of its slot in `flat` (multiple of 4)
  *   and element count.  The table is passed to the kernel by value: the host arrays may be freed on return and the launch can be
- *   captured in a CUDA graph (the captured addresses are the graph's own).  igcn_gather_flat_launches = kernels launched. */
+ *   captured in a CUDA graph (the captured addresses are the graph's own).  step_counter (device f32 scalar, may be NULL) is
+ *   incremented by 1: the optimizer's step count that igcn_adam_step / igcn_dp_allreduce_adam read next, so that the increment is
+ *   not a launch of its own between the gather and the update.  igcn_gather_flat_launches = kernels launched. */
 int igcn_gather_flat(const int64_t* host_src_ptrs, const int64_t* host_offsets, const int64_t* host_sizes, int64_t count,
-                     float* flat, int64_t flat_n, void* stream);
+                     float* flat, int64_t flat_n, float* step_counter, void* stream);
 int64_t igcn_gather_flat_launches(int64_t count);
 
 /* ------------------------------------------------------------------------------------------

@@ -51,7 +51,8 @@ def _worker(rank, world, port, out_dir):
     for p in opt.params:
         p.grad = None
     opt.flat_grad.copy_(grad)
-    opt.gather_grads = lambda: None                                      # the flat buffer already holds this rank's gradient
+    # the flat buffer already holds this rank's gradient; the gather launch also counts the step
+    opt.gather_grads = lambda count_step=False: (opt.step_t.add_(1.0) if count_step else None)
     opt.step()
     torch.cuda.synchronize()
     opt.check_dp_error()
