@@ -94,6 +94,11 @@ static GeoB2 bwd2_geo(int R, int M, int H, int64_t B) {
     const int tmax = (B * ((T + 5) / 6) >= (int64_t)8 * sm_count()) ? 6 : 3;
     g.nchunk = (T + tmax - 1) / tmax;
     g.TPI = (T + g.nchunk - 1) / g.nchunk;
+    static const int force = [] { const char* e = getenv("IGCN_ATTN_TPI"); return e ? atoi(e) : 0; }();
+    if (force >= 1 && force <= 6) {                          // experiment switch: fixed tiles per item (the last item of a graph may be short)
+        g.TPI = force < T ? force : T;
+        g.nchunk = (T + g.TPI - 1) / g.TPI;
+    }
     g.PS = g.MP == 8 ? 8 : (g.MP == 32 ? 40 : 24);          // row stride of the P / dS buffers: conflict-free as an MMA B operand
     g.rows_pad = 16 * g.TPI;
     g.nthreads = 32 * g.TPI;
