@@ -141,10 +141,11 @@ extern "C" int igcn_adam_step(float* params, const float* grads, float* exp_avg,
 //
 // Every rank keeps its flat gradient buffer in symmetric (peer-mapped) memory.  The kernel of rank r
 //   1. signals every peer and waits for every peer, block by block (all gradient buffers are complete and visible),
-//   2. loads each 16-byte gradient chunk from ALL ranks (its own through L2, the others over NVLink / NVSwitch), adds them in rank
-//      order -- so every rank computes bit-identical sums and the replicas never drift -- scales by 1/world and applies the Adam
-//      update to its own parameter replica,
-//   3. signals / waits again so no rank starts overwriting its gradients while a peer still reads them.
+//   2. for the slice it OWNS of every block's range: loads the chunks from ALL ranks (its own through L2, the others over
+//      NVLink / NVSwitch), adds them in rank order and stores the sum back into all ranks' buffers, in place -- every sum is computed
+//      once, so the replicas are bit-identical and never drift, and a rank moves n bytes each way whatever the world size,
+//   3. signals / waits again (all sums have landed everywhere; from here on a rank touches only its own memory),
+//   4. scales its now-reduced gradient by 1/world and applies the Adam update to its own parameter replica.
 // This replaces ncclAllReduce + a separate optimizer launch (at 1.66 MB per rank the collective is latency bound: two device-side
 // flag exchanges and one pass over the data instead of a ring).  Flags are one 32-bit word per (block, peer) in each rank's signal
 // pad, set with a release CAS 0 -> 1 by the sender and cleared with an acquire CAS 1 -> 0 by the receiver, so they reset themselves
@@ -157,7 +158,7 @@ namespace igcn {
 
 constexpr int DP_MAX_WORLD = 16;
 struct DpPeers {
-    const float* grad[DP_MAX_WORLD];     // gradient buffer of every rank (peer pointers)
+    float* grad[DP_MAX_WORLD];           // gradient buffer of every rank (peer pointers)
     uint32_t* signal[DP_MAX_WORLD];      // signal pad of every rank
 };
 
@@ -210,13 +211,36 @@ __global__ void __launch_bounds__(512) dp_allreduce_adam_kernel(DpPeers peers, i
     const float t = step[0];
     const float bias1 = 1.f - powf(beta1, t), bias2 = 1.f - powf(beta2, t);
     const float step_size = lr[0] / bias1, inv_sqrt_bias2 = rsqrtf(bias2), scale = 1.f / (float)world;
-    const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x;      // n is a multiple of 4 (FlatAdam pads every parameter)
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < world; ++r) {                                      // rank order: identical sums on every rank
-            const float4 x = reinterpret_cast<const float4*>(peers.grad[r])[i];
-            g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+    // block b of every rank works on the same contiguous range of 16-byte chunks [c0, c1); n is a multiple of 4 (FlatAdam pads)
+    const int64_t n4 = n >> 2, per = (n4 + gridDim.x - 1) / gridDim.x;
+    const int64_t c0 = min(n4, (int64_t)blockIdx.x * per), c1 = min(n4, c0 + per);
+    float* __restrict__ mine = peers.grad[rank];
+    if (world > 1) {
+        // Phase 1 (reduce-scatter + all-gather in place): rank r OWNS the r-th slice of the block's range; it reads the slice from all
+        // ranks, adds in rank order and stores the sum back into ALL ranks' buffers.  NVLink traffic per rank: n read + n written,
+        // independent of the world size (the one-shot version of round 1 read world * n per rank: 38 MB at 8 ranks, the 48 us that
+        // limited the scaling run), and all threads of the block share the slice, so it is one or two round trips deep.
+        const int64_t slice = (c1 - c0 + world - 1) / world;
+        const int64_t s0 = min(c1, c0 + (int64_t)rank * slice), s1 = min(c1, s0 + slice);
+        for (int64_t i = s0 + threadIdx.x; i < s1; i += blockDim.x) {
+            float4 x[DP_MAX_WORLD];
+#pragma unroll
+            for (int r = 0; r < DP_MAX_WORLD; ++r)
+                if (r < world) x[r] = reinterpret_cast<const float4*>(peers.grad[r])[i];
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < DP_MAX_WORLD; ++r)                              // rank order: the same sum as a serial loop over ranks
+                if (r < world) { g.x += x[r].x; g.y += x[r].y; g.z += x[r].z; g.w += x[r].w; }
+#pragma unroll
+            for (int r = 0; r < DP_MAX_WORLD; ++r)
+                if (r < world) reinterpret_cast<float4*>(peers.grad[r])[i] = g;
         }
+        // every rank's sums of this block's chunks have landed everywhere; after this point a rank touches only its own memory, so
+        // no closing barrier is needed (the next step's opening barrier orders the next gather against these reads)
+        dp_block_barrier(peers, rank, world, 1, timeout_cycles, error_flag);
+    }
+    for (int64_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+        const float4 g = __ldcg(reinterpret_cast<const float4*>(mine) + i);      // written by the owner rank: not through L1
         float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
 #define IGCN_ADAM1(C)                                                   \
     {                                                                   \
@@ -231,7 +255,6 @@ __global__ void __launch_bounds__(512) dp_allreduce_adam_kernel(DpPeers peers, i
         reinterpret_cast<float4*>(m)[i] = mv;
         reinterpret_cast<float4*>(v)[i] = vv;
     }
-    dp_block_barrier(peers, rank, world, 1, timeout_cycles, error_flag);
 }
 
 }  // namespace igcn
@@ -261,7 +284,7 @@ extern "C" int igcn_dp_allreduce_adam(const int64_t* host_grad_ptrs, const int64
                  (long long)signal_pad_bytes, (long long)world);
     DpPeers peers;
     for (int r = 0; r < DP_MAX_WORLD; ++r) {
-        peers.grad[r] = r < world ? reinterpret_cast<const float*>(host_grad_ptrs[r]) : nullptr;
+        peers.grad[r] = r < world ? reinterpret_cast<float*>(host_grad_ptrs[r]) : nullptr;
         peers.signal[r] = r < world ? reinterpret_cast<uint32_t*>(host_signal_ptrs[r]) : nullptr;
         IGCN_REQUIRE(r >= world || (peers.grad[r] && peers.signal[r] && ((uintptr_t)peers.grad[r] & 15) == 0), IGCN_ERR_BAD_ARG,
                      "dp_allreduce_adam: bad peer pointer for rank %d", r);

@@ -422,8 +422,9 @@ int igcn_step_loss_bwd(const float* reg, const float* target, int64_t n_reg, con
  *   phase (choose minutes: ranks may be seconds apart); on expiry the kernel stores ((phase << 8) | (peer + 1)) into `error_flag`
  *   (a device or mapped-host int the caller polls; the step's result is then invalid) or, when error_flag is NULL, traps.  All
  *   ranks must issue their steps in lock-step and should meet at a host barrier before the first fused launch.  The kernel
- *   sums the `world` gradients in rank order (bit-identical replicas), scales by 1/world and updates params / exp_avg / exp_avg_sq
- *   exactly as igcn_adam_step does.  n must be a multiple of 4.  igcn_dp_adam_blocks = CTAs used (0: signal pad too small).
+ *   sums the `world` gradients in rank order -- each chunk once, by its owner rank, which stores the sum back into EVERY
+ *   rank's gradient buffer (the buffers hold the un-scaled sum afterwards; bit-identical replicas; n bytes per rank each way over
+ *   NVLink whatever the world size) -- scales by 1/world and updates params / exp_avg / exp_avg_sq exactly as igcn_adam_step does.  n must be a multiple of 4.  igcn_dp_adam_blocks = CTAs used (0: signal pad too small).
  */
 int64_t igcn_dp_adam_blocks(int64_t n, int64_t world, int64_t signal_pad_bytes);
 int igcn_dp_allreduce_adam(const int64_t* host_grad_ptrs, const int64_t* host_signal_ptrs, int64_t rank, int64_t world,
