@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(512) dp_allreduce_adam_kernel(DpPeers peers, i
     if (world > 1) {
         // Phase 1 (reduce-scatter + all-gather in place): rank r OWNS the r-th slice of the block's range; it reads the slice from all
         // ranks, adds in rank order and stores the sum back into ALL ranks' buffers.  NVLink traffic per rank: n read + n written,
-        // independent of the world size (the one-shot version of round 1 read world * n per rank: 38 MB at 8 ranks, the 48 us that
-        // limited the scaling run), and all threads of the block share the slice, so it is one or two round trips deep.
+        // independent of the world size (the one-shot version of round 1 read world * n per rank), every sum is computed once, and
+        // all threads of the block share the slice, so the phase is one or two round trips deep.
         const int64_t slice = (c1 - c0 + world - 1) / world;
         const int64_t s0 = min(c1, c0 + (int64_t)rank * slice), s1 = min(c1, s0 + slice);
         for (int64_t i = s0 + threadIdx.x; i < s1; i += blockDim.x) {
