@@ -12,7 +12,8 @@ ADNI-shaped subjects.  Nothing is skipped inside the ti
   e2e   : graphs/s through the public API: pinned host arrays -> DataLoader-style collation (H2D + collate
           kernel) -> train step -> loss read back to the host, every step
   roofline     : the dominant igcn kernel, algorithmic bytes / CUDA-event duration measured inside the timed steps
-  cpu_baseline : the oracle port of the reference's CPU path (with its per-subject GO loop) on the host cores, bounded sample
+  cpu_baseline : the reference's own train() on the host cores (unmodified files from baseline/_ref, kind "reference"), else the
+                 oracle port of it with its per-subject GO loop (kind "port"); bounded sample
 """
 import argparse
 import json
@@ -393,7 +394,7 @@ def run_igcn(args, w):
     if world == 1 and args.workload == "config2" and not args.no_config4_kernels:
         out["roofline_config4"] = sgcn_kernels_at_config4(dev, peak, flush)
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(w, steps=3, warmup=1)
+        out["cpu_baseline"] = cpu_baseline_leg(args, w)
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(out), flush=True)
@@ -784,18 +785,108 @@ def cpu_baseline(w, steps, warmup, threads=None):
                        "oracle/igcn_oracle.py with the reference's per-subject GO loop" % (Bc, steps))
 
 
+def reference_cpu(w, steps, warmup, threads=None):
+    """The UNMODIFIED reference on the host cores: its own SGCN_GCN_IMGSNP (kernel/sgcn_img_snp.py), DataLoader / Batch
+    collation (dataloader.py, batch.py) and train() (kernel/train_eval_sgcn_img_snps.py:511-548) with torch.optim.Adam, imported
+    from baseline/_ref (a byte-for-byte copy checked against its MANIFEST.json; oracle/make_ref.py).  torch_geometric 2.0.2 /
+    torch_scatter are not installable here: their calls resolve to the restatement in oracle/shim.  One step = train() over a
+    loader holding one batch of the reference's default size, i.e. collation + both forwards + every loss term + backward + Adam."""
+    import hashlib
+    import warnings
+    from igcn_b200 import synthetic as syn
+    from oracle import ref_loader
+    root = ref_loader.TRAVEL_ROOT
+    man = json.load(open(os.path.join(root, "MANIFEST.json")))["files"]
+    for rel, h in man.items():
+        if hashlib.sha256(open(os.path.join(root, rel), "rb").read()).hexdigest() != h:
+            raise RuntimeError("baseline/_ref/%s differs from the copied reference file" % rel)
+    warnings.filterwarnings("ignore")
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    REF = ref_loader.load(root, with_train=True)
+    Bc = min(CPU_SAMPLE_B, w["B"])
+    adj, go_snps, pool_dim = syn.make_go_hierarchy(w["pool"], w["S"], seed=0)
+    A = torch.tensor(adj).float().t().to_sparse().coalesce()           # train_eval_sgcn_img_snps.py:69-70
+    A_g = torch.tensor(go_snps).float().to_sparse().coalesce()
+    torch.manual_seed(0)
+    model = REF.sgcn_img_snp.SGCN_GCN_IMGSNP(w["L"], w["H"], A_g, A, pool_dim, 32, "cpu", rois=w["R"], H_0=3,
+                                             num_classes=w["num_classes"], isCrossAtten=True, isSoftSimilarity=True, rbf_gamma=0.01,
+                                             isuseProb4Regr=True, num_regr=w["num_regr"], isImageOnly=False, isSNPsOnly=False)
+    if w["S"] != 54:                                                   # the reference hard-codes 54 SNPs (sgcn_img_snp.py:96)
+        raise RuntimeError("the unmodified reference model only takes 54 SNPs")
+    sub = syn.make_subjects(Bc, rois=w["R"], n_snps=w["S"], seed=1234, num_classes=w["num_classes"], num_regr=w["num_regr"])
+    ep = sub["edge_ptr"]
+    data = [REF.Data(x=torch.from_numpy(sub["x"][i]),
+                     edge_index=torch.from_numpy(np.vstack([sub["edge_src"][ep[i]:ep[i + 1]], sub["edge_dst"][ep[i]:ep[i + 1]]])),
+                     edge_attr=torch.from_numpy(sub["edge_attr"][ep[i]:ep[i + 1]]),
+                     y=torch.tensor([sub["y"][i]]), clust_y=torch.tensor([sub["clust_y"][i]]),
+                     snps_feat=torch.from_numpy(sub["snps_feat"][i:i + 1]), sbjID=torch.tensor([sub["sbjID"][i]]),
+                     tsne_fdim=torch.from_numpy(sub["tsne_fdim"][i:i + 1]), clini_score=torch.from_numpy(sub["clini_score"][i]))
+            for i in range(Bc)]
+    loader = REF.dataloader.DataLoader(data, batch_size=Bc, shuffle=False)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0)
+    crit = torch.nn.MSELoss(reduction="none")
+
+    def one():
+        return REF.train_eval.train(model, opt, loader, 0.01, LAMBDA, crit, True, "cpu")
+
+    for _ in range(warmup):
+        one()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        loss = one()
+        ts.append(time.perf_counter() - t0)
+    s = float(np.median(ts))
+    if not np.isfinite(loss):
+        raise RuntimeError("reference train() returned a non-finite loss")
+    return dict(value=Bc / s, unit=UNIT, cores=threads, kind="reference", s_per_step=s, loss_last=float(loss),
+                step_times_s=[round(t, 4) for t in ts],
+                sample="%d-graph batch (reference default batch size) of the same workload, %d timed calls of the reference's own "
+                       "train() (DataLoader collation + 2 forwards + all loss terms + backward + Adam), torch CPU fp32, unmodified "
+                       "reference files from baseline/_ref (%d files, sha256-checked); torch_geometric / torch_scatter calls resolve "
+                       "to the restatement in oracle/shim" % (Bc, steps, len(man)))
+
+
+def cpu_baseline_leg(args, w):
+    """cpu_baseline of the igcn line: the reference arm (6 timed steps) in a CHILD process, so that the reference's modules and
+    the oracle/shim stand-ins for torch_geometric never enter the process that runs the product path; falls back to the
+    in-process oracle port if the child fails."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
+                            "--steps", "6", "--warmup", "2"], capture_output=True, text=True, timeout=600,
+                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")})
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+        return json.loads(line)["cpu_baseline"]
+    except Exception as e:
+        sys.stderr.write("bench.py: reference child failed (%s: %s); timing the oracle port in process\n" % (type(e).__name__, e))
+        return cpu_baseline(w, steps=3, warmup=1)
+
+
 def run_reference(args, w):
-    """The reference arm: the reference's CPU implementation of the path (oracle port; the Python reference itself cannot
-    travel to the GPU box) with all host threads, on bounded samples of the same workload."""
+    """The reference arm: the reference's own CPU implementation of the path with all host threads, on bounded samples of the
+    same workload -- the unmodified reference files from baseline/_ref when that directory travelled with the snapshot
+    (kind "reference"), else the oracle port (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cb = cpu_baseline(w, steps=max(args.steps, 1), warmup=max(args.warmup, 1))
+    cb, why = None, None
+    if os.environ.get("IGCN_REFERENCE_ARM", "reference") != "port":
+        try:
+            cb = reference_cpu(w, steps=max(args.steps, 1), warmup=max(args.warmup, 1))
+        except Exception as e:                     # absent / damaged copy: say so and time the port instead
+            why = "%s: %s" % (type(e).__name__, e)
+            sys.stderr.write("bench.py: reference files unusable (%s); timing the oracle port\n" % why)
+    if cb is None:
+        cb = cpu_baseline(w, steps=max(args.steps, 1), warmup=max(args.warmup, 1))
+        if why:
+            cb["reference_unusable"] = why
     out = dict(impl="reference", metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                ms_per_step=cb["s_per_step"] * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                config=dict(workload=args.workload, description=w["desc"], graphs_per_step=min(CPU_SAMPLE_B, w["B"]), rois=w["R"],
-                           layers=w["L"], hidden=w["H"], step="zero_grad + plain fwd + explain fwd + losses + bwd + Adam (CPU)",
+                           layers=w["L"], hidden=w["H"], step="zero_grad + plain fwd + explain fwd + losses + bwd + Adam (CPU)" +
+                           ("; the reference's own train() incl. DataLoader collation and its zero-weight terms" if cb["kind"] == "reference" else ""),
                            lambda_loss=LAMBDA),
                cpu_baseline=cb,
                e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)

@@ -1,10 +1,13 @@
 """ORACLE / TEST INFRASTRUCTURE ONLY.
 
-Imports the UNMODIFIED reference files from /root/reference on CPU, on top of the
-pure-torch shim in oracle/shim.  This only works in the
-authoring container (the GPU box has no /root/reference); it is used by
-tests/golden/make_golden.py to pin the travelling oracle (oracle/igcn_oracle.py)
-against the reference's own outputs.
+Imports the UNMODIFIED reference files on CPU, on top of the pure-torch shim in
+oracle/shim.  Two roots:
+
+  * /root/reference (authoring container only): tests/golden/make_golden.py pins the
+    travelling oracle (oracle/igcn_oracle.py) against the reference's own outputs;
+  * baseline/_ref (git-ignored, NOT gpurun-ignored: it travels to the GPU box): a verbatim
+    copy of the path's files made by oracle/make_ref.py; `bench.py --impl reference`
+    imports the reference's own train() from there (cpu_baseline.kind = "reference").
 """
 import os
 import sys
@@ -14,22 +17,27 @@ REF_ROOT = os.environ.get("IGCN_REFERENCE_ROOT", "/root/reference")
 SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
 
 
-def available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "kernel", "sgcn_img_snp.py"))
+TRAVEL_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 
 
-def load():
-    """Returns a namespace with the reference's own classes/modules."""
-    if not available():
-        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
-    for p in (REF_ROOT, SHIM):
+def available(root=None) -> bool:
+    return os.path.isfile(os.path.join(root or REF_ROOT, "kernel", "sgcn_img_snp.py"))
+
+
+def load(root=None, with_train=False):
+    """Returns a namespace with the reference's own classes/modules, imported from `root` (default /root/reference).
+    One root per process: the modules are cached in sys.modules under the reference's own names."""
+    root = root or REF_ROOT
+    if not available(root):
+        raise RuntimeError("reference tree not present at %s" % root)
+    for p in (root, SHIM):
         if p in sys.path:
             sys.path.remove(p)
-    sys.path[:0] = [SHIM, REF_ROOT]
+    sys.path[:0] = [SHIM, root]
     # bypass kernel/__init__.py (it imports datasets.py -> TU datasets -> real PyG)
     if "kernel" not in sys.modules or not getattr(sys.modules["kernel"], "_igcn_stub", False):
         pkg = types.ModuleType("kernel")
-        pkg.__path__ = [os.path.join(REF_ROOT, "kernel")]
+        pkg.__path__ = [os.path.join(root, "kernel")]
         pkg._igcn_stub = True
         sys.modules["kernel"] = pkg
     import importlib
@@ -42,4 +50,7 @@ def load():
     ns.batch = importlib.import_module("batch")
     ns.dataloader = importlib.import_module("dataloader")
     ns.Data = importlib.import_module("torch_geometric.data").Data
+    if with_train:
+        ns.train_eval = importlib.import_module("kernel.train_eval_sgcn_img_snps")   # train(): :511-548
+    ns.root = root
     return ns
