@@ -14,6 +14,7 @@ x, edge_index, edge_attr, batch, y, snps_feat, clini_score, tsne_fdim, clust_y, 
 """
 from __future__ import annotations
 
+import weakref
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -70,17 +71,33 @@ class GraphCSR(object):
 _structures = {}
 
 
+def _structure_key(t):
+    return (t.data_ptr(), tuple(t.shape), str(t.device))
+
+
 def register_structure(csr, *tensors):
     for t in tensors:
         if t is not None:
-            _structures[(t.data_ptr(), tuple(t.shape), str(t.device))] = csr
+            _structures[_structure_key(t)] = (weakref.ref(t), t._version, csr)
     while len(_structures) > 64:
         _structures.pop(next(iter(_structures)))
 
 
 def lookup_structure(t):
-    """GraphCSR registered for this `edge_index` / `batch` tensor by Batch (same storage and shape), or None."""
-    return None if t is None else _structures.get((t.data_ptr(), tuple(t.shape), str(t.device)))
+    """GraphCSR registered for this `edge_index` / `batch` tensor by Batch (same storage and shape), or None.  An entry is valid
+    only while the tensor it was registered for is alive and unedited: once that tensor is freed the allocator may hand its
+    address to an unrelated tensor of the same shape (the next batch of a fixed-size loader), which must not inherit the structure."""
+    if t is None:
+        return None
+    key = _structure_key(t)
+    e = _structures.get(key)
+    if e is None:
+        return None
+    owner = e[0]()
+    if owner is None or owner._version != e[1]:
+        _structures.pop(key, None)
+        return None
+    return e[2]
 
 
 class SubjectSet(object):

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import math
 import os
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -48,6 +49,12 @@ class MaskedEncoderMixin:
     """cal_probability / loss bookkeeping shared by the SGCN model family."""
 
     def _csr_for(self, data, rois):
+        # Called first by every forward: a new forward may be a new batch, and `data.to(device)` of a fixed-size loader tends to
+        # land on the addresses the previous batch just freed, so nothing keyed on a device address may outlive the forward that
+        # made it.  The intended reuse survives: the explain forward of a step stores p_e for that step's loss_probability, and
+        # the first consist_loss of a step stores the similarity matrix for the second one.
+        self._pe_cache = None
+        self._w_cache = None
         csr = get_csr(data)
         if csr is None:
             b = Batch.from_device_tensors(data.x.detach(), data.edge_index, data.edge_attr, rois)
@@ -56,12 +63,13 @@ class MaskedEncoderMixin:
                 data._igcn_csr = csr
             except Exception:
                 pass
-        self._last_csr = (data.edge_index.data_ptr(), data.edge_index.shape[1], csr)
+        self._last_csr = (data.edge_index.data_ptr(), data.edge_index.shape[1], csr, weakref.ref(data.edge_index))
         return csr
 
     def _csr_lookup(self, x, edge_index, edge_weight):
         last = getattr(self, "_last_csr", None)
-        if last is not None and last[0] == edge_index.data_ptr() and last[1] == edge_index.shape[1]:
+        # valid only while the edge_index of the last forward is alive (its address cannot have been recycled then)
+        if last is not None and last[3]() is not None and last[0] == edge_index.data_ptr() and last[1] == edge_index.shape[1]:
             return last[2]
         return Batch.from_device_tensors(x.detach(), edge_index, edge_weight, self.rois).csr
 

@@ -37,7 +37,7 @@ from .data import Batch, lookup_structure
 
 # ---- graph structure cache --------------------------------------------------------------------------------------------------
 class _CSR(object):
-    __slots__ = ("rowptr_t", "csr_src", "csr_perm", "rowptr_s", "csc_pos", "N", "E")
+    __slots__ = ("rowptr_t", "csr_src", "csr_perm", "rowptr_s", "csc_pos", "N", "E", "keep")
 
 
 _csr_cache: "OrderedDict[tuple, _CSR]" = OrderedDict()
@@ -45,7 +45,9 @@ _csr_cache: "OrderedDict[tuple, _CSR]" = OrderedDict()
 
 def graph_csr(edge_index: torch.Tensor, num_nodes: int) -> _CSR:
     """Target-sorted CSR + source-sorted transposed index of an arbitrary (2, E) int64 edge_index, built on the device
-    (igcn_graph_csr) and cached per (storage, version, shape)."""
+    (igcn_graph_csr) and cached per (storage address, version, shape).  An entry holds a reference to the edge_index it was built from:
+    while it is cached its storage cannot be freed, so the allocator cannot hand the same address to a NEW edge_index of the same
+    shape (every batch of a fixed-size loader) and have it hit a stale entry; in-place edits change `_version`.  At most 8 entries."""
     _lib.require_cuda(edge_index)
     if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
         raise RuntimeError("edge_index must be an int64 tensor of shape (2, E)")
@@ -68,8 +70,9 @@ def graph_csr(edge_index: torch.Tensor, num_nodes: int) -> _CSR:
                   _lib.ptr(c.csc_pos), _lib.ptr(work), _lib.stream(), tag="graph_csr")
     if not torch.cuda.is_current_stream_capturing() and int(work[-1]) != 0:      # one host read per NEW edge_index
         raise RuntimeError("edge_index holds node ids outside [0, %d)" % N)
+    c.keep = ei
     _csr_cache[key] = c
-    while len(_csr_cache) > 16:
+    while len(_csr_cache) > 8:
         _csr_cache.popitem(last=False)
     return c
 

@@ -483,3 +483,58 @@ def test_fused_eval_loop_golden(case):
             r_, _, _ = O.train_step_loss(P64, prep, bb, L, R, lam, 0.01, training=False, with_orth=False)
             refs.append(float(r_) * bb["snps_feat"].shape[0])
         H.assert_close(torch.tensor(l2), torch.tensor(sum(refs) / B), what="eval loss, two batches")
+
+
+def test_batch_sequence_equals_fresh_model_per_batch():
+    """Nothing keyed on a device address may survive a batch.  A reference-style loop (train_eval_sgcn_img_snps.py:564-590) over
+    several equally shaped batches frees batch k before batch k+1 is moved to the device, so the new tensors tend to land on the
+    same addresses; the p_e, similarity-matrix and structure caches must not serve batch k's values for batch k+1.  Every per-batch
+    value of ONE long-lived model equals what a fresh copy of the model, which has seen nothing else, computes for that batch."""
+    import copy
+    import types
+    from igcn_b200 import synthetic as syn
+    from igcn_b200.data import Data, DataLoader
+    from igcn_b200.img_snp_model import SGCN_GCN_IMGSNP
+    hp = types.SimpleNamespace(lamda_x_l1=0.1, lamda_e_l1=0.1, lamda_x_ent=0.1, lamda_e_ent=0.1, lamda_mi=1, lamda_ce=1)
+    device = torch.device(DEV)
+    sub = syn.make_subjects(12, rois=90, n_snps=54, seed=21)
+    ep = sub["edge_ptr"]
+    dataset = [Data(x=torch.from_numpy(sub["x"][i]),
+                    edge_index=torch.from_numpy(np.vstack([sub["edge_src"][ep[i]:ep[i + 1]], sub["edge_dst"][ep[i]:ep[i + 1]]])),
+                    edge_attr=torch.from_numpy(sub["edge_attr"][ep[i]:ep[i + 1]]), y=torch.tensor([sub["y"][i]]),
+                    clust_y=torch.tensor([sub["clust_y"][i]]), snps_feat=torch.from_numpy(sub["snps_feat"][i:i + 1]),
+                    sbjID=torch.tensor([sub["sbjID"][i]]), tsne_fdim=torch.from_numpy(sub["tsne_fdim"][i:i + 1]),
+                    clini_score=torch.from_numpy(sub["clini_score"][i])) for i in range(12)]
+    adj, go_snps, pool_dim = syn.make_go_hierarchy(None, 54, seed=0)
+    A = torch.tensor(adj).float().t().to_sparse().coalesce().to(device)
+    A_g = torch.tensor(go_snps).float().to_sparse().coalesce().to(device)
+    torch.manual_seed(3)
+    model = SGCN_GCN_IMGSNP(2, 16, A_g, A, pool_dim, 32, device, rois=90, H_0=3, num_classes=3, isSoftSimilarity=True, rbf_gamma=0.01,
+                            isCrossAtten=True, num_regr=3, isuseProb4Regr=True, isImageOnly=False, isSNPsOnly=False).to(device)
+    model.eval()
+    state = copy.deepcopy(model.state_dict())
+
+    def values(m, data):
+        o = m(data, 0.1, device)
+        q = m(data, 0.1, device, isExplain=True)
+        c = m.consist_loss(o[2], data.tsne_fdim)
+        cp = m.consist_loss(q[2], data.tsne_fdim)
+        lp = m.loss_probability(data.x, data.edge_index, data.edge_attr, hp)
+        return torch.stack([c.detach().reshape(()), cp.detach().reshape(()), lp.detach().reshape(()), o[5].detach().sum(),
+                            q[5].detach().sum()]).cpu()
+
+    seq = []
+    for data in DataLoader(dataset, 4, shuffle=False):
+        data = data.to(device)
+        seq.append(values(model, data))
+        del data
+    assert len(seq) == 3
+    assert not torch.equal(seq[0], seq[1]) and not torch.equal(seq[1], seq[2])        # the batches do differ
+    for k, data in enumerate(DataLoader(dataset, 4, shuffle=False)):
+        fresh = SGCN_GCN_IMGSNP(2, 16, A_g, A, pool_dim, 32, device, rois=90, H_0=3, num_classes=3, isSoftSimilarity=True,
+                                rbf_gamma=0.01, isCrossAtten=True, num_regr=3, isuseProb4Regr=True, isImageOnly=False,
+                                isSNPsOnly=False).to(device)
+        fresh.load_state_dict(state)
+        fresh.eval()
+        ref = values(fresh, data.to(device))
+        assert torch.allclose(seq[k], ref, rtol=1e-6, atol=1e-7), (k, seq[k], ref)

@@ -157,3 +157,31 @@ def test_batch_utilities_general_case():
     H.assert_close(out, ref, what="scatter sum")
     out.sum().backward()
     assert torch.equal(src.grad, torch.ones_like(src))
+
+
+def test_graph_csr_cache_is_not_fooled_by_a_recycled_address():
+    """A loader with fixed-size batches frees one edge_index and allocates the next one, same shape, very likely at the same
+    device address: the structure cache must not return the previous batch's CSR for it."""
+    from igcn_b200 import pyg
+    N, E, C = 200, 900, 5
+    conv = pyg.GCNConv(C, 8).to(DEV)
+    x = torch.randn(N, C, generator=torch.Generator().manual_seed(0))
+    xc = x.to(DEV)
+    seen = set()
+    for seed in (21, 22, 23, 24):
+        ei, w = _random_graph(N, E, seed)
+        ei_dev = ei.to(DEV)
+        seen.add(ei_dev.data_ptr())
+        out = conv(xc, ei_dev, w.to(DEV))
+        ref = O.gcn_conv(x.double(), ei, w.double(), conv.lin.weight.detach().cpu().double(), conv.bias.detach().cpu().double())
+        H.assert_close(out, ref, what="out seed %d" % seed)
+        del ei_dev, out
+    # in-place edit of a cached edge_index: the version counter changes the key
+    ei, w = _random_graph(N, E, 30)
+    ei_dev = ei.to(DEV)
+    conv(xc, ei_dev, w.to(DEV))
+    ei2, _ = _random_graph(N, E, 31)
+    ei_dev.copy_(ei2.to(DEV))
+    out = conv(xc, ei_dev, w.to(DEV))
+    ref = O.gcn_conv(x.double(), ei2, w.double(), conv.lin.weight.detach().cpu().double(), conv.bias.detach().cpu().double())
+    H.assert_close(out, ref, what="out after in-place edit")
