@@ -286,3 +286,28 @@ def test_reference_arm_runs_the_unmodified_reference_files():
     # no tracked file of the repository is a copy of a reference file (baseline/_ref is git-ignored)
     tracked = subprocess.run(["git", "ls-files", "baseline"], cwd=root, capture_output=True, text=True).stdout.strip()
     assert tracked == ""
+
+
+def test_structure_registry_entries_die_with_their_tensor():
+    """data.register_structure / lookup_structure: a structure is found through the tensor it was registered for (or a view of the
+    same storage) only while that tensor is alive and unedited; a recycled address never inherits it."""
+    import gc
+    from igcn_b200 import data
+    t = torch.zeros(6, dtype=torch.int64)
+    data.register_structure("csr-of-t", t)
+    assert data.lookup_structure(t) == "csr-of-t"
+    assert data.lookup_structure(t[:]) == "csr-of-t"              # same storage, same shape
+    assert data.lookup_structure(torch.zeros(6, dtype=torch.int64)) is None
+    t.add_(1)                                                      # edited in place: the version differs
+    assert data.lookup_structure(t) is None
+    u = torch.zeros(6, dtype=torch.int64)
+    data.register_structure("csr-of-u", u)
+    key = data._structure_key(u)
+    del u
+    gc.collect()
+    entry = data._structures.get(key)
+    assert entry is not None and entry[0]() is None               # the owner is gone ...
+    fake = torch.zeros(6, dtype=torch.int64)
+    data._structures[data._structure_key(fake)] = entry           # ... so even a tensor that lands on that key gets nothing
+    assert data.lookup_structure(fake) is None
+    assert data.lookup_structure(None) is None
